@@ -1,0 +1,248 @@
+"""Seeded synthetic inputs shared by the golden generator, the tests and bench.py.
+
+Everything here is derived from ``numpy.random.default_rng`` (PCG64, stream-stable across
+numpy versions) so the golden fixtures generated in the build container can be regenerated
+bit-for-bit on the GPU box, where ``/root/reference`` does not exist.
+
+Shapes follow SURVEY.md section 8(d): 1920x1080 BGR uint8 frames, track boxes w~U(30,90),
+h~U(90,250), velocity N(0,3) px/frame, detector score U(0.7,0.95).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+
+PATCH_H, PATCH_W = 384, 128
+
+
+# ----------------------------------------------------------------------------------------
+# frames
+# ----------------------------------------------------------------------------------------
+def _upsample_linear(field_lr: np.ndarray, H: int, W: int) -> np.ndarray:
+    """Separable linear interpolation of a [h,w,3] field to [H,W,3] (numpy only)."""
+    h, w, _ = field_lr.shape
+    ys = np.linspace(0.0, h - 1.0, H)
+    xs = np.linspace(0.0, w - 1.0, W)
+    y0 = np.floor(ys).astype(np.int64).clip(0, h - 2)
+    x0 = np.floor(xs).astype(np.int64).clip(0, w - 2)
+    fy = (ys - y0)[:, None, None]
+    fx = (xs - x0)[None, :, None]
+    rows = field_lr[y0] * (1.0 - fy) + field_lr[y0 + 1] * fy          # [H,w,3]
+    return rows[:, x0] * (1.0 - fx) + rows[:, x0 + 1] * fx             # [H,W,3]
+
+
+def make_frame(seed: int, H: int = 1080, W: int = 1920, noise: float = 8.0) -> np.ndarray:
+    """Low-frequency colour field + Gaussian noise, uint8 BGR [H,W,3]."""
+    rng = np.random.default_rng(seed)
+    lr = rng.uniform(20.0, 235.0, size=(32, 32, 3))
+    img = _upsample_linear(lr, H, W)
+    img += rng.normal(0.0, noise, size=img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def next_frame(prev: np.ndarray, seed: int, noise: float = 4.0) -> np.ndarray:
+    """Previous frame shifted by one pixel in x plus fresh noise (cheap 'video')."""
+    rng = np.random.default_rng(seed)
+    out = np.roll(prev, 1, axis=1).astype(np.int16)
+    out += np.rint(rng.normal(0.0, noise, size=out.shape)).astype(np.int16)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------------
+# weights in the model_busca.pth layout
+# ----------------------------------------------------------------------------------------
+RESNET_LAYERS = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))  # (planes, blocks, stride)
+
+
+def reid_conv_specs():
+    """Yield (key_prefix, Cin, Cout, k, stride) for every conv of the ReID ResNet-50 in
+    forward order, plus the name of the BatchNorm that follows it."""
+    specs = [("conv1", "bn1", 3, 64, 7, 2)]
+    inplanes = 64
+    for li, (planes, blocks, stride) in enumerate(RESNET_LAYERS, start=1):
+        for b in range(blocks):
+            p = f"layer{li}.{b}"
+            s = stride if b == 0 else 1
+            specs.append((f"{p}.conv1", f"{p}.bn1", inplanes, planes, 1, 1))
+            specs.append((f"{p}.conv2", f"{p}.bn2", planes, planes, 3, s))
+            specs.append((f"{p}.conv3", f"{p}.bn3", planes, planes * 4, 1, 1))
+            if b == 0:
+                specs.append((f"{p}.downsample.0", f"{p}.downsample.1", inplanes, planes * 4, 1, s))
+            inplanes = planes * 4
+    return specs
+
+
+def make_weights(seed: int = 0, d_model: int = 512, ff: int = 1024, nlayer: int = 4,
+                 decoder_gain: float = 8.0, neg_bn_frac: float = 0.03) -> Dict[str, np.ndarray]:
+    """Random-init state dict with the reference's key names and shapes (fc.* omitted: the
+    reference drops them with ``ignore_reid_fc=True``, network.py:445-448)."""
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, np.ndarray] = {}
+    f32 = np.float32
+
+    def normal(shape, std):
+        return (rng.standard_normal(shape) * std).astype(f32)
+
+    def uniform(shape, bound):
+        return rng.uniform(-bound, bound, size=shape).astype(f32)
+
+    for name in ("sep_token", "non_token", "bad_token"):
+        sd[name] = normal((d_model,), 1.0)
+    sd["encoder.weight"] = uniform((d_model, d_model), 1.0 / math.sqrt(d_model))
+    sd["encoder.bias"] = uniform((d_model,), 1.0 / math.sqrt(d_model))
+    for l in range(nlayer):
+        p = f"transformer_encoder.layers.{l}"
+        sd[f"{p}.self_attn.in_proj_weight"] = uniform((3 * d_model, d_model), math.sqrt(6.0 / (4 * d_model)))
+        sd[f"{p}.self_attn.in_proj_bias"] = normal((3 * d_model,), 0.02)
+        sd[f"{p}.self_attn.out_proj.weight"] = uniform((d_model, d_model), 1.0 / math.sqrt(d_model))
+        sd[f"{p}.self_attn.out_proj.bias"] = normal((d_model,), 0.02)
+        sd[f"{p}.linear1.weight"] = uniform((ff, d_model), 1.0 / math.sqrt(d_model))
+        sd[f"{p}.linear1.bias"] = uniform((ff,), 1.0 / math.sqrt(d_model))
+        sd[f"{p}.linear2.weight"] = uniform((d_model, ff), 1.0 / math.sqrt(ff))
+        sd[f"{p}.linear2.bias"] = uniform((d_model,), 1.0 / math.sqrt(ff))
+        for n in ("norm1", "norm2"):
+            sd[f"{p}.{n}.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(f32)
+            sd[f"{p}.{n}.bias"] = normal((d_model,), 0.1)
+    sd["decoder.0.weight"] = (1.0 + 0.1 * rng.standard_normal(d_model)).astype(f32)
+    sd["decoder.0.bias"] = normal((d_model,), 0.1)
+    sd["decoder.1.weight"] = uniform((1, d_model), decoder_gain / math.sqrt(d_model))
+    sd["decoder.1.bias"] = uniform((1,), 1.0 / math.sqrt(d_model))
+
+    def bn(prefix, c):
+        g = rng.uniform(0.5, 1.5, size=c)
+        flip = rng.uniform(size=c) < neg_bn_frac          # a few negative scales on purpose
+        g = np.where(flip, -g, g)
+        sd[f"{prefix}.weight"] = g.astype(f32)
+        sd[f"{prefix}.bias"] = normal((c,), 0.2)
+        sd[f"{prefix}.running_mean"] = np.zeros(c, f32)
+        sd[f"{prefix}.running_var"] = np.ones(c, f32)
+        sd[f"{prefix}.num_batches_tracked"] = np.zeros((), np.int64)
+
+    r = "reid_encoder.model."
+    for conv, bnn, cin, cout, k, _s in reid_conv_specs():
+        sd[f"{r}{conv}.weight"] = normal((cout, cin, k, k), math.sqrt(2.0 / (cout * k * k)))
+        bn(f"{r}{bnn}", cout)
+    sd[f"{r}red.weight"] = uniform((512, 2048), 1.0 / math.sqrt(2048))
+    sd[f"{r}red.bias"] = uniform((512,), 1.0 / math.sqrt(2048))
+    return sd
+
+
+# ----------------------------------------------------------------------------------------
+# duck-typed tracks / detections (what adapters hand to BUSCA)
+# ----------------------------------------------------------------------------------------
+class SynthTrack:
+    """Minimal stand-in for the adapters' STrack as seen by BUSCA (byte_tracker.py:23-161):
+    ``images_mem`` (uint8 HWC BGR crops), ``tlwh_mem`` (fp64 ltwh, original-image coords),
+    ``scale``, ``tlwh``, ``tlbr``."""
+
+    def __init__(self, tlwh, scale=1.0, score=0.9):
+        self._tlwh = np.asarray(tlwh, dtype=np.float64).copy()
+        self.scale = scale
+        self.score = score
+        self.images_mem: List[np.ndarray] = []
+        self.tlwh_mem: List[np.ndarray] = []
+
+    @property
+    def tlwh(self):
+        return self._tlwh.copy()
+
+    @property
+    def tlbr(self):
+        r = self._tlwh.copy()
+        r[2:] += r[:2]
+        return r
+
+
+def random_boxes(rng, n, H=1080, W=1920, border_frac=0.02):
+    """ltwh fp64 boxes; a small fraction straddles the image border."""
+    w = rng.uniform(30, 90, n)
+    h = rng.uniform(90, 250, n)
+    x = rng.uniform(0, W - w)
+    y = rng.uniform(0, H - h)
+    straddle = rng.uniform(size=n) < border_frac
+    side = rng.uniform(size=n) < 0.5
+    x = np.where(straddle, np.where(side, -0.5 * w, W - 0.5 * w), x)
+    return np.stack([x, y, w, h], axis=1)
+
+
+@dataclass
+class AssocCase:
+    """One ``associate_embeddings`` invocation worth of inputs."""
+    frames: List[np.ndarray]
+    tracks: List[SynthTrack]
+    dets: List[SynthTrack]
+    kalman: List[SynthTrack]
+    frame: np.ndarray = field(default=None)
+
+
+def make_assoc_case(seed: int, T: int, D: int, L: int = 11, crop_fn=None, H: int = 1080, W: int = 1920,
+                    hist_frames: Optional[int] = None, short_history: int = 0, scale: float = 1.0) -> AssocCase:
+    """T unmatched tracks with >= L observed crops each (except ``short_history`` of them),
+    D current-frame detections and one Kalman proposal per track.
+
+    ``crop_fn(frame, boxes_x1y1x2y2) -> uint8 [N,384,128,3]`` supplies the crops (the reference's
+    ``get_image_crops`` when generating goldens, ours when testing)."""
+    rng = np.random.default_rng(seed)
+    hist_frames = hist_frames or (L + 2)
+    frames = [make_frame(seed * 1000 + 1, H, W)]
+    for i in range(1, hist_frames + 1):
+        frames.append(next_frame(frames[-1], seed * 1000 + 1 + i))
+    cur = frames[-1]
+
+    box0 = random_boxes(rng, T, H, W)
+    vel = rng.normal(0.0, 3.0, size=(T, 2))
+    tracks = [SynthTrack(box0[t], scale=scale) for t in range(T)]
+    for t, tr in enumerate(tracks):
+        n_obs = hist_frames if t >= short_history else max(1, L - 1 - t)
+        start = hist_frames - n_obs
+        for f in range(start, hist_frames):
+            b = box0[t].copy()
+            b[:2] += vel[t] * f
+            b[2:] *= (1.0 + 0.01 * rng.standard_normal(2))
+            tr.tlwh_mem.append(b / scale)
+        tr._tlwh = tr.tlwh_mem[-1].copy()
+    # crops: one call per history frame, like the adapters do
+    for f in range(hist_frames):
+        idx = [t for t, tr in enumerate(tracks) if len(tr.tlwh_mem) >= hist_frames - f]
+        if not idx:
+            continue
+        boxes = []
+        for t in idx:
+            b = tracks[t].tlwh_mem[f - (hist_frames - len(tracks[t].tlwh_mem))] * scale
+            boxes.append([b[0], b[1], b[0] + b[2], b[1] + b[3]])
+        crops = crop_fn(frames[f], np.asarray(boxes))
+        for j, t in enumerate(idx):
+            tracks[t].images_mem.append(crops[j])
+
+    # current-frame detections: half near tracks (jittered), half random
+    n_near = min(D, T) // 2
+    det_boxes = random_boxes(rng, D, H, W)
+    for j in range(n_near):
+        b = box0[j].copy()
+        b[:2] += vel[j] * hist_frames + rng.normal(0, 6.0, 2)
+        det_boxes[j] = b
+    dets = []
+    if D > 0:
+        x = det_boxes.copy()
+        x[:, 2:] += x[:, :2]
+        dcrops = crop_fn(cur, x.astype(np.float32))        # detector boxes are fp32 in the adapters
+        for j in range(D):
+            d = SynthTrack(det_boxes[j] / scale, scale=scale, score=float(rng.uniform(0.15, 0.95)))
+            d.tlwh_mem.append(d._tlwh.copy())
+            d.images_mem.append(dcrops[j])
+            dets.append(d)
+
+    kalman = []
+    for t, tr in enumerate(tracks):
+        b = tr.tlwh_mem[-1] * scale
+        b = b.copy()
+        b[:2] += vel[t] + rng.normal(0, 1.0, 2)
+        k = SynthTrack(b / scale, scale=scale, score=0.10000001)
+        k.tlwh_mem.append(k._tlwh.copy())
+        kb = k.tlbr * scale
+        k.images_mem.append(crop_fn(cur, [kb])[0])
+        kalman.append(k)
+    return AssocCase(frames=frames, tracks=tracks, dets=dets, kalman=kalman, frame=cur)

@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, imported read-only with the shims next to this file) on CPU.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The GPU box never runs this (it has no /root/reference); it only reads the .npz files.
+
+Inputs are not stored: they are regenerated from seeds by busca_b200.synth (numpy PCG64), so
+the fixtures stay small.  What is stored are the reference's outputs at the probe points listed
+in SURVEY.md Appendix B.
+"""
+import ast
+import hashlib
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path[:0] = [os.path.join(HERE, "shims"), REF, REPO]
+
+import numpy as np
+
+np.float = float  # alias removed in numpy>=1.24; the reference still uses it (tracking.py:43)
+import torch
+
+torch.set_num_threads(os.cpu_count())
+
+import busca.reid.resnet as _R
+
+_R.load_state_dict_from_url = lambda *a, **k: {}  # no network (resnet.py:346-360)
+import busca.encodings as ref_enc
+import busca.network as ref_net
+import busca.tracking as ref_trk
+from busca.option import load_args_from_config
+
+from busca_b200 import synth
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def build_reference(weights_seed=0):
+    targs, _ = load_args_from_config(os.path.join(REF, "config/ByteTrack/MOT20/config_bytetrack_mot20.yml"))
+    a = targs.transformer
+    a.device = torch.device("cpu")
+    a.reid_weights_file = "no"
+    model = ref_net.BUSCA(a).eval()
+    sd = synth.make_weights(weights_seed)
+    ref_keys = {k for k in model.state_dict().keys() if ".fc." not in k}
+    assert ref_keys == set(sd.keys()), (sorted(ref_keys - set(sd))[:5], sorted(set(sd) - ref_keys)[:5])
+    for k, v in model.state_dict().items():
+        if k in sd:
+            assert tuple(v.shape) == tuple(sd[k].shape), (k, v.shape, sd[k].shape)
+    path = "/tmp/busca_golden_weights.pth"
+    torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, path)
+    model.load_pretrained(path, ignore_reid_fc=True)
+    return model, targs
+
+
+# --------------------------------------------------------------------------------------
+def golden_crops(model):
+    """a6: get_image_crops / get_bbox_crop (network.py:492-507, tracking.py:62-113)."""
+    frame = synth.make_frame(4242)
+    H, W = frame.shape[:2]
+    rng = np.random.default_rng(7)
+    boxes = []
+    # inside
+    for _ in range(20):
+        w, h = rng.uniform(8, 400), rng.uniform(8, 900)
+        x, y = rng.uniform(0, W - w), rng.uniform(0, H - h)
+        boxes.append([x, y, x + w, y + h])
+    # straddling each border
+    for _ in range(16):
+        w, h = rng.uniform(20, 300), rng.uniform(40, 600)
+        cx = rng.choice([0.0, W, rng.uniform(0, W)])
+        cy = rng.choice([0.0, H, rng.uniform(0, H)])
+        boxes.append([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2])
+    # fully outside, degenerate, integer-aligned, exact 2x (INTER_AREA switch), tiny, huge
+    boxes += [[-300.0, -300.0, -100.0, -50.0], [W + 5.0, 10.0, W + 80.0, 200.0], [100.0, H + 1.0, 180.0, H + 300.0],
+              [500.0, 500.0, 500.0, 700.0], [500.0, 500.0, 600.0, 500.0],
+              [100.0, 100.0, 356.0, 868.0], [101.0, 57.0, 357.0, 825.0],
+              [64.0, 64.0, 192.0, 448.0], [10.0, 10.0, 11.0, 11.0], [10.2, 10.7, 12.1, 13.9],
+              [-50.0, -50.0, W + 50.0, H + 50.0], [0.0, 0.0, float(W), float(H)],
+              [1900.5, 1000.25, 1930.75, 1090.5], [-10.5, 500.0, 30.25, 620.0]]
+    boxes = np.asarray(boxes, dtype=np.float64)
+    crops64 = model.get_image_crops(frame, boxes, normalize=False)
+    crops32 = model.get_image_crops(frame, boxes.astype(np.float32), normalize=False)
+    assert crops64.dtype == np.uint8 and crops64.shape[1:] == (384, 128, 3)
+    empty = model.get_image_crops(frame, [], normalize=False)
+    np.savez_compressed(os.path.join(HERE, "crops.npz"), frame_seed=4242, boxes=boxes,
+                        sha64=np.array([sha(c) for c in crops64]), sha32=np.array([sha(c) for c in crops32]),
+                        full_idx=np.array([0, 20, 24, 36, 39, 41, 42, 46, 49]),
+                        full=crops64[[0, 20, 24, 36, 39, 41, 42, 46, 49]],
+                        empty_shape=np.array(empty.shape), empty_dtype=str(empty.dtype))
+    print("crops:", len(boxes), "boxes; fp32/fp64 digests differ on", int(sum(sha(a) != sha(b) for a, b in zip(crops64, crops32))))
+
+
+def _extract_function(path, name):
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = {"np": np, "torch": torch}
+            exec(compile(mod, path, "exec"), ns)
+            return ns[name]
+    raise KeyError(name)
+
+
+def golden_geometry():
+    """a1-a3: Kalman multi_predict mean, centre distance, IoU (+1 convention)."""
+    rng = np.random.default_rng(11)
+    a = synth.random_boxes(rng, 37)
+    b = synth.random_boxes(rng, 53)
+    b[:10] = a[:10] + rng.normal(0, 5, (10, 4))
+    a[:, 2:] += a[:, :2]
+    b[:, 2:] += b[:, :2]
+    b[11] = a[11]                                     # identical boxes -> IoU 1, distance 0
+    cd = ref_trk.center_distance(a, b)          # 2-D ndarrays (a list of arrays crashes the reference, tracking.py:45)
+    cdw = ref_trk.center_distance(a, b, weight_size=True)
+    # IoU: cython_bbox is not in the mount; the reference's own in-tree restatement
+    # (adapters/GHOST/src/tracking_utils.py:176-205) is executed instead.
+    bbox_overlaps = _extract_function(os.path.join(REF, "adapters/GHOST/src/tracking_utils.py"), "bbox_overlaps")
+    iou_ghost = bbox_overlaps(a.copy(), b.copy())
+    # Kalman (adapters/CenterTrack/src/lib/utils/mot_online/kalman_filter.py:154-191)
+    sys.path.insert(0, os.path.join(REF, "adapters/CenterTrack/src/lib/utils/mot_online"))
+    import kalman_filter as KF
+    kf = KF.KalmanFilter()
+    mean = np.concatenate([rng.uniform(0, 1900, (29, 2)), rng.uniform(0.2, 0.8, (29, 1)), rng.uniform(60, 300, (29, 1)),
+                           rng.normal(0, 3, (29, 4))], axis=1)
+    cov = np.stack([np.eye(8) * rng.uniform(0.5, 4.0) for _ in range(29)])
+    tracked = rng.uniform(size=29) < 0.7
+    m_in = mean.copy()
+    m_in[~tracked, 7] = 0                             # STrack.multi_predict, byte_tracker.py:54-56
+    m_out, _ = kf.multi_predict(m_in, cov)
+    np.savez_compressed(os.path.join(HERE, "geometry.npz"), a=a, b=b, center_distance=cd, center_distance_weighted=cdw,
+                        iou_ghost=iou_ghost, kf_mean_in=mean, kf_tracked=tracked, kf_mean_out=m_out)
+    print("geometry: cd", cd.shape, "iou", iou_ghost.shape)
+
+
+class Probe:
+    """Wrap bound methods of the reference model to capture intermediates without editing it."""
+
+    def __init__(self, model):
+        self.m = model
+        self.rec = {}
+        self._orig = []
+
+    def wrap(self, obj, name, key, multi=False):
+        orig = getattr(obj, name)
+        rec = self.rec
+
+        def wrapped(*a, **k):
+            out = orig(*a, **k)
+            if multi:
+                rec.setdefault(key, []).append(out)
+            else:
+                rec[key] = out
+            return out
+
+        setattr(obj, name, wrapped)
+        self._orig.append((obj, name, orig))
+
+    def restore(self):
+        for obj, name, orig in self._orig:
+            try:
+                delattr(obj, name)
+            except AttributeError:
+                setattr(obj, name, orig)
+
+
+def run_assoc(model, case, L, C, flavour64, contiguous=True, **kw):
+    """Run the reference's associate_embeddings; with ``flavour64`` the sentinel box is float64 as
+    under the pinned numpy 1.23.5.
+
+    ``contiguous``: the reference hands the ReID encoder a permuted (channels-last strided) view
+    (network.py:397-398).  On CPU, torch 2.11 then picks its channels-last batch-norm training kernel,
+    whose statistics are ~80x less accurate than the NCHW kernel (5e-5 vs 6e-7 per layer against
+    fp64; compounding to ~1e-2 on the embeddings over 53 layers).  With contiguous=True the very same
+    call is fed ``x.contiguous()`` so the accurate kernels run; the algorithm is unchanged.  The
+    primary fixtures use this; the as-is numbers are stored beside them (asis_*)."""
+    orig_mcb = ref_trk.missing_candidate_bbox
+    saved_fake = model.pos_encoder.distant_fake_bbox
+    if flavour64:
+        f64 = lambda seq_len=None, flavour="ltrb": orig_mcb(seq_len, flavour).astype(np.float64)
+        ref_enc.missing_candidate_bbox = f64
+        ref_net.missing_candidate_bbox = f64
+        model.pos_encoder.distant_fake_bbox = torch.from_numpy(f64(flavour="ltwh"))
+    else:
+        assert orig_mcb(flavour="ltwh").dtype == np.float32, "expected numpy>=2 behaviour in this container"
+    pr = Probe(model)
+    if contiguous:
+        enc_fwd = model.reid_encoder.forward
+        model.reid_encoder.forward = lambda x: enc_fwd(x.contiguous())
+        pr._orig.append((model.reid_encoder, "forward", enc_fwd))
+    pr.wrap(model.reid_encoder, "forward", "reid", multi=True)
+    pr.wrap(model.pos_encoder, "_get_temporal_ids", "tids")
+    pr.wrap(model.pos_encoder, "_get_spatial_ids", "sids")
+    pr.wrap(model.pos_encoder, "forward", "input_seq")
+    pr.wrap(model.transformer_encoder, "forward", "trans_out")
+    pr.wrap(model, "forward", "logits")
+    try:
+        dists = ref_trk.center_distance(case.tracks, case.dets) if len(case.dets) else np.zeros((len(case.tracks), 0))
+        with torch.no_grad():
+            probs_matrix, reliable = model.associate_embeddings(
+                tracks_embeddings=case.tracks, dets_embeddings=case.dets, dists_matrix=dists, seq_len=L, num_candidates=C,
+                use_broader_memory=True, extra_kalman_candidates=case.kalman, normalize_ims=True, **kw)
+    finally:
+        pr.restore()
+        ref_enc.missing_candidate_bbox = orig_mcb
+        ref_net.missing_candidate_bbox = orig_mcb
+        model.pos_encoder.distant_fake_bbox = saved_fake
+    r = pr.rec
+    T = len(case.tracks)
+    out = dict(dists=dists, probs_matrix=probs_matrix, reliable=reliable,
+               mem_emb=r["reid"][0][1].view(T, L, -1).numpy(), can_emb=r["reid"][1][1].view(T, C, -1).numpy(),
+               mem_t=r["tids"][0].numpy(), can_t=r["tids"][1].numpy(),
+               mem_xy=r["sids"][0][0].numpy(), mem_size=r["sids"][0][1].numpy(),
+               can_xy=r["sids"][1][0].numpy(), can_size=r["sids"][1][1].numpy(),
+               input_seq=r["input_seq"].numpy(), trans_out=r["trans_out"].numpy(),
+               cand_rows=model.logits.numpy(), mem_logits=model.mem_logits.numpy(), logits=r["logits"].numpy())
+    out["probs"] = torch.softmax(r["logits"], dim=-1).numpy()
+    return out
+
+
+def fp64_deviation(model, case, L, C):
+    """max|emb - emb_fp64| / max|emb_fp64| of the memory batch for the NCHW and the as-is
+    (channels-last) CPU paths: the evidence behind run_assoc's ``contiguous`` switch."""
+    grab = []
+    enc_fwd = model.reid_encoder.forward
+
+    def hook(x):
+        grab.append(x.clone())
+        return enc_fwd(x)
+
+    model.reid_encoder.forward = hook
+    try:
+        dists = ref_trk.center_distance(case.tracks, case.dets)
+        with torch.no_grad():
+            model.associate_embeddings(case.tracks, case.dets, dists, L, C, True, False,
+                                       extra_kalman_candidates=case.kalman, normalize_ims=True)
+    finally:
+        del model.reid_encoder.forward
+    x = grab[0]                                   # the memory batch, strided exactly as the reference passes it
+    net = model.reid_encoder.model
+    with torch.no_grad():
+        _, e_cl = net(x, output_option="plain")
+        _, e_nchw = net(x.contiguous(), output_option="plain")
+        net.double()
+        _, e64 = net(x.contiguous().double(), output_option="plain")
+        net.float()
+    d = lambda a: float((a.double() - e64).abs().max() / e64.abs().max())
+    print("fp64 deviation: nchw", d(e_nchw), "channels-last as-is", d(e_cl))
+    return d(e_nchw), d(e_cl)
+
+
+def golden_assoc(model):
+    ref_crop = lambda frame, boxes: model.get_image_crops(frame, boxes, normalize=False)
+    cases = {
+        # name: (seed, T, D, L, C, short_history)
+        "assoc_cfg1": (101, 16, 40, 11, 5, 1),       # BASELINE config 1: 16 tracks x 5 proposals
+        "assoc_fewdets": (102, 5, 3, 11, 5, 2),      # D < C: sentinel candidates, short histories
+        "assoc_nodets": (103, 3, 0, 11, 5, 0),       # Kalman proposal only
+    }
+    for name, (seed, T, D, L, C, short) in cases.items():
+        case = synth.make_assoc_case(seed, T, D, L, crop_fn=ref_crop, short_history=short)
+        store = {"meta": np.array([seed, T, D, L, C, short])}
+        for fl, tag in ((False, "f32"), (True, "f64")):
+            out = run_assoc(model, case, L, C, flavour64=fl, select_highest_candidate=False)
+            keep = ["probs_matrix", "reliable", "mem_t", "can_t", "mem_xy", "mem_size", "can_xy", "can_size",
+                    "cand_rows", "logits", "probs", "mem_logits"]
+            if tag == "f32":
+                keep += ["dists", "mem_emb", "can_emb"]
+                if T <= 5:
+                    keep += ["input_seq", "trans_out"]
+            for k in keep:
+                store[f"{tag}_{k}"] = out[k]
+            print(name, tag, "probs[0]", np.round(out["probs"][0], 4), "reliable", out["reliable"].astype(int))
+        # the reference exactly as it runs on CPU here (channels-last BN kernels), for the record
+        o = run_assoc(model, case, L, C, flavour64=True, contiguous=False, select_highest_candidate=False)
+        for k in ("mem_emb", "can_emb", "probs", "logits"):
+            store[f"asis_{k}"] = o[k]
+        if name == "assoc_fewdets":
+            store["fp64_dev"] = np.array(fp64_deviation(model, case, L, C))
+        # host post-processing variants (network.py:415-424); device work is identical
+        o = run_assoc(model, case, L, C, flavour64=True, select_highest_candidate=True)
+        store["f64_probs_matrix_highest"] = o["probs_matrix"]
+        o = run_assoc(model, case, L, C, flavour64=True, select_highest_candidate=True,
+                      highest_candidate_minimum_thresh=0.3, keep_highest_value=True)
+        store["f64_probs_matrix_highest_keep_thr"] = o["probs_matrix"]
+        # a sample of the crops the case is built from, to pin the synthetic generator itself
+        store["crop_sha_track0"] = np.array([sha(c) for c in case.tracks[0].images_mem])
+        store["crop_sha_kalman"] = np.array([sha(k.images_mem[-1]) for k in case.kalman])
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **store)
+
+
+def golden_pe(model):
+    """a10: closed-form samples of the 211x211x61x512 fp16 table (encodings.py:23-32) plus the three
+    separable 1-D tables it is made of, as the reference built them in this container."""
+    pe = model.pos_encoder.pe
+    assert pe.shape == (211, 211, 61, 512) and pe.dtype == torch.float16
+    rng = np.random.default_rng(3)
+    idx = np.stack([rng.integers(0, 211, 64), rng.integers(0, 211, 64), rng.integers(0, 61, 64)], axis=1)
+    vals = torch.stack([pe[i, j, k] for i, j, k in idx]).numpy()
+    np.savez_compressed(os.path.join(HERE, "pe.npz"), idx=idx, vals=vals,
+                        tab_x=pe[:, 0, 0, :172].numpy(), tab_y=pe[0, :, 0, 172:344].numpy(), tab_z=pe[0, 0, :, 344:].numpy())
+    print("pe samples", vals.shape, vals[0, :4])
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["crops", "geometry", "pe", "assoc"]
+    model, targs = build_reference()
+    if "crops" in which:
+        golden_crops(model)
+    if "geometry" in which:
+        golden_geometry()
+    if "pe" in which:
+        golden_pe(model)
+    if "assoc" in which:
+        golden_assoc(model)
