@@ -1,0 +1,867 @@
+// C ABI of libbusca_b200.so (include/busca_b200.h): context, weights, patch bank, workspace and the orchestration of
+// the per-frame hot path.  Kernels live in geometry.cu / crop.cu / reid.cu / conv_tc.cu / transformer.cu.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/busca_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int set_err(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_OK(expr)                                                                                           \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return set_err(BUSCA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostTensor {
+    std::vector<float> f;
+    std::vector<int64_t> shape;
+};
+
+struct TLayer {
+    float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b;
+};
+
+struct ProfEntry {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+struct busca_ctx {
+    busca_config cfg;
+    cudaStream_t stream = nullptr;
+    bool finalized = false;
+    std::map<std::string, HostTensor> host;      // staged until finalize
+    std::vector<void *> owned;                   // device allocations freed on destroy
+    // ReID
+    std::vector<ConvLayer> convs;
+    double *stats_pool = nullptr;
+    size_t stats_bytes = 0;
+    float *red_w = nullptr, *red_b = nullptr, *lut = nullptr;
+    // Transformer
+    float *enc_w = nullptr, *enc_b = nullptr, *sep = nullptr, *non = nullptr, *bad = nullptr;
+    std::vector<TLayer> layers;
+    float *dec_g = nullptr, *dec_b = nullptr, *dec_w = nullptr, *dec_bias = nullptr;
+    __half *pe_xy = nullptr, *pe_size = nullptr, *pe_t = nullptr;
+    // frame + bank
+    DevBuf frame;
+    int fH = 0, fW = 0;
+    int64_t fstride = 0;
+    uint8_t *bank = nullptr;
+    int64_t bank_slots = 0;
+    // scratch
+    DevBuf ws_reid, ws_tr, ws_io, ws_small;
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+    int64_t launches = 0;
+    // profiling
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::string prof_json;
+};
+
+static cudaEvent_t get_event(busca_ctx *c) {
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+static void prof_begin(busca_ctx *c, const char *name) {
+    if (!c->profiling) return;
+    ProfEntry pe{name, get_event(c), get_event(c)};
+    cudaEventRecord(pe.a, c->stream);
+    c->prof.push_back(pe);
+}
+static void prof_end(busca_ctx *c) {
+    if (!c->profiling) return;
+    cudaEventRecord(c->prof.back().b, c->stream);
+}
+static void prof_reset(busca_ctx *c) {
+    c->prof.clear();
+    c->ev_used = 0;
+}
+static void prof_collect(busca_ctx *c) {
+    if (!c->profiling) return;
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    for (auto &pe : c->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pe.a, pe.b);
+        if (!acc.count(pe.name)) order.push_back(pe.name);
+        acc[pe.name].first += ms;
+        acc[pe.name].second += 1;
+    }
+    std::string js = "{";
+    for (size_t i = 0; i < order.size(); ++i) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d}", i ? ", " : "", order[i].c_str(), acc[order[i]].first,
+                 acc[order[i]].second);
+        js += buf;
+    }
+    js += "}";
+    c->prof_json = js;
+}
+
+#define LAUNCH(ctx, name, call)                                                                            \
+    do {                                                                                                   \
+        prof_begin(ctx, name);                                                                             \
+        cudaError_t e_ = (call);                                                                           \
+        prof_end(ctx);                                                                                     \
+        (ctx)->launches++;                                                                                 \
+        if (e_ != cudaSuccess) return set_err(BUSCA_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+struct ConvSpec {
+    std::string conv, bn;
+    int cin, cout, k, stride;
+};
+static std::vector<ConvSpec> reid_specs() {
+    std::vector<ConvSpec> v;
+    v.push_back({"conv1", "bn1", 3, 64, 7, 2});
+    const int planes[4] = {64, 128, 256, 512}, blocks[4] = {3, 4, 6, 3}, strides[4] = {1, 2, 2, 2};
+    int inpl = 64;
+    for (int li = 0; li < 4; ++li)
+        for (int b = 0; b < blocks[li]; ++b) {
+            std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(b);
+            int s = b == 0 ? strides[li] : 1;
+            v.push_back({p + ".conv1", p + ".bn1", inpl, planes[li], 1, 1});
+            v.push_back({p + ".conv2", p + ".bn2", planes[li], planes[li], 3, s});
+            v.push_back({p + ".conv3", p + ".bn3", planes[li], planes[li] * 4, 1, 1});
+            if (b == 0) v.push_back({p + ".downsample.0", p + ".downsample.1", inpl, planes[li] * 4, 1, s});
+            inpl = planes[li] * 4;
+        }
+    return v;
+}
+
+extern "C" const char *busca_version(void) { return "busca_b200 0.1 (sm_100a)"; }
+extern "C" const char *busca_last_error(void) { return g_err; }
+
+extern "C" int busca_create(const busca_config *cfg, busca_ctx **out) {
+    if (!cfg || !out) return set_err(BUSCA_ERR_ARG, "null argument");
+    if (cfg->d_model != EMB_DIM || cfg->d_model % cfg->nhead != 0 || cfg->d_model / cfg->nhead != 128)
+        return set_err(BUSCA_ERR_ARG, "unsupported transformer shape d_model=%d nhead=%d (need 512 / head dim 128)", cfg->d_model, cfg->nhead);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(BUSCA_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return set_err(BUSCA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    busca_ctx *c = new busca_ctx();
+    c->cfg = *cfg;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    int64_t slots = cfg->bank_slots > 0 ? cfg->bank_slots : 1024;
+    return busca_bank_reserve(c, slots);
+}
+
+extern "C" void busca_destroy(busca_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    for (void *p : c->owned) cudaFree(p);
+    if (c->bank) cudaFree(c->bank);
+    c->frame.release();
+    c->ws_reid.release();
+    c->ws_tr.release();
+    c->ws_io.release();
+    c->ws_small.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int busca_load_tensor(busca_ctx *c, const char *name, const void *data, int32_t dtype, int32_t ndim, const int64_t *shape) {
+    if (!c || !name || (!data && ndim > 0)) return set_err(BUSCA_ERR_ARG, "null argument");
+    int64_t n = 1;
+    HostTensor t;
+    for (int i = 0; i < ndim; ++i) { n *= shape[i]; t.shape.push_back(shape[i]); }
+    t.f.resize((size_t)n);
+    if (dtype == BUSCA_F32) memcpy(t.f.data(), data, (size_t)n * 4);
+    else if (dtype == BUSCA_F16) { const __half *h = (const __half *)data; for (int64_t i = 0; i < n; ++i) t.f[i] = __half2float(h[i]); }
+    else if (dtype == BUSCA_I64) { const int64_t *h = (const int64_t *)data; for (int64_t i = 0; i < n; ++i) t.f[i] = (float)h[i]; }
+    else return set_err(BUSCA_ERR_ARG, "bad dtype %d for %s", dtype, name);
+    c->host[name] = std::move(t);
+    c->finalized = false;
+    return BUSCA_OK;
+}
+
+static const HostTensor *find(busca_ctx *c, const std::string &name, std::initializer_list<int64_t> shape) {
+    auto it = c->host.find(name);
+    if (it == c->host.end()) { set_err(BUSCA_ERR_STATE, "missing tensor '%s'", name.c_str()); return nullptr; }
+    std::vector<int64_t> want(shape);
+    if (it->second.shape != want) { set_err(BUSCA_ERR_STATE, "tensor '%s' has the wrong shape", name.c_str()); return nullptr; }
+    return &it->second;
+}
+template <typename T>
+static T *upload(busca_ctx *c, const T *src, size_t n) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T) + 16) != cudaSuccess) return nullptr;
+    cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    c->owned.push_back(p);
+    return (T *)p;
+}
+static float *upload_named(busca_ctx *c, const std::string &name, std::initializer_list<int64_t> shape) {
+    const HostTensor *t = find(c, name, shape);
+    return t ? upload(c, t->f.data(), t->f.size()) : nullptr;
+}
+#define NEED(ptr) do { if (!(ptr)) return g_err[0] ? BUSCA_ERR_STATE : set_err(BUSCA_ERR_NOMEM, "upload failed"); } while (0)
+
+extern "C" int busca_finalize(busca_ctx *c) {
+    if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    g_err[0] = 0;
+    for (void *p : c->owned) cudaFree(p);
+    c->owned.clear();
+    c->convs.clear();
+    c->layers.clear();
+    const std::string r = "reid_encoder.model.";
+    auto specs = reid_specs();
+    size_t stats_doubles = 0;
+    for (auto &sp : specs) stats_doubles += 2 * (size_t)sp.cout;
+    CUDA_OK(cudaMalloc((void **)&c->stats_pool, stats_doubles * sizeof(double)));
+    c->owned.push_back(c->stats_pool);
+    c->stats_bytes = stats_doubles * sizeof(double);
+    size_t soff = 0;
+    for (auto &sp : specs) {
+        ConvLayer L{};
+        L.cin = sp.cin; L.cout = sp.cout; L.k = sp.k; L.stride = sp.stride;
+        const HostTensor *w = find(c, r + sp.conv + ".weight", {sp.cout, sp.cin, sp.k, sp.k});
+        NEED(w);
+        std::vector<float> re((size_t)sp.cout * sp.k * sp.k * sp.cin);
+        if (sp.cin == 3) {
+            // stem: [tap = (ky*7+kx)*3 + c_bgr][cout]; the reference feeds RGB (network.py:397), the bank holds BGR
+            for (int o = 0; o < sp.cout; ++o)
+                for (int ci = 0; ci < 3; ++ci)
+                    for (int ky = 0; ky < 7; ++ky)
+                        for (int kx = 0; kx < 7; ++kx)
+                            re[(size_t)((ky * 7 + kx) * 3 + (2 - ci)) * 64 + o] = w->f[(((size_t)o * 3 + ci) * 7 + ky) * 7 + kx];
+        } else {
+            // OIHW -> O,kh,kw,I  (K-major rows for the implicit GEMM)
+            for (int o = 0; o < sp.cout; ++o)
+                for (int ci = 0; ci < sp.cin; ++ci)
+                    for (int ky = 0; ky < sp.k; ++ky)
+                        for (int kx = 0; kx < sp.k; ++kx)
+                            re[(((size_t)o * sp.k + ky) * sp.k + kx) * sp.cin + ci] = w->f[(((size_t)o * sp.cin + ci) * sp.k + ky) * sp.k + kx];
+        }
+        L.w32 = upload(c, re.data(), re.size());
+        NEED(L.w32);
+        if (sp.cin != 3) {
+            std::vector<__nv_bfloat16> h(re.size());
+            for (size_t i = 0; i < re.size(); ++i) h[i] = __float2bfloat16(re[i]);
+            L.w16 = upload(c, h.data(), h.size());
+            NEED(L.w16);
+        }
+        L.gamma = upload_named(c, r + sp.bn + ".weight", {sp.cout});
+        NEED(L.gamma);
+        L.beta = upload_named(c, r + sp.bn + ".bias", {sp.cout});
+        NEED(L.beta);
+        L.stats = c->stats_pool + soff;
+        soff += 2 * (size_t)sp.cout;
+        std::vector<float> z(2 * (size_t)sp.cout, 0.f);
+        L.scale = upload(c, z.data(), z.size());
+        NEED(L.scale);
+        L.shift = L.scale + sp.cout;
+        c->convs.push_back(L);
+    }
+    NEED(c->red_w = upload_named(c, r + "red.weight", {512, 2048}));
+    NEED(c->red_b = upload_named(c, r + "red.bias", {512}));
+    NEED(c->lut = upload_named(c, "norm.lut", {256, 3}));
+    const int d = c->cfg.d_model, ff = c->cfg.ff_size;
+    NEED(c->enc_w = upload_named(c, "encoder.weight", {d, d}));
+    NEED(c->enc_b = upload_named(c, "encoder.bias", {d}));
+    NEED(c->sep = upload_named(c, "sep_token", {d}));
+    NEED(c->non = upload_named(c, "non_token", {d}));
+    NEED(c->bad = upload_named(c, "bad_token", {d}));
+    for (int l = 0; l < c->cfg.num_layers; ++l) {
+        std::string p = "transformer_encoder.layers." + std::to_string(l) + ".";
+        TLayer t{};
+        NEED(t.in_w = upload_named(c, p + "self_attn.in_proj_weight", {3 * d, d}));
+        NEED(t.in_b = upload_named(c, p + "self_attn.in_proj_bias", {3 * d}));
+        NEED(t.out_w = upload_named(c, p + "self_attn.out_proj.weight", {d, d}));
+        NEED(t.out_b = upload_named(c, p + "self_attn.out_proj.bias", {d}));
+        NEED(t.l1_w = upload_named(c, p + "linear1.weight", {ff, d}));
+        NEED(t.l1_b = upload_named(c, p + "linear1.bias", {ff}));
+        NEED(t.l2_w = upload_named(c, p + "linear2.weight", {d, ff}));
+        NEED(t.l2_b = upload_named(c, p + "linear2.bias", {d}));
+        NEED(t.n1_g = upload_named(c, p + "norm1.weight", {d}));
+        NEED(t.n1_b = upload_named(c, p + "norm1.bias", {d}));
+        NEED(t.n2_g = upload_named(c, p + "norm2.weight", {d}));
+        NEED(t.n2_b = upload_named(c, p + "norm2.bias", {d}));
+        c->layers.push_back(t);
+    }
+    NEED(c->dec_g = upload_named(c, "decoder.0.weight", {d}));
+    NEED(c->dec_b = upload_named(c, "decoder.0.bias", {d}));
+    NEED(c->dec_w = upload_named(c, "decoder.1.weight", {1, d}));
+    NEED(c->dec_bias = upload_named(c, "decoder.1.bias", {1}));
+    auto upload_half = [&](const char *name, int64_t rows, int64_t cols) -> __half * {
+        const HostTensor *t = find(c, name, {rows, cols});
+        if (!t) return nullptr;
+        std::vector<__half> h(t->f.size());
+        for (size_t i = 0; i < h.size(); ++i) h[i] = __float2half(t->f[i]);   // exact: values were fp16
+        return upload(c, h.data(), h.size());
+    };
+    NEED(c->pe_xy = upload_half("pe.tab_xy", 2 * PE_MAX_XY + 1, PE_CH));
+    NEED(c->pe_size = upload_half("pe.tab_size", 2 * PE_MAX_SIZE + 1, PE_CH));
+    NEED(c->pe_t = upload_half("pe.tab_t", 2 * PE_MAX_T + 1, PE_CH_T));
+    c->host.clear();
+    c->finalized = true;
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame + bank
+// ------------------------------------------------------------------------------------------------
+extern "C" int busca_upload_frame(busca_ctx *c, const uint8_t *bgr, int32_t H, int32_t W, int64_t row_stride) {
+    if (!c || !bgr || H <= 0 || W <= 0 || row_stride < (int64_t)W * 3) return set_err(BUSCA_ERR_ARG, "bad frame");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    CUDA_OK(c->frame.ensure((size_t)H * W * 3 + 64));
+    CUDA_OK(cudaMemcpy2DAsync(c->frame.p, (size_t)W * 3, bgr, (size_t)row_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->fH = H; c->fW = W; c->fstride = (int64_t)W * 3;
+    return BUSCA_OK;
+}
+
+extern "C" int busca_bank_reserve(busca_ctx *c, int64_t n_slots) {
+    if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
+    if (n_slots <= c->bank_slots) return BUSCA_OK;
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    uint8_t *nb = nullptr;
+    cudaError_t e = cudaMalloc((void **)&nb, (size_t)n_slots * PATCH_BYTES);
+    if (e != cudaSuccess) return set_err(BUSCA_ERR_NOMEM, "patch bank of %lld slots: %s", (long long)n_slots, cudaGetErrorString(e));
+    if (c->bank) {
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        CUDA_OK(cudaMemcpy(nb, c->bank, (size_t)c->bank_slots * PATCH_BYTES, cudaMemcpyDeviceToDevice));
+        cudaFree(c->bank);
+    }
+    c->bank = nb;
+    c->bank_slots = n_slots;
+    return BUSCA_OK;
+}
+extern "C" int64_t busca_bank_capacity(busca_ctx *c) { return c ? c->bank_slots : 0; }
+
+static int check_slots(busca_ctx *c, const int32_t *slots, int n, bool allow_neg) {
+    for (int i = 0; i < n; ++i)
+        if (slots[i] >= c->bank_slots || (slots[i] < 0 && !allow_neg)) return set_err(BUSCA_ERR_ARG, "slot %d out of range (bank has %lld)", slots[i], (long long)c->bank_slots);
+    return BUSCA_OK;
+}
+
+extern "C" int busca_crop(busca_ctx *c, const double *boxes, int32_t n, const int32_t *slots, uint8_t *host_out) {
+    if (!c || n < 0 || (n > 0 && (!boxes || !slots))) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (n == 0) return BUSCA_OK;
+    if (!c->frame.p || c->fH == 0) return set_err(BUSCA_ERR_STATE, "busca_crop before busca_upload_frame");
+    int rc = check_slots(c, slots, n, false);
+    if (rc) return rc;
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    size_t bb = (size_t)n * 4 * sizeof(double), sb = (size_t)n * sizeof(int32_t);
+    CUDA_OK(c->ws_small.ensure(bb + sb + 64));
+    double *dbox = (double *)c->ws_small.p;
+    int32_t *dslots = (int32_t *)((char *)c->ws_small.p + bb);
+    CUDA_OK(cudaMemcpyAsync(dbox, boxes, bb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dslots, slots, sb, cudaMemcpyHostToDevice, c->stream));
+    prof_reset(c);
+    LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, dbox, n, dslots, c->bank, c->stream));
+    if (host_out) {
+        for (int i = 0; i < n; ++i)
+            CUDA_OK(cudaMemcpyAsync(host_out + (size_t)i * PATCH_BYTES, c->bank + (size_t)slots[i] * PATCH_BYTES, PATCH_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+extern "C" int busca_bank_upload(busca_ctx *c, const uint8_t *patches, int32_t n, const int32_t *slots) {
+    if (!c || n < 0 || (n > 0 && (!patches || !slots))) return set_err(BUSCA_ERR_ARG, "bad argument");
+    int rc = check_slots(c, slots, n, false);
+    if (rc) return rc;
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    for (int i = 0; i < n; ++i)
+        CUDA_OK(cudaMemcpyAsync(c->bank + (size_t)slots[i] * PATCH_BYTES, patches + (size_t)i * PATCH_BYTES, PATCH_BYTES, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BUSCA_OK;
+}
+
+extern "C" int busca_bank_download(busca_ctx *c, const int32_t *slots, int32_t n, uint8_t *host_out) {
+    if (!c || n < 0 || (n > 0 && (!host_out || !slots))) return set_err(BUSCA_ERR_ARG, "bad argument");
+    int rc = check_slots(c, slots, n, false);
+    if (rc) return rc;
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    for (int i = 0; i < n; ++i)
+        CUDA_OK(cudaMemcpyAsync(host_out + (size_t)i * PATCH_BYTES, c->bank + (size_t)slots[i] * PATCH_BYTES, PATCH_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------------
+static int pair_matrix(busca_ctx *c, const double *a, int na, const double *b, int nb, double *out, int want_iou) {
+    if (!c || na < 0 || nb < 0) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (na == 0 || nb == 0) return BUSCA_OK;
+    if (!a || !b || !out) return set_err(BUSCA_ERR_ARG, "null pointer");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    size_t ab = (size_t)na * 32, bb = (size_t)nb * 32, ob = (size_t)na * nb * 8;
+    CUDA_OK(c->ws_small.ensure(ab + bb + ob + 64));
+    double *da = (double *)c->ws_small.p, *db = da + (size_t)na * 4, *dout = db + (size_t)nb * 4;
+    CUDA_OK(cudaMemcpyAsync(da, a, ab, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(db, b, bb, cudaMemcpyHostToDevice, c->stream));
+    prof_reset(c);
+    LAUNCH(c, want_iou ? "iou_matrix" : "center_distance", launch_pair_matrix(da, na, db, nb, dout, want_iou, c->stream));
+    CUDA_OK(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+extern "C" int busca_center_distance(busca_ctx *c, const double *a, int32_t na, const double *b, int32_t nb, double *out) {
+    return pair_matrix(c, a, na, b, nb, out, 0);
+}
+extern "C" int busca_iou(busca_ctx *c, const double *a, int32_t na, const double *b, int32_t nb, double *out) {
+    return pair_matrix(c, a, na, b, nb, out, 1);
+}
+
+extern "C" int busca_frame_geometry(busca_ctx *c, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
+                                    int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
+                                    int32_t *cand) {
+    if (!c || T < 0 || D < 0 || C < 1 || !mean) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (T == 0) return BUSCA_OK;
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 63) & ~(size_t)63; return o; };
+    size_t o_mean = take((size_t)T * 64), o_trk = take(T), o_det = take((size_t)(D ? D : 1) * 32), o_tlwh = take((size_t)T * 32),
+           o_tlbr = take((size_t)T * 32), o_dist = take((size_t)T * (D ? D : 1) * 8), o_iou = take((size_t)T * (D ? D : 1) * 8),
+           o_cand = take((size_t)T * C * 4);
+    CUDA_OK(c->ws_small.ensure(off));
+    char *base = (char *)c->ws_small.p;
+    CUDA_OK(cudaMemcpyAsync(base + o_mean, mean, (size_t)T * 64, cudaMemcpyHostToDevice, c->stream));
+    if (tracked) CUDA_OK(cudaMemcpyAsync(base + o_trk, tracked, T, cudaMemcpyHostToDevice, c->stream));
+    if (D) CUDA_OK(cudaMemcpyAsync(base + o_det, det_tlbr, (size_t)D * 32, cudaMemcpyHostToDevice, c->stream));
+    GeomParams p{};
+    p.T = T; p.D = D; p.C = C; p.use_kalman = use_kalman; p.nbatch = 1;
+    p.mean = (const double *)(base + o_mean);
+    p.tracked = tracked ? (const uint8_t *)(base + o_trk) : nullptr;
+    p.det_tlbr = (const double *)(base + o_det);
+    p.tlwh_out = (double *)(base + o_tlwh);
+    p.tlbr_out = (double *)(base + o_tlbr);
+    p.dist_out = dist ? (double *)(base + o_dist) : nullptr;
+    p.iou_out = iou ? (double *)(base + o_iou) : nullptr;
+    p.cand_out = cand ? (int *)(base + o_cand) : nullptr;
+    prof_reset(c);
+    LAUNCH(c, "frame_geometry", launch_frame_geometry(p, c->stream));
+    if (tlwh) CUDA_OK(cudaMemcpyAsync(tlwh, base + o_tlwh, (size_t)T * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (tlbr) CUDA_OK(cudaMemcpyAsync(tlbr, base + o_tlbr, (size_t)T * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (dist && D) CUDA_OK(cudaMemcpyAsync(dist, base + o_dist, (size_t)T * D * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (iou && D) CUDA_OK(cudaMemcpyAsync(iou, base + o_iou, (size_t)T * D * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (cand) CUDA_OK(cudaMemcpyAsync(cand, base + o_cand, (size_t)T * C * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+extern "C" int busca_motion_proposals(busca_ctx *c, const double *mean, const uint8_t *tracked, int32_t n, double *mean_out,
+                                      double *tlwh, double *tlbr) {
+    if (!c || n < 0 || (n > 0 && !mean)) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (n == 0) return BUSCA_OK;
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    size_t need = (size_t)n * (64 + 64 + 64 + 32 + 32) + 256;
+    CUDA_OK(c->ws_small.ensure(need));
+    char *base = (char *)c->ws_small.p;
+    double *dmean = (double *)base, *dmo = dmean + (size_t)n * 8, *dtlwh = dmo + (size_t)n * 8, *dtlbr = dtlwh + (size_t)n * 4;
+    uint8_t *dtrk = (uint8_t *)(dtlbr + (size_t)n * 4);
+    CUDA_OK(cudaMemcpyAsync(dmean, mean, (size_t)n * 64, cudaMemcpyHostToDevice, c->stream));
+    if (tracked) CUDA_OK(cudaMemcpyAsync(dtrk, tracked, n, cudaMemcpyHostToDevice, c->stream));
+    GeomParams p{};
+    p.T = n; p.D = 0; p.C = 1; p.nbatch = 1;
+    p.mean = dmean; p.tracked = tracked ? dtrk : nullptr; p.det_tlbr = dmean;
+    p.mean_out = dmo; p.tlwh_out = dtlwh; p.tlbr_out = dtlbr;
+    prof_reset(c);
+    LAUNCH(c, "frame_geometry", launch_frame_geometry(p, c->stream));
+    if (mean_out) CUDA_OK(cudaMemcpyAsync(mean_out, dmo, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream));
+    if (tlwh) CUDA_OK(cudaMemcpyAsync(tlwh, dtlwh, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+    if (tlbr) CUDA_OK(cudaMemcpyAsync(tlbr, dtlbr, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ReID forward on one BatchNorm batch (device pointers)
+// ------------------------------------------------------------------------------------------------
+static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *d_emb) {
+    if (N <= 0) return BUSCA_OK;
+    const int bf16 = c->cfg.precision == BUSCA_PREC_BF16;
+    const size_t es = bf16 ? 2 : 4;
+    const size_t big = (size_t)786432 * N * es;
+    const size_t total = 4 * big + (size_t)393216 * N * es + (size_t)196608 * N * es + (size_t)N * 2048 * 4 + 1024;
+    cudaError_t e = c->ws_reid.ensure(total);
+    if (e != cudaSuccess) return set_err(BUSCA_ERR_NOMEM, "ReID workspace for %d patches (%.1f GB): %s", N, total / 1e9, cudaGetErrorString(e));
+    char *base = (char *)c->ws_reid.p;
+    void *A = base, *B = base + big, *R3 = base + 2 * big, *RDS = base + 3 * big;
+    void *R1 = base + 4 * big, *R2 = (char *)R1 + (size_t)393216 * N * es;
+    float *pooled = (float *)((char *)R2 + (size_t)196608 * N * es);
+    cudaStream_t s = c->stream;
+    CUDA_OK(cudaMemsetAsync(c->stats_pool, 0, c->stats_bytes, s));
+
+    ConvLayer &stem = c->convs[0];
+    LAUNCH(c, "stem_conv7x7", launch_stem(c->bank, d_slots, N, c->lut, stem, R3, bf16, s));
+    LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, (long long)N * 192 * 64, s));
+    LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(R3, A, N, 192, 64, 64, stem.scale, stem.shift, bf16, s));
+    void *x = A, *other = B;
+    int H = 96, W = 32;
+    size_t ci = 1;
+    const int blocks[4] = {3, 4, 6, 3};
+    for (int li = 0; li < 4; ++li)
+        for (int b = 0; b < blocks[li]; ++b) {
+            ConvLayer &c1 = c->convs[ci], &c2 = c->convs[ci + 1], &c3 = c->convs[ci + 2];
+            const int st = c2.stride, Ho = H / st, Wo = W / st;
+            ConvArgs a{};
+            a.N = N;
+            a.in = x; a.out = R1; a.H = H; a.W = W; a.Ho = H; a.Wo = W; a.in_scale = nullptr; a.in_shift = nullptr;
+            LAUNCH(c, "conv1x1", launch_conv_simt(c1, a, bf16, s));
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c1, (long long)N * H * W, s));
+            a.in = R1; a.out = R2; a.Ho = Ho; a.Wo = Wo; a.in_scale = c1.scale; a.in_shift = c1.shift;
+            LAUNCH(c, "conv3x3", launch_conv_simt(c2, a, bf16, s));
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c2, (long long)N * Ho * Wo, s));
+            a.in = R2; a.out = R3; a.H = Ho; a.W = Wo; a.in_scale = c2.scale; a.in_shift = c2.shift;
+            LAUNCH(c, "conv1x1", launch_conv_simt(c3, a, bf16, s));
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c3, (long long)N * Ho * Wo, s));
+            const long long rows = (long long)N * Ho * Wo;
+            if (b == 0) {
+                ConvLayer &ds = c->convs[ci + 3];
+                a.in = x; a.out = RDS; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.in_scale = nullptr; a.in_shift = nullptr;
+                LAUNCH(c, "conv1x1", launch_conv_simt(ds, a, bf16, s));
+                LAUNCH(c, "bn_finalize", launch_bn_finalize(ds, rows, s));
+                LAUNCH(c, "bn_add_relu", launch_bn_add_relu(R3, c3.scale, c3.shift, RDS, ds.scale, ds.shift, other, rows, c3.cout, bf16, s));
+                void *t = x; x = other; other = t;
+                ci += 4;
+            } else {
+                LAUNCH(c, "bn_add_relu", launch_bn_add_relu(R3, c3.scale, c3.shift, x, nullptr, nullptr, x, rows, c3.cout, bf16, s));
+                ci += 3;
+            }
+            H = Ho; W = Wo;
+        }
+    LAUNCH(c, "global_maxpool", launch_global_maxpool(x, pooled, N, H * W, 2048, bf16, s));
+    LinearArgs la{};
+    la.A = pooled; la.W = c->red_w; la.bias = c->red_b; la.residual = nullptr; la.out = d_emb; la.M = N; la.N = 512; la.K = 2048; la.alpha = 1.f; la.act = 0;
+    LAUNCH(c, "linear", launch_linear_f32(la, s));
+    LAUNCH(c, "l2norm", launch_l2norm_rows(d_emb, N, 512, s));
+    return BUSCA_OK;
+}
+
+extern "C" int busca_reid_embed(busca_ctx *c, const int32_t *slots, int32_t n, float *out) {
+    if (!c || n < 0 || (n > 0 && (!slots || !out))) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (!c->finalized) return set_err(BUSCA_ERR_STATE, "weights not finalized");
+    if (n == 0) return BUSCA_OK;
+    int rc = check_slots(c, slots, n, true);
+    if (rc) return rc;
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    CUDA_OK(c->ws_io.ensure((size_t)n * 4 + (size_t)n * 512 * 4 + 256));
+    int32_t *dsl = (int32_t *)c->ws_io.p;
+    float *demb = (float *)((char *)c->ws_io.p + (((size_t)n * 4 + 255) & ~(size_t)255));
+    CUDA_OK(cudaMemcpyAsync(dsl, slots, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    prof_reset(c);
+    rc = reid_forward_dev(c, dsl, n, demb);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(out, demb, (size_t)n * 512 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decision Transformer (device pointers).  Workspace carved from ws_tr.
+// ------------------------------------------------------------------------------------------------
+struct TrOut {
+    float *logits, *probs, *cand_rows, *mem_logits, *input_seq;   // device, may be null except logits/probs
+};
+static int transformer_dev(busca_ctx *c, int T, int L, int C, const float *mem_emb, const float *can_emb, const int32_t *idx, TrOut o) {
+    const int S = L + 2 * (C + 2), d = c->cfg.d_model, ff = c->cfg.ff_size;
+    const size_t rows = (size_t)T * S;
+    size_t off = 0;
+    auto take = [&](size_t n_floats) { size_t r = off; off += (n_floats * 4 + 255) & ~(size_t)255; return r; };
+    size_t o_me = take((size_t)T * L * d), o_ce = take((size_t)T * C * d), o_x = take(rows * d), o_y = take(rows * d), o_qkv = take(rows * 3 * d),
+           o_att = take(rows * d), o_h = take(rows * ff);
+    CUDA_OK(c->ws_tr.ensure(off));
+    char *b = (char *)c->ws_tr.p;
+    float *me = (float *)(b + o_me), *ce = (float *)(b + o_ce), *X = (float *)(b + o_x), *Y = (float *)(b + o_y), *QKV = (float *)(b + o_qkv),
+          *ATT = (float *)(b + o_att), *Hd = (float *)(b + o_h);
+    cudaStream_t s = c->stream;
+    const float alpha = (float)sqrt((double)d);                    // * np.sqrt(self.dim_model), network.py:203-204
+    LinearArgs la{};
+    la.alpha = alpha; la.act = 0; la.residual = nullptr; la.W = c->enc_w; la.bias = c->enc_b; la.N = d; la.K = d;
+    la.A = mem_emb; la.out = me; la.M = T * L;
+    LAUNCH(c, "linear", launch_linear_f32(la, s));
+    la.A = can_emb; la.out = ce; la.M = T * C;
+    LAUNCH(c, "linear", launch_linear_f32(la, s));
+    PeTables pe{c->pe_xy, c->pe_size, c->pe_t};
+    LAUNCH(c, "build_tokens", launch_build_tokens(me, ce, c->sep, c->non, c->bad, idx, pe, T, L, C, X, s));
+    if (o.input_seq) CUDA_OK(cudaMemcpyAsync(o.input_seq, X, rows * d * 4, cudaMemcpyDeviceToDevice, s));
+    const int act = c->cfg.activation == BUSCA_ACT_GELU ? 2 : 1;
+    for (auto &ly : c->layers) {
+        LinearArgs g{};
+        g.alpha = 1.f; g.M = (int)rows;
+        g.A = X; g.W = ly.in_w; g.bias = ly.in_b; g.residual = nullptr; g.out = QKV; g.N = 3 * d; g.K = d; g.act = 0;
+        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        LAUNCH(c, "attention", launch_attention(QKV, ATT, T, S, c->cfg.nhead, d / c->cfg.nhead, s));
+        g.A = ATT; g.W = ly.out_w; g.bias = ly.out_b; g.residual = X; g.out = Y; g.N = d; g.K = d;
+        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        LAUNCH(c, "layernorm", launch_layernorm(Y, ly.n1_g, ly.n1_b, X, (int)rows, d, s));
+        g.A = X; g.W = ly.l1_w; g.bias = ly.l1_b; g.residual = nullptr; g.out = Hd; g.N = ff; g.K = d; g.act = act;
+        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        g.A = Hd; g.W = ly.l2_w; g.bias = ly.l2_b; g.residual = X; g.out = Y; g.N = d; g.K = ff; g.act = 0;
+        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        LAUNCH(c, "layernorm", launch_layernorm(Y, ly.n2_g, ly.n2_b, X, (int)rows, d, s));
+    }
+    LAUNCH(c, "decoder", launch_decoder(X, T, S, L, C, c->dec_g, c->dec_b, c->dec_w, c->dec_bias, o.logits, o.probs, o.cand_rows, o.mem_logits, s));
+    return BUSCA_OK;
+}
+
+// carve helper for io scratch
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; }
+};
+
+extern "C" int busca_transformer(busca_ctx *c, int32_t T, int32_t L, int32_t C, const float *mem_emb, const float *can_emb,
+                                 const double *mem_ltwh, const double *can_ltwh, float *logits, float *probs, int32_t *pe_index,
+                                 float *cand_rows, float *input_seq) {
+    if (!c || T <= 0 || L < 1 || C < 1 || !mem_emb || !can_emb || !mem_ltwh || !can_ltwh) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (!c->finalized) return set_err(BUSCA_ERR_STATE, "weights not finalized");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const int S = L + 2 * (C + 2), nc = C + 2;
+    Carver cv;
+    size_t o_me = cv.take((size_t)T * L * 512 * 4), o_ce = cv.take((size_t)T * C * 512 * 4), o_mb = cv.take((size_t)T * L * 32), o_cb = cv.take((size_t)T * C * 32),
+           o_idx = cv.take((size_t)T * S * 12), o_lg = cv.take((size_t)T * nc * 4), o_pr = cv.take((size_t)T * nc * 4), o_cr = cv.take((size_t)T * nc * 512 * 4),
+           o_is = cv.take((size_t)T * S * 512 * 4);
+    CUDA_OK(c->ws_io.ensure(cv.off));
+    char *b = (char *)c->ws_io.p;
+    cudaStream_t s = c->stream;
+    CUDA_OK(cudaMemcpyAsync(b + o_me, mem_emb, (size_t)T * L * 512 * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b + o_ce, can_emb, (size_t)T * C * 512 * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b + o_mb, mem_ltwh, (size_t)T * L * 32, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b + o_cb, can_ltwh, (size_t)T * C * 32, cudaMemcpyHostToDevice, s));
+    prof_reset(c);
+    LAUNCH(c, "pe_index", launch_pe_index((const double *)(b + o_mb), (const double *)(b + o_cb), T, L, C, c->cfg.sentinel_fp64, (int32_t *)(b + o_idx), s));
+    TrOut o{(float *)(b + o_lg), (float *)(b + o_pr), cand_rows ? (float *)(b + o_cr) : nullptr, nullptr, input_seq ? (float *)(b + o_is) : nullptr};
+    int rc = transformer_dev(c, T, L, C, (const float *)(b + o_me), (const float *)(b + o_ce), (const int32_t *)(b + o_idx), o);
+    if (rc) return rc;
+    if (logits) CUDA_OK(cudaMemcpyAsync(logits, b + o_lg, (size_t)T * nc * 4, cudaMemcpyDeviceToHost, s));
+    if (probs) CUDA_OK(cudaMemcpyAsync(probs, b + o_pr, (size_t)T * nc * 4, cudaMemcpyDeviceToHost, s));
+    if (pe_index) CUDA_OK(cudaMemcpyAsync(pe_index, b + o_idx, (size_t)T * S * 12, cudaMemcpyDeviceToHost, s));
+    if (cand_rows) CUDA_OK(cudaMemcpyAsync(cand_rows, b + o_cr, (size_t)T * nc * 512 * 4, cudaMemcpyDeviceToHost, s));
+    if (input_seq) CUDA_OK(cudaMemcpyAsync(input_seq, b + o_is, (size_t)T * S * 512 * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// association (host pointers in, host pointers out)
+// ------------------------------------------------------------------------------------------------
+extern "C" int busca_associate(busca_ctx *c, const busca_assoc_args *a) {
+    if (!c || !a) return set_err(BUSCA_ERR_ARG, "null argument");
+    if (!c->finalized) return set_err(BUSCA_ERR_STATE, "weights not finalized");
+    const int T = a->T, D = a->D, L = a->L, C = a->C;
+    if (T <= 0 || D < 0 || L < 1 || C < 1 || C + 2 > 30 || L + 2 * (C + 2) > 64) return set_err(BUSCA_ERR_ARG, "unsupported sizes T=%d D=%d L=%d C=%d", T, D, L, C);
+    if (!a->mem_slots || !a->mem_ltwh || (D > 0 && (!a->det_slots || !a->det_ltwh || !a->dists))) return set_err(BUSCA_ERR_ARG, "null input");
+    if (a->use_kalman && (!a->kal_slots || !a->kal_ltwh)) return set_err(BUSCA_ERR_ARG, "use_kalman without kalman inputs");
+    if (D == 0 && !a->use_kalman) return set_err(BUSCA_ERR_ARG, "no detections and no kalman candidates (the reference returns None here)");
+    int rc = check_slots(c, a->mem_slots, T * L, true);
+    if (rc) return rc;
+    if (D) { rc = check_slots(c, a->det_slots, D, true); if (rc) return rc; }
+    if (a->use_kalman) { rc = check_slots(c, a->kal_slots, T, true); if (rc) return rc; }
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const int S = L + 2 * (C + 2), nc = C + 2, Dn = D ? D : 1;
+    Carver cv;
+    size_t o_ms = cv.take((size_t)T * L * 4), o_mb = cv.take((size_t)T * L * 32), o_ds = cv.take((size_t)Dn * 4), o_db = cv.take((size_t)Dn * 32),
+           o_dist = cv.take((size_t)T * Dn * 8), o_ks = cv.take((size_t)T * 4), o_kb = cv.take((size_t)T * 32), o_cand = cv.take((size_t)T * C * 4),
+           o_cb = cv.take((size_t)T * C * 32), o_cs = cv.take((size_t)T * C * 4), o_idx = cv.take((size_t)T * S * 12), o_me = cv.take((size_t)T * L * 512 * 4),
+           o_ce = cv.take((size_t)T * C * 512 * 4), o_lg = cv.take((size_t)T * nc * 4), o_pr = cv.take((size_t)T * nc * 4),
+           o_cr = cv.take((size_t)T * nc * 512 * 4), o_ml = cv.take((size_t)T * 512 * 4), o_is = cv.take((size_t)T * S * 512 * 4);
+    CUDA_OK(c->ws_io.ensure(cv.off));
+    char *b = (char *)c->ws_io.p;
+    cudaStream_t s = c->stream;
+    CUDA_OK(cudaMemcpyAsync(b + o_ms, a->mem_slots, (size_t)T * L * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b + o_mb, a->mem_ltwh, (size_t)T * L * 32, cudaMemcpyHostToDevice, s));
+    if (D) {
+        CUDA_OK(cudaMemcpyAsync(b + o_ds, a->det_slots, (size_t)D * 4, cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(b + o_db, a->det_ltwh, (size_t)D * 32, cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(b + o_dist, a->dists, (size_t)T * D * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (a->use_kalman) {
+        CUDA_OK(cudaMemcpyAsync(b + o_ks, a->kal_slots, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(b + o_kb, a->kal_ltwh, (size_t)T * 32, cudaMemcpyHostToDevice, s));
+    }
+    prof_reset(c);
+    GeomParams p{};
+    p.T = T; p.D = D; p.C = C; p.use_kalman = a->use_kalman ? 1 : 0; p.nbatch = 1;
+    p.mean = nullptr; p.trk_tlbr = (const double *)(b + o_mb);      // unused values: distances are given
+    p.det_tlbr = (const double *)(b + o_db);
+    p.dists_in = (const double *)(b + o_dist);
+    p.cand_out = (int *)(b + o_cand);
+    LAUNCH(c, "frame_geometry", launch_frame_geometry(p, s));
+    LAUNCH(c, "assemble_candidates", launch_assemble_candidates((const int *)(b + o_cand), T, D, C, (const double *)(b + o_db), (const int32_t *)(b + o_ds),
+                                                                 a->use_kalman ? (const double *)(b + o_kb) : nullptr,
+                                                                 a->use_kalman ? (const int32_t *)(b + o_ks) : nullptr, (double *)(b + o_cb),
+                                                                 (int32_t *)(b + o_cs), c->cfg.sentinel_fp64, s));
+    LAUNCH(c, "pe_index", launch_pe_index((const double *)(b + o_mb), (const double *)(b + o_cb), T, L, C, c->cfg.sentinel_fp64, (int32_t *)(b + o_idx), s));
+    rc = reid_forward_dev(c, (const int32_t *)(b + o_ms), T * L, (float *)(b + o_me));
+    if (rc) return rc;
+    rc = reid_forward_dev(c, (const int32_t *)(b + o_cs), T * C, (float *)(b + o_ce));
+    if (rc) return rc;
+    TrOut o{(float *)(b + o_lg), (float *)(b + o_pr), a->cand_rows ? (float *)(b + o_cr) : nullptr, a->mem_logits ? (float *)(b + o_ml) : nullptr,
+            a->input_seq ? (float *)(b + o_is) : nullptr};
+    rc = transformer_dev(c, T, L, C, (const float *)(b + o_me), (const float *)(b + o_ce), (const int32_t *)(b + o_idx), o);
+    if (rc) return rc;
+    if (a->probs) CUDA_OK(cudaMemcpyAsync(a->probs, b + o_pr, (size_t)T * nc * 4, cudaMemcpyDeviceToHost, s));
+    if (a->logits) CUDA_OK(cudaMemcpyAsync(a->logits, b + o_lg, (size_t)T * nc * 4, cudaMemcpyDeviceToHost, s));
+    if (a->cand) CUDA_OK(cudaMemcpyAsync(a->cand, b + o_cand, (size_t)T * C * 4, cudaMemcpyDeviceToHost, s));
+    if (a->pe_index) CUDA_OK(cudaMemcpyAsync(a->pe_index, b + o_idx, (size_t)T * S * 12, cudaMemcpyDeviceToHost, s));
+    if (a->mem_emb) CUDA_OK(cudaMemcpyAsync(a->mem_emb, b + o_me, (size_t)T * L * 512 * 4, cudaMemcpyDeviceToHost, s));
+    if (a->can_emb) CUDA_OK(cudaMemcpyAsync(a->can_emb, b + o_ce, (size_t)T * C * 512 * 4, cudaMemcpyDeviceToHost, s));
+    if (a->cand_rows) CUDA_OK(cudaMemcpyAsync(a->cand_rows, b + o_cr, (size_t)T * nc * 512 * 4, cudaMemcpyDeviceToHost, s));
+    if (a->mem_logits) CUDA_OK(cudaMemcpyAsync(a->mem_logits, b + o_ml, (size_t)T * 512 * 4, cudaMemcpyDeviceToHost, s));
+    if (a->input_seq) CUDA_OK(cudaMemcpyAsync(a->input_seq, b + o_is, (size_t)T * S * 512 * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident frame step
+// ------------------------------------------------------------------------------------------------
+__global__ void tlbr_to_ltwh_kernel(const double *__restrict__ tlbr, double *__restrict__ ltwh, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x1 = tlbr[4 * i], y1 = tlbr[4 * i + 1];
+    ltwh[4 * i] = x1; ltwh[4 * i + 1] = y1;
+    ltwh[4 * i + 2] = __dsub_rn(tlbr[4 * i + 2], x1);
+    ltwh[4 * i + 3] = __dsub_rn(tlbr[4 * i + 3], y1);
+}
+
+extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
+    if (!c || !a) return set_err(BUSCA_ERR_ARG, "null argument");
+    if (!c->finalized) return set_err(BUSCA_ERR_STATE, "weights not finalized");
+    const int T = a->T, D = a->D, L = a->L, C = a->C;
+    if (T <= 0 || D <= 0 || L < 1 || C < 1 || C + 2 > 30 || L + 2 * (C + 2) > 64) return set_err(BUSCA_ERR_ARG, "unsupported sizes");
+    if (!c->frame.p) return set_err(BUSCA_ERR_STATE, "no frame uploaded");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const int S = L + 2 * (C + 2), nc = C + 2;
+    Carver cv;
+    size_t o_tlwh = cv.take((size_t)T * 32), o_tlbr = cv.take((size_t)T * 32), o_dist = cv.take((size_t)T * D * 8), o_iou = cv.take((size_t)T * D * 8),
+           o_cand = cv.take((size_t)T * C * 4), o_dl = cv.take((size_t)D * 32), o_cb = cv.take((size_t)T * C * 32), o_cs = cv.take((size_t)T * C * 4),
+           o_idx = cv.take((size_t)T * S * 12), o_me = cv.take((size_t)T * L * 512 * 4), o_ce = cv.take((size_t)T * C * 512 * 4), o_lg = cv.take((size_t)T * nc * 4);
+    CUDA_OK(c->ws_io.ensure(cv.off));
+    char *b = (char *)c->ws_io.p;
+    cudaStream_t s = c->stream;
+    prof_reset(c);
+    GeomParams p{};
+    p.T = T; p.D = D; p.C = C; p.use_kalman = 1; p.nbatch = 1;
+    p.mean = a->track_mean_dev; p.tracked = a->tracked_dev; p.det_tlbr = a->det_tlbr_dev;
+    p.tlwh_out = (double *)(b + o_tlwh); p.tlbr_out = (double *)(b + o_tlbr);
+    p.dist_out = (double *)(b + o_dist); p.iou_out = (double *)(b + o_iou); p.cand_out = (int *)(b + o_cand);
+    LAUNCH(c, "frame_geometry", launch_frame_geometry(p, s));
+    // crops of the D detections and the T motion proposals, straight from the resident frame
+    LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, a->det_tlbr_dev, D, a->det_slots_dev, c->bank, s));
+    LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, (const double *)(b + o_tlbr), T, a->kal_slots_dev, c->bank, s));
+    prof_begin(c, "tlbr_to_ltwh");
+    tlbr_to_ltwh_kernel<<<ceil_div(D, 128), 128, 0, s>>>(a->det_tlbr_dev, (double *)(b + o_dl), D);
+    prof_end(c);
+    c->launches++;
+    LAUNCH(c, "assemble_candidates", launch_assemble_candidates((const int *)(b + o_cand), T, D, C, (const double *)(b + o_dl), a->det_slots_dev,
+                                                                 (const double *)(b + o_tlwh), a->kal_slots_dev, (double *)(b + o_cb), (int32_t *)(b + o_cs),
+                                                                 c->cfg.sentinel_fp64, s));
+    LAUNCH(c, "pe_index", launch_pe_index(a->mem_ltwh_dev, (const double *)(b + o_cb), T, L, C, c->cfg.sentinel_fp64, (int32_t *)(b + o_idx), s));
+    int rc = reid_forward_dev(c, a->mem_slots_dev, T * L, (float *)(b + o_me));
+    if (rc) return rc;
+    rc = reid_forward_dev(c, (const int32_t *)(b + o_cs), T * C, (float *)(b + o_ce));
+    if (rc) return rc;
+    TrOut o{(float *)(b + o_lg), a->probs_dev, nullptr, nullptr, nullptr};
+    rc = transformer_dev(c, T, L, C, (const float *)(b + o_me), (const float *)(b + o_ce), (const int32_t *)(b + o_idx), o);
+    if (rc) return rc;
+    if (a->keep_dev) LAUNCH(c, "decide", launch_decide(a->probs_dev, (const int *)(b + o_cand), a->reliable_dev, T, D, C, a->busca_thresh, a->keep_dev, s));
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plumbing
+// ------------------------------------------------------------------------------------------------
+extern "C" void *busca_dev_alloc(busca_ctx *c, int64_t bytes) {
+    if (!c || bytes <= 0) return nullptr;
+    cudaSetDevice(c->cfg.device);
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { set_err(BUSCA_ERR_NOMEM, "cudaMalloc(%lld) failed", (long long)bytes); return nullptr; }
+    return p;
+}
+extern "C" void busca_dev_free(busca_ctx *c, void *p) { if (c && p) { cudaSetDevice(c->cfg.device); cudaFree(p); } }
+extern "C" int busca_memcpy_h2d(busca_ctx *c, void *dst, const void *src, int64_t bytes) {
+    if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BUSCA_OK;
+}
+extern "C" int busca_memcpy_d2h(busca_ctx *c, void *dst, const void *src, int64_t bytes) {
+    if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BUSCA_OK;
+}
+extern "C" int busca_sync(busca_ctx *c) {
+    if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+extern "C" void *busca_stream(busca_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int64_t busca_kernel_launches(busca_ctx *c) { return c ? c->launches : 0; }
+extern "C" int busca_set_profiling(busca_ctx *c, int32_t on) {
+    if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
+    c->profiling = on != 0;
+    prof_reset(c);
+    return BUSCA_OK;
+}
+extern "C" const char *busca_last_profile(busca_ctx *c) { return c ? c->prof_json.c_str() : "{}"; }

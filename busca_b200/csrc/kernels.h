@@ -1,0 +1,88 @@
+// Internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cuda_fp16.h>
+
+// ---------------------------------------------------------------- geometry.cu
+struct GeomParams {
+    int T, D, C, use_kalman, nbatch;
+    const double *mean;        // [B,T,8] or null (then trk_tlbr is used as given)
+    const uint8_t *tracked;    // [B,T]   or null (= all tracked)
+    const double *trk_tlbr;    // [B,T,4] used when mean == null
+    const double *det_tlbr;    // [B,D,4]
+    const double *dists_in;    // [B,T,D] or null (then computed from the boxes)
+    double *mean_out;          // [B,T,8] | null
+    double *tlwh_out;          // [B,T,4] | null
+    double *tlbr_out;          // [B,T,4] | null
+    double *dist_out;          // [B,T,D] | null
+    double *iou_out;           // [B,T,D] | null
+    int *cand_out;             // [B,T,C] | null
+};
+cudaError_t launch_frame_geometry(const GeomParams &p, cudaStream_t s);
+cudaError_t launch_pair_matrix(const double *a, int na, const double *b, int nb, double *out, int want_iou, cudaStream_t s);
+
+// ---------------------------------------------------------------- crop.cu
+// boxes [n,4] (x1,y1,x2,y2) fp64 device; slots [n] device; bank = patch bank base.
+cudaError_t launch_crop_resize(const uint8_t *frame, int H, int W, int64_t row_stride, const double *boxes, int n,
+                               const int32_t *slots, uint8_t *bank, cudaStream_t s);
+
+// ---------------------------------------------------------------- reid.cu
+struct ConvLayer {
+    int cin, cout, k, stride;
+    float *w32;                 // [cout][k][k][cin] fp32
+    void *w16;                  // same layout, bf16 (bf16 mode)
+    float *gamma, *beta;        // BatchNorm affine
+    double *stats;              // [2*cout] sum, sum of squares of the raw conv output (this batch)
+    float *scale, *shift;       // finalised: y = x*scale + shift
+};
+struct ConvArgs {
+    const void *in;             // NHWC activations (float or bf16)
+    void *out;                  // [M, cout] raw conv output
+    int N, H, W;                // input spatial size
+    int Ho, Wo;
+    const float *in_scale, *in_shift;   // deferred BN+ReLU of the producer applied on load (null = identity)
+};
+cudaError_t launch_stem(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const ConvLayer &L, void *out,
+                        int bf16, cudaStream_t s);
+cudaError_t launch_conv_simt(const ConvLayer &L, const ConvArgs &a, int bf16, cudaStream_t s);
+cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t s);
+cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,
+                                   const float *shift, int bf16, cudaStream_t s);
+// out = relu(raw*scale+shift + (idt_scale ? idt*idt_scale+idt_shift : idt)); out may alias idt
+cudaError_t launch_bn_add_relu(const void *raw, const float *scale, const float *shift, const void *idt,
+                               const float *idt_scale, const float *idt_shift, void *out, long long rows, int C, int bf16,
+                               cudaStream_t s);
+cudaError_t launch_global_maxpool(const void *x, float *out, int N, int HW, int C, int bf16, cudaStream_t s);
+cudaError_t launch_l2norm_rows(float *x, int rows, int cols, cudaStream_t s);
+
+// ---------------------------------------------------------------- linear (reid.cu): out = act((A W^T + b) * alpha) + res
+struct LinearArgs {
+    const float *A;             // [M,K]
+    const float *W;             // [N,K]
+    const float *bias;          // [N] | null
+    const float *residual;      // [M,N] | null
+    float *out;                 // [M,N]
+    int M, N, K;
+    float alpha;                // applied after bias
+    int act;                    // 0 none, 1 relu, 2 gelu(erf)
+};
+cudaError_t launch_linear_f32(const LinearArgs &a, cudaStream_t s);
+
+// ---------------------------------------------------------------- transformer.cu
+struct PeTables { const __half *xy, *size, *t; };
+cudaError_t launch_assemble_candidates(const int *cand, int T, int D, int C, const double *det_ltwh, const int32_t *det_slots,
+                                       const double *kal_ltwh, const int32_t *kal_slots, double *can_ltwh, int32_t *can_slots,
+                                       int sentinel_fp64, cudaStream_t s);
+cudaError_t launch_pe_index(const double *mem_ltwh, const double *can_ltwh, int T, int L, int C, int sentinel_fp64,
+                            int32_t *idx /*[T,S,3]*/, cudaStream_t s);
+cudaError_t launch_build_tokens(const float *mem_enc, const float *can_enc, const float *sep, const float *non, const float *bad,
+                                const int32_t *idx, PeTables pe, int T, int L, int C, float *x, cudaStream_t s);
+cudaError_t launch_attention(const float *qkv, float *out, int T, int S, int nhead, int dh, cudaStream_t s);
+cudaError_t launch_layernorm(const float *x, const float *gamma, const float *beta, float *out, int rows, int cols,
+                             cudaStream_t s);
+cudaError_t launch_decoder(const float *x, int T, int S, int L, int C, const float *ln_g, const float *ln_b, const float *w,
+                           const float *b, float *logits, float *probs, float *cand_rows, float *mem_logits,
+                           cudaStream_t s);
+cudaError_t launch_decide(const float *probs, const int *cand, const uint8_t *reliable, int T, int D, int C, float thresh,
+                          uint8_t *keep, cudaStream_t s);

@@ -1,0 +1,483 @@
+// ReID ResNet-50 with batch-statistic BatchNorm (busca/reid/resnet.py:85-128, 266-322; network.py:542-570),
+// exact-arithmetic path: SIMT fp32 implicit-GEMM convolutions.  This is the fp32 parity mode and the on-device
+// reference the tcgen05 bf16 path (conv_tc.cu) is validated against.
+//
+// Layout: activations NHWC ([N*H*W, C] row-major), weights [Cout][kh][kw][Cin] (K-major), so every convolution is
+// C[M, Cout] = A[M, K] * W[Cout, K]^T with M = N*Ho*Wo, K = kh*kw*Cin and the A rows gathered on the fly.
+// BatchNorm in training mode needs the statistics of the WHOLE batch before anything can be normalised, so every
+// conv kernel (a) writes the raw output, (b) accumulates per-channel sum / sum-of-squares in its epilogue, and the
+// consumer applies y = relu(x*scale + shift) while loading its A operand ("deferred BN").  Residual joins are
+// materialised by bn_add_relu.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// generic implicit-GEMM conv / linear, SIMT fp32 accumulate
+// ------------------------------------------------------------------------------------------------
+struct IGemmParams {
+    const void *in;
+    void *out;
+    const float *w;                  // [Cout][K]
+    int N, H, W, Cin, Ho, Wo, Cout, ksz, stride, pad;
+    long long M;
+    int K;
+    const float *in_scale, *in_shift;
+    const float *bias;
+    const float *residual;           // fp32 [M,Cout]
+    float alpha;
+    int act;
+    double *stats;
+};
+
+constexpr int BM = 128, BK = 16, IG_THREADS = 256;
+
+template <typename TIn, typename TOut, int BN>
+__global__ void __launch_bounds__(IG_THREADS, 2) igemm_simt_kernel(IGemmParams p) {
+    constexpr int TN = BN / 16;
+    constexpr int AS = BM + 4, BS = BN + 4;
+    __shared__ __align__(16) float As[2][BK][AS];
+    __shared__ __align__(16) float Bs[2][BK][BS];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const TIn *in = reinterpret_cast<const TIn *>(p.in);
+
+    // ---- A-load bookkeeping
+    constexpr bool kF32 = sizeof(TIn) == 4;
+    constexpr int AROWS = kF32 ? 2 : 1;
+    int a_row[AROWS], a_hi0[AROWS], a_wi0[AROWS];
+    long long a_img[AROWS];
+    bool a_ok[AROWS];
+    const int a_kq = kF32 ? (tid & 3) : (tid & 1);           // which 4-float (or 8-bf16) group of the 16-wide k tile
+#pragma unroll
+    for (int i = 0; i < AROWS; ++i) {
+        a_row[i] = kF32 ? ((tid >> 2) + i * 64) : (tid >> 1);
+        long long m = m0 + a_row[i];
+        a_ok[i] = m < p.M;
+        long long mm = a_ok[i] ? m : 0;
+        int wo = (int)(mm % p.Wo);
+        long long t = mm / p.Wo;
+        int ho = (int)(t % p.Ho);
+        a_img[i] = (t / p.Ho) * (long long)p.H * p.W;
+        a_hi0[i] = ho * p.stride - p.pad;
+        a_wi0[i] = wo * p.stride - p.pad;
+    }
+    // ---- B-load bookkeeping: BN x 16 floats = BN*4 float4
+    constexpr int BLOADS = BN * 4 / IG_THREADS;
+    float areg[AROWS][kF32 ? 4 : 8];
+    float4 breg[BLOADS];
+
+    auto load_tiles = [&](int kt) {
+        const int kbase = kt * BK;
+        const int tap = kbase / p.Cin;
+        const int c0 = kbase - tap * p.Cin + a_kq * (kF32 ? 4 : 8);
+        const int r = tap / p.ksz, s = tap - r * p.ksz;
+#pragma unroll
+        for (int i = 0; i < AROWS; ++i) {
+            const int hi = a_hi0[i] + r, wi = a_wi0[i] + s;
+            const bool ok = a_ok[i] && hi >= 0 && hi < p.H && wi >= 0 && wi < p.W;
+            constexpr int NV = kF32 ? 4 : 8;
+            if (ok) {
+                const TIn *src = in + ((a_img[i] + (long long)hi * p.W + wi) * p.Cin + c0);
+                if constexpr (kF32) {
+                    float4 v = __ldg(reinterpret_cast<const float4 *>(src));
+                    areg[i][0] = v.x; areg[i][1] = v.y; areg[i][2] = v.z; areg[i][3] = v.w;
+                } else {
+                    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float2 f = __bfloat1622float2(h[j]);
+                        areg[i][2 * j] = f.x; areg[i][2 * j + 1] = f.y;
+                    }
+                }
+                if (p.in_scale) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        areg[i][j] = fmaxf(fmaf(areg[i][j], __ldg(p.in_scale + c0 + j), __ldg(p.in_shift + c0 + j)), 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) areg[i][j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BLOADS; ++i) {
+            const int idx = tid + i * IG_THREADS;
+            const int col = idx >> 2, kq = idx & 3;
+            breg[i] = (n0 + col < p.Cout)
+                          ? __ldg(reinterpret_cast<const float4 *>(p.w + (long long)(n0 + col) * p.K + kbase + kq * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < AROWS; ++i) {
+            constexpr int NV = kF32 ? 4 : 8;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) As[buf][a_kq * NV + j][a_row[i]] = areg[i][j];
+        }
+#pragma unroll
+        for (int i = 0; i < BLOADS; ++i) {
+            const int idx = tid + i * IG_THREADS;
+            const int col = idx >> 2, kq = idx & 3;
+            Bs[buf][kq * 4 + 0][col] = breg[i].x;
+            Bs[buf][kq * 4 + 1][col] = breg[i].y;
+            Bs[buf][kq * 4 + 2][col] = breg[i].z;
+            Bs[buf][kq * 4 + 3][col] = breg[i].w;
+        }
+    };
+
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int nk = p.K / BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) load_tiles(kt + 1);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[8], b[TN];
+            *reinterpret_cast<float4 *>(&a[0]) = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8]);
+            *reinterpret_cast<float4 *>(&a[4]) = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 8 + 4]);
+#pragma unroll
+            for (int j = 0; j < TN; j += 4)
+                *reinterpret_cast<float4 *>(&b[j]) = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * TN + j]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) store_tiles(buf ^ 1);
+        __syncthreads();
+    }
+
+    // ---- per-channel batch statistics of the RAW output (rows beyond M are exact zeros)
+    if (p.stats) {
+        float *red = &As[0][0][0];                      // [16][BN] sums, then [16][BN] squares (fits: 2*16*BN <= 2*16*132)
+        float *red2 = &Bs[0][0][0];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s += acc[i][j]; q = fmaf(acc[i][j], acc[i][j], q); }
+            red[ty * BN + tx * TN + j] = s;
+            red2[ty * BN + tx * TN + j] = q;
+        }
+        __syncthreads();
+        if (tid < BN && n0 + tid < p.Cout) {
+            double s = 0.0, q = 0.0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) { s += (double)red[r * BN + tid]; q += (double)red2[r * BN + tid]; }
+            atomicAdd(p.stats + n0 + tid, s);
+            atomicAdd(p.stats + p.Cout + n0 + tid, q);
+        }
+    }
+
+    // ---- epilogue
+    TOut *out = reinterpret_cast<TOut *>(p.out);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long m = m0 + ty * 8 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= p.Cout) continue;
+            float v = acc[i][j];
+            if (p.bias) v += __ldg(p.bias + n);
+            v *= p.alpha;
+            if (p.act == 1) v = fmaxf(v, 0.f);
+            else if (p.act == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+            if (p.residual) v += __ldg(p.residual + m * p.Cout + n);
+            ActIO<TOut>::st(out + m * p.Cout + n, v);
+        }
+    }
+}
+
+template <typename TIn, typename TOut>
+cudaError_t run_igemm(const IGemmParams &p, cudaStream_t s) {
+    if (p.K % BK != 0 || p.Cin % (sizeof(TIn) == 4 ? 4 : 8) != 0 || p.Cin % BK != 0) return cudaErrorInvalidValue;
+    if (p.M <= 0) return cudaSuccess;
+    if (p.Cout <= 64) {
+        dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, 64));
+        igemm_simt_kernel<TIn, TOut, 64><<<grid, IG_THREADS, 0, s>>>(p);
+    } else {
+        dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, 128));
+        igemm_simt_kernel<TIn, TOut, 128><<<grid, IG_THREADS, 0, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: 7x7 stride-2 conv straight from the uint8 BGR patch (normalisation LUT, BGR->RGB and the layout
+// change of network.py:470-478, 397-398 are folded into the load), raw output + statistics
+// ------------------------------------------------------------------------------------------------
+constexpr int STEM_ROWS = 4;                               // output rows per CTA (x 64 output columns)
+constexpr int STEM_IN_ROWS = STEM_ROWS * 2 + 5;            // 13
+constexpr int STEM_IN_COLS = 134;                          // 2*63 + 7 = 133, padded
+constexpr int STEM_K = 147;
+constexpr int STEM_SMEM = (STEM_IN_ROWS * STEM_IN_COLS * 3 + STEM_K * 64 + 2 * 8 * 64) * 4;
+
+template <typename TOut>
+__global__ void __launch_bounds__(256) stem_kernel(const uint8_t *__restrict__ bank, const int32_t *__restrict__ slots,
+                                                   const float *__restrict__ lut, const float *__restrict__ w /*[147][64]*/,
+                                                   TOut *__restrict__ out, double *__restrict__ stats) {
+    extern __shared__ __align__(16) float smem[];
+    float *sin = smem;                                              // [13][134][3]
+    float *sw = smem + STEM_IN_ROWS * STEM_IN_COLS * 3;             // [147][64]
+    float *sred = sw + STEM_K * 64;                                 // [2][8][64]
+    __shared__ float slut[256 * 3];
+
+    const int tid = threadIdx.x;
+    const int n = blockIdx.y, oy0 = blockIdx.x * STEM_ROWS;
+    const int slot = slots[n];
+    for (int i = tid; i < 768; i += 256) slut[i] = lut[i];
+    for (int i = tid; i < STEM_K * 64 / 4; i += 256) reinterpret_cast<float4 *>(sw)[i] = __ldg(reinterpret_cast<const float4 *>(w) + i);
+    __syncthreads();
+    const uint8_t *patch = slot >= 0 ? bank + (size_t)slot * PATCH_BYTES : nullptr;
+    const int iy0 = oy0 * 2 - 3;
+    for (int i = tid; i < STEM_IN_ROWS * STEM_IN_COLS * 3; i += 256) {
+        const int c = i % 3, t = i / 3;
+        const int col = t % STEM_IN_COLS, row = t / STEM_IN_COLS;
+        const int iy = iy0 + row, ix = col - 3;
+        float v = 0.f;                                              // conv zero padding (normalised domain)
+        if (iy >= 0 && iy < PATCH_H && ix >= 0 && ix < PATCH_W) {
+            const int u = patch ? (int)__ldg(patch + ((size_t)iy * PATCH_W + ix) * 3 + c) : 0;
+            v = slut[u * 3 + c];
+        }
+        sin[i] = v;
+    }
+    __syncthreads();
+
+    const int prow = tid >> 6, pcol = tid & 63;
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 7; ++ky) {
+        const float *irow = sin + ((prow * 2 + ky) * STEM_IN_COLS + pcol * 2) * 3;
+        const float *wrow = sw + ky * 21 * 64;
+#pragma unroll 3
+        for (int t = 0; t < 21; ++t) {                              // (kx, c) flattened: contiguous in both arrays
+            const float v = irow[t];
+            const float4 *w4 = reinterpret_cast<const float4 *>(wrow + t * 64);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 ww = w4[j];
+                acc[4 * j + 0] = fmaf(v, ww.x, acc[4 * j + 0]);
+                acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
+                acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]);
+                acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]);
+            }
+        }
+    }
+    // raw output, NHWC [N,192,64,64]
+    TOut *o = out + (((size_t)n * 192 + oy0 + prow) * 64 + pcol) * 64;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) ActIO<TOut>::st(o + j, acc[j]);
+    // statistics
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        float s = warp_sum(acc[j]);
+        float q = warp_sum(acc[j] * acc[j]);
+        if (lane == 0) { sred[warp * 64 + j] = s; sred[512 + warp * 64 + j] = q; }
+    }
+    __syncthreads();
+    if (tid < 128) {
+        const int j = tid & 63, which = tid >> 6;
+        double s = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += (double)sred[which * 512 + wv * 64 + j];
+        atomicAdd(stats + which * 64 + j, s);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double *__restrict__ stats, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, int C, double inv_count, float *__restrict__ scale,
+                                   float *__restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = stats[c] * inv_count;
+    double var = stats[C + c] * inv_count - mean * mean;           // biased variance, as F.batch_norm(training=True)
+    var = var > 0.0 ? var : 0.0;
+    const double a = (double)gamma[c] / sqrt(var + 1e-5);
+    scale[c] = (float)a;
+    shift[c] = (float)((double)beta[c] - mean * a);
+}
+
+// relu(bn(x)) followed by MaxPool2d(3, stride 2, pad 1)           resnet.py:271-272
+template <typename T>
+__global__ void bn_relu_maxpool_kernel(const T *__restrict__ raw, T *__restrict__ out, int N, int H, int W, int C,
+                                       const float *__restrict__ scale, const float *__restrict__ shift) {
+    const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+    const long long total = (long long)N * Ho * Wo * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const long long n = t / Ho;
+        float sc[4], sh[4], best[4] = {0.f, 0.f, 0.f, 0.f};      // relu output >= 0 and the window is never empty
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; }
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int iy = 2 * oy + dy;
+            if (iy < 0 || iy >= H) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int ix = 2 * ox + dx;
+                if (ix < 0 || ix >= W) continue;
+                const T *p = raw + ((n * H + iy) * W + ix) * C + c;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) best[j] = fmaxf(best[j], fmaf(ActIO<T>::ld(p + j), sc[j], sh[j]));
+            }
+        }
+        T *o = out + ((n * Ho + oy) * Wo + ox) * C + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ActIO<T>::st(o + j, best[j]);
+    }
+}
+
+// block output: relu(bn3(raw) + identity) with identity either an activated tensor or bn_ds(raw_ds)   resnet.py:107-128
+template <typename T>
+__global__ void bn_add_relu_kernel(const T *__restrict__ raw, const float *__restrict__ scale, const float *__restrict__ shift,
+                                   const T *idt, const float *__restrict__ iscale, const float *__restrict__ ishift, T *out,
+                                   long long rows, int C) {
+    const int C4 = C / 4;
+    const long long total = rows * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        const long long off = (i / C4) * C + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float v = fmaf(ActIO<T>::ld(raw + off + j), scale[c + j], shift[c + j]);
+            float d = ActIO<T>::ld(idt + off + j);
+            if (iscale) d = fmaf(d, iscale[c + j], ishift[c + j]);
+            ActIO<T>::st(out + off + j, fmaxf(v + d, 0.f));
+        }
+    }
+}
+
+template <typename T>
+__global__ void global_maxpool_kernel(const T *__restrict__ x, float *__restrict__ out, int N, int HW, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * C) return;
+    const int c = (int)(i % C);
+    const long long n = i / C;
+    float m = -CUDART_INF_F;
+    for (int p = 0; p < HW; ++p) m = fmaxf(m, ActIO<T>::ld(x + (n * HW + p) * C + c));
+    out[i] = m;
+}
+
+// F.normalize(x, p=2, dim=1): x / max(||x||_2, 1e-12)              resnet.py:319-322
+__global__ void l2norm_rows_kernel(float *x, int rows, int cols) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float *p = x + (long long)row * cols;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s = fmaf(p[c], p[c], s);
+    s = warp_sum(s);
+    const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);
+    for (int c = lane; c < cols; c += 32) p[c] *= inv;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_stem(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const ConvLayer &L, void *out,
+                        int bf16, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    dim3 grid(192 / STEM_ROWS, N);
+    cudaError_t e;
+    if (bf16) {
+        e = cudaFuncSetAttribute(stem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+        if (e != cudaSuccess) return e;
+        stem_kernel<__nv_bfloat16><<<grid, 256, STEM_SMEM, s>>>(bank, slots, lut, L.w32, (__nv_bfloat16 *)out, L.stats);
+    } else {
+        e = cudaFuncSetAttribute(stem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM);
+        if (e != cudaSuccess) return e;
+        stem_kernel<float><<<grid, 256, STEM_SMEM, s>>>(bank, slots, lut, L.w32, (float *)out, L.stats);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_simt(const ConvLayer &L, const ConvArgs &a, int bf16, cudaStream_t s) {
+    IGemmParams p{};
+    p.in = a.in; p.out = a.out; p.w = L.w32;
+    p.N = a.N; p.H = a.H; p.W = a.W; p.Cin = L.cin; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = L.cout;
+    p.ksz = L.k; p.stride = L.stride; p.pad = L.k / 2;
+    p.M = (long long)a.N * a.Ho * a.Wo; p.K = L.k * L.k * L.cin;
+    p.in_scale = a.in_scale; p.in_shift = a.in_shift;
+    p.bias = nullptr; p.residual = nullptr; p.alpha = 1.f; p.act = 0; p.stats = L.stats;
+    return bf16 ? run_igemm<__nv_bfloat16, __nv_bfloat16>(p, s) : run_igemm<float, float>(p, s);
+}
+
+cudaError_t launch_linear_f32(const LinearArgs &a, cudaStream_t s) {
+    IGemmParams p{};
+    p.in = a.A; p.out = a.out; p.w = a.W;
+    p.N = a.M; p.H = 1; p.W = 1; p.Cin = a.K; p.Ho = 1; p.Wo = 1; p.Cout = a.N;
+    p.ksz = 1; p.stride = 1; p.pad = 0; p.M = a.M; p.K = a.K;
+    p.bias = a.bias; p.residual = a.residual; p.alpha = a.alpha; p.act = a.act; p.stats = nullptr;
+    return run_igemm<float, float>(p, s);
+}
+
+cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t s) {
+    bn_finalize_kernel<<<ceil_div(L.cout, 128), 128, 0, s>>>(L.stats, L.gamma, L.beta, L.cout, 1.0 / (double)count, L.scale, L.shift);
+    return cudaGetLastError();
+}
+
+static int ew_grid(long long total) {
+    long long b = (total + 255) / 256;
+    return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
+}
+
+cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,
+                                   const float *shift, int bf16, cudaStream_t s) {
+    long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
+    if (total == 0) return cudaSuccess;
+    if (bf16)
+        bn_relu_maxpool_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)raw, (__nv_bfloat16 *)out, N, H, W, C, scale, shift);
+    else
+        bn_relu_maxpool_kernel<float><<<ew_grid(total), 256, 0, s>>>((const float *)raw, (float *)out, N, H, W, C, scale, shift);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bn_add_relu(const void *raw, const float *scale, const float *shift, const void *idt,
+                               const float *idt_scale, const float *idt_shift, void *out, long long rows, int C, int bf16,
+                               cudaStream_t s) {
+    long long total = rows * (C / 4);
+    if (total == 0) return cudaSuccess;
+    if (bf16)
+        bn_add_relu_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)raw, scale, shift, (const __nv_bfloat16 *)idt, idt_scale, idt_shift, (__nv_bfloat16 *)out, rows, C);
+    else
+        bn_add_relu_kernel<float><<<ew_grid(total), 256, 0, s>>>((const float *)raw, scale, shift, (const float *)idt, idt_scale, idt_shift, (float *)out, rows, C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_global_maxpool(const void *x, float *out, int N, int HW, int C, int bf16, cudaStream_t s) {
+    long long total = (long long)N * C;
+    if (total == 0) return cudaSuccess;
+    if (bf16)
+        global_maxpool_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, s>>>((const __nv_bfloat16 *)x, out, N, HW, C);
+    else
+        global_maxpool_kernel<float><<<ceil_div(total, 256), 256, 0, s>>>((const float *)x, out, N, HW, C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_l2norm_rows(float *x, int rows, int cols, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    l2norm_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, cols);
+    return cudaGetLastError();
+}

@@ -1,0 +1,279 @@
+"""Thin Python owner of one ``busca_ctx`` (one per tracker, like the reference's one BUSCA per
+BYTETracker, byte_tracker.py:217-221).  Everything numeric happens in libbusca_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import AssocArgs, Config, StepArgs, check
+
+PATCH_SHAPE = (384, 128, 3)
+PATCH_BYTES = 384 * 128 * 3
+
+MEAN_BGR = np.array([0.406, 0.456, 0.485])
+STD_BGR = np.array([0.225, 0.224, 0.299])    # sic: the reference's "ghost_normalize" constants (network.py:471-472)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def normalize_lut() -> np.ndarray:
+    """The 256x3 table of BUSCA._normalize_embeddings_batch (network.py:470-478): fp32 division by 255,
+    then float64 subtract / divide rounded back to fp32 after each step (numpy in-place semantics)."""
+    v = (np.arange(256, dtype=np.float32) / np.float32(255.0)).astype(np.float32)
+    lut = np.empty((256, 3), np.float32)
+    for c in range(3):
+        a = (v.astype(np.float64) - MEAN_BGR[c]).astype(np.float32)
+        lut[:, c] = (a.astype(np.float64) / STD_BGR[c]).astype(np.float32)
+    return lut
+
+
+def pe_tables(d_model: int = 512):
+    """Separable factors of the reference's 211x211x61xd fp16 table (encodings.py:23-32 with
+    positional_encodings 6.0.x): sin/cos interleaved, computed in fp32 with torch exactly as the
+    reference does, then cast to fp16.  2.6 GiB in the reference, 166 KB here."""
+    import torch
+    ch = int(np.ceil(d_model / 6) * 2)
+    ch += ch % 2
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, ch, 2).float() / ch))
+
+    def code(n):
+        s = torch.einsum("i,j->ij", torch.arange(n, dtype=torch.float32), inv_freq)
+        return torch.flatten(torch.stack((s.sin(), s.cos()), dim=-1), -2, -1)
+
+    return (code(211).to(torch.float16).numpy(), code(211).to(torch.float16).numpy(),
+            code(61)[:, : d_model - 2 * ch].to(torch.float16).numpy())
+
+
+class Engine:
+    def __init__(self, device: int = 0, d_model: int = 512, nhead: int = 4, ff_size: int = 1024, num_layers: int = 4,
+                 activation: str = "relu", precision: str = "fp32", sentinel_fp64: bool = True, bank_slots: int = 2048):
+        self.L = _lib.load()
+        cfg = Config(device=device, d_model=d_model, nhead=nhead, ff_size=ff_size, num_layers=num_layers,
+                     activation={"relu": 0, "gelu": 1}[activation], precision={"fp32": 0, "bf16": 1}[precision],
+                     sentinel_fp64=int(bool(sentinel_fp64)), bank_slots=bank_slots)
+        h = C.c_void_p()
+        check(self.L.busca_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.precision = precision
+        self.d_model = d_model
+        self._free = list(range(bank_slots - 1, -1, -1))
+        self._cap = bank_slots
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.busca_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights --------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, np.ndarray]):
+        """Feed every entry of a model_busca.pth-layout state dict (numpy or torch tensors)."""
+        for k, v in sd.items():
+            a = v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)
+            if a.dtype == np.int64:
+                dt = 2
+            elif a.dtype == np.float16:
+                dt = 1
+            else:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                dt = 0
+            a = np.ascontiguousarray(a)
+            shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+            check(self.L.busca_load_tensor(self.h, k.encode(), _ptr(a), dt, a.ndim, shape))
+        tx, ty, tz = pe_tables(self.d_model)
+        extra = {"pe.tab_xy": tx, "pe.tab_size": ty, "pe.tab_t": tz, "norm.lut": normalize_lut()}
+        for k, a in extra.items():
+            a = np.ascontiguousarray(a)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            check(self.L.busca_load_tensor(self.h, k.encode(), _ptr(a), 1 if a.dtype == np.float16 else 0, a.ndim, shape))
+        check(self.L.busca_finalize(self.h))
+
+    # ---- patch bank -----------------------------------------------------------------------
+    def alloc_slots(self, n: int) -> np.ndarray:
+        if n > len(self._free):
+            new_cap = max(self._cap * 2, self._cap + n)
+            check(self.L.busca_bank_reserve(self.h, new_cap))
+            self._free = list(range(new_cap - 1, self._cap - 1, -1)) + self._free
+            self._cap = new_cap
+        out = np.array([self._free.pop() for _ in range(n)], dtype=np.int32)
+        return out
+
+    def free_slots(self, slots: Iterable[int]):
+        self._free.extend(int(s) for s in slots)
+
+    def upload_frame(self, image: np.ndarray):
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise ValueError("frame must be uint8 [H,W,3] BGR")
+        if image.strides[2] != 1 or image.strides[1] != 3:
+            image = np.ascontiguousarray(image)
+        check(self.L.busca_upload_frame(self.h, _ptr(image), image.shape[0], image.shape[1], image.strides[0]))
+
+    def crop(self, boxes: np.ndarray, slots: np.ndarray, to_host: bool = True) -> Optional[np.ndarray]:
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 4)
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        out = np.empty((len(boxes),) + PATCH_SHAPE, np.uint8) if to_host else None
+        check(self.L.busca_crop(self.h, _ptr(boxes), len(boxes), _ptr(slots), _ptr(out)))
+        return out
+
+    def bank_upload(self, patches: np.ndarray, slots: np.ndarray):
+        patches = np.ascontiguousarray(patches, dtype=np.uint8).reshape(-1, *PATCH_SHAPE)
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        check(self.L.busca_bank_upload(self.h, _ptr(patches), len(slots), _ptr(slots)))
+
+    def bank_download(self, slots: np.ndarray) -> np.ndarray:
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        out = np.empty((len(slots),) + PATCH_SHAPE, np.uint8)
+        check(self.L.busca_bank_download(self.h, _ptr(slots), len(slots), _ptr(out)))
+        return out
+
+    # ---- geometry -------------------------------------------------------------------------
+    def center_distance(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, np.float64).reshape(-1, 4)
+        out = np.zeros((len(a), len(b)), np.float64)
+        check(self.L.busca_center_distance(self.h, _ptr(a), len(a), _ptr(b), len(b), _ptr(out)))
+        return out
+
+    def iou(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.float64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, np.float64).reshape(-1, 4)
+        out = np.zeros((len(a), len(b)), np.float64)
+        check(self.L.busca_iou(self.h, _ptr(a), len(a), _ptr(b), len(b), _ptr(out)))
+        return out
+
+    def motion_proposals(self, mean: np.ndarray, tracked: Optional[np.ndarray] = None):
+        mean = np.ascontiguousarray(mean, np.float64).reshape(-1, 8)
+        n = len(mean)
+        trk = None if tracked is None else np.ascontiguousarray(tracked, np.uint8)
+        mo, tlwh, tlbr = np.empty((n, 8)), np.empty((n, 4)), np.empty((n, 4))
+        check(self.L.busca_motion_proposals(self.h, _ptr(mean), _ptr(trk), n, _ptr(mo), _ptr(tlwh), _ptr(tlbr)))
+        return mo, tlwh, tlbr
+
+    def frame_geometry(self, mean, tracked, det_tlbr, C_: int, use_kalman: bool = True):
+        mean = np.ascontiguousarray(mean, np.float64).reshape(-1, 8)
+        det = np.ascontiguousarray(det_tlbr, np.float64).reshape(-1, 4)
+        T, D = len(mean), len(det)
+        trk = None if tracked is None else np.ascontiguousarray(tracked, np.uint8)
+        tlwh, tlbr = np.empty((T, 4)), np.empty((T, 4))
+        dist, iou = np.zeros((T, D)), np.zeros((T, D))
+        cand = np.empty((T, C_), np.int32)
+        check(self.L.busca_frame_geometry(self.h, _ptr(mean), _ptr(trk), T, _ptr(det), D, C_, int(use_kalman),
+                                          _ptr(tlwh), _ptr(tlbr), _ptr(dist), _ptr(iou), _ptr(cand)))
+        return dict(tlwh=tlwh, tlbr=tlbr, dist=dist, iou=iou, cand=cand)
+
+    # ---- network --------------------------------------------------------------------------
+    def reid_embed(self, slots: np.ndarray) -> np.ndarray:
+        slots = np.ascontiguousarray(slots, dtype=np.int32).reshape(-1)
+        out = np.empty((len(slots), 512), np.float32)
+        check(self.L.busca_reid_embed(self.h, _ptr(slots), len(slots), _ptr(out)))
+        return out
+
+    def transformer(self, mem_emb, can_emb, mem_ltwh, can_ltwh, want=("logits", "probs", "pe_index")):
+        mem_emb = np.ascontiguousarray(mem_emb, np.float32)
+        can_emb = np.ascontiguousarray(can_emb, np.float32)
+        T, L, _ = mem_emb.shape
+        C_ = can_emb.shape[1]
+        S = L + 2 * (C_ + 2)
+        mem_ltwh = np.ascontiguousarray(mem_ltwh, np.float64).reshape(T, L, 4)
+        can_ltwh = np.ascontiguousarray(can_ltwh, np.float64).reshape(T, C_, 4)
+        bufs = dict(logits=np.empty((T, C_ + 2), np.float32), probs=np.empty((T, C_ + 2), np.float32),
+                    pe_index=np.empty((T, S, 3), np.int32), cand_rows=np.empty((T, C_ + 2, 512), np.float32),
+                    input_seq=np.empty((T, S, 512), np.float32))
+        g = lambda k: _ptr(bufs[k]) if k in want else None
+        check(self.L.busca_transformer(self.h, T, L, C_, _ptr(mem_emb), _ptr(can_emb), _ptr(mem_ltwh), _ptr(can_ltwh),
+                                       g("logits"), g("probs"), g("pe_index"), g("cand_rows"), g("input_seq")))
+        return {k: bufs[k] for k in want}
+
+    def associate(self, mem_slots, mem_ltwh, det_slots, det_ltwh, dists, kal_slots, kal_ltwh, L: int, C_: int,
+                  want=("probs", "cand")) -> Dict[str, np.ndarray]:
+        mem_slots = np.ascontiguousarray(mem_slots, np.int32)
+        T = mem_slots.shape[0]
+        D = 0 if det_slots is None else len(det_slots)
+        S = L + 2 * (C_ + 2)
+        mem_ltwh = np.ascontiguousarray(mem_ltwh, np.float64).reshape(T, L, 4)
+        use_kal = kal_slots is not None
+        keep = [mem_slots, mem_ltwh]
+        a = AssocArgs(T=T, D=D, L=L, C=C_, use_kalman=int(use_kal))
+        a.mem_slots = mem_slots.ctypes.data_as(_lib.c_i32p)
+        a.mem_ltwh = mem_ltwh.ctypes.data_as(_lib.c_f64p)
+        if D:
+            ds = np.ascontiguousarray(det_slots, np.int32)
+            db = np.ascontiguousarray(det_ltwh, np.float64).reshape(D, 4)
+            dd = np.ascontiguousarray(dists, np.float64).reshape(T, D)
+            keep += [ds, db, dd]
+            a.det_slots = ds.ctypes.data_as(_lib.c_i32p)
+            a.det_ltwh = db.ctypes.data_as(_lib.c_f64p)
+            a.dists = dd.ctypes.data_as(_lib.c_f64p)
+        if use_kal:
+            ks = np.ascontiguousarray(kal_slots, np.int32)
+            kb = np.ascontiguousarray(kal_ltwh, np.float64).reshape(T, 4)
+            keep += [ks, kb]
+            a.kal_slots = ks.ctypes.data_as(_lib.c_i32p)
+            a.kal_ltwh = kb.ctypes.data_as(_lib.c_f64p)
+        shapes = dict(probs=((T, C_ + 2), np.float32), logits=((T, C_ + 2), np.float32), cand=((T, C_), np.int32),
+                      pe_index=((T, S, 3), np.int32), mem_emb=((T, L, 512), np.float32), can_emb=((T, C_, 512), np.float32),
+                      cand_rows=((T, C_ + 2, 512), np.float32), mem_logits=((T, 512), np.float32),
+                      input_seq=((T, S, 512), np.float32))
+        out = {}
+        for k in want:
+            shp, dt = shapes[k]
+            out[k] = np.empty(shp, dt)
+            setattr(a, k, out[k].ctypes.data_as(_lib.c_i32p if dt == np.int32 else _lib.c_f32p))
+        check(self.L.busca_associate(self.h, C.byref(a)))
+        return out
+
+    # ---- device-resident path ---------------------------------------------------------------
+    def dev_alloc(self, nbytes: int) -> int:
+        p = self.L.busca_dev_alloc(self.h, nbytes)
+        if not p:
+            raise _lib.BuscaError(self.L.busca_last_error().decode())
+        return p
+
+    def dev_free(self, p: int):
+        self.L.busca_dev_free(self.h, p)
+
+    def to_dev(self, a: np.ndarray) -> int:
+        a = np.ascontiguousarray(a)
+        p = self.dev_alloc(max(a.nbytes, 16))
+        check(self.L.busca_memcpy_h2d(self.h, p, _ptr(a), a.nbytes))
+        return p
+
+    def h2d(self, p: int, a: np.ndarray):
+        a = np.ascontiguousarray(a)
+        check(self.L.busca_memcpy_h2d(self.h, p, _ptr(a), a.nbytes))
+
+    def from_dev(self, p: int, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype)
+        check(self.L.busca_memcpy_d2h(self.h, _ptr(out), p, out.nbytes))
+        return out
+
+    def frame_step_dev(self, args: StepArgs):
+        check(self.L.busca_frame_step_dev(self.h, C.byref(args)))
+
+    def sync(self):
+        check(self.L.busca_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return self.L.busca_stream(self.h)
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.busca_kernel_launches(self.h))
+
+    def set_profiling(self, on: bool):
+        check(self.L.busca_set_profiling(self.h, int(on)))
+
+    def last_profile(self) -> dict:
+        return json.loads(self.L.busca_last_profile(self.h).decode() or "{}")

@@ -1,0 +1,279 @@
+"""Host mirror of the reference's ``busca.network.BUSCA`` (busca/network.py:11-507): the object every adapter
+constructs and calls.  Same constructor argument, same public methods, same return types; everything
+numeric runs in libbusca_b200.so on the B200 (no CPU fallback).
+
+    tracker = BUSCA(args.transformer).to(device); tracker.load_pretrained(ckpt, ignore_reid_fc=True); tracker.eval()
+    crops  = tracker.get_image_crops(image=frame, bboxes=boxes, normalize=False)        # uint8 [N,384,128,3]
+    probs, reliable = tracker.associate_embeddings(tracks, dets, dists, seq_len, num_candidates, ...)
+
+Patches never have to leave the GPU: ``get_image_crops`` returns a real numpy array (adapters store its rows in
+``track.images_mem``) AND remembers which patch-bank slot holds each row; ``associate_embeddings`` resolves every
+``images_mem`` entry back to its slot by host address and only uploads arrays it has never seen.
+"""
+from __future__ import annotations
+
+import weakref
+import zlib
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import custom_layers, tracking
+from .engine import PATCH_BYTES, PATCH_SHAPE, Engine
+
+
+def _device_index(device) -> int:
+    if device is None:
+        return 0
+    idx = getattr(device, "index", None)
+    if idx is not None:
+        return int(idx)
+    s = str(device)
+    if s.startswith("cpu"):
+        raise RuntimeError("busca_b200 runs on a B200 only (args.device is '%s'); there is no CPU path" % s)
+    return int(s.split(":")[1]) if ":" in s else 0
+
+
+class _PatchRegistry:
+    """host address of a crop row  ->  patch-bank slot.  Slots are released when the numpy array that
+    ``get_image_crops`` returned (the base of every row view) is garbage collected."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.slot_of: Dict[int, int] = {}
+
+    def register(self, arr: np.ndarray, slots: np.ndarray):
+        base = arr.ctypes.data
+        keys = [base + i * PATCH_BYTES for i in range(len(slots))]
+        for k, s in zip(keys, slots):
+            self.slot_of[k] = int(s)
+        weakref.finalize(arr, _PatchRegistry._release, weakref.ref(self), keys, [int(s) for s in slots])
+
+    @staticmethod
+    def _release(self_ref, keys, slots):
+        self = self_ref()
+        if self is None or self.engine.h is None:
+            return
+        for k in keys:
+            self.slot_of.pop(k, None)
+        self.engine.free_slots(slots)
+
+    def lookup(self, patch: np.ndarray) -> Optional[int]:
+        if patch.dtype != np.uint8 or patch.shape != PATCH_SHAPE or not patch.flags["C_CONTIGUOUS"]:
+            return None
+        return self.slot_of.get(patch.ctypes.data)
+
+
+class BUSCA:
+    def __init__(self, args):
+        self.args = args
+        self.dim_embedding = args.dim_embedding
+        self.dim_model = args.trans_dim
+        if args.input_flavour != "MEM-SEP-CAN-BAD" or args.output_flavour != "CAN" or not args.encode_separator_as_reference \
+                or args.encode_special_tokens:
+            # every shipped YAML uses this one flavour; CLS-* flavours are broken in the reference (encodings.py:161)
+            raise NotImplementedError("busca_b200 implements input_flavour MEM-SEP-CAN-BAD / output_flavour CAN only")
+        self.activation = custom_layers.effective_activation(args.activation, getattr(args, "follow_reference_activation", True))
+        self.precision = getattr(args, "precision", "fp32")
+        self.legacy_float64_sentinel = bool(getattr(args, "legacy_float64_sentinel", True))
+        self.engine = Engine(device=_device_index(getattr(args, "device", None)), d_model=self.dim_model, nhead=args.nhead,
+                             ff_size=args.ff_size, num_layers=args.num_layer, activation=self.activation,
+                             precision=self.precision, sentinel_fp64=self.legacy_float64_sentinel,
+                             bank_slots=int(getattr(args, "bank_slots", 2048)))
+        self.expected_image_size = (384, 128)           # ReID_Encoder.PRETRAINED_SIZE (network.py:512)
+        self._registry = _PatchRegistry(self.engine)
+        self._frame_key = None
+        self.attentions = None
+        self.logits = None
+        self.mem_logits = None
+        self.store_logits = True
+        self.training = False
+
+    # nn.Module-ish surface the adapters touch (byte_tracker.py:217-221)
+    def to(self, device):
+        return self
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    # ---- weights: load_pretrained (network.py:432-467) -------------------------------------------------
+    def load_pretrained(self, path, ignore_reid=False, ignore_reid_fc=False):
+        import torch
+        state_dict = torch.load(path, map_location="cpu")
+        sd = state_dict["model_state_dict"] if "model_state_dict" in state_dict else state_dict
+        self.load_state_dict(sd, ignore_reid=ignore_reid, ignore_reid_fc=ignore_reid_fc)
+
+    def load_state_dict(self, sd, ignore_reid=False, ignore_reid_fc=False):
+        if ignore_reid:
+            raise NotImplementedError("ignore_reid=True needs separately loaded ReID weights (model_feats.pth); "
+                                      "pass them in the same dict")
+        keep = {}
+        for k, v in sd.items():
+            if "reid_encoder.model.fc." in k or "reid_encoder.model.fc_person." in k:
+                continue                                  # the classifier head is never used on this path
+            if k == "cls_token":
+                print("WARNING: Loading a model with a cls_token, but the current model does not have a cls_token. "
+                      "The cls_token will be ignored")
+                continue
+            if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
+                continue                                  # train-mode BN never reads them (network.py:553-556)
+            keep[k] = v
+        self.engine.load_state_dict(keep)
+
+    # ---- crops: get_image_crops (network.py:492-507) ----------------------------------------------------
+    def _ensure_frame(self, image: np.ndarray):
+        # The adapters call this 3 + T times per frame with the same image (byte_tracker.py:278-282, 468-479);
+        # re-uploading 6 MB each time would dominate.  A sampled CRC guards against address reuse.
+        sample = np.ascontiguousarray(image.reshape(-1)[::97]) if image.flags["C_CONTIGUOUS"] else np.ascontiguousarray(image[::7, ::11])
+        key = (image.ctypes.data, image.shape, image.strides, zlib.crc32(sample))
+        if key != self._frame_key:
+            self.engine.upload_frame(image)
+            self._frame_key = key
+
+    def set_frame(self, image: np.ndarray):
+        """Explicitly (re)upload the current frame."""
+        self.engine.upload_frame(image)
+        self._frame_key = None
+
+    def get_image_crops(self, image, bboxes, output_size=None, normalize=True):
+        if output_size is None:
+            output_size = (self.expected_image_size[1], self.expected_image_size[0])
+        if tuple(output_size) != (128, 384):
+            raise NotImplementedError("crops are fixed at 128x384")
+        boxes = [np.asarray(b, dtype=np.float64).reshape(4) for b in bboxes]
+        if len(boxes) == 0:
+            return np.zeros([0, output_size[0], output_size[1], 3])       # float64, dims swapped - as network.py:503
+        assert image is not None, "Image is None"
+        self._ensure_frame(image)
+        slots = self.engine.alloc_slots(len(boxes))
+        crops = self.engine.crop(np.stack(boxes), slots, to_host=True)
+        self._registry.register(crops, slots)
+        if normalize:
+            return np.stack([tracking.normalize_crop(c) for c in crops], axis=0)
+        return crops
+
+    # ---- memory sampling: _get_track_mem (network.py:247-279) --------------------------------------------
+    @staticmethod
+    def _memory_indices(n_obs: int, seq_len: int, use_broader_memory: bool) -> List[int]:
+        if use_broader_memory and not (seq_len == 1 and n_obs >= 1) and n_obs >= seq_len:
+            sep = float(n_obs - 1) / float(seq_len - 1)
+            return [int(i * sep) for i in range(seq_len)]
+        return list(range(max(0, n_obs - seq_len), n_obs))
+
+    def _get_track_mem(self, track, seq_len, use_broader_memory):
+        sel = self._memory_indices(len(track.images_mem), seq_len, use_broader_memory)
+        mem = [track.images_mem[j] for j in sel]
+        boxes = np.array([track.tlwh_mem[j] for j in sel]) * track.scale if sel else np.zeros((0, 4))
+        return mem, boxes
+
+    # ---- association: associate_embeddings (network.py:282-429) -------------------------------------------
+    def associate_embeddings(self, tracks_embeddings, dets_embeddings, dists_matrix, seq_len, num_candidates, use_broader_memory,
+                             select_highest_candidate, highest_candidate_minimum_thresh=None, keep_highest_value=False,
+                             extra_kalman_candidates=[], plot_results=False, normalize_ims=False):
+        T, D, K = len(tracks_embeddings), len(dets_embeddings), len(extra_kalman_candidates)
+        if T == 0:
+            return None, None
+        if D == 0 and K == 0:
+            return None, None
+        if not normalize_ims:
+            raise NotImplementedError("busca_b200 expects uint8 crops (normalize_ims=True), as every adapter passes")
+        if plot_results:
+            raise NotImplementedError("plot_results needs the debug GUI, which is out of scope")
+        if K not in (0, T):
+            raise ValueError("extra_kalman_candidates must be empty or hold one entry per track")
+        L, C = int(seq_len), int(num_candidates)
+        temp_slots: List[int] = []
+        pending = []                                       # (patch array, slot) uploads for arrays we have never seen
+
+        def slot_for(patch) -> int:
+            s = self._registry.lookup(patch) if isinstance(patch, np.ndarray) else None
+            if s is None:
+                arr = np.ascontiguousarray(np.asarray(patch), dtype=np.uint8)
+                if arr.shape != PATCH_SHAPE:
+                    raise ValueError("images_mem entries must be uint8 [384,128,3] crops, got %s" % (arr.shape,))
+                s = int(self.engine.alloc_slots(1)[0])
+                temp_slots.append(s)
+                pending.append((arr, s))
+            return s
+
+        try:
+            mem_slots = np.full((T, L), -1, np.int32)
+            mem_ltwh = np.empty((T, L, 4), np.float64)
+            reliable = np.zeros(T, dtype=bool)
+            for t, track in enumerate(tracks_embeddings):
+                sel = self._memory_indices(len(track.images_mem), L, use_broader_memory)
+                if len(sel) == L:
+                    reliable[t] = True
+                    for i, j in enumerate(sel):
+                        mem_slots[t, i] = slot_for(track.images_mem[j])
+                        mem_ltwh[t, i] = np.asarray(track.tlwh_mem[j], np.float64) * track.scale
+                else:                                      # incomplete history: zero images + filler box (network.py:304-308)
+                    mem_ltwh[t] = np.array([250.0, 250.0, 500.0, 500.0])
+            det_slots = np.empty(D, np.int32)
+            det_ltwh = np.empty((D, 4), np.float64)
+            for j, det in enumerate(dets_embeddings):
+                det_slots[j] = slot_for(det.images_mem[-1])
+                det_ltwh[j] = np.asarray(det.tlwh_mem[-1], np.float64) * det.scale
+            kal_slots = kal_ltwh = None
+            if K:
+                kal_slots = np.empty(T, np.int32)
+                kal_ltwh = np.empty((T, 4), np.float64)
+                for t, kd in enumerate(extra_kalman_candidates):
+                    kal_slots[t] = slot_for(kd.images_mem[-1])
+                    kal_ltwh[t] = np.asarray(kd.tlwh, np.float64) * kd.scale
+            if pending:
+                self.engine.bank_upload(np.stack([p for p, _ in pending]), np.array([s for _, s in pending], np.int32))
+            dists = np.asarray(dists_matrix, np.float64).reshape(T, D) if D else None
+            want = ("probs", "cand") + (("cand_rows", "mem_logits") if self.store_logits else ())
+            out = self.engine.associate(mem_slots, mem_ltwh, det_slots if D else None, det_ltwh if D else None, dists,
+                                        kal_slots, kal_ltwh, L, C, want=want)
+        finally:
+            if temp_slots:
+                self.engine.free_slots(temp_slots)
+        if self.store_logits:
+            self.logits, self.mem_logits = out["cand_rows"], out["mem_logits"]
+        probs, cand = out["probs"], out["cand"]
+
+        # scatter into the global matrix (network.py:407-425)
+        n_avail = min(D + 1, C) if K else min(D, C)
+        probs_matrix = np.zeros([T, D + K])
+        for t in range(T):
+            p = probs[t]
+            if select_highest_candidate:
+                q = np.zeros_like(p)
+                thr = highest_candidate_minimum_thresh
+                if thr is None or thr == 0 or (thr > 0.0 and np.max(p) >= thr):
+                    q[np.argmax(p)] = np.max(p) if keep_highest_value else 1.0
+                p = q
+            probs_matrix[t, cand[t, :n_avail]] = p[:n_avail]
+        return probs_matrix, reliable
+
+    @staticmethod
+    def ltwh_to_ltrb(ltwh):
+        ret = np.array(ltwh, copy=True)
+        ret[..., 2:] += ret[..., :2]
+        return ret
+
+
+class ReID_Encoder:
+    """Name kept for API parity (network.py:510-575).  The encoder is part of the library; this wrapper embeds
+    uint8 BGR crops as ONE BatchNorm batch (train-mode statistics, like the reference's domain adaptation)."""
+    PRETRAINED_SIZE = (384, 128)
+
+    def __init__(self, busca: BUSCA):
+        self.busca = busca
+
+    def embed_patches(self, patches_u8: np.ndarray) -> np.ndarray:
+        patches_u8 = np.ascontiguousarray(patches_u8, dtype=np.uint8).reshape(-1, *PATCH_SHAPE)
+        eng = self.busca.engine
+        slots = eng.alloc_slots(len(patches_u8))
+        try:
+            eng.bank_upload(patches_u8, slots)
+            return eng.reid_embed(slots)
+        finally:
+            eng.free_slots(slots)

@@ -1,0 +1,109 @@
+"""Host mirror of the reference's busca/tracking.py: same names, argument meaning and error behaviour;
+the arithmetic runs in libbusca_b200.so.
+
+  center_distance        tracking.py:23-60   -> busca_center_distance (fp64, bit-exact vs scipy cdist)
+  get_bbox_crop          tracking.py:62-78   -> busca_crop (integer-exact vs cv2.resize INTER_LINEAR)
+  _cutout_with_pad       tracking.py:80-113  -> fused into the gather (no cut-out is materialised)
+  missing_candidate_bbox tracking.py:7-20    -> host constant (and its device twin in transformer.cu)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import engine as _engine
+
+_default = None
+
+
+def default_engine() -> "_engine.Engine":
+    """Module-level functions have no BUSCA instance to hang on to, so they share one small context."""
+    global _default
+    if _default is None:
+        _default = _engine.Engine(device=0, bank_slots=8)
+    return _default
+
+
+def missing_candidate_bbox(seq_len=None, flavour="ltrb", legacy_float64=True):
+    """The 'very unrealistic' filler box.  Under the reference's pinned numpy 1.23.5 the array is float64
+    (``np.float32 / 100.0`` promotes); under numpy>=2 it is float32.  ``legacy_float64`` picks which
+    (default: the pinned environment)."""
+    fmin = np.finfo("float32").min
+    if legacy_float64:
+        lo, q = float(fmin), float(fmin) / 100.0
+        dt = np.float64
+    else:
+        lo, q = fmin, np.float32(fmin) / np.float32(100.0)
+        dt = np.float32
+    if flavour == "ltrb":
+        bbox = np.array([lo, lo, q, q], dtype=dt)
+    elif flavour == "ltwh":
+        bbox = np.array([lo, lo, -q, -q], dtype=dt)
+    else:
+        raise ValueError("Unknown flavour: {}".format(flavour))
+    if seq_len is not None:
+        bbox = np.tile(bbox, (seq_len, 1))
+    return bbox
+
+
+def _as_tlbr(tracks):
+    if len(tracks) > 0 and isinstance(tracks[0], np.ndarray):
+        return np.asarray(tracks, dtype=np.float64).reshape(-1, 4)
+    return np.array([t.tlbr for t in tracks], dtype=np.float64).reshape(-1, 4)
+
+
+def center_distance(atracks, btracks, weight_size=False, engine=None):
+    """Centre-to-centre distances, float64 [len(a), len(b)].  Accepts lists of objects with ``.tlbr`` or
+    arrays of tlbr rows (the reference crashes on a *list* of arrays, tracking.py:45; accepted here)."""
+    a, b = _as_tlbr(atracks), _as_tlbr(btracks)
+    if len(a) == 0 or len(b) == 0:
+        return np.zeros((len(atracks), len(btracks)), dtype=np.float64)
+    d = (engine or default_engine()).center_distance(a, b)
+    if weight_size:                                     # unused by every adapter; host post-scale as tracking.py:50-58
+        sa = np.sqrt((a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]))
+        sb = np.sqrt((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]))
+        sa = np.tile(sa, (len(sb), 1)).T
+        sb = np.tile(sb, (len(sa), 1))
+        d = d * np.maximum(sa / sb, sb / sa)
+    return d
+
+
+def iou_distance(atlbrs, btlbrs, engine=None):
+    """matching.iou_distance (adapters/ByteTrack/yolox/tracker/matching.py:73-91): 1 - IoU with the +1 pixel
+    convention of cython_bbox.  Offered here because north_star puts the IoU matrix on the path."""
+    a, b = _as_tlbr(atlbrs), _as_tlbr(btlbrs)
+    if len(a) == 0 or len(b) == 0:
+        return np.zeros((len(a), len(b)), dtype=np.float64)
+    return 1 - (engine or default_engine()).iou(a, b)
+
+
+def get_bbox_crop(im, bbox_real_scale, output_size=(128, 384), normalize=True, ghost_normalize=True, engine=None):
+    """One crop (x1,y1,x2,y2 in ``im`` pixels) -> [384,128,3]; uint8 BGR, or float32 normalised when
+    ``normalize`` (host LUT, bit-equal to the reference's float arithmetic)."""
+    assert im is not None, "Image is None"
+    if tuple(output_size) != (128, 384):
+        raise NotImplementedError("busca_b200 crops are fixed at 128x384 (ReID_Encoder.PRETRAINED_SIZE)")
+    eng = engine or default_engine()
+    eng.upload_frame(im)
+    slots = eng.alloc_slots(1)
+    try:
+        crop = eng.crop(np.asarray(bbox_real_scale, dtype=np.float64).reshape(1, 4), slots)[0]
+    finally:
+        eng.free_slots(slots)
+    if normalize:
+        crop = normalize_crop(crop, ghost_normalize)
+    return crop
+
+
+def normalize_crop(crop_u8, ghost_normalize=True):
+    std_r = 0.299 if ghost_normalize else 0.229
+    mean = np.array([0.406, 0.456, 0.485])
+    std = np.array([0.225, 0.224, std_r])
+    out = crop_u8.astype(np.float32) / 255.0
+    out -= mean
+    out /= std
+    return out
+
+
+def _cutout_with_pad(im, bbox):
+    raise NotImplementedError("the padded cut-out is never materialised: the gather reads the frame directly "
+                              "(busca_b200/csrc/crop.cu); use get_bbox_crop")

@@ -1,0 +1,168 @@
+/*
+ * busca_b200.h - C ABI of libbusca_b200.so: BUSCA's per-frame association hot path on B200 (sm_100a).
+ *
+ * The reference (lorenzovaquero/BUSCA @ 88a9ed7e) has no FFI of its own: its boundary is the Python
+ * object protocol of busca.network.BUSCA.  Each entry point below names the
+ * reference interface it replaces (file:line under /root/reference).  The Python mirror in busca_b200/
+ * binds these with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes, caller-owned buffers, int return code (0 = OK, <0 = error,
+ * text via busca_last_error).  One context per tracker; a context is NOT thread-safe; different
+ * contexts (and devices) are independent.  Unless a name ends in _dev every pointer is HOST memory and
+ * the call returns after its results are on the host.
+ */
+#ifndef BUSCA_B200_H
+#define BUSCA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BUSCA_PATCH_H 384
+#define BUSCA_PATCH_W 128
+#define BUSCA_PATCH_BYTES (384 * 128 * 3)
+#define BUSCA_EMB_DIM 512
+
+typedef struct busca_ctx busca_ctx;
+
+enum { BUSCA_OK = 0, BUSCA_ERR_ARG = -1, BUSCA_ERR_CUDA = -2, BUSCA_ERR_STATE = -3, BUSCA_ERR_NOMEM = -4 };
+enum { BUSCA_F32 = 0, BUSCA_F16 = 1, BUSCA_I64 = 2 };                 /* busca_load_tensor dtype */
+enum { BUSCA_PREC_FP32 = 0, BUSCA_PREC_BF16 = 1 };                    /* arithmetic of the conv / GEMM path */
+enum { BUSCA_ACT_RELU = 0, BUSCA_ACT_GELU = 1 };
+
+/* Mirrors the YAML `transformer:` block read by BUSCA.__init__/build (busca/network.py:12-96). */
+typedef struct busca_config {
+    int32_t device;          /* CUDA ordinal */
+    int32_t d_model;         /* trans_dim == dim_embedding == 512 */
+    int32_t nhead;           /* 4 */
+    int32_t ff_size;         /* 1024 */
+    int32_t num_layers;      /* 4 */
+    int32_t activation;      /* what the reference EXECUTES: BUSCA_ACT_RELU (parity traps) */
+    int32_t precision;       /* BUSCA_PREC_* */
+    int32_t sentinel_fp64;   /* 1: numpy-1.23.5 behaviour of missing_candidate_bbox */
+    int64_t bank_slots;      /* initial patch-bank capacity (147,456 B each); grows on demand */
+} busca_config;
+
+const char *busca_version(void);
+const char *busca_last_error(void);
+
+/* BUSCA(args) + .to(device)            busca/network.py:11-101; byte_tracker.py:217-221 */
+int busca_create(const busca_config *cfg, busca_ctx **out);
+void busca_destroy(busca_ctx *ctx);
+
+/* load_pretrained                      busca/network.py:432-467; load_trained_net.py:44-62
+ * One call per state-dict entry, key names as in model_busca.pth ("encoder.weight",
+ * "reid_encoder.model.layer1.0.conv1.weight", ...).  Unknown / ignored keys return BUSCA_OK.
+ * Extra names: "pe.tab_xy" [211,172] f16, "pe.tab_size" [211,172] f16, "pe.tab_t" [61,168] f16
+ * (the separable factors of encodings.py:23-32) and "norm.lut" [256,3] f32 BGR (network.py:470-478). */
+int busca_load_tensor(busca_ctx *ctx, const char *name, const void *data, int32_t dtype, int32_t ndim,
+                      const int64_t *shape);
+/* Verifies that every tensor of the path is present and builds derived layouts. */
+int busca_finalize(busca_ctx *ctx);
+
+/* ---- frame + patch bank --------------------------------------------------------------------- */
+/* the `image` argument of get_image_crops: uint8 BGR HWC, row stride in bytes      network.py:492 */
+int busca_upload_frame(busca_ctx *ctx, const uint8_t *bgr, int32_t H, int32_t W, int64_t row_stride);
+int busca_bank_reserve(busca_ctx *ctx, int64_t n_slots);
+int64_t busca_bank_capacity(busca_ctx *ctx);
+/* get_image_crops -> get_bbox_crop -> _cutout_with_pad + cv2.resize     network.py:492-507; tracking.py:62-113
+ * boxes: n x (x1,y1,x2,y2) float64 in frame pixels.  Crop i is written to bank slot slots[i] and, when
+ * host_out != NULL, also copied to host_out[i*BUSCA_PATCH_BYTES] (uint8 [384,128,3] BGR). */
+int busca_crop(busca_ctx *ctx, const double *boxes, int32_t n, const int32_t *slots, uint8_t *host_out);
+/* crops that did not come from busca_crop (an adapter's own arrays): host -> bank */
+int busca_bank_upload(busca_ctx *ctx, const uint8_t *patches, int32_t n, const int32_t *slots);
+int busca_bank_download(busca_ctx *ctx, const int32_t *slots, int32_t n, uint8_t *host_out);
+
+/* ---- geometry -------------------------------------------------------------------------------- */
+/* busca.tracking.center_distance (weight_size=False)                    tracking.py:23-60
+ * a [na,4], b [nb,4] tlbr float64 -> out [na,nb] float64 */
+int busca_center_distance(busca_ctx *ctx, const double *a, int32_t na, const double *b, int32_t nb, double *out);
+/* matching.ious -> cython_bbox.bbox_overlaps (+1 convention)            matching.py:53-70 */
+int busca_iou(busca_ctx *ctx, const double *a, int32_t na, const double *b, int32_t nb, double *out);
+/* STrack.multi_predict (mean only) + STrack.tlwh/tlbr                   byte_tracker.py:50-61,140-161
+ * mean [n,8] float64 (x,y,a,h,vx,vy,va,vh); tracked [n] (0: mean[7] is zeroed first).
+ * Outputs (any may be NULL): mean_out [n,8], tlwh [n,4], tlbr [n,4]. */
+int busca_motion_proposals(busca_ctx *ctx, const double *mean, const uint8_t *tracked, int32_t n, double *mean_out,
+                           double *tlwh, double *tlbr);
+/* All of the above plus candidate selection in ONE launch (north_star: "one vectorised kernel per frame"):
+ * proposals from Kalman means, T x D centre-distance and IoU matrices, per-track top-C detections.
+ * Outputs may be NULL. cand [T,C] int32: detection index, D+t for the motion proposal, -1 = missing. */
+int busca_frame_geometry(busca_ctx *ctx, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
+                         int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
+                         int32_t *cand);
+
+/* ---- appearance embedding -------------------------------------------------------------------- */
+/* ReID_Encoder.get_features on ONE BatchNorm batch                      network.py:542-570; resnet.py:266-322
+ * slots [n]: bank slots (-1 = the all-zero image, network.py:306,354).  out [n,512] float32 unit norm.
+ * Normalisation, BGR->RGB and layout change (network.py:470-478, 397-398) are fused into the stem. */
+int busca_reid_embed(busca_ctx *ctx, const int32_t *slots, int32_t n, float *out);
+
+/* ---- association ----------------------------------------------------------------------------- */
+typedef struct busca_assoc_args {
+    int32_t T, D, L, C;            /* tracks, detections, seq_len, num_candidates */
+    int32_t use_kalman;            /* len(extra_kalman_candidates) > 0 */
+    const int32_t *mem_slots;      /* [T,L] bank slot per memory token; -1 = zero image */
+    const double *mem_ltwh;        /* [T,L,4] tlwh_mem * scale (network.py:277); the [250,250,500,500] filler included */
+    const int32_t *det_slots;      /* [D]  det.images_mem[-1] */
+    const double *det_ltwh;        /* [D,4] det.tlwh_mem[-1] * det.scale (network.py:349) */
+    const double *dists;           /* [T,D] the caller's dists_matrix (network.py:332) */
+    const int32_t *kal_slots;      /* [T] or NULL */
+    const double *kal_ltwh;        /* [T,4] new_det.tlwh * scale (network.py:370) or NULL */
+    /* outputs, any may be NULL */
+    float *probs;                  /* [T,C+2] softmax over [C candidates, NON, BAD]  (network.py:403) */
+    float *logits;                 /* [T,C+2]                                       (network.py:244) */
+    int32_t *cand;                 /* [T,C]   dets_embeddings_inds                  (network.py:327-378) */
+    int32_t *pe_index;             /* [T,S,3] (xy, size, t) bins, S = L + 2(C+2)    (encodings.py:150-235) */
+    float *mem_emb;                /* [T,L,512]                                     (network.py:196) */
+    float *can_emb;                /* [T,C,512]                                     (network.py:197) */
+    float *cand_rows;              /* [T,C+2,512] pre-decoder rows = self.logits    (network.py:225) */
+    float *mem_logits;             /* [T,512] mean of MEM rows = self.mem_logits    (network.py:226-229) */
+    float *input_seq;              /* [T,S,512] pos_encoder output                  (network.py:213) */
+} busca_assoc_args;
+
+/* BUSCA.associate_embeddings -> forward                                 network.py:282-429, 176-244 */
+int busca_associate(busca_ctx *ctx, const busca_assoc_args *args);
+
+/* Decision Transformer alone, from given embeddings (stage-wise parity)   network.py:203-232 */
+int busca_transformer(busca_ctx *ctx, int32_t T, int32_t L, int32_t C, const float *mem_emb, const float *can_emb,
+                      const double *mem_ltwh, const double *can_ltwh, float *logits, float *probs, int32_t *pe_index,
+                      float *cand_rows, float *input_seq);
+
+/* ---- device-resident step (bench `value`: inputs already in HBM) ------------------------------ */
+typedef struct busca_step_args {
+    int32_t T, D, L, C;
+    const double *track_mean_dev;   /* [T,8]  Kalman means BEFORE prediction */
+    const uint8_t *tracked_dev;     /* [T] */
+    const double *det_tlbr_dev;     /* [D,4] frame coordinates */
+    const int32_t *mem_slots_dev;   /* [T,L] */
+    const double *mem_ltwh_dev;     /* [T,L,4] */
+    const int32_t *det_slots_dev;   /* [D]  slots the D detection crops are written to */
+    const int32_t *kal_slots_dev;   /* [T]  slots the T motion-proposal crops are written to */
+    float busca_thresh;             /* byte_tracker.py:504-526 */
+    const uint8_t *reliable_dev;    /* [T] */
+    /* outputs (device) */
+    float *probs_dev;               /* [T,C+2] */
+    uint8_t *keep_dev;              /* [T] decision: reliable && p[kalman slot] > thresh */
+} busca_step_args;
+/* One frame of the whole hot path with everything resident: motion proposals + geometry + crops of the
+ * D detections and T proposals from the uploaded frame + ReID (2 batches) + Transformer + decision. */
+int busca_frame_step_dev(busca_ctx *ctx, const busca_step_args *args);
+
+/* ---- plumbing -------------------------------------------------------------------------------- */
+void *busca_dev_alloc(busca_ctx *ctx, int64_t bytes);
+void busca_dev_free(busca_ctx *ctx, void *p);
+int busca_memcpy_h2d(busca_ctx *ctx, void *dst_dev, const void *src, int64_t bytes);
+int busca_memcpy_d2h(busca_ctx *ctx, void *dst, const void *src_dev, int64_t bytes);
+int busca_sync(busca_ctx *ctx);
+void *busca_stream(busca_ctx *ctx);               /* cudaStream_t the context launches on */
+int64_t busca_kernel_launches(busca_ctx *ctx);    /* kernels launched by this context so far */
+/* per-kernel device time of the most recent associate / step, name -> ms, as JSON (CUDA events) */
+int busca_set_profiling(busca_ctx *ctx, int32_t on);
+const char *busca_last_profile(busca_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUSCA_B200_H */
