@@ -227,7 +227,8 @@ constexpr int STEM_ROWS = 4;                               // output rows per CT
 constexpr int STEM_IN_ROWS = STEM_ROWS * 2 + 5;            // 13
 constexpr int STEM_IN_COLS = 134;                          // 2*63 + 7 = 133, padded
 constexpr int STEM_K = 147;
-constexpr int STEM_SMEM = (STEM_IN_ROWS * STEM_IN_COLS * 3 + STEM_K * 64 + 2 * 8 * 64) * 4;
+constexpr int STEM_IN_FLOATS = (STEM_IN_ROWS * STEM_IN_COLS * 3 + 3) / 4 * 4;   // keeps the weight tile 16-byte aligned
+constexpr int STEM_SMEM = (STEM_IN_FLOATS + STEM_K * 64 + 2 * 8 * 64) * 4;
 
 template <typename TOut>
 __global__ void __launch_bounds__(256) stem_kernel(const uint8_t *__restrict__ bank, const int32_t *__restrict__ slots,
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t *__restrict__ b
                                                    TOut *__restrict__ out, double *__restrict__ stats) {
     extern __shared__ __align__(16) float smem[];
     float *sin = smem;                                              // [13][134][3]
-    float *sw = smem + STEM_IN_ROWS * STEM_IN_COLS * 3;             // [147][64]
+    float *sw = smem + STEM_IN_FLOATS;                              // [147][64]
     float *sred = sw + STEM_K * 64;                                 // [2][8][64]
     __shared__ float slut[256 * 3];
 

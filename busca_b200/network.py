@@ -25,9 +25,12 @@ from .engine import PATCH_BYTES, PATCH_SHAPE, Engine
 def _device_index(device) -> int:
     if device is None:
         return 0
-    idx = getattr(device, "index", None)
-    if idx is not None:
-        return int(idx)
+    if not isinstance(device, (str, int)):
+        idx = getattr(device, "index", None)              # torch.device
+        if isinstance(idx, int):
+            return idx
+    if isinstance(device, int):
+        return device
     s = str(device)
     if s.startswith("cpu"):
         raise RuntimeError("busca_b200 runs on a B200 only (args.device is '%s'); there is no CPU path" % s)
