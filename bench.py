@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py - decisions/sec of BUSCA's per-frame association hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one frame of the hot path: motion proposals + centre-distance/IoU + candidate selection, crop-and-resize
+gather of the D detections and T motion proposals, ReID embedding of T*(L+C) patches (two BatchNorm batches), the
+Decision Transformer and the decision, for T unmatched tracks.  One decision = one unmatched track evaluated in one
+frame, so a step yields T decisions.
+
+`value`  : inputs already resident in HBM (frame, patch bank, boxes): busca_frame_step_dev.
+`e2e`    : the same step through the reference-facing plug-in API (BUSCA.get_image_crops / center_distance /
+           associate_embeddings) with HOST buffers; H2D of the frame/boxes and D2H of crops/probabilities are inside
+           the timed region.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from busca_b200 import synth  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: MOT20-scale dense crowd, ~200 unmatched tracks/frame (the scale the metric is quoted on)
+    "mot20": dict(T=200, D=300, L=11, C=5, desc="MOT20-scale synthetic 1920x1080 frames, 200 unmatched tracks x 5 proposals, 300 detections, L=11"),
+    # configs[1]
+    "mot17": dict(T=50, D=60, L=11, C=5, desc="MOT17-scale synthetic 1920x1080 frames, 50 unmatched tracks x 5 proposals, 60 detections, L=11"),
+    # configs[0]
+    "cfg1": dict(T=16, D=40, L=11, C=5, desc="1 synthetic 1920x1080 frame, 16 unmatched tracks x 5 proposals, 40 detections"),
+}
+
+
+def conv_flops(n_patches: int):
+    """Algorithmic FLOPs (2*MACs) of the ReID convolutions for n_patches, by kernel class:
+    8.0075 GFLOP per 384x128 patch in total."""
+    out = {"stem_conv7x7": 2.0 * 192 * 64 * 64 * 3 * 49, "conv1x1": 0.0, "conv3x3": 0.0}
+    H, W, inpl = 96, 32, 64
+    for planes, blocks, stride in synth.RESNET_LAYERS:
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            Ho, Wo = H // s, W // s
+            out["conv1x1"] += 2.0 * H * W * inpl * planes               # conv1
+            out["conv3x3"] += 2.0 * Ho * Wo * planes * planes * 9       # conv2 (carries the stride)
+            out["conv1x1"] += 2.0 * Ho * Wo * planes * planes * 4       # conv3
+            if b == 0:
+                out["conv1x1"] += 2.0 * Ho * Wo * inpl * planes * 4     # downsample
+            inpl, H, W = planes * 4, Ho, Wo
+    return {k: v * n_patches for k, v in out.items()}
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of the profiling recipe, sampled DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._th = None
+        self._proc = None
+
+    def start(self):
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._proc = None
+            return
+        self._th = threading.Thread(target=self._read, daemon=True)
+        self._th.start()
+
+    def _read(self):
+        for line in self._proc.stdout:
+            if self._stop.is_set():
+                break
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        self._stop.set()
+        if self._proc:
+            self._proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.rows)}
+        sm = []
+        reasons = set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+            out["sm_mhz"] = float(np.median(busy))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------------
+def build_model(precision: str, device: int):
+    from busca_b200.network import BUSCA
+    from busca_b200.option import load_args_from_config
+    targs, _ = load_args_from_config(os.path.join(REPO, "busca_b200", "configs", "bytetrack_mot20.yml"))
+    a = targs.transformer
+    a.device = f"cuda:{device}"
+    a.precision = precision
+    a.bank_slots = 8192
+    m = BUSCA(a).eval()
+    m.load_state_dict(synth.make_weights(0))
+    return m, targs
+
+
+class Scene:
+    """Synthetic MOT20-like state for one sequence: T unmatched tracks with L-deep histories, D detections."""
+
+    def __init__(self, model, T, D, L, C, seed, n_frames=3):
+        rng = np.random.default_rng(seed)
+        self.T, self.D, self.L, self.C = T, D, L, C
+        self.frames = [synth.make_frame(seed * 10 + 1)]
+        for i in range(1, n_frames):
+            self.frames.append(synth.next_frame(self.frames[-1], seed * 10 + 1 + i))
+        H, W = self.frames[0].shape[:2]
+        box = synth.random_boxes(rng, T, H, W)                     # ltwh
+        vel = rng.normal(0, 3, (T, 2))
+        # Kalman state (cx, cy, a, h, vx, vy, va, vh) one step before the current frame
+        self.mean = np.concatenate([box[:, :2] + box[:, 2:] / 2, (box[:, 2] / box[:, 3])[:, None], box[:, 3:4], vel,
+                                    rng.normal(0, 1e-3, (T, 1)), rng.normal(0, 0.5, (T, 1))], axis=1)
+        self.tracked = (rng.uniform(size=T) < 0.8)
+        # history: L observations per track along its motion (5 % of the tracks have a short history -> unreliable)
+        self.reliable = rng.uniform(size=T) >= 0.05
+        hist_boxes = np.empty((T, L, 4))
+        for i in range(L):
+            b = box.copy()
+            b[:, :2] -= vel * (L - i)
+            b[:, 2:] *= 1 + 0.01 * rng.standard_normal((T, 2))
+            hist_boxes[:, i] = b
+        self.mem_ltwh = hist_boxes.copy()
+        self.mem_ltwh[~self.reliable] = np.array([250.0, 250.0, 500.0, 500.0])
+        # detections: half near the tracks, half elsewhere
+        det = synth.random_boxes(rng, D, H, W)
+        n_near = min(D, T) // 2
+        det[:n_near] = box[:n_near] + np.concatenate([vel[:n_near] + rng.normal(0, 6, (n_near, 2)), np.zeros((n_near, 2))], 1)
+        self.det_ltwh = det
+        self.det_tlbr = det.copy()
+        self.det_tlbr[:, 2:] += self.det_tlbr[:, :2]
+        self.hist_tlbr = hist_boxes.copy()
+        self.hist_tlbr[..., 2:] += self.hist_tlbr[..., :2]
+        self.model = model
+
+    # ---- resident path -------------------------------------------------------------------------------
+    def setup_resident(self):
+        from busca_b200._lib import StepArgs
+        eng = self.model.engine
+        T, D, L, C = self.T, self.D, self.L, self.C
+        eng.upload_frame(self.frames[0])
+        mem_slots = eng.alloc_slots(T * L).reshape(T, L)
+        eng.crop(self.hist_tlbr.reshape(-1, 4), mem_slots.reshape(-1), to_host=False)
+        mem_slots = mem_slots.copy()
+        mem_slots[~self.reliable] = -1
+        self.det_slots = eng.alloc_slots(D)
+        self.kal_slots = eng.alloc_slots(T)
+        a = StepArgs(T=T, D=D, L=L, C=C)
+        a.track_mean_dev = eng.to_dev(self.mean)
+        a.tracked_dev = eng.to_dev(self.tracked.astype(np.uint8))
+        a.det_tlbr_dev = eng.to_dev(self.det_tlbr)
+        a.mem_slots_dev = eng.to_dev(mem_slots.astype(np.int32))
+        a.mem_ltwh_dev = eng.to_dev(self.mem_ltwh)
+        a.det_slots_dev = eng.to_dev(self.det_slots)
+        a.kal_slots_dev = eng.to_dev(self.kal_slots)
+        a.busca_thresh = 0.3
+        a.reliable_dev = eng.to_dev(self.reliable.astype(np.uint8))
+        self.probs_dev = eng.dev_alloc(T * (C + 2) * 4)
+        self.keep_dev = eng.dev_alloc(max(T, 16))
+        a.probs_dev = self.probs_dev
+        a.keep_dev = self.keep_dev
+        self.step_args = a
+
+    def step_resident(self):
+        self.model.engine.frame_step_dev(self.step_args)
+
+    # ---- plug-in API path (host buffers) -----------------------------------------------------------------
+    def setup_e2e(self):
+        m = self.model
+        T, L = self.T, self.L
+        self.tracks = []
+        crops = m.get_image_crops(self.frames[0], self.hist_tlbr.reshape(-1, 4), normalize=False).reshape(T, L, 384, 128, 3)
+        self._keepalive = crops
+        for t in range(T):
+            tr = synth.SynthTrack(self.hist_tlbr[t, -1] * 0, scale=1.0)
+            n = L if self.reliable[t] else L - 3
+            tr.images_mem = [crops[t, i] for i in range(L - n, L)]
+            b = self.mem_ltwh[t] if self.reliable[t] else None
+            hb = self.hist_tlbr[t].copy()
+            hb[:, 2:] -= hb[:, :2]
+            tr.tlwh_mem = [hb[i] for i in range(L - n, L)]
+            tr._tlwh = tr.tlwh_mem[-1].copy()
+            self.tracks.append(tr)
+        self.h2d = self.d2h = 0
+
+    def step_e2e(self, i):
+        from busca_b200 import tracking
+        m = self.model
+        frame = self.frames[i % len(self.frames)]
+        T, D, L, C = self.T, self.D, self.L, self.C
+        _mo, tlwh, tlbr = m.engine.motion_proposals(self.mean, self.tracked)
+        det_crops = m.get_image_crops(frame, self.det_tlbr.astype(np.float32), normalize=False)
+        dets = []
+        for j in range(D):
+            d = synth.SynthTrack(self.det_ltwh[j], scale=1.0)
+            d.tlwh_mem = [d._tlwh]
+            d.images_mem = [det_crops[j]]
+            dets.append(d)
+        kal_crops = m.get_image_crops(frame, tlbr, normalize=False)
+        kal = []
+        for t in range(T):
+            k = synth.SynthTrack(tlwh[t], scale=1.0)
+            k.images_mem = [kal_crops[t]]
+            kal.append(k)
+            self.tracks[t]._tlwh = tlwh[t]
+        dists = tracking.center_distance(tlbr, self.det_tlbr, engine=m.engine)
+        pm, reliable = m.associate_embeddings(self.tracks, dets, dists, L, C, use_broader_memory=True, select_highest_candidate=False,
+                                              extra_kalman_candidates=kal, normalize_ims=True)
+        keep = reliable & (pm[np.arange(T), D + np.arange(T)] > 0.3)
+        self.h2d = frame.nbytes + self.mean.nbytes + T + 2 * (D + T) * 32 + (T + D) * 32 + dists.nbytes + (T * L + D + T) * 4 + T * L * 32 + (D + T) * 32
+        self.d2h = det_crops.nbytes + kal_crops.nbytes + T * 64 + dists.nbytes + T * (C + 2) * 4 + T * C * 4 + T * (C + 2) * 512 * 4 + T * 512 * 4
+        return keep
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = WORKLOADS[args.workload]
+    T, D, L, C = wl["T"], wl["D"], wl["L"], wl["C"]
+    model, targs = build_model(args.precision, local)
+    eng = model.engine
+    scene = Scene(model, T, D, L, C, seed=100 + rank)       # independent sequence per rank (sequence sharding, no collective)
+    scene.setup_resident()
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize(local)
+        eng.sync()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- resident (`value`)
+    for _ in range(args.warmup):
+        scene.step_resident()
+    eng.sync()
+    eng.set_profiling(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launches
+    prof_acc = {}
+    lat = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        scene.step_resident()
+        eng.sync()                                            # per-frame latency needs the frame boundary anyway
+        lat.append((time.perf_counter() - t0) * 1e3)
+        for k, v in eng.last_profile().items():
+            a = prof_acc.setdefault(k, {"ms": 0.0, "launches": 0})
+            a["ms"] += v["ms"]
+            a["launches"] += v["launches"]
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = eng.launches - launches0
+    eng.set_profiling(False)
+    keep = eng.from_dev(scene.keep_dev, (T,), np.uint8)
+    probs = eng.from_dev(scene.probs_dev, (T, C + 2), np.float32)
+    assert np.isfinite(probs).all() and abs(float(probs.sum()) - T) < 1e-2 * T
+
+    # ---- plug-in API (`e2e`)
+    scene.setup_e2e()
+    for i in range(min(args.warmup, 3)):
+        scene.step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        scene.step_e2e(i)
+    eng.sync()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        kept = torch.tensor([int(keep.sum())], device=f"cuda:{local}")
+        gathered = [torch.zeros_like(kept) for _ in range(world)]
+        dist.all_gather(gathered, kept)                       # NCCL only gathers per-rank results
+    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md 1.4 PF sustained)"
+    fl = conv_flops(T * (L + C))
+    conv_classes = {k: prof_acc[k] for k in ("conv1x1", "conv3x3", "stem_conv7x7") if k in prof_acc}
+    dom = max(conv_classes, key=lambda k: conv_classes[k]["ms"]) if conv_classes else None
+    roofline = None
+    if dom:
+        per_launch_flops = fl[dom] * args.steps / conv_classes[dom]["launches"]
+        avg_ms = conv_classes[dom]["ms"] / conv_classes[dom]["launches"]
+        achieved = per_launch_flops / (avg_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 3), "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": round(achieved / peak_tf, 5), "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": round(avg_ms, 4), "launches": conv_classes[dom]["launches"],
+                    "share_of_step": round(conv_classes[dom]["ms"] / max(1e-9, sum(v["ms"] for v in prof_acc.values())), 4)}
+    total_prof = sum(v["ms"] for v in prof_acc.values())
+    kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 4), "launches_per_step": v["launches"] / args.steps,
+                   "share": round(v["ms"] / max(total_prof, 1e-9), 4)} for k, v in sorted(prof_acc.items(), key=lambda kv: -kv[1]["ms"])}
+    cpu = cpu_baseline(args) if not args.no_cpu_baseline else None
+    out = {
+        "metric": "decisions/sec", "value": round(world * T * args.steps / (ms_max * 1e-3), 3), "unit": "decisions/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload, "T": T, "D": D, "L": L, "C": C, "patches_per_step": T * (L + C),
+                   "weights": "random-init (numpy PCG64 seed 0), model_busca.pth layout",
+                   "l2": "inputs larger than L2: every step streams GBs of ReID activations through HBM (L2 is 126 MB)",
+                   "parallelism": f"{world} independent sequences, one per GPU, no hot-path collective"},
+        "p50_frame_latency_ms": round(float(np.median(lat)), 3),
+        "e2e": {"value": round(world * T * args.steps / (e2e_ms_max * 1e-3), 3), "unit": "decisions/s",
+                "h2d_bytes_per_step": int(scene.h2d), "d2h_bytes_per_step": int(scene.d2h),
+                "api": "BUSCA.get_image_crops + center_distance + associate_embeddings (host numpy in/out)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "kept_tracks": int(keep.sum()),
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------
+def cpu_sample_case(T, D, L, seed=5):
+    from oracle import crop as ocrop
+    return synth.make_assoc_case(seed, T, D, L, crop_fn=ocrop.get_image_crops)
+
+
+def time_oracle(T, D, L, C, reps, warm):
+    """The reference's algorithm (CPU oracle port: crops, geometry, ReID, Transformer) on the host cores."""
+    import torch
+    from oracle import geometry as ogeo
+    from oracle import network as onet
+    torch.set_num_threads(os.cpu_count())
+    weights = synth.make_weights(0)
+    case = cpu_sample_case(T, D, L)
+    times = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        dists = ogeo.center_distance([t.tlbr for t in case.tracks], [d.tlbr for d in case.dets])
+        pm, rel = onet.associate(weights, case.tracks, case.dets, dists, L, C, True, kalman=case.kalman)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return times
+
+
+def cpu_baseline(args):
+    wl = WORKLOADS[args.workload]
+    Ts = args.cpu_tracks
+    times = time_oracle(Ts, min(wl["D"], 4 * Ts), wl["L"], wl["C"], reps=1, warm=0)
+    return {"value": round(Ts / float(np.median(times)), 4), "unit": "decisions/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{Ts} unmatched tracks x {wl['C']} proposals of the same workload ({Ts * (wl['L'] + wl['C'])} ReID patches), "
+                      f"1 repetition, torch CPU fp32 with {os.cpu_count()} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    Ts = args.cpu_tracks
+    times = time_oracle(Ts, min(wl["D"], 4 * Ts), wl["L"], wl["C"], reps=args.steps, warm=min(args.warmup, 1))
+    tot = float(np.sum(times))
+    val = round(Ts * len(times) / tot, 4)
+    sample = (f"each step = {Ts} unmatched tracks x {wl['C']} proposals of the same workload ({Ts * (wl['L'] + wl['C'])} ReID patches); "
+              f"oracle port of the reference algorithm, torch CPU fp32, {os.cpu_count()} threads")
+    out = {"impl": "reference", "metric": "decisions/sec", "value": val, "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(tot / len(times) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": wl["desc"], "name": args.workload, "T": wl["T"], "D": wl["D"], "L": wl["L"], "C": wl["C"]},
+           "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "decisions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mot20", choices=list(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("BUSCA_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-tracks", type=int, default=16, help="size of the bounded CPU sample (unmatched tracks)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -2,6 +2,7 @@
 // the per-frame hot path.  Kernels live in geometry.cu / crop.cu / reid.cu / conv_tc.cu / transformer.cu.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -89,6 +90,7 @@ struct busca_ctx {
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     int64_t launches = 0;
+    bool use_tc = false;                          // bf16 mode: tcgen05 convolutions (BUSCA_CONV=simt forces the SIMT bf16 path)
     // profiling
     bool profiling = false;
     std::vector<ProfEntry> prof;
@@ -190,6 +192,8 @@ extern "C" int busca_create(const busca_config *cfg, busca_ctx **out) {
     if (prop.major != 10) return set_err(BUSCA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
     busca_ctx *c = new busca_ctx();
     c->cfg = *cfg;
+    const char *cm = getenv("BUSCA_CONV");
+    c->use_tc = cfg->precision == BUSCA_PREC_BF16 && !(cm && strcmp(cm, "simt") == 0);
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c;
     int64_t slots = cfg->bank_slots > 0 ? cfg->bank_slots : 1024;
@@ -551,6 +555,22 @@ static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *
     int H = 96, W = 32;
     size_t ci = 1;
     const int blocks[4] = {3, 4, 6, 3};
+    const bool tc = c->use_tc;
+    // One convolution.  SIMT path: the producer's BN+ReLU is applied while loading A (deferred).  tcgen05 path: TMA feeds
+    // the tensor core directly from HBM, so the activated tensor is materialised in place first.
+    auto conv = [&](ConvLayer &L, ConvArgs a, const char *name) -> int {
+        if (tc) {
+            if (a.in_scale) {
+                LAUNCH(c, "bn_relu", launch_bn_relu_inplace(const_cast<void *>(a.in), a.in_scale, a.in_shift, (long long)a.N * a.H * a.W, L.cin, bf16, s));
+                a.in_scale = a.in_shift = nullptr;
+            }
+            LAUNCH(c, name, launch_conv_tc(L, a, s));
+        } else {
+            LAUNCH(c, name, launch_conv_simt(L, a, bf16, s));
+        }
+        return BUSCA_OK;
+    };
+    int rc;
     for (int li = 0; li < 4; ++li)
         for (int b = 0; b < blocks[li]; ++b) {
             ConvLayer &c1 = c->convs[ci], &c2 = c->convs[ci + 1], &c3 = c->convs[ci + 2];
@@ -558,19 +578,19 @@ static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *
             ConvArgs a{};
             a.N = N;
             a.in = x; a.out = R1; a.H = H; a.W = W; a.Ho = H; a.Wo = W; a.in_scale = nullptr; a.in_shift = nullptr;
-            LAUNCH(c, "conv1x1", launch_conv_simt(c1, a, bf16, s));
+            if ((rc = conv(c1, a, "conv1x1"))) return rc;
             LAUNCH(c, "bn_finalize", launch_bn_finalize(c1, (long long)N * H * W, s));
             a.in = R1; a.out = R2; a.Ho = Ho; a.Wo = Wo; a.in_scale = c1.scale; a.in_shift = c1.shift;
-            LAUNCH(c, "conv3x3", launch_conv_simt(c2, a, bf16, s));
+            if ((rc = conv(c2, a, "conv3x3"))) return rc;
             LAUNCH(c, "bn_finalize", launch_bn_finalize(c2, (long long)N * Ho * Wo, s));
             a.in = R2; a.out = R3; a.H = Ho; a.W = Wo; a.in_scale = c2.scale; a.in_shift = c2.shift;
-            LAUNCH(c, "conv1x1", launch_conv_simt(c3, a, bf16, s));
+            if ((rc = conv(c3, a, "conv1x1"))) return rc;
             LAUNCH(c, "bn_finalize", launch_bn_finalize(c3, (long long)N * Ho * Wo, s));
             const long long rows = (long long)N * Ho * Wo;
             if (b == 0) {
                 ConvLayer &ds = c->convs[ci + 3];
                 a.in = x; a.out = RDS; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.in_scale = nullptr; a.in_shift = nullptr;
-                LAUNCH(c, "conv1x1", launch_conv_simt(ds, a, bf16, s));
+                if ((rc = conv(ds, a, "conv1x1"))) return rc;
                 LAUNCH(c, "bn_finalize", launch_bn_finalize(ds, rows, s));
                 LAUNCH(c, "bn_add_relu", launch_bn_add_relu(R3, c3.scale, c3.shift, RDS, ds.scale, ds.shift, other, rows, c3.cout, bf16, s));
                 void *t = x; x = other; other = t;
@@ -821,6 +841,40 @@ extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
     rc = transformer_dev(c, T, L, C, (const float *)(b + o_me), (const float *)(b + o_ce), (const int32_t *)(b + o_idx), o);
     if (rc) return rc;
     if (a->keep_dev) LAUNCH(c, "decide", launch_decide(a->probs_dev, (const int *)(b + o_cand), a->reliable_dev, T, D, C, a->busca_thresh, a->keep_dev, s));
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hook: one convolution of the ReID network on caller-provided bf16 NHWC input
+// ------------------------------------------------------------------------------------------------
+extern "C" int busca_debug_conv(busca_ctx *c, int32_t conv_index, const uint16_t *in_bf16, int32_t N, int32_t H, int32_t W, int32_t use_tc,
+                                uint16_t *out_bf16, double *stats_out) {
+    if (!c || !c->finalized || conv_index < 1 || conv_index >= (int)c->convs.size() || !in_bf16 || !out_bf16) return set_err(BUSCA_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    ConvLayer &L = c->convs[conv_index];
+    const int Ho = H / L.stride, Wo = W / L.stride;
+    const size_t in_b = (size_t)N * H * W * L.cin * 2, out_b = (size_t)N * Ho * Wo * L.cout * 2;
+    CUDA_OK(c->ws_reid.ensure(in_b + out_b + 512));
+    char *din = (char *)c->ws_reid.p, *dout = din + ((in_b + 255) & ~(size_t)255);
+    cudaStream_t s = c->stream;
+    CUDA_OK(cudaMemcpyAsync(din, in_bf16, in_b, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(dout, 0xff, out_b, s));
+    CUDA_OK(cudaMemsetAsync(L.stats, 0, 2 * (size_t)L.cout * sizeof(double), s));
+    ConvArgs a{};
+    a.in = din; a.out = dout; a.N = N; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo;
+    prof_reset(c);
+    if (use_tc) LAUNCH(c, "conv_tc", launch_conv_tc(L, a, s));
+    else LAUNCH(c, "conv_simt", launch_conv_simt(L, a, 1, s));
+    CUDA_OK(cudaMemcpyAsync(out_bf16, dout, out_b, cudaMemcpyDeviceToHost, s));
+    if (stats_out) CUDA_OK(cudaMemcpyAsync(stats_out, L.stats, 2 * (size_t)L.cout * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+extern "C" int busca_conv_info(busca_ctx *c, int32_t conv_index, int32_t *out4) {
+    if (!c || !c->finalized || conv_index < 0 || conv_index >= (int)c->convs.size()) return set_err(BUSCA_ERR_ARG, "bad argument");
+    ConvLayer &L = c->convs[conv_index];
+    out4[0] = L.cin; out4[1] = L.cout; out4[2] = L.k; out4[3] = L.stride;
     return BUSCA_OK;
 }
 

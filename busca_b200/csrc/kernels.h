@@ -47,6 +47,10 @@ cudaError_t launch_stem(const uint8_t *bank, const int32_t *slots, int N, const 
                         int bf16, cudaStream_t s);
 cudaError_t launch_conv_simt(const ConvLayer &L, const ConvArgs &a, int bf16, cudaStream_t s);
 cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t s);
+// conv_tc.cu: tcgen05 / TMEM / TMA implicit GEMM (bf16 activations, input must already be activated: no deferred BN)
+cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, cudaStream_t s);
+// x = relu(x*scale + shift) in place (bf16 or float), rows x C
+cudaError_t launch_bn_relu_inplace(void *x, const float *scale, const float *shift, long long rows, int C, int bf16, cudaStream_t s);
 cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,
                                    const float *shift, int bf16, cudaStream_t s);
 // out = relu(raw*scale+shift + (idt_scale ? idt*idt_scale+idt_shift : idt)); out may alias idt
@@ -68,6 +72,7 @@ struct LinearArgs {
     int act;                    // 0 none, 1 relu, 2 gelu(erf)
 };
 cudaError_t launch_linear_f32(const LinearArgs &a, cudaStream_t s);
+cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const LinearArgs &la, cudaStream_t s);
 
 // ---------------------------------------------------------------- transformer.cu
 struct PeTables { const __half *xy, *size, *t; };

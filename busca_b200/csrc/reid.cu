@@ -370,6 +370,32 @@ __global__ void bn_add_relu_kernel(const T *__restrict__ raw, const float *__res
     }
 }
 
+// relu(bn(x)) in place: materialises the activated tensor for the TMA-fed tensor-core convolutions
+template <typename T>
+__global__ void bn_relu_inplace_kernel(T *x, const float *__restrict__ scale, const float *__restrict__ shift, long long rows, int C) {
+    const int C8 = C / 8;
+    const long long total = rows * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        T *p = x + (i / C8) * C + c;
+        if constexpr (sizeof(T) == 2) {
+            uint4 v = *reinterpret_cast<const uint4 *>(p);
+            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = __bfloat1622float2(h[j]);
+                f.x = fmaxf(fmaf(f.x, scale[c + 2 * j], shift[c + 2 * j]), 0.f);
+                f.y = fmaxf(fmaf(f.y, scale[c + 2 * j + 1], shift[c + 2 * j + 1]), 0.f);
+                h[j] = __floats2bfloat162_rn(f.x, f.y);
+            }
+            *reinterpret_cast<uint4 *>(p) = v;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ActIO<T>::st(p + j, fmaxf(fmaf(ActIO<T>::ld(p + j), scale[c + j], shift[c + j]), 0.f));
+        }
+    }
+}
+
 template <typename T>
 __global__ void global_maxpool_kernel(const T *__restrict__ x, float *__restrict__ out, int N, int HW, int C) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,6 +490,16 @@ cudaError_t launch_bn_add_relu(const void *raw, const float *scale, const float 
         bn_add_relu_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)raw, scale, shift, (const __nv_bfloat16 *)idt, idt_scale, idt_shift, (__nv_bfloat16 *)out, rows, C);
     else
         bn_add_relu_kernel<float><<<ew_grid(total), 256, 0, s>>>((const float *)raw, scale, shift, (const float *)idt, idt_scale, idt_shift, (float *)out, rows, C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bn_relu_inplace(void *x, const float *scale, const float *shift, long long rows, int C, int bf16, cudaStream_t s) {
+    long long total = rows * (C / 8);
+    if (total == 0) return cudaSuccess;
+    if (bf16)
+        bn_relu_inplace_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((__nv_bfloat16 *)x, scale, shift, rows, C);
+    else
+        bn_relu_inplace_kernel<float><<<ew_grid(total), 256, 0, s>>>((float *)x, scale, shift, rows, C);
     return cudaGetLastError();
 }
 

@@ -150,6 +150,11 @@ typedef struct busca_step_args {
  * D detections and T proposals from the uploaded frame + ReID (2 batches) + Transformer + decision. */
 int busca_frame_step_dev(busca_ctx *ctx, const busca_step_args *args);
 
+/* ---- test hooks (tests/test_gpu_conv_tc.py): one ReID convolution on caller-provided bf16 NHWC input ---------- */
+int busca_debug_conv(busca_ctx *ctx, int32_t conv_index, const uint16_t *in_bf16, int32_t N, int32_t H, int32_t W, int32_t use_tc,
+                     uint16_t *out_bf16, double *stats_out /* [2*cout] or NULL */);
+int busca_conv_info(busca_ctx *ctx, int32_t conv_index, int32_t *cin_cout_k_stride);
+
 /* ---- plumbing -------------------------------------------------------------------------------- */
 void *busca_dev_alloc(busca_ctx *ctx, int64_t bytes);
 void busca_dev_free(busca_ctx *ctx, void *p);
