@@ -328,6 +328,14 @@ def run_ours(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md 1.4 PF sustained)"
     fl = conv_flops(T * (L + C))
+    by_class = {}
+    for k, v in prof_acc.items():                          # "conv1x1_tc[64>256 s1 96x32]" -> class "conv1x1"
+        cls = k.split("_tc[")[0]
+        a = by_class.setdefault(cls, {"ms": 0.0, "launches": 0})
+        a["ms"] += v["ms"]
+        a["launches"] += v["launches"]
+    detail = {k: round(v["ms"] / args.steps, 4) for k, v in prof_acc.items() if "_tc[" in k}
+    prof_acc = by_class
     conv_classes = {k: prof_acc[k] for k in ("conv1x1", "conv3x3", "stem_conv7x7") if k in prof_acc}
     dom = max(conv_classes, key=lambda k: conv_classes[k]["ms"]) if conv_classes else None
     roofline = None
@@ -360,6 +368,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roofline,
         "kernels": kernels,
+        "conv_detail_ms_per_step": detail,
         "cpu_baseline": cpu,
         "kept_tracks": int(keep.sum()),
     }

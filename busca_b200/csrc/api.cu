@@ -290,14 +290,17 @@ extern "C" int busca_finalize(busca_ctx *c) {
                         for (int kx = 0; kx < sp.k; ++kx)
                             re[(((size_t)o * sp.k + ky) * sp.k + kx) * sp.cin + ci] = w->f[(((size_t)o * sp.cin + ci) * sp.k + ky) * sp.k + kx];
         }
-        L.w32 = upload(c, re.data(), re.size());
-        NEED(L.w32);
         if (sp.cin != 3) {
             std::vector<__nv_bfloat16> h(re.size());
             for (size_t i = 0; i < re.size(); ++i) h[i] = __float2bfloat16(re[i]);
             L.w16 = upload(c, h.data(), h.size());
             NEED(L.w16);
+            // bf16 mode: the SIMT kernel multiplies by the same bf16-rounded weights as the tensor-core kernel
+            if (c->cfg.precision == BUSCA_PREC_BF16)
+                for (size_t i = 0; i < re.size(); ++i) re[i] = __bfloat162float(h[i]);
         }
+        L.w32 = upload(c, re.data(), re.size());
+        NEED(L.w32);
         L.gamma = upload_named(c, r + sp.bn + ".weight", {sp.cout});
         NEED(L.gamma);
         L.beta = upload_named(c, r + sp.bn + ".bias", {sp.cout});
@@ -564,7 +567,9 @@ static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *
                 LAUNCH(c, "bn_relu", launch_bn_relu_inplace(const_cast<void *>(a.in), a.in_scale, a.in_shift, (long long)a.N * a.H * a.W, L.cin, bf16, s));
                 a.in_scale = a.in_shift = nullptr;
             }
-            LAUNCH(c, name, launch_conv_tc(L, a, s));
+            char nm[64];
+            snprintf(nm, sizeof(nm), "%s_tc[%d>%d s%d %dx%d]", name, L.cin, L.cout, L.stride, a.H, a.W);
+            LAUNCH(c, c->profiling ? nm : name, launch_conv_tc(L, a, s));
         } else {
             LAUNCH(c, name, launch_conv_simt(L, a, bf16, s));
         }

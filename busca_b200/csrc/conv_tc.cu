@@ -16,7 +16,12 @@
 // * Persistent: one CTA per SM, static round-robin over (pixel-tile, channel-tile) pairs, channel-tile fastest so
 //   CTAs running concurrently share the same A boxes through L2.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// * The bf16 output tile is staged in shared memory (128-byte swizzle, 64 channels per group, double buffered) and
+//   written with TMA stores, so HBM sees whole 128-byte lines; the per-channel statistics are reduced from the
+//   staged tile (thread = channel, no shuffles).
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (warp % 4 = TMEM lane quarter, two warps per quarter split the 64-channel group).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -26,7 +31,8 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;            // bf16 elements per K block = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+constexpr int TC_EPI_THREADS = 256;
 constexpr int TC_MAX_TAPS = 9;
 
 struct TcParams {
@@ -111,40 +117,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 
-// sum over the 32 lanes of each of 32 per-lane values; lane l ends up with the total of value index l.
-__device__ __forceinline__ float butterfly32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
-        const bool hi = (lane & o) != 0;
-#pragma unroll
-        for (int j = 0; j < n / 2; ++j) {
-            const float send = hi ? v[j] : v[j + n / 2];
-            const float keep = hi ? v[j + n / 2] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    return v[0];
-}
-
 template <int BN>
 struct TcCfg {
-    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 5 : 6);
+    static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
+    static constexpr int OUT_STAGE_BYTES = TC_BM * 128;              // one 64-channel bf16 group of the output tile
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;                // 16 KB
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STATS_FLOATS = 2 * 2048;                    // per-CTA sum / sum-of-squares for up to 2048 channels
-    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + STATS_FLOATS * 4 + 256;
+    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + STATS_FLOATS * 4 + 256;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                                                                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                                                                 const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+                                                                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                                                                 const TcParams p) {
     using Cfg = TcCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t *tiles = smem;
-    float *s_stats = reinterpret_cast<float *>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint8_t *ostage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                              // 2 x [128 rows][128 B], swizzled
+    float *s_stats = reinterpret_cast<float *>(ostage + 2 * Cfg::OUT_STAGE_BYTES);
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_stats + Cfg::STATS_FLOATS);
     uint64_t *full = bars, *empty = bars + Cfg::STAGES, *tfull = bars + 2 * Cfg::STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
@@ -154,7 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     }
@@ -219,52 +213,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         }
     } else {
-        // ===================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
-        const int q = warp & 3;
+        // ===================================================== epilogue (warps 2..9)
+        const int e = threadIdx.x - 64;                // 0..255
+        const int q = warp & 3;                        // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;              // which 32 of the 64 channels of a group
         const int row = q * 32 + lane;
         const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / (p.BW * p.BH);
-        int it = 0;
+        int it = 0, gcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
-            const int img = n0 + ni;
-            const bool valid = img < p.Nimg;
-            const long long m = ((long long)img * p.Ho + h0 + hi) * p.Wo + wi;
             mbar_wait(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (!p.out_f32) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const int col0 = n_tile * BN + c * 32;
-                if (p.stats) {                                  // rows beyond the batch are exact zeros (TMA zero fill)
-                    float v[32];
+                for (int g = 0; g < BN / 64; ++g, ++gcount) {
+                    uint8_t *st = ostage + (gcount & 1) * Cfg::OUT_STAGE_BYTES;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + acc * 256 + g * 64 + half * 32 + ((uint32_t)(q * 32) << 16), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    const float s = butterfly32(v, lane);
+                    for (int j = 0; j < 4; ++j) {       // 4 x 16 B = this thread's 32 channels of its row, swizzled like the TMA box
+                        uint32_t w[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { const float x = __uint_as_float(r[j]); v[j] = x * x; }
-                    const float sq = butterfly32(v, lane);
-                    atomicAdd(&s_stats[col0 + lane], s);
-                    atomicAdd(&s_stats[p.Cout + col0 + lane], sq);
-                }
-                if (valid) {
-                    if (!p.out_f32) {
-                        __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + m * p.Cout + col0;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
-                                w[j] = *reinterpret_cast<uint32_t *>(&h);
-                            }
-                            reinterpret_cast<uint4 *>(o)[g] = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int k = 0; k < 4; ++k) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * k]), __uint_as_float(r[j * 8 + 2 * k + 1]));
+                            w[k] = *reinterpret_cast<uint32_t *>(&h2);
                         }
-                    } else {
+                        const int chunk = (half * 4 + j) ^ (row & 7);
+                        *reinterpret_cast<uint4 *>(st + row * 128 + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // store(g-1) has released the buffer group g+1 will overwrite
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (e == 0) {
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)&mapOut),
+                                     "r"(smem_u32(st)), "r"(n_tile * BN + g * 64), "r"(0), "r"(h0), "r"(n0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (p.stats) {                      // thread = channel: 32 rows of one channel from the staged bf16 tile
+                        const int col = e & 63, part = e >> 6;
+                        float sum = 0.f, sq = 0.f;
+#pragma unroll 8
+                        for (int i = 0; i < 32; ++i) {
+                            const int rr = part * 32 + i;
+                            const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16 *>(st + rr * 128 + (((col >> 3) ^ (rr & 7)) << 4) + (col & 7) * 2);
+                            const float x = __bfloat162float(v);
+                            sum += x;
+                            sq = fmaf(x, x, sq);
+                        }
+                        atomicAdd(&s_stats[n_tile * BN + g * 64 + col], sum);
+                        atomicAdd(&s_stats[p.Cout + n_tile * BN + g * 64 + col], sq);
+                    }
+                }
+            } else if (half == 0) {
+                // fp32 output with bias / scale / activation / residual (linear layers): direct stores, 4 warps
+                const int img = n0 + ni;
+                const bool valid = img < p.Nimg;
+                const long long m = ((long long)img * p.Ho + h0 + hi) * p.Wo + wi;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (valid) {
+                        const int col0 = n_tile * BN + c * 32;
                         float *o = reinterpret_cast<float *>(p.out) + m * p.Cout + col0;
                         const float *res = p.residual ? p.residual + m * p.Cout + col0 : nullptr;
 #pragma unroll
@@ -284,6 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     __syncthreads();
@@ -339,7 +356,7 @@ bool make_map2(CUtensorMap *m, const void *base, long long K, long long rows, in
 int g_num_sms = 0;
 
 template <int BN>
-cudaError_t launch_tc(const CUtensorMap *maps, const CUtensorMap &mapB, const TcParams &p, cudaStream_t s) {
+cudaError_t launch_tc(const CUtensorMap *maps, const CUtensorMap &mapB, const CUtensorMap &mapOut, const TcParams &p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM);
@@ -353,7 +370,7 @@ cudaError_t launch_tc(const CUtensorMap *maps, const CUtensorMap &mapB, const Tc
     }
     const int total = p.tiles_m * p.tiles_n;
     const int grid = total < g_num_sms ? total : g_num_sms;
-    conv_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+    conv_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapOut, p);
     return cudaGetLastError();
 }
 
@@ -411,13 +428,15 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, cudaStream_t s
                 p.tap_dw[r * L.k + q] = (ox - pw) / 2;
             }
     }
-    CUtensorMap mapB;
+    CUtensorMap mapB, mapOut;
     ok = ok && make_map2(&mapB, L.w16, (long long)p.ntaps * L.cin, L.cout, BN);
+    // output [N][Ho][Wo][Cout] bf16, stored one 64-channel group of a tile at a time; images beyond N are clipped by TMA
+    ok = ok && make_map4(&mapOut, a.out, L.cout, a.Wo, a.Ho, a.N, L.cout, (long long)a.Wo * L.cout, (long long)a.Ho * a.Wo * L.cout, p.BW, p.BH, p.BI);
     if (!ok) return cudaErrorInvalidValue;
     switch (BN) {
-        case 256: return launch_tc<256>(maps, mapB, p, s);
-        case 128: return launch_tc<128>(maps, mapB, p, s);
-        default: return launch_tc<64>(maps, mapB, p, s);
+        case 256: return launch_tc<256>(maps, mapB, mapOut, p, s);
+        case 128: return launch_tc<128>(maps, mapB, mapOut, p, s);
+        default: return launch_tc<64>(maps, mapB, mapOut, p, s);
     }
 }
 
@@ -442,8 +461,8 @@ cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const Linea
     ok = ok && make_map2(&mapB, W_bf16, la.K, la.N, BN);
     if (!ok) return cudaErrorInvalidValue;
     switch (BN) {
-        case 256: return launch_tc<256>(maps, mapB, p, s);
-        case 128: return launch_tc<128>(maps, mapB, p, s);
-        default: return launch_tc<64>(maps, mapB, p, s);
+        case 256: return launch_tc<256>(maps, mapB, maps[0], p, s);      // no TMA store on the fp32-output path
+        case 128: return launch_tc<128>(maps, mapB, maps[0], p, s);
+        default: return launch_tc<64>(maps, mapB, maps[0], p, s);
     }
 }

@@ -275,3 +275,60 @@ def test_stagewise_embeddings_vs_reference(busca, golden_dir):
     assert rel(out["can_emb"], g["f32_can_emb"]) < FP32_TOL
     assert np.abs(out["logits"] - g["f64_logits"]).max() < FP32_TOL * np.abs(g["f64_logits"]).max()
     assert np.abs(out["probs"] - g["f64_probs"]).max() < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------ bf16 mode (tcgen05 path)
+BF16_EMB_COS = 0.999       # stated bf16 tolerance: cosine >= 0.999, rel-L2 <= 2e-2 on embeddings,
+BF16_EMB_L2 = 2e-2         # |dp| <= 1e-2 on probabilities, decisions identical outside |margin| < 2e-2 near-ties
+BF16_PROB = 1e-2
+
+
+@pytest.fixture(scope="module")
+def busca_bf16(weights):
+    from busca_b200.network import BUSCA
+    a, _ = make_args(precision="bf16")
+    m = BUSCA(a)
+    m.load_state_dict(weights)
+    assert m.engine.precision == "bf16"
+    return m.eval()
+
+
+@pytest.mark.parametrize("name", ["assoc_cfg1", "assoc_fewdets", "assoc_nodets"])
+def test_bf16_association_vs_reference(busca_bf16, golden_dir, name):
+    from busca_b200 import tracking
+    m = busca_bf16
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    seed, T, D, L, C, short = (int(v) for v in g["meta"])
+    case = synth.make_assoc_case(seed, T, D, L, crop_fn=lambda f, b: m.get_image_crops(f, b, normalize=False), short_history=short)
+    dists = tracking.center_distance(case.tracks, case.dets, engine=m.engine)
+    mem_slots = np.full((T, L), -1, np.int32)
+    mem_ltwh = np.tile(np.array([250.0, 250.0, 500.0, 500.0]), (T, L, 1))
+    for t, tr in enumerate(case.tracks):
+        sel = m._memory_indices(len(tr.images_mem), L, True)
+        if len(sel) == L:
+            for i, j in enumerate(sel):
+                mem_slots[t, i] = m._registry.lookup(tr.images_mem[j])
+                mem_ltwh[t, i] = tr.tlwh_mem[j] * tr.scale
+    det_slots = np.array([m._registry.lookup(d.images_mem[-1]) for d in case.dets], np.int32) if D else None
+    det_ltwh = np.array([d.tlwh_mem[-1] * d.scale for d in case.dets]) if D else None
+    kal_slots = np.array([m._registry.lookup(k.images_mem[-1]) for k in case.kalman], np.int32)
+    kal_ltwh = np.array([k.tlwh * k.scale for k in case.kalman])
+    out = m.engine.associate(mem_slots, mem_ltwh, det_slots, det_ltwh, dists if D else None, kal_slots, kal_ltwh, L, C,
+                             want=("probs", "cand", "mem_emb", "can_emb", "pe_index"))
+    for mine, ref in ((out["mem_emb"], g["f32_mem_emb"]), (out["can_emb"], g["f32_can_emb"])):
+        a, b = mine.reshape(-1, 512), ref.reshape(-1, 512)
+        cos = (a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+        l2 = np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+        assert cos.min() >= BF16_EMB_COS, cos.min()
+        assert l2.max() <= BF16_EMB_L2, l2.max()
+    ref_p = g["f64_probs"]
+    assert np.abs(out["probs"] - ref_p).max() < BF16_PROB, np.abs(out["probs"] - ref_p).max()
+    # index work is precision independent: bit-exact
+    assert np.array_equal(out["pe_index"][:, :L, 0], g["f64_mem_xy"]) and np.array_equal(out["pe_index"][:, L:, 1], g["f64_can_size"])
+    kslot = min(D, C - 1)
+    thr = float(np.median(ref_p[:, kslot]))
+    clear = np.abs(ref_p[:, kslot] - thr) > 2e-2
+    assert np.array_equal((out["probs"][:, kslot] > thr)[clear], (ref_p[:, kslot] > thr)[clear])
+    srt = np.sort(ref_p, axis=1)
+    clear_top = (srt[:, -1] - srt[:, -2]) > 2e-2
+    assert np.array_equal(out["probs"].argmax(1)[clear_top], ref_p.argmax(1)[clear_top])
