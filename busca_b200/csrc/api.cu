@@ -290,6 +290,17 @@ extern "C" int busca_finalize(busca_ctx *c) {
                         for (int kx = 0; kx < sp.k; ++kx)
                             re[(((size_t)o * sp.k + ky) * sp.k + kx) * sp.cin + ci] = w->f[(((size_t)o * sp.cin + ci) * sp.k + ky) * sp.k + kx];
         }
+        if (sp.cin == 3) {
+            // tensor-core stem weights: bf16 [cout][ky][kx*4 + c_bgr] with kx padded to 8 and c to 4 (zeros)
+            std::vector<__nv_bfloat16> h((size_t)64 * 7 * 32, __float2bfloat16(0.f));
+            for (int o = 0; o < 64; ++o)
+                for (int ci = 0; ci < 3; ++ci)
+                    for (int ky = 0; ky < 7; ++ky)
+                        for (int kx = 0; kx < 7; ++kx)
+                            h[((size_t)o * 7 + ky) * 32 + kx * 4 + (2 - ci)] = __float2bfloat16(w->f[(((size_t)o * 3 + ci) * 7 + ky) * 7 + kx]);
+            L.w16 = upload(c, h.data(), h.size());
+            NEED(L.w16);
+        }
         if (sp.cin != 3) {
             std::vector<__nv_bfloat16> h(re.size());
             for (size_t i = 0; i < re.size(); ++i) h[i] = __float2bfloat16(re[i]);
@@ -551,7 +562,10 @@ static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *
     CUDA_OK(cudaMemsetAsync(c->stats_pool, 0, c->stats_bytes, s));
 
     ConvLayer &stem = c->convs[0];
-    LAUNCH(c, "stem_conv7x7", launch_stem(c->bank, d_slots, N, c->lut, stem, R3, bf16, s));
+    if (c->use_tc && stem_tc_scratch_bytes(N) <= big)          // scratch = the (still unused) second block buffer
+        LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, B, R3, stem.stats, s));
+    else
+        LAUNCH(c, "stem_conv7x7", launch_stem(c->bank, d_slots, N, c->lut, stem, R3, bf16, s));
     LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, (long long)N * 192 * 64, s));
     LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(R3, A, N, 192, 64, 64, stem.scale, stem.shift, bf16, s));
     void *x = A, *other = B;
@@ -872,6 +886,26 @@ extern "C" int busca_debug_conv(busca_ctx *c, int32_t conv_index, const uint16_t
     else LAUNCH(c, "conv_simt", launch_conv_simt(L, a, 1, s));
     CUDA_OK(cudaMemcpyAsync(out_bf16, dout, out_b, cudaMemcpyDeviceToHost, s));
     if (stats_out) CUDA_OK(cudaMemcpyAsync(stats_out, L.stats, 2 * (size_t)L.cout * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+extern "C" int busca_debug_stem(busca_ctx *c, const int32_t *slots, int32_t N, int32_t use_tc, uint16_t *out_bf16, double *stats_out) {
+    if (!c || !c->finalized || !slots || N <= 0 || !out_bf16) return set_err(BUSCA_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    ConvLayer &L = c->convs[0];
+    const size_t out_b = (size_t)N * 192 * 64 * 64 * 2, scr = stem_tc_scratch_bytes(N);
+    CUDA_OK(c->ws_reid.ensure(out_b + scr + (size_t)N * 4 + 1024));
+    char *dout = (char *)c->ws_reid.p, *dscr = dout + ((out_b + 255) & ~(size_t)255);
+    int32_t *dsl = (int32_t *)(dscr + ((scr + 255) & ~(size_t)255));
+    cudaStream_t s = c->stream;
+    CUDA_OK(cudaMemcpyAsync(dsl, slots, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(L.stats, 0, 2 * 64 * sizeof(double), s));
+    prof_reset(c);
+    if (use_tc) LAUNCH(c, "stem_tc", launch_stem_tc(c->bank, dsl, N, c->lut, L.w16, dscr, dout, L.stats, s));
+    else LAUNCH(c, "stem_simt", launch_stem(c->bank, dsl, N, c->lut, L, dout, 1, s));
+    CUDA_OK(cudaMemcpyAsync(out_bf16, dout, out_b, cudaMemcpyDeviceToHost, s));
+    if (stats_out) CUDA_OK(cudaMemcpyAsync(stats_out, L.stats, 2 * 64 * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
     prof_collect(c);
     return BUSCA_OK;

@@ -86,10 +86,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start>>4 | LBO(1)<<16 | SBO(1024 B >> 4)<<32 | version 1 <<46 | SWIZZLE_128B(2) <<61
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), rows of KB bytes (128 or 64):
+// start>>4 | LBO(1)<<16 | SBO(8 rows * KB bytes >> 4)<<32 | version 1 <<46 | layout (SWIZZLE_128B = 2, SWIZZLE_64B = 4) <<61
+template <int KB>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(8 * KB / 16) << 32) | (1ull << 46) | ((uint64_t)(KB == 128 ? 2 : 4) << 61);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -117,23 +118,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 
-template <int BN>
+template <int BN, int KB>
 struct TcCfg {
+    static constexpr int BKE = KB / 2;                               // bf16 elements per K block
     static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
     static constexpr int OUT_STAGE_BYTES = TC_BM * 128;              // one 64-channel bf16 group of the output tile
-    static constexpr int A_BYTES = TC_BM * TC_BK * 2;                // 16 KB
-    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int A_BYTES = TC_BM * KB;                       // 16 KB (8 KB for the 64-byte stem rows)
+    static constexpr int B_BYTES = BN * KB;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STATS_FLOATS = 2 * 2048;                    // per-CTA sum / sum-of-squares for up to 2048 channels
     static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + STATS_FLOATS * 4 + 256;
 };
 
-template <int BN>
+template <int BN, int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                                                                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                                                                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                                                                  const TcParams p) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, KB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t *tiles = smem;
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     const int m = p.tap_map[tap];
                     const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
-                    tma_load_4d(a_dst, mp, &full[stage], cb * TC_BK, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                    tma_load_2d(b_dst, &mapB, &full[stage], kt * TC_BK, n_tile * BN);
+                    tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+                    tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -202,9 +204,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     mbar_wait(&full[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-                    const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + Cfg::A_BYTES);
+                    const uint64_t da = umma_desc<KB>(a_addr), db = umma_desc<KB>(a_addr + Cfg::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k)       // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
+                    for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
                         umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kt | k) != 0);
                     umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs retire
                     if (kt == p.k_iters - 1) umma_commit(&tfull[acc]);
@@ -332,34 +334,37 @@ EncodeTiledFn get_encode() {
 }
 
 // 4-D bf16 map: dims {C, W, H, N} (elements), strides in elements for W, H, N; box {64, bw, bh, bi}
-bool make_map4(CUtensorMap *m, const void *base, int C, int W, int H, int N, long long sW, long long sH, long long sN, int bw, int bh, int bi) {
+bool make_map4(CUtensorMap *m, const void *base, int C, int W, int H, int N, long long sW, long long sH, long long sN, int bw, int bh, int bi,
+               int inner = TC_BK) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
+    cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bi};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-bool make_map2(CUtensorMap *m, const void *base, long long K, long long rows, int box_rows) {
+bool make_map2(CUtensorMap *m, const void *base, long long K, long long rows, int box_rows, int inner = TC_BK) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)inner, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int g_num_sms = 0;
 
-template <int BN>
+template <int BN, int KB = 128>
 cudaError_t launch_tc(const CUtensorMap *maps, const CUtensorMap &mapB, const CUtensorMap &mapOut, const TcParams &p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, KB>::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -370,7 +375,7 @@ cudaError_t launch_tc(const CUtensorMap *maps, const CUtensorMap &mapB, const CU
     }
     const int total = p.tiles_m * p.tiles_n;
     const int grid = total < g_num_sms ? total : g_num_sms;
-    conv_tc_kernel<BN><<<grid, TC_THREADS, TcCfg<BN>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapOut, p);
+    conv_tc_kernel<BN, KB><<<grid, TC_THREADS, TcCfg<BN, KB>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapOut, p);
     return cudaGetLastError();
 }
 
@@ -465,4 +470,77 @@ cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const Linea
         case 128: return launch_tc<128>(maps, mapB, maps[0], p, s);
         default: return launch_tc<64>(maps, mapB, maps[0], p, s);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stem on tensor cores.  The 7x7 stride-2 convolution over 3 channels becomes a GEMM with K = 7 tap-rows x 32:
+// a pre-pass writes the normalised patch as bf16 with 4 channels per pixel (B,G,R,0) and 3+5 zero pixels of horizontal
+// padding per row; then, for one tap-row ky, the 7x4 (+4 zero) window of output pixel ox is 32 CONTIGUOUS elements
+// starting 16 bytes after the window of ox-1.  An overlapping-stride tensor map {32 el, 64 ox (stride 16 B), rows of
+// one parity (stride 2 rows), N} therefore delivers the im2col tile directly; vertical padding is TMA zero fill.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int STEM_PITCH_PX = 136;                       // 3 zero px + 128 px + 5 zero px
+__global__ void __launch_bounds__(256) stem_prepass_kernel(const uint8_t *__restrict__ bank, const int32_t *__restrict__ slots,
+                                                           const float *__restrict__ lut, uint2 *__restrict__ out, long long total_px) {
+    __shared__ float slut[768];
+    for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_px; i += (long long)gridDim.x * blockDim.x) {
+        const int px = (int)(i % STEM_PITCH_PX);
+        const long long t = i / STEM_PITCH_PX;
+        const int y = (int)(t % PATCH_H);
+        const int n = (int)(t / PATCH_H);
+        uint2 v = make_uint2(0u, 0u);
+        const int x = px - 3;
+        if (x >= 0 && x < PATCH_W) {
+            const int slot = slots[n];
+            int b = 0, g = 0, r = 0;
+            if (slot >= 0) {
+                const uint8_t *p = bank + (size_t)slot * PATCH_BYTES + ((size_t)y * PATCH_W + x) * 3;
+                b = p[0]; g = p[1]; r = p[2];
+            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(slut[b * 3 + 0], slut[g * 3 + 1]);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(slut[r * 3 + 2], 0.f);
+            v.x = *reinterpret_cast<uint32_t *>(&lo);
+            v.y = *reinterpret_cast<uint32_t *>(&hi);
+        }
+        out[i] = v;
+    }
+}
+}  // namespace
+
+size_t stem_tc_scratch_bytes(int N) { return (size_t)N * PATCH_H * STEM_PITCH_PX * 4 * 2; }
+
+// wstem: bf16 [64][7*32], element (ky, kx*4 + c_bgr) ; scratch: stem_tc_scratch_bytes(N); out: bf16 [N,192,64,64]
+cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem, void *scratch, void *out,
+                           double *stats, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    const long long total_px = (long long)N * PATCH_H * STEM_PITCH_PX;
+    long long blocks = (total_px + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    stem_prepass_kernel<<<(int)blocks, 256, 0, s>>>(bank, slots, lut, (uint2 *)scratch, total_px);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    TcParams p{};
+    p.BW = 64; p.BH = 2; p.BI = 1;
+    p.tiles_n = 1; p.h_tiles = 192 / 2; p.tiles_m = N * p.h_tiles;
+    p.cin_blocks = 1; p.ntaps = 7; p.k_iters = 7;
+    for (int ky = 0; ky < 7; ++ky) {
+        const int oy = ky - 3, ph = oy & 1;
+        p.tap_map[ky] = ph; p.tap_dh[ky] = (oy - ph) / 2; p.tap_dw[ky] = 0;
+    }
+    p.Ho = 192; p.Wo = 64; p.Nimg = N; p.Cout = 64;
+    p.out = out; p.stats = stats; p.alpha = 1.f;
+    const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(scratch);
+    const long long pitch = (long long)STEM_PITCH_PX * 4;             // elements per padded row
+    CUtensorMap maps[4], mapB, mapOut;
+    bool ok = true;
+    for (int ph = 0; ph < 2; ++ph)      // dims {32 window elements, 64 ox (stride 8 el = 16 B), 192 rows of this parity, N}
+        ok = ok && make_map4(&maps[ph], in + ph * pitch, 32, 64, 192, N, 8, 2 * pitch, (long long)PATCH_H * pitch, 64, 2, 1, 32);
+    maps[2] = maps[3] = maps[0];
+    ok = ok && make_map2(&mapB, wstem, 7 * 32, 64, 64, 32);
+    ok = ok && make_map4(&mapOut, out, 64, 64, 192, N, 64, 64 * 64, 192LL * 64 * 64, 64, 2, 1);
+    if (!ok) return cudaErrorInvalidValue;
+    return launch_tc<64, 64>(maps, mapB, mapOut, p, s);
 }

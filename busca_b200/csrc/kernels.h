@@ -49,6 +49,9 @@ cudaError_t launch_conv_simt(const ConvLayer &L, const ConvArgs &a, int bf16, cu
 cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t s);
 // conv_tc.cu: tcgen05 / TMEM / TMA implicit GEMM (bf16 activations, input must already be activated: no deferred BN)
 cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, cudaStream_t s);
+size_t stem_tc_scratch_bytes(int N);
+cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem_bf16, void *scratch, void *out,
+                           double *stats, cudaStream_t s);
 // x = relu(x*scale + shift) in place (bf16 or float), rows x C
 cudaError_t launch_bn_relu_inplace(void *x, const float *scale, const float *shift, long long rows, int C, int bf16, cudaStream_t s);
 cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,

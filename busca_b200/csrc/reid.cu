@@ -420,6 +420,79 @@ __global__ void l2norm_rows_kernel(float *x, int rows, int cols) {
     for (int c = lane; c < cols; c += 32) p[c] *= inv;
 }
 
+// ---- bf16 fast paths: 8 channels (16 bytes) per thread ---------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8]) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    return v;
+}
+__device__ __forceinline__ void load8(const float *__restrict__ p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+__global__ void __launch_bounds__(256) bn_add_relu_bf16_kernel(const uint4 *__restrict__ raw, const float *__restrict__ scale,
+                                                                const float *__restrict__ shift, const uint4 *idt, const float *__restrict__ iscale,
+                                                                const float *__restrict__ ishift, uint4 *out, long long total8, int C8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        float x[8], d[8], sc[8], sh[8];
+        unpack8(raw[i], x);
+        unpack8(idt[i], d);
+        load8(scale + c, sc);
+        load8(shift + c, sh);
+        if (iscale) {
+            float a[8], b[8];
+            load8(iscale + c, a);
+            load8(ishift + c, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = fmaf(d[j], a[j], b[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = fmaxf(fmaf(x[j], sc[j], sh[j]) + d[j], 0.f);
+        out[i] = pack8(x);
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_maxpool_bf16_kernel(const uint4 *__restrict__ raw, uint4 *__restrict__ out, int N, int H, int W, int C8,
+                                                                    const float *__restrict__ scale, const float *__restrict__ shift) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)N * Ho * Wo * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        long long t = i / C8;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const long long n = t / Ho;
+        float sc[8], sh[8], best[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        load8(scale + c8 * 8, sc);
+        load8(shift + c8 * 8, sh);
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int iy = 2 * oy + dy;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int ix = 2 * ox + dx;
+                if (ix < 0 || ix >= W) continue;
+                float x[8];
+                unpack8(__ldg(raw + ((n * H + iy) * W + ix) * C8 + c8), x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], fmaf(x[j], sc[j], sh[j]));
+            }
+        }
+        out[i] = pack8(best);
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -467,14 +540,17 @@ cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t
 
 static int ew_grid(long long total) {
     long long b = (total + 255) / 256;
-    return (int)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
+    return (int)(b < 148 * 32 ? (b > 0 ? b : 1) : 148 * 32);
 }
 
 cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,
                                    const float *shift, int bf16, cudaStream_t s) {
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
     if (total == 0) return cudaSuccess;
-    if (bf16)
+    if (bf16 && C % 8 == 0) {
+        const long long t8 = (long long)N * (H / 2) * (W / 2) * (C / 8);
+        bn_relu_maxpool_bf16_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift);
+    } else if (bf16)
         bn_relu_maxpool_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)raw, (__nv_bfloat16 *)out, N, H, W, C, scale, shift);
     else
         bn_relu_maxpool_kernel<float><<<ew_grid(total), 256, 0, s>>>((const float *)raw, (float *)out, N, H, W, C, scale, shift);
@@ -486,7 +562,10 @@ cudaError_t launch_bn_add_relu(const void *raw, const float *scale, const float 
                                cudaStream_t s) {
     long long total = rows * (C / 4);
     if (total == 0) return cudaSuccess;
-    if (bf16)
+    if (bf16 && C % 8 == 0) {
+        const long long t8 = rows * (C / 8);
+        bn_add_relu_bf16_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, scale, shift, (const uint4 *)idt, idt_scale, idt_shift, (uint4 *)out, t8, C / 8);
+    } else if (bf16)
         bn_add_relu_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)raw, scale, shift, (const __nv_bfloat16 *)idt, idt_scale, idt_shift, (__nv_bfloat16 *)out, rows, C);
     else
         bn_add_relu_kernel<float><<<ew_grid(total), 256, 0, s>>>((const float *)raw, scale, shift, (const float *)idt, idt_scale, idt_shift, (float *)out, rows, C);

@@ -154,6 +154,8 @@ int busca_frame_step_dev(busca_ctx *ctx, const busca_step_args *args);
 int busca_debug_conv(busca_ctx *ctx, int32_t conv_index, const uint16_t *in_bf16, int32_t N, int32_t H, int32_t W, int32_t use_tc,
                      uint16_t *out_bf16, double *stats_out /* [2*cout] or NULL */);
 int busca_conv_info(busca_ctx *ctx, int32_t conv_index, int32_t *cin_cout_k_stride);
+int busca_debug_stem(busca_ctx *ctx, const int32_t *slots, int32_t N, int32_t use_tc, uint16_t *out_bf16 /* [N,192,64,64] */,
+                     double *stats_out /* [128] or NULL */);
 
 /* ---- plumbing -------------------------------------------------------------------------------- */
 void *busca_dev_alloc(busca_ctx *ctx, int64_t bytes);

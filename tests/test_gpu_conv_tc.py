@@ -80,3 +80,33 @@ def test_conv_tc_matches_simt(engine, idx, H, W, N):
     assert err < 1e-2, f"conv {idx} cin={cin} cout={cout} k={k} s={stride} {H}x{W} N={N}: max rel err {err}"   # <= 1 bf16 ulp of the largest value
     assert np.mean(tc != ref) < 0.05                      # the two fp32 accumulation orders round differently only rarely
     assert np.allclose(stats[1], stats[0], rtol=2e-3, atol=2e-3 * np.abs(stats[0]).max())
+
+
+@pytest.mark.parametrize("N", [1, 5])
+def test_stem_tc_matches_simt(engine, N):
+    """7x7 stride-2 stem as an overlapping-window TMA GEMM vs the direct SIMT kernel (fp32 weights / inputs)."""
+    from oracle import crop as ocrop
+    rng = np.random.default_rng(N)
+    frame = synth.make_frame(3 + N)
+    b = synth.random_boxes(rng, N)
+    b[:, 2:] += b[:, :2]
+    patches = ocrop.get_image_crops(frame, b)
+    slots = engine.alloc_slots(N)
+    engine.bank_upload(patches, slots)
+    sl = np.ascontiguousarray(slots, np.int32)
+    if N > 1:
+        sl[-1] = -1                                   # the all-zero filler image
+    outs, stats = [], []
+    for use_tc in (0, 1):
+        o = np.empty((N, 192, 64, 64), np.uint16)
+        st = np.empty(128, np.float64)
+        rc = engine.L.busca_debug_stem(engine.h, sl.ctypes.data_as(C.c_void_p), N, use_tc, o.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
+        assert rc == 0, engine.L.busca_last_error().decode()
+        outs.append(bf16_to_f32(o))
+        stats.append(st)
+    engine.free_slots(slots)
+    ref, tc = outs
+    assert np.isfinite(tc).all()
+    err = np.abs(tc - ref).max() / np.abs(ref).max()
+    assert err < 2e-2, err
+    assert np.allclose(stats[1], stats[0], rtol=2e-2, atol=2e-2 * np.abs(stats[0]).max())
