@@ -41,13 +41,21 @@ class StepArgs(C.Structure):
                 ("probs_dev", C.c_void_p), ("keep_dev", C.c_void_p)]
 
 
+class DebugConvArgs(C.Structure):
+    _fields_ = [("conv_index", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("use_tc", C.c_int32),
+                ("mode", C.c_int32), ("in_bf16", C.c_void_p), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p),
+                ("e_scale", C.c_void_p), ("e_shift", C.c_void_p), ("idt_bf16", C.c_void_p), ("ds_index", C.c_int32),
+                ("ds_H", C.c_int32), ("ds_W", C.c_int32), ("ds_in_bf16", C.c_void_p), ("ds_scale", C.c_void_p),
+                ("ds_shift", C.c_void_p), ("out_bf16", C.c_void_p), ("stats_out", C.c_void_p)]
+
+
 EXPORTS = [
     "busca_version", "busca_last_error", "busca_create", "busca_destroy", "busca_load_tensor", "busca_finalize",
     "busca_upload_frame", "busca_bank_reserve", "busca_bank_capacity", "busca_crop", "busca_bank_upload",
     "busca_bank_download", "busca_center_distance", "busca_iou", "busca_motion_proposals", "busca_frame_geometry",
     "busca_reid_embed", "busca_associate", "busca_transformer", "busca_frame_step_dev", "busca_dev_alloc",
     "busca_dev_free", "busca_memcpy_h2d", "busca_memcpy_d2h", "busca_sync", "busca_stream", "busca_kernel_launches",
-    "busca_set_profiling", "busca_last_profile", "busca_debug_conv", "busca_conv_info", "busca_debug_stem",
+    "busca_set_profiling", "busca_last_profile", "busca_debug_conv", "busca_debug_conv_ex", "busca_conv_info", "busca_debug_stem",
 ]
 
 
@@ -105,6 +113,7 @@ def load(build_if_missing: bool = True):
     L.busca_last_profile.argtypes = [vp]
     L.busca_last_profile.restype = C.c_char_p
     L.busca_debug_conv.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    L.busca_debug_conv_ex.argtypes = [vp, C.POINTER(DebugConvArgs)]
     L.busca_conv_info.argtypes = [vp, C.c_int32, vp]
     L.busca_debug_stem.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp]
     _lib = L

@@ -56,6 +56,7 @@ struct HostTensor {
 
 struct TLayer {
     float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b;
+    void *in_w16, *out_w16, *l1_w16, *l2_w16;      // bf16 copies for the tensor-core linears (bf16 mode)
 };
 
 struct ProfEntry {
@@ -76,6 +77,7 @@ struct busca_ctx {
     float *red_w = nullptr, *red_b = nullptr, *lut = nullptr;
     // Transformer
     float *enc_w = nullptr, *enc_b = nullptr, *sep = nullptr, *non = nullptr, *bad = nullptr;
+    void *enc_w16 = nullptr;
     std::vector<TLayer> layers;
     float *dec_g = nullptr, *dec_b = nullptr, *dec_w = nullptr, *dec_bias = nullptr;
     __half *pe_xy = nullptr, *pe_size = nullptr, *pe_t = nullptr;
@@ -251,6 +253,13 @@ static float *upload_named(busca_ctx *c, const std::string &name, std::initializ
     const HostTensor *t = find(c, name, shape);
     return t ? upload(c, t->f.data(), t->f.size()) : nullptr;
 }
+static void *upload_named_bf16(busca_ctx *c, const std::string &name, std::initializer_list<int64_t> shape) {
+    const HostTensor *t = find(c, name, shape);
+    if (!t) return nullptr;
+    std::vector<__nv_bfloat16> h(t->f.size());
+    for (size_t i = 0; i < h.size(); ++i) h[i] = __float2bfloat16(t->f[i]);
+    return upload(c, h.data(), h.size());
+}
 #define NEED(ptr) do { if (!(ptr)) return g_err[0] ? BUSCA_ERR_STATE : set_err(BUSCA_ERR_NOMEM, "upload failed"); } while (0)
 
 extern "C" int busca_finalize(busca_ctx *c) {
@@ -306,6 +315,16 @@ extern "C" int busca_finalize(busca_ctx *c) {
             for (size_t i = 0; i < re.size(); ++i) h[i] = __float2bfloat16(re[i]);
             L.w16 = upload(c, h.data(), h.size());
             NEED(L.w16);
+            if (c->cfg.precision == BUSCA_PREC_BF16 && sp.cin <= 512) {
+                // tensor-core path: unrounded master + scratch for the per-call folded weights and transform parameters
+                L.w32m = upload(c, re.data(), re.size());
+                NEED(L.w32m);
+                L.w16s = upload(c, h.data(), h.size());
+                NEED(L.w16s);
+                std::vector<uint16_t> z(2 * (size_t)sp.cin, 0);
+                L.xf = upload(c, z.data(), z.size());
+                NEED(L.xf);
+            }
             // bf16 mode: the SIMT kernel multiplies by the same bf16-rounded weights as the tensor-core kernel
             if (c->cfg.precision == BUSCA_PREC_BF16)
                 for (size_t i = 0; i < re.size(); ++i) re[i] = __bfloat162float(h[i]);
@@ -330,6 +349,7 @@ extern "C" int busca_finalize(busca_ctx *c) {
     const int d = c->cfg.d_model, ff = c->cfg.ff_size;
     NEED(c->enc_w = upload_named(c, "encoder.weight", {d, d}));
     NEED(c->enc_b = upload_named(c, "encoder.bias", {d}));
+    NEED(c->enc_w16 = upload_named_bf16(c, "encoder.weight", {d, d}));
     NEED(c->sep = upload_named(c, "sep_token", {d}));
     NEED(c->non = upload_named(c, "non_token", {d}));
     NEED(c->bad = upload_named(c, "bad_token", {d}));
@@ -348,6 +368,10 @@ extern "C" int busca_finalize(busca_ctx *c) {
         NEED(t.n1_b = upload_named(c, p + "norm1.bias", {d}));
         NEED(t.n2_g = upload_named(c, p + "norm2.weight", {d}));
         NEED(t.n2_b = upload_named(c, p + "norm2.bias", {d}));
+        NEED(t.in_w16 = upload_named_bf16(c, p + "self_attn.in_proj_weight", {3 * d, d}));
+        NEED(t.out_w16 = upload_named_bf16(c, p + "self_attn.out_proj.weight", {d, d}));
+        NEED(t.l1_w16 = upload_named_bf16(c, p + "linear1.weight", {ff, d}));
+        NEED(t.l2_w16 = upload_named_bf16(c, p + "linear2.weight", {d, ff}));
         c->layers.push_back(t);
     }
     NEED(c->dec_g = upload_named(c, "decoder.0.weight", {d}));
@@ -546,8 +570,87 @@ extern "C" int busca_motion_proposals(busca_ctx *c, const double *mean, const ui
 // ------------------------------------------------------------------------------------------------
 // ReID forward on one BatchNorm batch (device pointers)
 // ------------------------------------------------------------------------------------------------
+// tcgen05 path (bf16): per bottleneck  conv1 -> conv2 -> conv3 (statistics only) [-> downsample (statistics only)] -> conv3 again
+// with BN3 + identity/downsample + ReLU in its epilogue.  BN + ReLU of conv1 / conv2 is applied to the consumer's A tile in
+// shared memory, so no elementwise pass and no raw conv3 / downsample tensor ever touches HBM.
+static int reid_forward_tc(busca_ctx *c, const int32_t *d_slots, int N, float *d_emb) {
+    const size_t big = (size_t)786432 * N * 2;
+    const size_t total = 3 * big + (size_t)393216 * N * 2 + (size_t)196608 * N * 2 + (size_t)N * 2048 * 4 + 1024;
+    cudaError_t e = c->ws_reid.ensure(total);
+    if (e != cudaSuccess) return set_err(BUSCA_ERR_NOMEM, "ReID workspace for %d patches (%.1f GB): %s", N, total / 1e9, cudaGetErrorString(e));
+    char *base = (char *)c->ws_reid.p;
+    void *X0 = base, *X1 = base + big, *RS = base + 2 * big;
+    void *R1 = base + 3 * big, *R2 = (char *)R1 + (size_t)393216 * N * 2;
+    float *pooled = (float *)((char *)R2 + (size_t)196608 * N * 2);
+    cudaStream_t s = c->stream;
+    CUDA_OK(cudaMemsetAsync(c->stats_pool, 0, c->stats_bytes, s));
+    ConvLayer &stem = c->convs[0];
+    if (stem_tc_scratch_bytes(N) > big) return set_err(BUSCA_ERR_STATE, "stem scratch does not fit");
+    LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, X1, RS, stem.stats, s));
+    LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, (long long)N * 192 * 64, s));
+    LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(RS, X0, N, 192, 64, 64, stem.scale, stem.shift, 1, s));
+    void *x = X0, *other = X1;
+    int H = 96, W = 32;
+    size_t ci = 1;
+    const int blocks[4] = {3, 4, 6, 3};
+    auto conv = [&](ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, const char *name) -> int {
+        char nm[96];
+        if (c->profiling)
+            snprintf(nm, sizeof(nm), "%s_tc[%d>%d s%d %dx%d%s]", name, L.cin, L.cout, L.stride, a.H, a.W,
+                     o.mode == TC_MODE_STATS ? " stats" : (o.mode == TC_MODE_FINAL ? (o.ds ? " final+ds" : " final") : ""));
+        LAUNCH(c, c->profiling ? nm : name, launch_conv_tc(L, a, o, s));
+        return BUSCA_OK;
+    };
+    int rc;
+    for (int li = 0; li < 4; ++li)
+        for (int b = 0; b < blocks[li]; ++b) {
+            ConvLayer &c1 = c->convs[ci], &c2 = c->convs[ci + 1], &c3 = c->convs[ci + 2];
+            const int st = c2.stride, Ho = H / st, Wo = W / st;
+            ConvArgs a{};
+            ConvTcOpts raw{}, stats{}, fin{};
+            stats.mode = TC_MODE_STATS;
+            fin.mode = TC_MODE_FINAL;
+            a.N = N;
+            a.in = x; a.out = R1; a.H = H; a.W = W; a.Ho = H; a.Wo = W; a.in_scale = nullptr; a.in_shift = nullptr;
+            if ((rc = conv(c1, a, raw, "conv1x1"))) return rc;
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c1, (long long)N * H * W, s));
+            LAUNCH(c, "bn_fold", launch_bn_fold(c1.scale, c1.shift, c2, s));
+            a.in = R1; a.out = R2; a.Ho = Ho; a.Wo = Wo; a.in_xf = c2.xf;
+            if ((rc = conv(c2, a, raw, "conv3x3"))) return rc;
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c2, (long long)N * Ho * Wo, s));
+            LAUNCH(c, "bn_fold", launch_bn_fold(c2.scale, c2.shift, c3, s));
+            ConvArgs a3{};
+            a3.N = N; a3.in = R2; a3.out = other; a3.H = Ho; a3.W = Wo; a3.Ho = Ho; a3.Wo = Wo; a3.in_xf = c3.xf;
+            if ((rc = conv(c3, a3, stats, "conv1x1"))) return rc;
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c3, (long long)N * Ho * Wo, s));
+            fin.e_scale = c3.scale; fin.e_shift = c3.shift;
+            if (b == 0) {
+                ConvLayer &ds = c->convs[ci + 3];
+                ConvArgs ad{};
+                ad.N = N; ad.in = x; ad.out = other; ad.H = H; ad.W = W; ad.Ho = Ho; ad.Wo = Wo;
+                if ((rc = conv(ds, ad, stats, "conv1x1"))) return rc;
+                LAUNCH(c, "bn_finalize", launch_bn_finalize(ds, (long long)N * Ho * Wo, s));
+                fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W; fin.ds_scale = ds.scale; fin.ds_shift = ds.shift;
+                ci += 4;
+            } else {
+                fin.idt = x;
+                ci += 3;
+            }
+            if ((rc = conv(c3, a3, fin, "conv1x1"))) return rc;
+            void *t = x; x = other; other = t;
+            H = Ho; W = Wo;
+        }
+    LAUNCH(c, "global_maxpool", launch_global_maxpool(x, pooled, N, H * W, 2048, 1, s));
+    LinearArgs la{};
+    la.A = pooled; la.W = c->red_w; la.bias = c->red_b; la.residual = nullptr; la.out = d_emb; la.M = N; la.N = 512; la.K = 2048; la.alpha = 1.f; la.act = 0;
+    LAUNCH(c, "linear", launch_linear_f32(la, s));
+    LAUNCH(c, "l2norm", launch_l2norm_rows(d_emb, N, 512, s));
+    return BUSCA_OK;
+}
+
 static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *d_emb) {
     if (N <= 0) return BUSCA_OK;
+    if (c->use_tc) return reid_forward_tc(c, d_slots, N, d_emb);
     const int bf16 = c->cfg.precision == BUSCA_PREC_BF16;
     const size_t es = bf16 ? 2 : 4;
     const size_t big = (size_t)786432 * N * es;
@@ -562,31 +665,16 @@ static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *
     CUDA_OK(cudaMemsetAsync(c->stats_pool, 0, c->stats_bytes, s));
 
     ConvLayer &stem = c->convs[0];
-    if (c->use_tc && stem_tc_scratch_bytes(N) <= big)          // scratch = the (still unused) second block buffer
-        LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, B, R3, stem.stats, s));
-    else
-        LAUNCH(c, "stem_conv7x7", launch_stem(c->bank, d_slots, N, c->lut, stem, R3, bf16, s));
+    LAUNCH(c, "stem_conv7x7", launch_stem(c->bank, d_slots, N, c->lut, stem, R3, bf16, s));
     LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, (long long)N * 192 * 64, s));
     LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(R3, A, N, 192, 64, 64, stem.scale, stem.shift, bf16, s));
     void *x = A, *other = B;
     int H = 96, W = 32;
     size_t ci = 1;
     const int blocks[4] = {3, 4, 6, 3};
-    const bool tc = c->use_tc;
-    // One convolution.  SIMT path: the producer's BN+ReLU is applied while loading A (deferred).  tcgen05 path: TMA feeds
-    // the tensor core directly from HBM, so the activated tensor is materialised in place first.
+    // SIMT path (fp32 parity mode, or bf16 storage with BUSCA_CONV=simt): the producer's BN+ReLU is applied while loading A
     auto conv = [&](ConvLayer &L, ConvArgs a, const char *name) -> int {
-        if (tc) {
-            if (a.in_scale) {
-                LAUNCH(c, "bn_relu", launch_bn_relu_inplace(const_cast<void *>(a.in), a.in_scale, a.in_shift, (long long)a.N * a.H * a.W, L.cin, bf16, s));
-                a.in_scale = a.in_shift = nullptr;
-            }
-            char nm[64];
-            snprintf(nm, sizeof(nm), "%s_tc[%d>%d s%d %dx%d]", name, L.cin, L.cout, L.stride, a.H, a.W);
-            LAUNCH(c, c->profiling ? nm : name, launch_conv_tc(L, a, s));
-        } else {
-            LAUNCH(c, name, launch_conv_simt(L, a, bf16, s));
-        }
+        LAUNCH(c, name, launch_conv_simt(L, a, bf16, s));
         return BUSCA_OK;
     };
     int rc;
@@ -660,19 +748,32 @@ static int transformer_dev(busca_ctx *c, int T, int L, int C, const float *mem_e
     size_t off = 0;
     auto take = [&](size_t n_floats) { size_t r = off; off += (n_floats * 4 + 255) & ~(size_t)255; return r; };
     size_t o_me = take((size_t)T * L * d), o_ce = take((size_t)T * C * d), o_x = take(rows * d), o_y = take(rows * d), o_qkv = take(rows * 3 * d),
-           o_att = take(rows * d), o_h = take(rows * ff);
+           o_att = take(rows * d), o_h = take(rows * ff), o_a16 = take(rows * (size_t)(ff > d ? ff : d) / 2 + 64);
     CUDA_OK(c->ws_tr.ensure(off));
     char *b = (char *)c->ws_tr.p;
     float *me = (float *)(b + o_me), *ce = (float *)(b + o_ce), *X = (float *)(b + o_x), *Y = (float *)(b + o_y), *QKV = (float *)(b + o_qkv),
           *ATT = (float *)(b + o_att), *Hd = (float *)(b + o_h);
     cudaStream_t s = c->stream;
     const float alpha = (float)sqrt((double)d);                    // * np.sqrt(self.dim_model), network.py:203-204
+    // bf16 mode: the GEMMs run on the tensor cores (A cast to bf16 per call, fp32 accumulate / bias / residual / output)
+    const bool tc = c->use_tc;
+    void *A16 = b + o_a16;
+    auto linear = [&](const LinearArgs &g, const void *w16) -> int {
+        if (tc) {
+            LAUNCH(c, "cast_bf16", launch_cast_bf16(g.A, A16, (long long)g.M * g.K, s));
+            LAUNCH(c, "linear", launch_linear_tc(A16, w16, g, s));
+        } else {
+            LAUNCH(c, "linear", launch_linear_f32(g, s));
+        }
+        return BUSCA_OK;
+    };
+    int rc;
     LinearArgs la{};
     la.alpha = alpha; la.act = 0; la.residual = nullptr; la.W = c->enc_w; la.bias = c->enc_b; la.N = d; la.K = d;
     la.A = mem_emb; la.out = me; la.M = T * L;
-    LAUNCH(c, "linear", launch_linear_f32(la, s));
+    if ((rc = linear(la, c->enc_w16))) return rc;
     la.A = can_emb; la.out = ce; la.M = T * C;
-    LAUNCH(c, "linear", launch_linear_f32(la, s));
+    if ((rc = linear(la, c->enc_w16))) return rc;
     PeTables pe{c->pe_xy, c->pe_size, c->pe_t};
     LAUNCH(c, "build_tokens", launch_build_tokens(me, ce, c->sep, c->non, c->bad, idx, pe, T, L, C, X, s));
     if (o.input_seq) CUDA_OK(cudaMemcpyAsync(o.input_seq, X, rows * d * 4, cudaMemcpyDeviceToDevice, s));
@@ -681,15 +782,15 @@ static int transformer_dev(busca_ctx *c, int T, int L, int C, const float *mem_e
         LinearArgs g{};
         g.alpha = 1.f; g.M = (int)rows;
         g.A = X; g.W = ly.in_w; g.bias = ly.in_b; g.residual = nullptr; g.out = QKV; g.N = 3 * d; g.K = d; g.act = 0;
-        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        if ((rc = linear(g, ly.in_w16))) return rc;
         LAUNCH(c, "attention", launch_attention(QKV, ATT, T, S, c->cfg.nhead, d / c->cfg.nhead, s));
         g.A = ATT; g.W = ly.out_w; g.bias = ly.out_b; g.residual = X; g.out = Y; g.N = d; g.K = d;
-        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        if ((rc = linear(g, ly.out_w16))) return rc;
         LAUNCH(c, "layernorm", launch_layernorm(Y, ly.n1_g, ly.n1_b, X, (int)rows, d, s));
         g.A = X; g.W = ly.l1_w; g.bias = ly.l1_b; g.residual = nullptr; g.out = Hd; g.N = ff; g.K = d; g.act = act;
-        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        if ((rc = linear(g, ly.l1_w16))) return rc;
         g.A = Hd; g.W = ly.l2_w; g.bias = ly.l2_b; g.residual = X; g.out = Y; g.N = d; g.K = ff; g.act = 0;
-        LAUNCH(c, "linear", launch_linear_f32(g, s));
+        if ((rc = linear(g, ly.l2_w16))) return rc;
         LAUNCH(c, "layernorm", launch_layernorm(Y, ly.n2_g, ly.n2_b, X, (int)rows, d, s));
     }
     LAUNCH(c, "decoder", launch_decoder(X, T, S, L, C, c->dec_g, c->dec_b, c->dec_w, c->dec_bias, o.logits, o.probs, o.cand_rows, o.mem_logits, s));
@@ -866,29 +967,70 @@ extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
 // ------------------------------------------------------------------------------------------------
 // test hook: one convolution of the ReID network on caller-provided bf16 NHWC input
 // ------------------------------------------------------------------------------------------------
-extern "C" int busca_debug_conv(busca_ctx *c, int32_t conv_index, const uint16_t *in_bf16, int32_t N, int32_t H, int32_t W, int32_t use_tc,
-                                uint16_t *out_bf16, double *stats_out) {
-    if (!c || !c->finalized || conv_index < 1 || conv_index >= (int)c->convs.size() || !in_bf16 || !out_bf16) return set_err(BUSCA_ERR_ARG, "bad argument");
+extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d) {
+    if (!c || !d || !c->finalized || d->conv_index < 1 || d->conv_index >= (int)c->convs.size() || !d->in_bf16) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (!d->use_tc && d->mode != 0) return set_err(BUSCA_ERR_ARG, "the SIMT kernel only has the raw mode");
     CUDA_OK(cudaSetDevice(c->cfg.device));
-    ConvLayer &L = c->convs[conv_index];
-    const int Ho = H / L.stride, Wo = W / L.stride;
+    ConvLayer &L = c->convs[d->conv_index];
+    const int N = d->N, H = d->H, W = d->W, Ho = H / L.stride, Wo = W / L.stride;
+    const ConvLayer *DS = d->ds_index >= 0 ? &c->convs[d->ds_index] : nullptr;
+    Carver cv;
     const size_t in_b = (size_t)N * H * W * L.cin * 2, out_b = (size_t)N * Ho * Wo * L.cout * 2;
-    CUDA_OK(c->ws_reid.ensure(in_b + out_b + 512));
-    char *din = (char *)c->ws_reid.p, *dout = din + ((in_b + 255) & ~(size_t)255);
+    const size_t ds_b = DS ? (size_t)N * d->ds_H * d->ds_W * DS->cin * 2 : 0;
+    size_t o_in = cv.take(in_b), o_out = cv.take(out_b), o_idt = cv.take(out_b), o_ds = cv.take(ds_b + 16), o_par = cv.take((size_t)(2 * L.cin + 4 * L.cout) * 4);
+    CUDA_OK(c->ws_reid.ensure(cv.off + 512));
+    char *b = (char *)c->ws_reid.p;
+    float *par = (float *)(b + o_par);
+    float *in_sc = par, *in_sh = par + L.cin, *e_sc = in_sh + L.cin, *e_sh = e_sc + L.cout, *d_sc = e_sh + L.cout, *d_sh = d_sc + L.cout;
     cudaStream_t s = c->stream;
-    CUDA_OK(cudaMemcpyAsync(din, in_bf16, in_b, cudaMemcpyHostToDevice, s));
-    CUDA_OK(cudaMemsetAsync(dout, 0xff, out_b, s));
+    CUDA_OK(cudaMemcpyAsync(b + o_in, d->in_bf16, in_b, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(b + o_out, 0xff, out_b, s));
     CUDA_OK(cudaMemsetAsync(L.stats, 0, 2 * (size_t)L.cout * sizeof(double), s));
     ConvArgs a{};
-    a.in = din; a.out = dout; a.N = N; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo;
+    a.in = b + o_in; a.out = b + o_out; a.N = N; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo;
+    if (d->in_scale) {
+        CUDA_OK(cudaMemcpyAsync(in_sc, d->in_scale, (size_t)L.cin * 4, cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(in_sh, d->in_shift, (size_t)L.cin * 4, cudaMemcpyHostToDevice, s));
+        a.in_scale = in_sc; a.in_shift = in_sh;
+        if (d->use_tc) {
+            LAUNCH(c, "bn_fold", launch_bn_fold(in_sc, in_sh, L, s));
+            a.in_xf = L.xf;
+        }
+    }
+    ConvTcOpts o{};
+    o.mode = d->mode;
+    if (d->mode == TC_MODE_FINAL) {
+        if (!d->e_scale || !d->e_shift) return set_err(BUSCA_ERR_ARG, "final mode needs e_scale / e_shift");
+        CUDA_OK(cudaMemcpyAsync(e_sc, d->e_scale, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
+        CUDA_OK(cudaMemcpyAsync(e_sh, d->e_shift, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
+        o.e_scale = e_sc; o.e_shift = e_sh;
+        if (DS) {
+            if (!d->ds_in_bf16 || !d->ds_scale || !d->ds_shift) return set_err(BUSCA_ERR_ARG, "downsample inputs missing");
+            CUDA_OK(cudaMemcpyAsync(b + o_ds, d->ds_in_bf16, ds_b, cudaMemcpyHostToDevice, s));
+            CUDA_OK(cudaMemcpyAsync(d_sc, d->ds_scale, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
+            CUDA_OK(cudaMemcpyAsync(d_sh, d->ds_shift, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
+            o.ds = DS; o.ds_in = b + o_ds; o.ds_H = d->ds_H; o.ds_W = d->ds_W; o.ds_scale = d_sc; o.ds_shift = d_sh;
+        } else {
+            if (!d->idt_bf16) return set_err(BUSCA_ERR_ARG, "final mode needs an identity tensor or a downsample conv");
+            CUDA_OK(cudaMemcpyAsync(b + o_idt, d->idt_bf16, out_b, cudaMemcpyHostToDevice, s));
+            o.idt = b + o_idt;
+        }
+    }
     prof_reset(c);
-    if (use_tc) LAUNCH(c, "conv_tc", launch_conv_tc(L, a, s));
+    if (d->use_tc) LAUNCH(c, "conv_tc", launch_conv_tc(L, a, o, s));
     else LAUNCH(c, "conv_simt", launch_conv_simt(L, a, 1, s));
-    CUDA_OK(cudaMemcpyAsync(out_bf16, dout, out_b, cudaMemcpyDeviceToHost, s));
-    if (stats_out) CUDA_OK(cudaMemcpyAsync(stats_out, L.stats, 2 * (size_t)L.cout * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (d->out_bf16) CUDA_OK(cudaMemcpyAsync(d->out_bf16, b + o_out, out_b, cudaMemcpyDeviceToHost, s));
+    if (d->stats_out) CUDA_OK(cudaMemcpyAsync(d->stats_out, L.stats, 2 * (size_t)L.cout * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
     prof_collect(c);
     return BUSCA_OK;
+}
+extern "C" int busca_debug_conv(busca_ctx *c, int32_t conv_index, const uint16_t *in_bf16, int32_t N, int32_t H, int32_t W, int32_t use_tc,
+                                uint16_t *out_bf16, double *stats_out) {
+    busca_debug_conv_args d{};
+    d.conv_index = conv_index; d.N = N; d.H = H; d.W = W; d.use_tc = use_tc; d.mode = 0; d.in_bf16 = in_bf16; d.ds_index = -1;
+    d.out_bf16 = out_bf16; d.stats_out = stats_out;
+    return busca_debug_conv_ex(c, &d);
 }
 extern "C" int busca_debug_stem(busca_ctx *c, const int32_t *slots, int32_t N, int32_t use_tc, uint16_t *out_bf16, double *stats_out) {
     if (!c || !c->finalized || !slots || N <= 0 || !out_bf16) return set_err(BUSCA_ERR_ARG, "bad argument");

@@ -8,20 +8,34 @@
 //   out-of-bounds fill; stride-2 convolutions read one of four "parity" views of the input (a strided 4-D tensor
 //   map per parity), so no gather code and no elementStrides are needed.
 // * W tiles ([BN out-channels x 64] of the [Cout][K] weight matrix) arrive the same way.
+// * Batch-statistic BatchNorm makes every conv output wait for a grid-wide reduction, so the BN + ReLU of the
+//   PRODUCING convolution is applied here, to the A tile, in shared memory ("transform" warps: TMA -> smem ->
+//   transform -> tcgen05.mma), as ONE exact packed-bf16 instruction per two elements:
+//       relu(s*x + t) = |s| * max(sgn(s)*x, theta) + t,      theta = -t/|s|
+//   The transform writes a = max(x ^ signmask, theta) (max.bf16x2: no rounding at all), |s| is folded into this
+//   conv's weights once per call (bn_fold: bf16(W*|s|), a single rounding), and the "+ t" term only adds a per-
+//   output-channel constant sum(W*t) to the raw output - which the batch-statistic BN that follows EVERY conv
+//   removes exactly.  Spatial padding (and rows of images beyond N) must read theta, not 0, for that constant to be
+//   uniform: |s|*theta + t = 0 is the zero padding of the reference.  The raw conv output therefore makes exactly
+//   one HBM round trip, no separate BN-apply pass exists and the activation is never re-rounded to bf16.
 // * One elected thread issues tcgen05.mma (M=128, N=BN, K=16) four times per 64-wide K block; the fp32 accumulator
 //   lives in TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1).
-// * Epilogue warps read the accumulator with tcgen05.ld (thread = output pixel, registers = channels), reduce the
-//   per-channel sum / sum-of-squares needed by batch-statistic BatchNorm with a shuffle butterfly into a per-CTA
-//   shared-memory accumulator (flushed once per CTA with fp64 atomics), and store bf16 NHWC.
+// * Epilogue modes:
+//     RAW    tcgen05.ld -> bf16 -> 128B-swizzled staging tile -> TMA store; per-channel sum / sum of squares of the
+//            (bf16-rounded) output are read back from the staging tile with 64-bit shared loads into per-thread
+//            register accumulators that live across tiles (no shuffles, no atomics in the loop).
+//     STATS  the same without the store: the statistics-only first pass of a bottleneck's last 1x1 convolution.
+//     FINAL  second pass of that convolution: out = relu(acc*s3 + t3 + identity) where the identity tile is TMA-
+//            loaded into the staging buffer the result is then stored from; with DUAL the downsample 1x1 conv is
+//            accumulated in a second TMEM accumulator by the same kernel: relu(acc*s3+t3 + acc_ds*s_ds+t_ds).
+//            The raw output of conv3 / downsample is therefore NEVER written to HBM.
+//     F32    fp32 output with bias / scale / activation / residual (Transformer linears).
 // * Persistent: one CTA per SM, static round-robin over (pixel-tile, channel-tile) pairs, channel-tile fastest so
 //   CTAs running concurrently share the same A boxes through L2.
 //
-// * The bf16 output tile is staged in shared memory (128-byte swizzle, 64 channels per group, double buffered) and
-//   written with TMA stores, so HBM sees whole 128-byte lines; the per-channel statistics are reduced from the
-//   staged tile (thread = channel, no shuffles).
-//
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
-// (warp % 4 = TMEM lane quarter, two warps per quarter split the 64-channel group).
+// Warp roles (480 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = A-tile
+// transform, warps 6-13 = epilogue (warp % 4 = TMEM lane quarter, two warps per quarter split a 64-channel group),
+// warp 14 = identity-tile loader (FINAL mode).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,22 +45,33 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;            // bf16 elements per K block = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 320;
-constexpr int TC_EPI_THREADS = 256;
+constexpr int TC_THREADS = 480;
+constexpr int TC_XF_WARP0 = 2;       // transform warps 2..5
+constexpr int TC_EPI_WARP0 = 6;      // epilogue warps 6..13
+constexpr int TC_IDT_WARP = 14;
 constexpr int TC_MAX_TAPS = 9;
+constexpr int TC_XBUFS = 3;          // staging tiles (128 rows x 128 B)
+
+enum { MODE_RAW = 0, MODE_STATS = 1, MODE_FINAL = 2, MODE_F32 = 3 };
 
 struct TcParams {
     int tiles_m, tiles_n, k_iters, cin_blocks, ntaps;
+    int k1_iters;                    // k-iterations of the main operand (== k_iters unless DUAL)
     int tap_map[TC_MAX_TAPS], tap_dw[TC_MAX_TAPS], tap_dh[TC_MAX_TAPS];
+    int tap_bit[TC_MAX_TAPS];        // (dh+1)*3 + (dw+1): bit of the per-row 3x3 in-bounds mask
     int BW, BH, BI;                  // output-tile geometry, BW*BH*BI == 128, BW == Wo
     int Ho, Wo, Nimg, Cout, h_tiles; // h_tiles = Ho / BH
-    void *out;                       // bf16 [M, Cout] (out_f32 == 0) or float [M, Cout]
+    int Hv, Wv;                      // extent of the (parity view of the) input the taps index: padding mask of the transform
+    int mode;
+    const uint16_t *a_xf;            // [2*Cin] theta (bf16) then sign masks: transform of the A tile in shared memory, or null
+    const float *e_scale, *e_shift;  // FINAL: BN of this conv           [Cout]
+    const float *d_scale, *d_shift;  // FINAL + DUAL: BN of the downsample conv
+    void *out;                       // F32: float [M, Cout]
     double *stats;                   // [2*Cout] or null
-    const float *bias;               // [Cout] or null
-    const float *residual;           // float [M, Cout] or null (fp32 output only)
+    const float *bias;               // F32: [Cout] or null
+    const float *residual;           // F32: float [M, Cout] or null
     float alpha;
-    int act;                         // 0 none, 1 relu, 2 gelu
-    int out_f32;
+    int act;                         // F32: 0 none, 1 relu, 2 gelu
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -55,17 +80,25 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// SLEEP_NS > 0: back off between polls so a waiting role does not steal issue slots from the working warps
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try(bar, parity)) {
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -83,8 +116,43 @@ __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, 
                  "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void *smem, const CUtensorMap *map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h2);
 }
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), rows of KB bytes (128 or 64):
 // start>>4 | LBO(1)<<16 | SBO(8 rows * KB bytes >> 4)<<32 | version 1 <<46 | layout (SWIZZLE_128B = 2, SWIZZLE_64B = 4) <<61
@@ -117,45 +185,67 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+#define TMEM_LD_WAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+#define EPI_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
 
-template <int BN, int KB>
+template <int BN, int KB, bool DUAL>
 struct TcCfg {
     static constexpr int BKE = KB / 2;                               // bf16 elements per K block
-    static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 5 : 6);
-    static constexpr int OUT_STAGE_BYTES = TC_BM * 128;              // one 64-channel bf16 group of the output tile
+    static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
+    static constexpr int XBUF_BYTES = TC_BM * 128;                   // one 64-channel bf16 group of an output / identity tile
     static constexpr int A_BYTES = TC_BM * KB;                       // 16 KB (8 KB for the 64-byte stem rows)
     static constexpr int B_BYTES = BN * KB;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STATS_FLOATS = 2 * 2048;                    // per-CTA sum / sum-of-squares for up to 2048 channels
-    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + STATS_FLOATS * 4 + 256;
+    static constexpr int PAR_FLOATS = DUAL ? 4 * 2048 : 2 * 2048;    // statistics (RAW/STATS) or epilogue BN parameters (FINAL)
+    static constexpr int APAR_FLOATS = 512;                          // transform parameters: theta bf16 [512], sign mask u16 [512]
+    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + TC_XBUFS * XBUF_BYTES + (PAR_FLOATS + APAR_FLOATS) * 4 + 512;
 };
 
-template <int BN, int KB>
+template <int BN, int KB, bool DUAL>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                                                                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                                                                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                                                                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
+                                                                 const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapIdt,
                                                                  const TcParams p) {
-    using Cfg = TcCfg<BN, KB>;
+    using Cfg = TcCfg<BN, KB, DUAL>;
+    constexpr int G = BN / 64;                                                            // 64-channel groups per tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t *tiles = smem;
-    uint8_t *ostage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                              // 2 x [128 rows][128 B], swizzled
-    float *s_stats = reinterpret_cast<float *>(ostage + 2 * Cfg::OUT_STAGE_BYTES);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_stats + Cfg::STATS_FLOATS);
-    uint64_t *full = bars, *empty = bars + Cfg::STAGES, *tfull = bars + 2 * Cfg::STAGES, *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint8_t *xbuf = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                                // TC_XBUFS x [128 rows][128 B], swizzled
+    float *s_par = reinterpret_cast<float *>(xbuf + TC_XBUFS * Cfg::XBUF_BYTES);
+    float *s_apar = s_par + Cfg::PAR_FLOATS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + Cfg::APAR_FLOATS);
+    uint64_t *full = bars, *empty = full + Cfg::STAGES, *ready = empty + Cfg::STAGES, *tfull = ready + Cfg::STAGES, *tempty = tfull + 2;
+    uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xfree + TC_XBUFS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.tiles_m * p.tiles_n;
+    const bool xform = p.a_xf != nullptr;
+    const bool want_stats = p.stats != nullptr && (p.mode == MODE_RAW || p.mode == MODE_STATS);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        for (int b = 0; b < TC_XBUFS; ++b) { mbar_init(&xfull[b], 1); mbar_init(&xfree[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     }
-    if (p.stats)
-        for (int i = threadIdx.x; i < 2 * p.Cout; i += TC_THREADS) s_stats[i] = 0.f;
+    if (want_stats)
+        for (int i = threadIdx.x; i < 2 * p.Cout; i += TC_THREADS) s_par[i] = 0.f;
+    if (p.mode == MODE_FINAL) {
+        for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
+            s_par[i] = p.e_scale[i];
+            s_par[p.Cout + i] = p.e_shift[i];
+            if (DUAL) { s_par[2 * p.Cout + i] = p.d_scale[i]; s_par[3 * p.Cout + i] = p.d_shift[i]; }
+        }
+    }
+    if (xform) {
+        const int cin = p.cin_blocks * Cfg::BKE;
+        uint16_t *sp = reinterpret_cast<uint16_t *>(s_apar);
+        for (int i = threadIdx.x; i < cin; i += TC_THREADS) { sp[i] = p.a_xf[i]; sp[512 + i] = p.a_xf[cin + i]; }
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -174,14 +264,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
                 for (int kt = 0; kt < p.k_iters; ++kt) {
-                    const int tap = kt / p.cin_blocks, cb = kt - tap * p.cin_blocks;
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait<32>(&empty[stage], phase ^ 1);
                     uint8_t *a_dst = tiles + stage * Cfg::STAGE_BYTES, *b_dst = a_dst + Cfg::A_BYTES;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                    const int m = p.tap_map[tap];
-                    const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
-                    tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                    tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
+                    if (!DUAL || kt < p.k1_iters) {
+                        const int tap = kt / p.cin_blocks, cb = kt - tap * p.cin_blocks;
+                        const int m = p.tap_map[tap];
+                        const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
+                        tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+                        tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
+                    } else {                                     // downsample branch: 1x1 (strided view) on the block input
+                        const int cb = kt - p.k1_iters;
+                        tma_load_4d(a_dst, &mapA1, &full[stage], cb * Cfg::BKE, 0, h0, n0);
+                        tma_load_2d(b_dst, &mapB2, &full[stage], cb * Cfg::BKE, n_tile * BN);
+                    }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -197,90 +293,253 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                mbar_wait<32>(&tempty[acc], acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int kt = 0; kt < p.k_iters; ++kt) {
-                    mbar_wait(&full[stage], phase);
+                    const bool main_op = !DUAL || kt < p.k1_iters;
+                    mbar_wait<0>(&full[stage], phase);
+                    if (xform) mbar_wait<0>(&ready[stage], phase);      // the transform warps have rewritten the A tile
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + acc * 256 + (main_op ? 0 : BN);
+                    const bool first = main_op ? kt == 0 : kt == p.k1_iters;
                     const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = umma_desc<KB>(a_addr), db = umma_desc<KB>(a_addr + Cfg::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kt | k) != 0);
+                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
                     umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs retire
                     if (kt == p.k_iters - 1) umma_commit(&tfull[acc]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else {
-        // ===================================================== epilogue (warps 2..9)
-        const int e = threadIdx.x - 64;                // 0..255
-        const int q = warp & 3;                        // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;              // which 32 of the 64 channels of a group
+    } else if (warp < TC_EPI_WARP0) {
+        // ===================================================== A-tile transform: a = max(x ^ signmask, theta); theta in the padding
+        if (xform) {
+            const int tt = threadIdx.x - TC_XF_WARP0 * 32;   // 0..127
+            const int c = tt & 7, rb = tt >> 3;               // logical 16-byte chunk (8 channels), first row
+            const uint32_t col_off = (uint32_t)((c ^ (rb & 7)) << 4);
+            int r_hi[8], r_ni[8];
+            uint32_t r_wb[8];                                 // bit (dw+1): column r_wi+dw is inside the (view of the) input
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rb + 16 * i;
+                const int wi = r % p.BW;
+                r_hi[i] = (r / p.BW) % p.BH;
+                r_ni[i] = r / (p.BW * p.BH);
+                r_wb[i] = ((unsigned)(wi - 1) < (unsigned)p.Wv ? 1u : 0u) | ((unsigned)wi < (unsigned)p.Wv ? 2u : 0u) | ((unsigned)(wi + 1) < (unsigned)p.Wv ? 4u : 0u);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.tiles_n;
+                const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
+                // per row: bit (dh+1)*3+(dw+1) = the tap reads inside the input; bit 9 = row of an image beyond N (stays all-zero, so
+                // its output is exactly 0 and drops out of the batch statistics, as with the TMA zero fill of the untransformed path)
+                uint32_t m9[8], all9 = 0x1ffu;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int hh = h0 + r_hi[i];
+                    uint32_t m = 0x200u;
+                    if (n0 + r_ni[i] < p.Nimg) {
+                        m = 0;
+                        if ((unsigned)(hh - 1) < (unsigned)p.Hv) m |= r_wb[i];
+                        if ((unsigned)hh < (unsigned)p.Hv) m |= r_wb[i] << 3;
+                        if ((unsigned)(hh + 1) < (unsigned)p.Hv) m |= r_wb[i] << 6;
+                    }
+                    m9[i] = m;
+                    all9 &= m;
+                }
+                for (int kt = 0; kt < p.k_iters; ++kt) {
+                    if (!DUAL || kt < p.k1_iters) {
+                        const int tap = kt / p.cin_blocks, cb = kt - tap * p.cin_blocks;
+                        const int bit = p.tap_bit[tap];
+                        const uint32_t par = smem_u32(s_apar) + (uint32_t)(cb * 64 + c * 8) * 2;
+                        const uint4 th = lds128(par), sg = lds128(par + 1024);
+                        mbar_wait<0>(&full[stage], phase);
+                        const uint32_t base = smem_u32(tiles + stage * Cfg::STAGE_BYTES) + col_off;
+                        if ((all9 >> bit) & 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t addr = base + (uint32_t)(rb + 16 * i) * 128;
+                                uint4 v = lds128(addr);
+                                v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
+                                v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
+                                sts128(addr, v);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t addr = base + (uint32_t)(rb + 16 * i) * 128;
+                                uint4 v = lds128(addr);
+                                if ((m9[i] >> bit) & 1) {
+                                    v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
+                                    v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
+                                } else {
+                                    v = (m9[i] & 0x200u) ? make_uint4(0u, 0u, 0u, 0u) : th;
+                                }
+                                sts128(addr, v);
+                            }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA (async proxy)
+                    } else {
+                        mbar_wait<0>(&full[stage], phase);
+                    }
+                    mbar_arrive(&ready[stage]);     // every k-iteration, so the barrier phase tracks the stage ring
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < TC_IDT_WARP) {
+        // ===================================================== epilogue (warps 6..13)
+        const int e = threadIdx.x - TC_EPI_WARP0 * 32;   // 0..255
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int half = (warp - TC_EPI_WARP0) >> 2;     // which 32 of the 64 channels of a group
         const int row = q * 32 + lane;
-        const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / (p.BW * p.BH);
+        const uint32_t xb0 = smem_u32(xbuf);
+        const uint32_t row_off = (uint32_t)row * 128;
+        // statistics mapping: 4 channels (8 bytes) x 8 rows per thread and group
+        const int cq = e & 15, rsub = e >> 4;
+        const uint32_t st_off = (uint32_t)rsub * 128 + (uint32_t)((((cq >> 1) ^ (rsub & 7)) << 4) + (cq & 1) * 8);
+        float acc_s[G][4], acc_q[G][4];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc_s[g][j] = 0.f; acc_q[g][j] = 0.f; }
+        int stats_ntile = -1;
+        auto flush_stats = [&]() {
+            if (stats_ntile < 0) return;
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = stats_ntile * BN + g * 64 + cq * 4 + j;
+                    atomicAdd(&s_par[ch], acc_s[g][j]);
+                    atomicAdd(&s_par[p.Cout + ch], acc_q[g][j]);
+                    acc_s[g][j] = 0.f;
+                    acc_q[g][j] = 0.f;
+                }
+        };
         int it = 0, gcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
-            mbar_wait(&tfull[acc], acc_phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (!p.out_f32) {
-#pragma unroll 1
-                for (int g = 0; g < BN / 64; ++g, ++gcount) {
-                    uint8_t *st = ostage + (gcount & 1) * Cfg::OUT_STAGE_BYTES;
+            const uint32_t t_acc = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+            if (p.mode == MODE_RAW || p.mode == MODE_STATS) {
+                if (want_stats && n_tile != stats_ntile) { flush_stats(); stats_ntile = n_tile; }
+                mbar_wait<0>(&tfull[acc], acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < G; ++g, ++gcount) {
+                    const uint32_t st = xb0 + (gcount & 1) * Cfg::XBUF_BYTES;
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + acc * 256 + g * 64 + half * 32 + ((uint32_t)(q * 32) << 16), r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    tmem_ld32(t_acc + g * 64 + half * 32, r);
+                    TMEM_LD_WAIT();
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {       // 4 x 16 B = this thread's 32 channels of its row, swizzled like the TMA box
-                        uint32_t w[4];
+                        uint4 w;
+                        w.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+                        w.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+                        w.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+                        w.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+                        sts128(st + row_off + (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4), w);
+                    }
+                    if (p.mode == MODE_RAW) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // store(g-1) has released the buffer group g+1 will overwrite
+                    }
+                    EPI_BAR();
+                    if (p.mode == MODE_RAW && e == 0) tma_store_4d(xbuf + (gcount & 1) * Cfg::XBUF_BYTES, &mapOut, n_tile * BN + g * 64, 0, h0, n0);
+                    if (want_stats) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[j * 8 + 2 * k]), __uint_as_float(r[j * 8 + 2 * k + 1]));
-                            w[k] = *reinterpret_cast<uint32_t *>(&h2);
+                        for (int i = 0; i < 8; ++i) {
+                            const uint2 v = lds64(st + st_off + (uint32_t)i * 2048);
+                            const float x0 = bf_lo(v.x), x1 = bf_hi(v.x), x2 = bf_lo(v.y), x3 = bf_hi(v.y);
+                            acc_s[g][0] += x0; acc_q[g][0] = fmaf(x0, x0, acc_q[g][0]);
+                            acc_s[g][1] += x1; acc_q[g][1] = fmaf(x1, x1, acc_q[g][1]);
+                            acc_s[g][2] += x2; acc_q[g][2] = fmaf(x2, x2, acc_q[g][2]);
+                            acc_s[g][3] += x3; acc_q[g][3] = fmaf(x3, x3, acc_q[g][3]);
                         }
-                        const int chunk = (half * 4 + j) ^ (row & 7);
-                        *reinterpret_cast<uint4 *>(st + row * 128 + chunk * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            } else if (p.mode == MODE_FINAL) {
+                mbar_wait<0>(&tfull[acc], acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int g = 0; g < G; ++g, ++gcount) {
+                    const int b = gcount % TC_XBUFS;
+                    const uint32_t xph = (uint32_t)(gcount / TC_XBUFS) & 1;
+                    const uint32_t st = xb0 + b * Cfg::XBUF_BYTES;
+                    const int col0 = n_tile * BN + g * 64 + half * 32;
+                    uint32_t r[32];
+                    tmem_ld32(t_acc + g * 64 + half * 32, r);
+                    TMEM_LD_WAIT();
+                    const uint32_t ps = smem_u32(s_par) + (uint32_t)col0 * 4, pt = ps + (uint32_t)p.Cout * 4;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 s4 = lds128f(ps + j * 16), t4 = lds128f(pt + j * 16);
+                        v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), s4.x, t4.x);
+                        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, t4.y);
+                        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, t4.z);
+                        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, t4.w);
+                    }
+                    if (DUAL) {
+                        tmem_ld32(t_acc + BN + g * 64 + half * 32, r);
+                        TMEM_LD_WAIT();
+                        const uint32_t ds = ps + (uint32_t)p.Cout * 8, dt = ps + (uint32_t)p.Cout * 12;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 s4 = lds128f(ds + j * 16), t4 = lds128f(dt + j * 16);
+                            v[4 * j + 0] += fmaf(__uint_as_float(r[4 * j + 0]), s4.x, t4.x);
+                            v[4 * j + 1] += fmaf(__uint_as_float(r[4 * j + 1]), s4.y, t4.y);
+                            v[4 * j + 2] += fmaf(__uint_as_float(r[4 * j + 2]), s4.z, t4.z);
+                            v[4 * j + 3] += fmaf(__uint_as_float(r[4 * j + 3]), s4.w, t4.w);
+                        }
+                    } else {
+                        mbar_wait<0>(&xfull[b], xph);           // identity tile of this group has landed in the staging buffer
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t addr = st + row_off + (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
+                        uint4 w;
+                        if (!DUAL) {
+                            const uint4 d = lds128(addr);
+                            w.x = pack_bf16(fmaxf(v[8 * j + 0] + bf_lo(d.x), 0.f), fmaxf(v[8 * j + 1] + bf_hi(d.x), 0.f));
+                            w.y = pack_bf16(fmaxf(v[8 * j + 2] + bf_lo(d.y), 0.f), fmaxf(v[8 * j + 3] + bf_hi(d.y), 0.f));
+                            w.z = pack_bf16(fmaxf(v[8 * j + 4] + bf_lo(d.z), 0.f), fmaxf(v[8 * j + 5] + bf_hi(d.z), 0.f));
+                            w.w = pack_bf16(fmaxf(v[8 * j + 6] + bf_lo(d.w), 0.f), fmaxf(v[8 * j + 7] + bf_hi(d.w), 0.f));
+                        } else {
+                            w.x = pack_bf16(fmaxf(v[8 * j + 0], 0.f), fmaxf(v[8 * j + 1], 0.f));
+                            w.y = pack_bf16(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f));
+                            w.z = pack_bf16(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f));
+                            w.w = pack_bf16(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f));
+                        }
+                        sts128(addr, w);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // store(g-1) has released the buffer group g+1 will overwrite
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (e == 0) {
-                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)&mapOut),
-                                     "r"(smem_u32(st)), "r"(n_tile * BN + g * 64), "r"(0), "r"(h0), "r"(n0)
-                                     : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // every earlier store has finished reading its buffer
+                        if (gcount > 0) mbar_arrive(&xfree[(gcount - 1) % TC_XBUFS]);
                     }
-                    if (p.stats) {                      // thread = channel: 32 rows of one channel from the staged bf16 tile
-                        const int col = e & 63, part = e >> 6;
-                        float sum = 0.f, sq = 0.f;
-#pragma unroll 8
-                        for (int i = 0; i < 32; ++i) {
-                            const int rr = part * 32 + i;
-                            const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16 *>(st + rr * 128 + (((col >> 3) ^ (rr & 7)) << 4) + (col & 7) * 2);
-                            const float x = __bfloat162float(v);
-                            sum += x;
-                            sq = fmaf(x, x, sq);
-                        }
-                        atomicAdd(&s_stats[n_tile * BN + g * 64 + col], sum);
-                        atomicAdd(&s_stats[p.Cout + n_tile * BN + g * 64 + col], sq);
-                    }
+                    EPI_BAR();
+                    if (e == 0) tma_store_4d(xbuf + b * Cfg::XBUF_BYTES, &mapOut, n_tile * BN + g * 64, 0, h0, n0);
                 }
             } else if (half == 0) {
                 // fp32 output with bias / scale / activation / residual (linear layers): direct stores, 4 warps
+                mbar_wait<0>(&tfull[acc], acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int wi = row % p.BW, hi = (row / p.BW) % p.BH, ni = row / (p.BW * p.BH);
                 const int img = n0 + ni;
                 const bool valid = img < p.Nimg;
                 const long long m = ((long long)img * p.Ho + h0 + hi) * p.Wo + wi;
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + acc * 256 + c * 32 + ((uint32_t)(q * 32) << 16), r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    tmem_ld32(t_acc + c * 32, r);
+                    TMEM_LD_WAIT();
                     if (valid) {
                         const int col0 = n_tile * BN + c * 32;
                         float *o = reinterpret_cast<float *>(p.out) + m * p.Cout + col0;
@@ -297,18 +556,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         }
                     }
                 }
+            } else {
+                mbar_wait<0>(&tfull[acc], acc_phase);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        if (want_stats) flush_stats();
         if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+        // ===================================================== identity-tile loader (FINAL, single accumulator)
+        if (p.mode == MODE_FINAL && !DUAL && lane == 0) {
+            int gcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+                const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
+                for (int g = 0; g < G; ++g, ++gcount) {
+                    const int b = gcount % TC_XBUFS;
+                    const uint32_t xph = (uint32_t)(gcount / TC_XBUFS) & 1;
+                    mbar_wait<64>(&xfree[b], xph ^ 1);
+                    mbar_expect_tx(&xfull[b], Cfg::XBUF_BYTES);
+                    tma_load_4d(xbuf + b * Cfg::XBUF_BYTES, &mapIdt, &xfull[b], n_tile * BN + g * 64, 0, h0, n0);
+                }
+            }
+        }
     }
 
     __syncthreads();
-    if (p.stats) {
+    if (want_stats) {
         for (int i = threadIdx.x; i < 2 * p.Cout; i += TC_THREADS) {
-            const float v = s_stats[i];
+            const float v = s_par[i];
             if (v != 0.f) atomicAdd(p.stats + i, (double)v);
         }
     }
@@ -360,11 +638,15 @@ bool make_map2(CUtensorMap *m, const void *base, long long K, long long rows, in
 
 int g_num_sms = 0;
 
-template <int BN, int KB = 128>
-cudaError_t launch_tc(const CUtensorMap *maps, const CUtensorMap &mapB, const CUtensorMap &mapOut, const TcParams &p, cudaStream_t s) {
+struct TcMaps {
+    CUtensorMap a[4], b, b2, out, idt;
+};
+
+template <int BN, int KB = 128, bool DUAL = false>
+cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, KB>::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, KB, DUAL>::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -374,8 +656,10 @@ cudaError_t launch_tc(const CUtensorMap *maps, const CUtensorMap &mapB, const CU
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int total = p.tiles_m * p.tiles_n;
-    const int grid = total < g_num_sms ? total : g_num_sms;
-    conv_tc_kernel<BN, KB><<<grid, TC_THREADS, TcCfg<BN, KB>::SMEM, s>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapOut, p);
+    int grid = total < g_num_sms ? total : g_num_sms;
+    // keep a CTA on one channel tile (its statistics accumulators stay in registers) when that costs < 3 % of the SMs
+    if (p.tiles_n > 1 && grid > p.tiles_n && grid % p.tiles_n != 0 && (grid % p.tiles_n) * 32 < grid) grid -= grid % p.tiles_n;
+    conv_tc_kernel<BN, KB, DUAL><<<grid, TC_THREADS, TcCfg<BN, KB, DUAL>::SMEM, s>>>(m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
     return cudaGetLastError();
 }
 
@@ -393,36 +677,49 @@ static bool tile_geometry(int Ho, int Wo, int &BW, int &BH, int &BI) {
     return true;
 }
 
-cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, cudaStream_t s) {
+cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s) {
     if (L.cin % TC_BK != 0 || L.cout % 64 != 0 || !L.w16) return cudaErrorInvalidValue;
     if (L.stride != 1 && L.stride != 2) return cudaErrorInvalidValue;
     if (L.stride == 2 && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
+    if (a.in_xf && (L.cin > 512 || !L.w16s)) return cudaErrorInvalidValue;
+    const bool dual = o.mode == TC_MODE_FINAL && o.ds != nullptr;
+    if (o.mode == TC_MODE_FINAL && (L.k != 1 || L.stride != 1 || !o.e_scale || !o.e_shift || (!dual && !o.idt))) return cudaErrorInvalidValue;
+    if (dual && (o.ds->k != 1 || o.ds->cout != L.cout || o.ds->cin % TC_BK != 0 || !o.ds->w16 || !o.ds_in || !o.ds_scale || !o.ds_shift)) return cudaErrorInvalidValue;
     TcParams p{};
     if (!tile_geometry(a.Ho, a.Wo, p.BW, p.BH, p.BI)) return cudaErrorInvalidValue;
-    const int BN = L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64);
+    const int BN = dual ? 128 : (L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64));
+    if (L.cout % BN != 0) return cudaErrorInvalidValue;
     p.tiles_n = L.cout / BN;
     p.h_tiles = a.Ho / p.BH;
     p.tiles_m = ((a.N + p.BI - 1) / p.BI) * p.h_tiles;
     p.cin_blocks = L.cin / TC_BK;
     p.ntaps = L.k * L.k;
-    p.k_iters = p.ntaps * p.cin_blocks;
+    p.k1_iters = p.ntaps * p.cin_blocks;
+    p.k_iters = p.k1_iters + (dual ? o.ds->cin / TC_BK : 0);
     p.Ho = a.Ho; p.Wo = a.Wo; p.Nimg = a.N; p.Cout = L.cout;
-    p.out = a.out; p.stats = L.stats; p.bias = nullptr; p.residual = nullptr; p.alpha = 1.f; p.act = 0; p.out_f32 = 0;
-    CUtensorMap maps[4];
+    p.Hv = a.H / L.stride; p.Wv = a.W / L.stride;
+    p.mode = o.mode == TC_MODE_FINAL ? MODE_FINAL : (o.mode == TC_MODE_STATS ? MODE_STATS : MODE_RAW);
+    p.a_xf = a.in_xf;
+    p.e_scale = o.e_scale; p.e_shift = o.e_shift; p.d_scale = o.ds_scale; p.d_shift = o.ds_shift;
+    p.out = a.out; p.stats = p.mode == MODE_FINAL ? nullptr : L.stats; p.bias = nullptr; p.residual = nullptr; p.alpha = 1.f; p.act = 0;
+    TcMaps m;
     const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(a.in);
     const long long C = L.cin, W = a.W, H = a.H;
     bool ok = true;
     if (L.stride == 1) {
-        ok = make_map4(&maps[0], in, (int)C, a.W, a.H, a.N, C, W * C, H * W * C, p.BW, p.BH, p.BI);
-        maps[1] = maps[2] = maps[3] = maps[0];
+        ok = make_map4(&m.a[0], in, (int)C, a.W, a.H, a.N, C, W * C, H * W * C, p.BW, p.BH, p.BI);
+        m.a[1] = m.a[2] = m.a[3] = m.a[0];
         const int pad = L.k / 2;
         for (int r = 0; r < L.k; ++r)
-            for (int q = 0; q < L.k; ++q) { p.tap_map[r * L.k + q] = 0; p.tap_dh[r * L.k + q] = r - pad; p.tap_dw[r * L.k + q] = q - pad; }
+            for (int q = 0; q < L.k; ++q) {
+                p.tap_map[r * L.k + q] = 0; p.tap_dh[r * L.k + q] = r - pad; p.tap_dw[r * L.k + q] = q - pad;
+                p.tap_bit[r * L.k + q] = (r - pad + 1) * 3 + (q - pad + 1);
+            }
     } else {
         // parity views: input pixel (2*ho + r - pad, 2*wo + q - pad) = view[ph][pw] at (ho + dh, wo + dw)
         for (int ph = 0; ph < 2; ++ph)
             for (int pw = 0; pw < 2; ++pw)
-                ok = ok && make_map4(&maps[ph * 2 + pw], in + (ph * W + pw) * C, (int)C, a.W / 2, a.H / 2, a.N, 2 * C, 2 * W * C, H * W * C, p.BW, p.BH, p.BI);
+                ok = ok && make_map4(&m.a[ph * 2 + pw], in + (ph * W + pw) * C, (int)C, a.W / 2, a.H / 2, a.N, 2 * C, 2 * W * C, H * W * C, p.BW, p.BH, p.BI);
         const int pad = L.k / 2;
         for (int r = 0; r < L.k; ++r)
             for (int q = 0; q < L.k; ++q) {
@@ -431,17 +728,30 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, cudaStream_t s
                 p.tap_map[r * L.k + q] = ph * 2 + pw;
                 p.tap_dh[r * L.k + q] = (oy - ph) / 2;         // -1 -> -1, 0 -> 0, +1 -> 0
                 p.tap_dw[r * L.k + q] = (ox - pw) / 2;
+                p.tap_bit[r * L.k + q] = (p.tap_dh[r * L.k + q] + 1) * 3 + (p.tap_dw[r * L.k + q] + 1);
             }
     }
-    CUtensorMap mapB, mapOut;
-    ok = ok && make_map2(&mapB, L.w16, (long long)p.ntaps * L.cin, L.cout, BN);
+    ok = ok && make_map2(&m.b, a.in_xf ? L.w16s : L.w16, (long long)p.ntaps * L.cin, L.cout, BN);   // w16s = bf16(W * |scale_in|)
+    m.b2 = m.b;
+    if (dual) {
+        // downsample branch: 1x1 conv (stride ds->stride) on the block input [N, ds_H, ds_W, ds->cin]; view (0,0) for stride 2
+        const long long Cd = o.ds->cin, Wd = o.ds_W, Hd = o.ds_H;
+        const int sd = o.ds->stride;
+        if (Hd / sd != a.Ho || Wd / sd != a.Wo) return cudaErrorInvalidValue;
+        ok = ok && make_map4(&m.a[1], o.ds_in, (int)Cd, (int)(Wd / sd), (int)(Hd / sd), a.N, sd * Cd, sd * Wd * Cd, Hd * Wd * Cd, p.BW, p.BH, p.BI);
+        ok = ok && make_map2(&m.b2, o.ds->w16, Cd, L.cout, BN);
+    }
     // output [N][Ho][Wo][Cout] bf16, stored one 64-channel group of a tile at a time; images beyond N are clipped by TMA
-    ok = ok && make_map4(&mapOut, a.out, L.cout, a.Wo, a.Ho, a.N, L.cout, (long long)a.Wo * L.cout, (long long)a.Ho * a.Wo * L.cout, p.BW, p.BH, p.BI);
+    ok = ok && make_map4(&m.out, a.out, L.cout, a.Wo, a.Ho, a.N, L.cout, (long long)a.Wo * L.cout, (long long)a.Ho * a.Wo * L.cout, p.BW, p.BH, p.BI);
+    m.idt = m.out;
+    if (p.mode == MODE_FINAL && !dual)
+        ok = ok && make_map4(&m.idt, o.idt, L.cout, a.Wo, a.Ho, a.N, L.cout, (long long)a.Wo * L.cout, (long long)a.Ho * a.Wo * L.cout, p.BW, p.BH, p.BI);
     if (!ok) return cudaErrorInvalidValue;
+    if (dual) return launch_tc<128, 128, true>(m, p, s);
     switch (BN) {
-        case 256: return launch_tc<256>(maps, mapB, mapOut, p, s);
-        case 128: return launch_tc<128>(maps, mapB, mapOut, p, s);
-        default: return launch_tc<64>(maps, mapB, mapOut, p, s);
+        case 256: return launch_tc<256>(m, p, s);
+        case 128: return launch_tc<128>(m, p, s);
+        default: return launch_tc<64>(m, p, s);
     }
 }
 
@@ -456,19 +766,22 @@ cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const Linea
     p.tiles_m = (la.M + 127) / 128;
     p.cin_blocks = la.K / TC_BK;
     p.ntaps = 1;
-    p.k_iters = p.cin_blocks;
+    p.k_iters = p.k1_iters = p.cin_blocks;
     p.tap_map[0] = 0; p.tap_dw[0] = 0; p.tap_dh[0] = 0;
-    p.Ho = 1; p.Wo = 1; p.Nimg = la.M; p.Cout = la.N;
-    p.out = la.out; p.stats = nullptr; p.bias = la.bias; p.residual = la.residual; p.alpha = la.alpha; p.act = la.act; p.out_f32 = 1;
-    CUtensorMap maps[4], mapB;
-    bool ok = make_map4(&maps[0], A_bf16, la.K, 1, 1, la.M, la.K, la.K, la.K, 1, 1, 128);
-    maps[1] = maps[2] = maps[3] = maps[0];
-    ok = ok && make_map2(&mapB, W_bf16, la.K, la.N, BN);
+    p.Ho = 1; p.Wo = 1; p.Nimg = la.M; p.Cout = la.N; p.Hv = 1; p.Wv = 1;
+    p.mode = MODE_F32;
+    p.out = la.out; p.stats = nullptr; p.bias = la.bias; p.residual = la.residual; p.alpha = la.alpha; p.act = la.act;
+    TcMaps m;
+    bool ok = make_map4(&m.a[0], A_bf16, la.K, 1, 1, la.M, la.K, la.K, la.K, 1, 1, 128);
+    m.a[1] = m.a[2] = m.a[3] = m.a[0];
+    ok = ok && make_map2(&m.b, W_bf16, la.K, la.N, BN);
     if (!ok) return cudaErrorInvalidValue;
+    m.b2 = m.b;
+    m.out = m.idt = m.a[0];                                      // no TMA store on the fp32-output path
     switch (BN) {
-        case 256: return launch_tc<256>(maps, mapB, maps[0], p, s);      // no TMA store on the fp32-output path
-        case 128: return launch_tc<128>(maps, mapB, maps[0], p, s);
-        default: return launch_tc<64>(maps, mapB, maps[0], p, s);
+        case 256: return launch_tc<256>(m, p, s);
+        case 128: return launch_tc<128>(m, p, s);
+        default: return launch_tc<64>(m, p, s);
     }
 }
 
@@ -525,22 +838,25 @@ cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, con
     TcParams p{};
     p.BW = 64; p.BH = 2; p.BI = 1;
     p.tiles_n = 1; p.h_tiles = 192 / 2; p.tiles_m = N * p.h_tiles;
-    p.cin_blocks = 1; p.ntaps = 7; p.k_iters = 7;
+    p.cin_blocks = 1; p.ntaps = 7; p.k_iters = p.k1_iters = 7;
     for (int ky = 0; ky < 7; ++ky) {
         const int oy = ky - 3, ph = oy & 1;
         p.tap_map[ky] = ph; p.tap_dh[ky] = (oy - ph) / 2; p.tap_dw[ky] = 0;
     }
-    p.Ho = 192; p.Wo = 64; p.Nimg = N; p.Cout = 64;
+    p.Ho = 192; p.Wo = 64; p.Nimg = N; p.Cout = 64; p.Hv = 192; p.Wv = 64;
+    p.mode = MODE_RAW;
     p.out = out; p.stats = stats; p.alpha = 1.f;
     const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(scratch);
     const long long pitch = (long long)STEM_PITCH_PX * 4;             // elements per padded row
-    CUtensorMap maps[4], mapB, mapOut;
+    TcMaps m;
     bool ok = true;
     for (int ph = 0; ph < 2; ++ph)      // dims {32 window elements, 64 ox (stride 8 el = 16 B), 192 rows of this parity, N}
-        ok = ok && make_map4(&maps[ph], in + ph * pitch, 32, 64, 192, N, 8, 2 * pitch, (long long)PATCH_H * pitch, 64, 2, 1, 32);
-    maps[2] = maps[3] = maps[0];
-    ok = ok && make_map2(&mapB, wstem, 7 * 32, 64, 64, 32);
-    ok = ok && make_map4(&mapOut, out, 64, 64, 192, N, 64, 64 * 64, 192LL * 64 * 64, 64, 2, 1);
+        ok = ok && make_map4(&m.a[ph], in + ph * pitch, 32, 64, 192, N, 8, 2 * pitch, (long long)PATCH_H * pitch, 64, 2, 1, 32);
+    m.a[2] = m.a[3] = m.a[0];
+    ok = ok && make_map2(&m.b, wstem, 7 * 32, 64, 64, 32);
+    ok = ok && make_map4(&m.out, out, 64, 64, 192, N, 64, 64 * 64, 192LL * 64 * 64, 64, 2, 1);
     if (!ok) return cudaErrorInvalidValue;
-    return launch_tc<64, 64>(maps, mapB, mapOut, p, s);
+    m.b2 = m.b;
+    m.idt = m.out;
+    return launch_tc<64, 64>(m, p, s);
 }

@@ -30,8 +30,11 @@ cudaError_t launch_crop_resize(const uint8_t *frame, int H, int W, int64_t row_s
 // ---------------------------------------------------------------- reid.cu
 struct ConvLayer {
     int cin, cout, k, stride;
-    float *w32;                 // [cout][k][k][cin] fp32
-    void *w16;                  // same layout, bf16 (bf16 mode)
+    float *w32;                 // [cout][k][k][cin] fp32 (bf16 mode: rounded to bf16 values, so SIMT and tensor-core kernels agree)
+    float *w32m;                // unrounded fp32 master of the same layout (source of the folded weights)
+    void *w16;                  // same layout, bf16
+    void *w16s;                 // bf16(W * |scale of the input BN|): rewritten by launch_bn_fold on every call
+    uint16_t *xf;               // [2*cin] transform of this conv's input: theta = -shift/|scale| (bf16), then sign masks
     float *gamma, *beta;        // BatchNorm affine
     double *stats;              // [2*cout] sum, sum of squares of the raw conv output (this batch)
     float *scale, *shift;       // finalised: y = x*scale + shift
@@ -41,14 +44,31 @@ struct ConvArgs {
     void *out;                  // [M, cout] raw conv output
     int N, H, W;                // input spatial size
     int Ho, Wo;
-    const float *in_scale, *in_shift;   // deferred BN+ReLU of the producer applied on load (null = identity)
+    const float *in_scale, *in_shift;   // SIMT kernel: deferred BN+ReLU of the producer applied on load (null = identity)
+    const uint16_t *in_xf;              // tensor-core kernel: the same as an exact max-transform (ConvLayer::xf), weights = w16s
 };
 cudaError_t launch_stem(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const ConvLayer &L, void *out,
                         int bf16, cudaStream_t s);
 cudaError_t launch_conv_simt(const ConvLayer &L, const ConvArgs &a, int bf16, cudaStream_t s);
 cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t s);
-// conv_tc.cu: tcgen05 / TMEM / TMA implicit GEMM (bf16 activations, input must already be activated: no deferred BN)
-cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, cudaStream_t s);
+// Fold relu(scale*x + shift) of the producing BN ([consumer.cin] values) into the consumer conv for the tensor-core kernel:
+// consumer.xf = {bf16(-shift/|scale|), sign masks}, consumer.w16s = bf16(consumer.w32m * |scale|)    (see conv_tc.cu)
+cudaError_t launch_bn_fold(const float *scale, const float *shift, const ConvLayer &consumer, cudaStream_t s);
+// conv_tc.cu: tcgen05 / TMEM / TMA implicit GEMM on bf16 NHWC activations.  ConvArgs::in_scale/in_shift (the BN + ReLU
+// of the producing conv) are applied to the A tile in shared memory.
+enum { TC_MODE_RAW = 0,      // raw bf16 output + batch statistics
+       TC_MODE_STATS = 1,    // batch statistics only (nothing is written)
+       TC_MODE_FINAL = 2 };  // out = relu(acc*e_scale + e_shift + identity), identity = idt tensor or BN(downsample conv)
+struct ConvTcOpts {
+    int mode = TC_MODE_RAW;
+    const float *e_scale = nullptr, *e_shift = nullptr;    // FINAL: this conv's finalised BN
+    const void *idt = nullptr;                             // FINAL: identity tensor [M, cout] bf16 (no downsample)
+    const ConvLayer *ds = nullptr;                         // FINAL: downsample 1x1 conv accumulated by the same kernel
+    const void *ds_in = nullptr;                           //        its input [N, ds_H, ds_W, ds->cin] bf16 (activated)
+    int ds_H = 0, ds_W = 0;
+    const float *ds_scale = nullptr, *ds_shift = nullptr;  //        its finalised BN
+};
+cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s);
 size_t stem_tc_scratch_bytes(int N);
 cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem_bf16, void *scratch, void *out,
                            double *stats, cudaStream_t s);
@@ -76,6 +96,7 @@ struct LinearArgs {
 };
 cudaError_t launch_linear_f32(const LinearArgs &a, cudaStream_t s);
 cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const LinearArgs &la, cudaStream_t s);
+cudaError_t launch_cast_bf16(const float *in, void *out_bf16, long long n, cudaStream_t s);
 
 // ---------------------------------------------------------------- transformer.cu
 struct PeTables { const __half *xy, *size, *t; };

@@ -317,6 +317,32 @@ __global__ void bn_finalize_kernel(const double *__restrict__ stats, const float
     shift[c] = (float)((double)beta[c] - mean * a);
 }
 
+// relu(s*x + t) = |s| * max(sgn(s)*x, -t/|s|) + t : theta / sign masks for the A-tile transform and |s| folded into the weights
+__global__ void __launch_bounds__(256) bn_fold_kernel(const float *__restrict__ scale, const float *__restrict__ shift, int C,
+                                                       const float4 *__restrict__ w32, uint2 *__restrict__ w16s, uint16_t *__restrict__ xf,
+                                                       long long total4) {
+    __shared__ float sabs[512];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float sc = scale[c];
+        if (!(fabsf(sc) >= 1e-20f)) sc = 1e-20f;                   // scale == 0: relu(t) is reproduced by a huge |theta|
+        const float a = fabsf(sc);
+        sabs[c] = a;
+        if (blockIdx.x == 0) {
+            const __nv_bfloat16 th = __float2bfloat16_rn(-shift[c] / a);
+            xf[c] = *reinterpret_cast<const uint16_t *>(&th);
+            xf[C + c] = sc < 0.f ? 0x8000u : 0u;
+        }
+    }
+    __syncthreads();
+    const int C4 = C / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        const float4 w = w32[i];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(w.x * sabs[c], w.y * sabs[c + 1]), hi = __floats2bfloat162_rn(w.z * sabs[c + 2], w.w * sabs[c + 3]);
+        w16s[i] = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+    }
+}
+
 // relu(bn(x)) followed by MaxPool2d(3, stride 2, pad 1)           resnet.py:271-272
 template <typename T>
 __global__ void bn_relu_maxpool_kernel(const T *__restrict__ raw, T *__restrict__ out, int N, int H, int W, int C,
@@ -393,6 +419,15 @@ __global__ void bn_relu_inplace_kernel(T *x, const float *__restrict__ scale, co
 #pragma unroll
             for (int j = 0; j < 8; ++j) ActIO<T>::st(p + j, fmaxf(fmaf(ActIO<T>::ld(p + j), scale[c + j], shift[c + j]), 0.f));
         }
+    }
+}
+
+// fp32 -> bf16 copy (A operand of the tensor-core linears)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4 *__restrict__ in, uint2 *__restrict__ out, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        out[i] = make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
     }
 }
 
@@ -538,6 +573,15 @@ cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t
     return cudaGetLastError();
 }
 
+cudaError_t launch_bn_fold(const float *scale, const float *shift, const ConvLayer &L, cudaStream_t s) {
+    if (L.cin > 512 || L.cin % 4 != 0 || !L.w32m || !L.w16s || !L.xf) return cudaErrorInvalidValue;
+    const long long total4 = (long long)L.cout * L.k * L.k * L.cin / 4;
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    bn_fold_kernel<<<(int)blocks, 256, 0, s>>>(scale, shift, L.cin, (const float4 *)L.w32m, (uint2 *)L.w16s, L.xf, total4);
+    return cudaGetLastError();
+}
+
 static int ew_grid(long long total) {
     long long b = (total + 255) / 256;
     return (int)(b < 148 * 32 ? (b > 0 ? b : 1) : 148 * 32);
@@ -579,6 +623,13 @@ cudaError_t launch_bn_relu_inplace(void *x, const float *scale, const float *shi
         bn_relu_inplace_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((__nv_bfloat16 *)x, scale, shift, rows, C);
     else
         bn_relu_inplace_kernel<float><<<ew_grid(total), 256, 0, s>>>((float *)x, scale, shift, rows, C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cast_bf16(const float *in, void *out, long long n, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    if (n % 4 != 0) return cudaErrorInvalidValue;
+    cast_bf16_kernel<<<ew_grid(n / 4), 256, 0, s>>>((const float4 *)in, (uint2 *)out, n / 4);
     return cudaGetLastError();
 }
 

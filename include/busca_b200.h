@@ -154,6 +154,21 @@ int busca_frame_step_dev(busca_ctx *ctx, const busca_step_args *args);
 int busca_debug_conv(busca_ctx *ctx, int32_t conv_index, const uint16_t *in_bf16, int32_t N, int32_t H, int32_t W, int32_t use_tc,
                      uint16_t *out_bf16, double *stats_out /* [2*cout] or NULL */);
 int busca_conv_info(busca_ctx *ctx, int32_t conv_index, int32_t *cin_cout_k_stride);
+/* every mode of the tensor-core convolution: mode 0 raw output + statistics (optionally with the producer's BN+ReLU applied
+ * to the input on load), 1 statistics only, 2 final: out = relu(conv*e_scale + e_shift + identity | BN(downsample conv)). */
+typedef struct busca_debug_conv_args {
+    int32_t conv_index, N, H, W, use_tc, mode;
+    const uint16_t *in_bf16;                 /* [N,H,W,cin] */
+    const float *in_scale, *in_shift;        /* [cin] or NULL */
+    const float *e_scale, *e_shift;          /* mode 2: [cout] */
+    const uint16_t *idt_bf16;                /* mode 2 without downsample: [N,Ho,Wo,cout] */
+    int32_t ds_index, ds_H, ds_W;            /* mode 2 with downsample: conv index (or -1) and its input size */
+    const uint16_t *ds_in_bf16;              /* [N,ds_H,ds_W,cin of the downsample conv] */
+    const float *ds_scale, *ds_shift;        /* [cout] */
+    uint16_t *out_bf16;                      /* [N,Ho,Wo,cout] or NULL */
+    double *stats_out;                       /* [2*cout] or NULL */
+} busca_debug_conv_args;
+int busca_debug_conv_ex(busca_ctx *ctx, const busca_debug_conv_args *args);
 int busca_debug_stem(busca_ctx *ctx, const int32_t *slots, int32_t N, int32_t use_tc, uint16_t *out_bf16 /* [N,192,64,64] */,
                      double *stats_out /* [128] or NULL */);
 

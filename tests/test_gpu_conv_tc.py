@@ -110,3 +110,136 @@ def test_stem_tc_matches_simt(engine, N):
     err = np.abs(tc - ref).max() / np.abs(ref).max()
     assert err < 2e-2, err
     assert np.allclose(stats[1], stats[0], rtol=2e-2, atol=2e-2 * np.abs(stats[0]).max())
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the fused modes of the tensor-core convolution (busca_debug_conv_ex)
+# --------------------------------------------------------------------------------------------------------------------
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run_conv(engine, idx, xb, N, H, W, use_tc, mode=0, in_scale=None, in_shift=None, e_scale=None, e_shift=None, idt=None,
+             ds_index=-1, ds_in=None, ds_H=0, ds_W=0, ds_scale=None, ds_shift=None):
+    from busca_b200._lib import DebugConvArgs
+    L = engine.L
+    info = (C.c_int32 * 4)()
+    assert L.busca_conv_info(engine.h, idx, info) == 0
+    cin, cout, k, stride = list(info)
+    Ho, Wo = H // stride, W // stride
+    out = np.full((N, Ho, Wo, cout), 0xAAAA, np.uint16)
+    st = np.zeros(2 * cout, np.float64)
+    keep = [np.ascontiguousarray(a, np.float32) if a is not None else None for a in (in_scale, in_shift, e_scale, e_shift, ds_scale, ds_shift)]
+    d = DebugConvArgs(conv_index=idx, N=N, H=H, W=W, use_tc=use_tc, mode=mode, in_bf16=_ptr(xb), in_scale=_ptr(keep[0]), in_shift=_ptr(keep[1]),
+                      e_scale=_ptr(keep[2]), e_shift=_ptr(keep[3]), idt_bf16=_ptr(idt), ds_index=ds_index, ds_H=ds_H, ds_W=ds_W,
+                      ds_in_bf16=_ptr(ds_in), ds_scale=_ptr(keep[4]), ds_shift=_ptr(keep[5]), out_bf16=_ptr(out), stats_out=_ptr(st))
+    rc = L.busca_debug_conv_ex(engine.h, C.byref(d))
+    assert rc == 0, L.busca_last_error().decode()
+    return out, st, (cin, cout, k, stride)
+
+
+def bn_params(rng, c):
+    scale = rng.uniform(0.5, 1.5, c).astype(np.float32) * np.where(rng.uniform(size=c) < 0.05, -1, 1).astype(np.float32)
+    shift = (0.3 * rng.standard_normal(c)).astype(np.float32)
+    return scale, shift
+
+
+def conv_roles():
+    """(name, conv index, input H, W) for every conv, in forward order."""
+    specs = synth.reid_conv_specs()
+    out = []
+    H, W = 96, 32
+    i = 1
+    for planes, blocks, stride in synth.RESNET_LAYERS:
+        for b in range(blocks):
+            s = stride if b == 0 else 1
+            out.append((specs[i][0], i, H, W))
+            out.append((specs[i + 1][0], i + 1, H, W))
+            out.append((specs[i + 2][0], i + 2, H // s, W // s))
+            if b == 0:
+                out.append((specs[i + 3][0], i + 3, H, W))
+            i += 4 if b == 0 else 3
+            H, W = H // s, W // s
+    return out
+
+
+ROLES = conv_roles()
+XFORM = [(n, i, h, w) for n, i, h, w in ROLES if (n.endswith("conv2") or n.endswith("conv3")) and n.split(".")[1] in ("0", "1")]
+
+
+def fold_const(weights, name, shift):
+    """sum_k W[o,k,taps] * shift[k]: the per-output-channel constant the max-transform drops (conv_tc.cu header): the kernel computes
+    conv(relu(BN(x))) - const, which the batch-statistic BN after the conv cannot see."""
+    w = np.asarray(weights["reid_encoder.model." + name + ".weight"], np.float64)       # [cout, cin, k, k]
+    return w.sum(axis=(2, 3)) @ shift.astype(np.float64)
+
+
+@pytest.mark.parametrize("name,idx,H,W", XFORM)
+@pytest.mark.parametrize("N", [3, 9])
+def test_conv_tc_input_bn_relu_in_smem(engine, weights, name, idx, H, W, N):
+    """RAW and STATS modes with the producer's BN+ReLU applied to the A tile in shared memory as the exact max-transform (incl.
+    the padding of 3x3 taps and of images beyond N) == the SIMT kernel fed the pre-activated bf16 tensor, up to the dropped
+    per-channel constant."""
+    rng = np.random.default_rng(idx * 10 + N)
+    info = (C.c_int32 * 4)()
+    engine.L.busca_conv_info(engine.h, idx, info)
+    cin = info[0]
+    xb, xr = bf16_round(rng.standard_normal((N, H, W, cin)).astype(np.float32))
+    sc, sh = bn_params(rng, cin)
+    if idx % 2 == 0:
+        sc[3] = 0.0                                                  # degenerate BN scale: relu(shift) everywhere
+    act = np.maximum(xr.astype(np.float64) * sc + sh, 0).astype(np.float32)
+    ab, _ = bf16_round(act)
+    ref_o, _, _ = run_conv(engine, idx, ab, N, H, W, use_tc=0)
+    tc_o, tc_st, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=0, in_scale=sc, in_shift=sh)
+    ref, tc = bf16_to_f32(ref_o).astype(np.float64), bf16_to_f32(tc_o).astype(np.float64)
+    assert np.isfinite(tc).all()
+    got = tc + fold_const(weights, name, sh)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 2e-2, (name, err)
+    assert np.abs(got - ref).mean() / np.abs(ref).mean() < 5e-3
+    cout = tc.shape[-1]
+    want_st = np.concatenate([tc.reshape(-1, cout).sum(0), (tc.reshape(-1, cout) ** 2).sum(0)])
+    assert np.allclose(tc_st, want_st, rtol=1e-3, atol=1e-3 * np.abs(want_st).max())
+    so_o, so_st, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=1, in_scale=sc, in_shift=sh)
+    assert (so_o == 0xFFFF).all()                                   # statistics-only pass writes nothing
+    assert np.allclose(so_st, tc_st, rtol=1e-6, atol=1e-6 * np.abs(tc_st).max())
+
+
+FINALS = [(n, i, h, w) for n, i, h, w in ROLES if n.endswith("conv3") and n.split(".")[1] in ("0", "1")]
+
+
+@pytest.mark.parametrize("name,idx,H,W", FINALS)
+@pytest.mark.parametrize("N", [2, 7])
+def test_conv_tc_final_epilogue(engine, weights, name, idx, H, W, N):
+    """FINAL mode: out = relu(BN3(conv3(relu(BN2(raw2)))) + identity), identity = a tensor (blocks 1..) or BN_ds(downsample conv(x))
+    accumulated in a second TMEM accumulator (block 0), against numpy on the SIMT kernel's raw outputs."""
+    rng = np.random.default_rng(idx * 7 + N)
+    info = (C.c_int32 * 4)()
+    engine.L.busca_conv_info(engine.h, idx, info)
+    cin, cout = info[0], info[1]
+    xb, xr = bf16_round(rng.standard_normal((N, H, W, cin)).astype(np.float32))
+    sc, sh = bn_params(rng, cin)
+    ab, _ = bf16_round(np.maximum(xr.astype(np.float64) * sc + sh, 0).astype(np.float32))
+    raw3 = bf16_to_f32(run_conv(engine, idx, ab, N, H, W, use_tc=0)[0]).astype(np.float64) - fold_const(weights, name, sh)
+    es, et = bn_params(rng, cout)
+    if name.split(".")[1] == "0":
+        ds_idx = idx + 1
+        engine.L.busca_conv_info(engine.h, ds_idx, info)
+        dcin, dstride = info[0], info[3]
+        dH, dW = H * dstride, W * dstride
+        db, _ = bf16_round(np.maximum(rng.standard_normal((N, dH, dW, dcin)), 0).astype(np.float32))
+        rawd = bf16_to_f32(run_conv(engine, ds_idx, db, N, dH, dW, use_tc=0)[0]).astype(np.float64)
+        dsc, dsh = bn_params(rng, cout)
+        want = np.maximum(raw3 * es + et + rawd * dsc + dsh, 0)
+        got, _, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=2, in_scale=sc, in_shift=sh, e_scale=es, e_shift=et,
+                             ds_index=ds_idx, ds_in=db, ds_H=dH, ds_W=dW, ds_scale=dsc, ds_shift=dsh)
+    else:
+        ib, ir = bf16_round(np.maximum(rng.standard_normal((N, H, W, cout)), 0).astype(np.float32))
+        want = np.maximum(raw3 * es + et + ir, 0)
+        got, _, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=2, in_scale=sc, in_shift=sh, e_scale=es, e_shift=et, idt=ib)
+    got = bf16_to_f32(got)
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err < 2e-2, (name, err)                                  # raw3/rawd reference values are bf16-rounded, the kernel's are fp32
+    assert np.abs(got - want).mean() / np.abs(want).mean() < 5e-3
