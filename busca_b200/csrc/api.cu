@@ -145,12 +145,16 @@ static void prof_collect(busca_ctx *c) {
     c->prof_json = js;
 }
 
+// BUSCA_TRACE=1: print every kernel name and synchronise after it (attributing a hang or a fault to one launch)
+static const bool g_trace = getenv("BUSCA_TRACE") != nullptr;
 #define LAUNCH(ctx, name, call)                                                                            \
     do {                                                                                                   \
+        if (g_trace) { fprintf(stderr, "[busca] %s ...", name); fflush(stderr); }                          \
         prof_begin(ctx, name);                                                                             \
         cudaError_t e_ = (call);                                                                           \
         prof_end(ctx);                                                                                     \
         (ctx)->launches++;                                                                                 \
+        if (g_trace && e_ == cudaSuccess) { e_ = cudaStreamSynchronize((ctx)->stream); fprintf(stderr, " %s\n", cudaGetErrorString(e_)); } \
         if (e_ != cudaSuccess) return set_err(BUSCA_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e_)); \
     } while (0)
 

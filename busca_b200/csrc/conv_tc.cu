@@ -33,9 +33,10 @@
 // * Persistent: one CTA per SM, static round-robin over (pixel-tile, channel-tile) pairs, channel-tile fastest so
 //   CTAs running concurrently share the same A boxes through L2.
 //
-// Warp roles (480 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = A-tile
-// transform, warps 6-13 = epilogue (warp % 4 = TMEM lane quarter, two warps per quarter split a 64-channel group),
-// warp 14 = identity-tile loader (FINAL mode).
+// Warp roles (608 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = A-tile
+// transform (two groups of four warps take alternate k-iterations, so the fixed wait / proxy-fence / arrive latency
+// of one stage overlaps the other group's work), warps 10-17 = epilogue (warp % 4 = TMEM lane quarter, two warps per
+// quarter split a 64-channel group), warp 18 = identity-tile loader (FINAL mode).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -45,10 +46,10 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;            // bf16 elements per K block = 128 bytes = one swizzle row
-constexpr int TC_THREADS = 480;
-constexpr int TC_XF_WARP0 = 2;       // transform warps 2..5
-constexpr int TC_EPI_WARP0 = 6;      // epilogue warps 6..13
-constexpr int TC_IDT_WARP = 14;
+constexpr int TC_THREADS = 608;
+constexpr int TC_XF_WARP0 = 2;       // transform warps 2..9: two groups of four, alternating k-iterations
+constexpr int TC_EPI_WARP0 = 10;     // epilogue warps 10..17
+constexpr int TC_IDT_WARP = 18;
 constexpr int TC_MAX_TAPS = 9;
 constexpr int TC_XBUFS = 3;          // staging tiles (128 rows x 128 B)
 
@@ -185,6 +186,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 #define TMEM_LD_WAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 #define EPI_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
 
@@ -263,20 +273,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
+                int tap = 0, cb = 0;
                 for (int kt = 0; kt < p.k_iters; ++kt) {
                     mbar_wait<32>(&empty[stage], phase ^ 1);
                     uint8_t *a_dst = tiles + stage * Cfg::STAGE_BYTES, *b_dst = a_dst + Cfg::A_BYTES;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     if (!DUAL || kt < p.k1_iters) {
-                        const int tap = kt / p.cin_blocks, cb = kt - tap * p.cin_blocks;
                         const int m = p.tap_map[tap];
                         const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
                         tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
                         tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
+                        if (++cb == p.cin_blocks) { cb = 0; ++tap; }
                     } else {                                     // downsample branch: 1x1 (strided view) on the block input
-                        const int cb = kt - p.k1_iters;
-                        tma_load_4d(a_dst, &mapA1, &full[stage], cb * Cfg::BKE, 0, h0, n0);
-                        tma_load_2d(b_dst, &mapB2, &full[stage], cb * Cfg::BKE, n_tile * BN);
+                        const int cb2 = kt - p.k1_iters;
+                        tma_load_4d(a_dst, &mapA1, &full[stage], cb2 * Cfg::BKE, 0, h0, n0);
+                        tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
                     }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -304,9 +315,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const bool first = main_op ? kt == 0 : kt == p.k1_iters;
                     const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = umma_desc<KB>(a_addr), db = umma_desc<KB>(a_addr + Cfg::A_BYTES);
+                    if (BN == 256 && !DUAL && p.mode == MODE_STATS) {
+                        // statistics-only pass: D^T = W * A^T (operands swapped: M = 128 output channels, N = 128 pixels, two channel
+                        // halves), so that TMEM lanes are CHANNELS and the per-channel sums over pixels are thread-local in the epilogue
+                        const uint32_t idesc_t = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 #pragma unroll
-                    for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                        for (int h = 0; h < 2; ++h)
+#pragma unroll
+                            for (int k = 0; k < Cfg::BKE / 16; ++k)
+                                umma_bf16(tmem_base + acc * 256 + h * 128, db + (uint64_t)(h * (128 * KB / 16)) + 2 * k, da + 2 * k, idesc_t, !(first && k == 0));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
+                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                    }
                     umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs retire
                     if (kt == p.k_iters - 1) umma_commit(&tfull[acc]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -316,7 +338,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     } else if (warp < TC_EPI_WARP0) {
         // ===================================================== A-tile transform: a = max(x ^ signmask, theta); theta in the padding
         if (xform) {
-            const int tt = threadIdx.x - TC_XF_WARP0 * 32;   // 0..127
+            const int grp = (warp - TC_XF_WARP0) >> 2;        // this group handles k-iterations with (global index & 1) == grp
+            const int tt = (threadIdx.x - TC_XF_WARP0 * 32) & 127;
             const int c = tt & 7, rb = tt >> 3;               // logical 16-byte chunk (8 channels), first row
             const uint32_t col_off = (uint32_t)((c ^ (rb & 7)) << 4);
             int r_hi[8], r_ni[8];
@@ -329,8 +352,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 r_ni[i] = r / (p.BW * p.BH);
                 r_wb[i] = ((unsigned)(wi - 1) < (unsigned)p.Wv ? 1u : 0u) | ((unsigned)wi < (unsigned)p.Wv ? 2u : 0u) | ((unsigned)(wi + 1) < (unsigned)p.Wv ? 4u : 0u);
             }
-            int stage = 0;
-            uint32_t phase = 0;
+            const uint32_t par0 = smem_u32(s_apar) + (uint32_t)c * 16;
+            const uint32_t tiles0 = smem_u32(tiles) + col_off + (uint32_t)rb * 128;
+            uint32_t ki = 0;                                  // global k-iteration counter (stage ring position)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.tiles_n;
                 const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
@@ -350,43 +374,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     m9[i] = m;
                     all9 &= m;
                 }
-                for (int kt = 0; kt < p.k_iters; ++kt) {
-                    if (!DUAL || kt < p.k1_iters) {
-                        const int tap = kt / p.cin_blocks, cb = kt - tap * p.cin_blocks;
-                        const int bit = p.tap_bit[tap];
-                        const uint32_t par = smem_u32(s_apar) + (uint32_t)(cb * 64 + c * 8) * 2;
-                        const uint4 th = lds128(par), sg = lds128(par + 1024);
+                int tap = 0, cb = 0;
+                for (int kt = 0; kt < p.k_iters; ++kt, ++ki) {
+                    const bool main_op = !DUAL || kt < p.k1_iters;
+                    const uint32_t stage = ki % Cfg::STAGES, phase = (ki / Cfg::STAGES) & 1;
+                    // BOTH groups observe every phase of every stage (with an odd number of stages a group would otherwise skip
+                    // every second phase of a stage, and a parity wait can only tell phases apart that are at most one apart)
+                    if ((int)(ki & 1) != grp) {
                         mbar_wait<0>(&full[stage], phase);
-                        const uint32_t base = smem_u32(tiles + stage * Cfg::STAGE_BYTES) + col_off;
-                        if ((all9 >> bit) & 1) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const uint32_t addr = base + (uint32_t)(rb + 16 * i) * 128;
-                                uint4 v = lds128(addr);
-                                v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
-                                v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
-                                sts128(addr, v);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const uint32_t addr = base + (uint32_t)(rb + 16 * i) * 128;
-                                uint4 v = lds128(addr);
-                                if ((m9[i] >> bit) & 1) {
-                                    v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
-                                    v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
-                                } else {
-                                    v = (m9[i] & 0x200u) ? make_uint4(0u, 0u, 0u, 0u) : th;
-                                }
-                                sts128(addr, v);
-                            }
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA (async proxy)
                     } else {
-                        mbar_wait<0>(&full[stage], phase);
+                        if (main_op) {
+                            const int bit = p.tap_bit[tap];
+                            const uint4 th = lds128(par0 + (uint32_t)cb * 128), sg = lds128(par0 + (uint32_t)cb * 128 + 1024);
+                            mbar_wait<0>(&full[stage], phase);
+                            const uint32_t base = tiles0 + stage * Cfg::STAGE_BYTES;
+                            if ((all9 >> bit) & 1) {
+                                uint4 v[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = lds128(base + (uint32_t)i * 2048);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    v[i].x = max_bf16x2(v[i].x ^ sg.x, th.x); v[i].y = max_bf16x2(v[i].y ^ sg.y, th.y);
+                                    v[i].z = max_bf16x2(v[i].z ^ sg.z, th.z); v[i].w = max_bf16x2(v[i].w ^ sg.w, th.w);
+                                    sts128(base + (uint32_t)i * 2048, v[i]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const uint32_t addr = base + (uint32_t)i * 2048;
+                                    uint4 v = lds128(addr);
+                                    if ((m9[i] >> bit) & 1) {
+                                        v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
+                                        v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
+                                    } else {
+                                        v = (m9[i] & 0x200u) ? make_uint4(0u, 0u, 0u, 0u) : th;
+                                    }
+                                    sts128(addr, v);
+                                }
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA (async proxy)
+                        } else {
+                            mbar_wait<0>(&full[stage], phase);
+                        }
+                        mbar_arrive(&ready[stage]);     // every k-iteration, so the barrier phase tracks the stage ring
                     }
-                    mbar_arrive(&ready[stage]);     // every k-iteration, so the barrier phase tracks the stage ring
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (main_op && ++cb == p.cin_blocks) { cb = 0; ++tap; }
                 }
             }
         }
@@ -420,6 +452,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     acc_q[g][j] = 0.f;
                 }
         };
+        float ts[2] = {0.f, 0.f}, tq[2] = {0.f, 0.f};   // transposed statistics pass: channel = n_tile*256 + h*128 + q*32 + lane
+        auto flush_stats_t = [&]() {
+            if (stats_ntile < 0) return;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ch = stats_ntile * BN + h * 128 + q * 32 + lane;
+                atomicAdd(&s_par[ch], ts[h]);
+                atomicAdd(&s_par[p.Cout + ch], tq[h]);
+                ts[h] = 0.f;
+                tq[h] = 0.f;
+            }
+        };
+        const bool stats_t = BN == 256 && !DUAL && p.mode == MODE_STATS;
         int it = 0, gcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -427,7 +472,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
             const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
             const uint32_t t_acc = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-            if (p.mode == MODE_RAW || p.mode == MODE_STATS) {
+            if (BN == 256 && !DUAL && p.mode == MODE_STATS) {
+                // transposed accumulator (see the MMA issuer): lane = channel, columns = pixels; this warp sums 64 of the 128 pixels
+                if (n_tile != stats_ntile) { flush_stats_t(); stats_ntile = n_tile; }
+                mbar_wait<0>(&tfull[acc], acc_phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        uint32_t r[32];
+                        tmem_ld32(t_acc + h * 128 + half * 64 + c2 * 32, r);
+                        TMEM_LD_WAIT();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = __uint_as_float(r[j]);
+                            ts[h] += x;
+                            tq[h] = fmaf(x, x, tq[h]);
+                        }
+                    }
+            } else if (p.mode == MODE_RAW || p.mode == MODE_STATS) {
                 if (want_stats && n_tile != stats_ntile) { flush_stats(); stats_ntile = n_tile; }
                 mbar_wait<0>(&tfull[acc], acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -473,30 +537,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const uint32_t xph = (uint32_t)(gcount / TC_XBUFS) & 1;
                     const uint32_t st = xb0 + b * Cfg::XBUF_BYTES;
                     const int col0 = n_tile * BN + g * 64 + half * 32;
-                    uint32_t r[32];
+                    uint32_t r[32];                             // accumulator, then (in place) the BN-applied value as float bits
                     tmem_ld32(t_acc + g * 64 + half * 32, r);
                     TMEM_LD_WAIT();
                     const uint32_t ps = smem_u32(s_par) + (uint32_t)col0 * 4, pt = ps + (uint32_t)p.Cout * 4;
-                    float v[32];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 s4 = lds128f(ps + j * 16), t4 = lds128f(pt + j * 16);
-                        v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), s4.x, t4.x);
-                        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, t4.y);
-                        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, t4.z);
-                        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, t4.w);
+                        r[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 0]), s4.x, t4.x));
+                        r[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 1]), s4.y, t4.y));
+                        r[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 2]), s4.z, t4.z));
+                        r[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 3]), s4.w, t4.w));
                     }
                     if (DUAL) {
-                        tmem_ld32(t_acc + BN + g * 64 + half * 32, r);
-                        TMEM_LD_WAIT();
                         const uint32_t ds = ps + (uint32_t)p.Cout * 8, dt = ps + (uint32_t)p.Cout * 12;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 s4 = lds128f(ds + j * 16), t4 = lds128f(dt + j * 16);
-                            v[4 * j + 0] += fmaf(__uint_as_float(r[4 * j + 0]), s4.x, t4.x);
-                            v[4 * j + 1] += fmaf(__uint_as_float(r[4 * j + 1]), s4.y, t4.y);
-                            v[4 * j + 2] += fmaf(__uint_as_float(r[4 * j + 2]), s4.z, t4.z);
-                            v[4 * j + 3] += fmaf(__uint_as_float(r[4 * j + 3]), s4.w, t4.w);
+                        for (int hh = 0; hh < 2; ++hh) {         // downsample accumulator, 16 columns at a time (register budget)
+                            uint32_t r2[16];
+                            tmem_ld16(t_acc + BN + g * 64 + half * 32 + hh * 16, r2);
+                            TMEM_LD_WAIT();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 s4 = lds128f(ds + (hh * 4 + j) * 16), t4 = lds128f(dt + (hh * 4 + j) * 16);
+                                const int o = hh * 16 + 4 * j;
+                                r[o + 0] = __float_as_uint(__uint_as_float(r[o + 0]) + fmaf(__uint_as_float(r2[4 * j + 0]), s4.x, t4.x));
+                                r[o + 1] = __float_as_uint(__uint_as_float(r[o + 1]) + fmaf(__uint_as_float(r2[4 * j + 1]), s4.y, t4.y));
+                                r[o + 2] = __float_as_uint(__uint_as_float(r[o + 2]) + fmaf(__uint_as_float(r2[4 * j + 2]), s4.z, t4.z));
+                                r[o + 3] = __float_as_uint(__uint_as_float(r[o + 3]) + fmaf(__uint_as_float(r2[4 * j + 3]), s4.w, t4.w));
+                            }
                         }
                     } else {
                         mbar_wait<0>(&xfull[b], xph);           // identity tile of this group has landed in the staging buffer
@@ -504,18 +572,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t addr = st + row_off + (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
+                        const float *v = reinterpret_cast<const float *>(r) + 8 * j;
                         uint4 w;
                         if (!DUAL) {
                             const uint4 d = lds128(addr);
-                            w.x = pack_bf16(fmaxf(v[8 * j + 0] + bf_lo(d.x), 0.f), fmaxf(v[8 * j + 1] + bf_hi(d.x), 0.f));
-                            w.y = pack_bf16(fmaxf(v[8 * j + 2] + bf_lo(d.y), 0.f), fmaxf(v[8 * j + 3] + bf_hi(d.y), 0.f));
-                            w.z = pack_bf16(fmaxf(v[8 * j + 4] + bf_lo(d.z), 0.f), fmaxf(v[8 * j + 5] + bf_hi(d.z), 0.f));
-                            w.w = pack_bf16(fmaxf(v[8 * j + 6] + bf_lo(d.w), 0.f), fmaxf(v[8 * j + 7] + bf_hi(d.w), 0.f));
+                            w.x = pack_bf16(fmaxf(v[0] + bf_lo(d.x), 0.f), fmaxf(v[1] + bf_hi(d.x), 0.f));
+                            w.y = pack_bf16(fmaxf(v[2] + bf_lo(d.y), 0.f), fmaxf(v[3] + bf_hi(d.y), 0.f));
+                            w.z = pack_bf16(fmaxf(v[4] + bf_lo(d.z), 0.f), fmaxf(v[5] + bf_hi(d.z), 0.f));
+                            w.w = pack_bf16(fmaxf(v[6] + bf_lo(d.w), 0.f), fmaxf(v[7] + bf_hi(d.w), 0.f));
                         } else {
-                            w.x = pack_bf16(fmaxf(v[8 * j + 0], 0.f), fmaxf(v[8 * j + 1], 0.f));
-                            w.y = pack_bf16(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f));
-                            w.z = pack_bf16(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f));
-                            w.w = pack_bf16(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f));
+                            w.x = pack_bf16(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
+                            w.y = pack_bf16(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+                            w.z = pack_bf16(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
+                            w.w = pack_bf16(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
                         }
                         sts128(addr, w);
                     }
@@ -563,7 +632,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        if (want_stats) flush_stats();
+        if (want_stats) { if (stats_t) flush_stats_t(); else flush_stats(); }
         if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
         // ===================================================== identity-tile loader (FINAL, single accumulator)

@@ -203,7 +203,7 @@ def test_conv_tc_input_bn_relu_in_smem(engine, weights, name, idx, H, W, N):
     assert np.allclose(tc_st, want_st, rtol=1e-3, atol=1e-3 * np.abs(want_st).max())
     so_o, so_st, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=1, in_scale=sc, in_shift=sh)
     assert (so_o == 0xFFFF).all()                                   # statistics-only pass writes nothing
-    assert np.allclose(so_st, tc_st, rtol=1e-6, atol=1e-6 * np.abs(tc_st).max())
+    assert np.allclose(so_st, tc_st, rtol=2e-3, atol=2e-3 * np.abs(tc_st).max())   # fp32 accumulators vs the bf16-rounded stored values
 
 
 FINALS = [(n, i, h, w) for n, i, h, w in ROLES if n.endswith("conv3") and n.split(".")[1] in ("0", "1")]
