@@ -31,7 +31,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-from busca_b200 import synth  # noqa: E402
+from busca_b200 import sharding, synth  # noqa: E402
 
 WORKLOADS = {
     # BASELINE.json configs[2]: MOT20-scale dense crowd, ~200 unmatched tracks/frame (the scale the metric is quoted on)
@@ -256,7 +256,8 @@ def run_ours(args):
     T, D, L, C = wl["T"], wl["D"], wl["L"], wl["C"]
     model, targs = build_model(args.precision, local)
     eng = model.engine
-    scene = Scene(model, T, D, L, C, seed=100 + rank)       # independent sequence per rank (sequence sharding, no collective)
+    # sequence sharding, no hot-path collective: every rank owns its own sequence (weak scaling, fixed work per GPU)
+    scene = Scene(model, T, D, L, C, seed=sharding.sequence_seeds(world, rank, 1)[0])
     scene.setup_resident()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
 
@@ -309,13 +310,12 @@ def run_ours(args):
     eng.sync()
     e2e_s = time.perf_counter() - t0
 
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        kept = torch.tensor([int(keep.sum())], device=f"cuda:{local}")
-        gathered = [torch.zeros_like(kept) for _ in range(world)]
-        dist.all_gather(gathered, kept)                       # NCCL only gathers per-rank results
-    ms_max, e2e_ms_max = float(times[0]), float(times[1])
+    # NCCL only here: max over ranks of the device-timed regions, and the gather of the per-rank result tables
+    ms_max, e2e_ms_max = sharding.reduce_max([ms, e2e_s * 1e3], dist, device=f"cuda:{local}")
+    mb = scene.mean                                           # surviving tracks: (cx, cy, a, h) -> ltwh of the last state
+    rows = sharding.pack_results([(rank, args.steps, t, mb[t, 0] - mb[t, 2] * mb[t, 3] / 2, mb[t, 1] - mb[t, 3] / 2, mb[t, 2] * mb[t, 3], mb[t, 3],
+                                   float(probs[t, C - 1])) for t in range(T) if keep[t]])
+    table = sharding.gather_results(rows, dist, device=f"cuda:{local}")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -370,7 +370,7 @@ def run_ours(args):
         "kernels": kernels,
         "conv_detail_ms_per_step": detail,
         "cpu_baseline": cpu,
-        "kept_tracks": int(keep.sum()),
+        "kept_tracks": int(table.shape[0]),
     }
     print(json.dumps(out))
     if dist is not None:
