@@ -277,6 +277,7 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.launches
+    run0, tot0 = eng.counter("reid_images_run"), eng.counter("reid_images_total")
     prof_acc = {}
     lat = []
     e0.record(stream)
@@ -286,29 +287,35 @@ def run_ours(args):
         eng.sync()                                            # per-frame latency needs the frame boundary anyway
         lat.append((time.perf_counter() - t0) * 1e3)
         for k, v in eng.last_profile().items():
-            a = prof_acc.setdefault(k, {"ms": 0.0, "launches": 0})
+            a = prof_acc.setdefault(k, {"ms": 0.0, "launches": 0, "flops": 0.0, "kernel": v.get("kernel", "")})
             a["ms"] += v["ms"]
             a["launches"] += v["launches"]
+            a["flops"] += v.get("flops", 0.0)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = eng.launches - launches0
+    images_run = (eng.counter("reid_images_run") - run0) / args.steps          # distinct patches the encoder ran per step
+    images_total = (eng.counter("reid_images_total") - tot0) / args.steps      # patches of the stacked batches (T*(L+C))
     eng.set_profiling(False)
     keep = eng.from_dev(scene.keep_dev, (T,), np.uint8)
     probs = eng.from_dev(scene.probs_dev, (T, C + 2), np.float32)
     assert np.isfinite(probs).all() and abs(float(probs.sum()) - T) < 1e-2 * T
 
     # ---- plug-in API (`e2e`)
-    scene.setup_e2e()
-    for i in range(min(args.warmup, 3)):
-        scene.step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        scene.step_e2e(i)
-    eng.sync()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = float("nan")
+    scene.h2d = scene.d2h = 0
+    if not args.no_e2e:
+        scene.setup_e2e()
+        for i in range(max(1, min(args.warmup, 3))):
+            scene.step_e2e(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            scene.step_e2e(i)
+        eng.sync()
+        e2e_s = time.perf_counter() - t0
 
     # NCCL only here: max over ranks of the device-timed regions, and the gather of the per-rank result tables
     ms_max, e2e_ms_max = sharding.reduce_max([ms, e2e_s * 1e3], dist, device=f"cuda:{local}")
@@ -327,27 +334,41 @@ def run_ours(args):
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md 1.4 PF sustained)"
-    fl = conv_flops(T * (L + C))
-    by_class = {}
+    # per-layer table -> (a) classes for the share table, (b) the __global__ instantiations ncu names, for the roofline
+    by_class, by_kernel = {}, {}
     for k, v in prof_acc.items():                          # "conv1x1_tc[64>256 s1 96x32]" -> class "conv1x1"
         cls = k.split("_tc[")[0]
         a = by_class.setdefault(cls, {"ms": 0.0, "launches": 0})
         a["ms"] += v["ms"]
         a["launches"] += v["launches"]
+        if v.get("kernel") and v.get("flops", 0.0) > 0:
+            b = by_kernel.setdefault(v["kernel"], {"ms": 0.0, "launches": 0, "flops": 0.0})
+            b["ms"] += v["ms"]
+            b["launches"] += v["launches"]
+            b["flops"] += v["flops"]
     detail = {k: round(v["ms"] / args.steps, 4) for k, v in prof_acc.items() if "_tc[" in k}
-    prof_acc = by_class
-    conv_classes = {k: prof_acc[k] for k in ("conv1x1", "conv3x3", "stem_conv7x7") if k in prof_acc}
-    dom = max(conv_classes, key=lambda k: conv_classes[k]["ms"]) if conv_classes else None
+    total_prof = sum(v["ms"] for v in by_class.values())
     roofline = None
-    if dom:
-        per_launch_flops = fl[dom] * args.steps / conv_classes[dom]["launches"]
-        avg_ms = conv_classes[dom]["ms"] / conv_classes[dom]["launches"]
-        achieved = per_launch_flops / (avg_ms * 1e-3) / 1e12
+    if by_kernel:
+        dom = max(by_kernel, key=lambda k: by_kernel[k]["ms"])   # dominant kernel = the instantiation with the most device time
+        d = by_kernel[dom]
+        avg_ms = d["ms"] / d["launches"]
+        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12          # executed algorithmic FLOPs / CUDA-event time of those launches
+        traffic = None
+        try:                                                     # DRAM bytes per launch of the same kernel, from the committed ncu capture
+            tr = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+            traffic = tr["kernels"][dom]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 3), "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": round(achieved / peak_tf, 5), "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": round(avg_ms, 4), "launches": conv_classes[dom]["launches"],
-                    "share_of_step": round(conv_classes[dom]["ms"] / max(1e-9, sum(v["ms"] for v in prof_acc.values())), 4)}
-    total_prof = sum(v["ms"] for v in prof_acc.values())
+                    "frac": round(achieved / peak_tf, 5), "traffic": traffic, "peak_source": peak_src,
+                    "avg_launch_ms": round(avg_ms, 4), "launches": d["launches"],
+                    "flops_per_launch": round(d["flops"] / d["launches"], 1),
+                    "share_of_step": round(d["ms"] / max(1e-9, total_prof), 4),
+                    "all_conv_kernels": {k: {"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1), "ms_per_step": round(v["ms"] / args.steps, 3),
+                                             "launches_per_step": v["launches"] / args.steps} for k, v in by_kernel.items()},
+                    "whole_step_tflops": round(sum(v["flops"] for v in by_kernel.values()) / (ms * 1e-3) / 1e12, 1)}
+    prof_acc = by_class
     kernels = {k: {"ms_per_step": round(v["ms"] / args.steps, 4), "launches_per_step": v["launches"] / args.steps,
                    "share": round(v["ms"] / max(total_prof, 1e-9), 4)} for k, v in sorted(prof_acc.items(), key=lambda kv: -kv[1]["ms"])}
     cpu = cpu_baseline(args) if not args.no_cpu_baseline else None
@@ -361,7 +382,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2: every step streams GBs of ReID activations through HBM (L2 is 126 MB)",
                    "parallelism": f"{world} independent sequences, one per GPU, no hot-path collective"},
         "p50_frame_latency_ms": round(float(np.median(lat)), 3),
-        "e2e": {"value": round(world * T * args.steps / (e2e_ms_max * 1e-3), 3), "unit": "decisions/s",
+        "e2e": {"value": round(world * T * args.steps / (e2e_ms_max * 1e-3), 3) if e2e_ms_max == e2e_ms_max else None, "unit": "decisions/s",
                 "h2d_bytes_per_step": int(scene.h2d), "d2h_bytes_per_step": int(scene.d2h),
                 "api": "BUSCA.get_image_crops + center_distance + associate_embeddings (host numpy in/out)"},
         "gpu_launches": int(launches),
@@ -439,9 +460,10 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mot20", choices=list(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("BUSCA_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("BUSCA_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--cpu-tracks", type=int, default=16, help="size of the bounded CPU sample (unmatched tracks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the plug-in API leg (profiler runs)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

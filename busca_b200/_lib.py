@@ -54,8 +54,8 @@ EXPORTS = [
     "busca_upload_frame", "busca_bank_reserve", "busca_bank_capacity", "busca_crop", "busca_bank_upload",
     "busca_bank_download", "busca_center_distance", "busca_iou", "busca_motion_proposals", "busca_frame_geometry",
     "busca_reid_embed", "busca_associate", "busca_transformer", "busca_frame_step_dev", "busca_dev_alloc",
-    "busca_dev_free", "busca_memcpy_h2d", "busca_memcpy_d2h", "busca_sync", "busca_stream", "busca_kernel_launches",
-    "busca_set_profiling", "busca_last_profile", "busca_debug_conv", "busca_debug_conv_ex", "busca_conv_info", "busca_debug_stem",
+    "busca_dev_free", "busca_host_alloc", "busca_host_free", "busca_memcpy_h2d", "busca_memcpy_d2h", "busca_sync", "busca_stream", "busca_kernel_launches",
+    "busca_set_profiling", "busca_last_profile", "busca_set_option", "busca_counter", "busca_debug_conv", "busca_debug_conv_ex", "busca_conv_info", "busca_debug_stem",
 ]
 
 
@@ -102,6 +102,10 @@ def load(build_if_missing: bool = True):
     L.busca_dev_alloc.restype = vp
     L.busca_dev_free.argtypes = [vp, vp]
     L.busca_dev_free.restype = None
+    L.busca_host_alloc.argtypes = [vp, C.c_int64]
+    L.busca_host_alloc.restype = vp
+    L.busca_host_free.argtypes = [vp, vp]
+    L.busca_host_free.restype = None
     L.busca_memcpy_h2d.argtypes = [vp, vp, vp, C.c_int64]
     L.busca_memcpy_d2h.argtypes = [vp, vp, vp, C.c_int64]
     L.busca_sync.argtypes = [vp]
@@ -112,6 +116,9 @@ def load(build_if_missing: bool = True):
     L.busca_set_profiling.argtypes = [vp, C.c_int32]
     L.busca_last_profile.argtypes = [vp]
     L.busca_last_profile.restype = C.c_char_p
+    L.busca_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.busca_counter.argtypes = [vp, C.c_char_p]
+    L.busca_counter.restype = C.c_int64
     L.busca_debug_conv.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]
     L.busca_debug_conv_ex.argtypes = [vp, C.POINTER(DebugConvArgs)]
     L.busca_conv_info.argtypes = [vp, C.c_int32, vp]

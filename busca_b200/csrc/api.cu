@@ -62,6 +62,8 @@ struct TLayer {
 struct ProfEntry {
     std::string name;
     cudaEvent_t a, b;
+    double flops;                                 // algorithmic FLOPs of the launch (convolutions; 0 = not tracked)
+    std::string kernel;                           // the __global__ instantiation, as the ncu launch list names it
 };
 
 struct busca_ctx {
@@ -93,12 +95,21 @@ struct busca_ctx {
     size_t pinned_cap = 0;
     int64_t launches = 0;
     bool use_tc = false;                          // bf16 mode: tcgen05 convolutions (BUSCA_CONV=simt forces the SIMT bf16 path)
+    // duplicate elimination inside a BatchNorm batch (tensor-core path; BUSCA_DEDUP=0 / busca_set_option("dedup", 0) disables)
+    bool dedup = true;
+    int *dedup_table = nullptr;                   // [bank_slots + 1], all 0x7f7f7f7f between kernels
+    DevBuf ws_dedup[2];                           // per planned batch: uniq | map | weight | count
+    int *h_nuniq = nullptr;                       // pinned: distinct-image counts of the (up to two) planned batches
+    cudaEvent_t ev_plan = nullptr;
+    int64_t reid_images_run = 0, reid_images_total = 0;
     // profiling
     bool profiling = false;
     std::vector<ProfEntry> prof;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::string prof_json;
+    double next_flops = 0.0;                      // consumed by the next prof_begin
+    std::string next_kernel;
 };
 
 static cudaEvent_t get_event(busca_ctx *c) {
@@ -111,7 +122,9 @@ static cudaEvent_t get_event(busca_ctx *c) {
 }
 static void prof_begin(busca_ctx *c, const char *name) {
     if (!c->profiling) return;
-    ProfEntry pe{name, get_event(c), get_event(c)};
+    ProfEntry pe{name, get_event(c), get_event(c), c->next_flops, c->next_kernel};
+    c->next_flops = 0.0;
+    c->next_kernel.clear();
     cudaEventRecord(pe.a, c->stream);
     c->prof.push_back(pe);
 }
@@ -125,20 +138,22 @@ static void prof_reset(busca_ctx *c) {
 }
 static void prof_collect(busca_ctx *c) {
     if (!c->profiling) return;
-    std::map<std::string, std::pair<double, int>> acc;
+    struct Acc { double ms = 0, flops = 0; int n = 0; std::string kernel; };
+    std::map<std::string, Acc> acc;
     std::vector<std::string> order;
     for (auto &pe : c->prof) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, pe.a, pe.b);
         if (!acc.count(pe.name)) order.push_back(pe.name);
-        acc[pe.name].first += ms;
-        acc[pe.name].second += 1;
+        Acc &a = acc[pe.name];
+        a.ms += ms; a.flops += pe.flops; a.n += 1; a.kernel = pe.kernel;
     }
     std::string js = "{";
     for (size_t i = 0; i < order.size(); ++i) {
-        char buf[256];
-        snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d}", i ? ", " : "", order[i].c_str(), acc[order[i]].first,
-                 acc[order[i]].second);
+        char buf[512];
+        const Acc &a = acc[order[i]];
+        snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d, \"flops\": %.6e, \"kernel\": \"%s\"}", i ? ", " : "", order[i].c_str(),
+                 a.ms, a.n, a.flops, a.kernel.c_str());
         js += buf;
     }
     js += "}";
@@ -200,7 +215,11 @@ extern "C" int busca_create(const busca_config *cfg, busca_ctx **out) {
     c->cfg = *cfg;
     const char *cm = getenv("BUSCA_CONV");
     c->use_tc = cfg->precision == BUSCA_PREC_BF16 && !(cm && strcmp(cm, "simt") == 0);
+    const char *dd = getenv("BUSCA_DEDUP");
+    c->dedup = !(dd && strcmp(dd, "0") == 0);
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaHostAlloc((void **)&c->h_nuniq, 4 * sizeof(int), cudaHostAllocPortable));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming));
     *out = c;
     int64_t slots = cfg->bank_slots > 0 ? cfg->bank_slots : 1024;
     return busca_bank_reserve(c, slots);
@@ -212,6 +231,11 @@ extern "C" void busca_destroy(busca_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (void *p : c->owned) cudaFree(p);
     if (c->bank) cudaFree(c->bank);
+    if (c->dedup_table) cudaFree(c->dedup_table);
+    if (c->h_nuniq) cudaFreeHost(c->h_nuniq);
+    if (c->ev_plan) cudaEventDestroy(c->ev_plan);
+    c->ws_dedup[0].release();
+    c->ws_dedup[1].release();
     c->frame.release();
     c->ws_reid.release();
     c->ws_tr.release();
@@ -424,6 +448,10 @@ extern "C" int busca_bank_reserve(busca_ctx *c, int64_t n_slots) {
     }
     c->bank = nb;
     c->bank_slots = n_slots;
+    if (c->dedup_table) cudaFree(c->dedup_table);
+    c->dedup_table = nullptr;
+    CUDA_OK(cudaMalloc((void **)&c->dedup_table, ((size_t)n_slots + 1) * sizeof(int)));
+    CUDA_OK(cudaMemset(c->dedup_table, 0x7f, ((size_t)n_slots + 1) * sizeof(int)));
     return BUSCA_OK;
 }
 extern "C" int64_t busca_bank_capacity(busca_ctx *c) { return c ? c->bank_slots : 0; }
@@ -431,6 +459,22 @@ extern "C" int64_t busca_bank_capacity(busca_ctx *c) { return c ? c->bank_slots 
 static int check_slots(busca_ctx *c, const int32_t *slots, int n, bool allow_neg) {
     for (int i = 0; i < n; ++i)
         if (slots[i] >= c->bank_slots || (slots[i] < 0 && !allow_neg)) return set_err(BUSCA_ERR_ARG, "slot %d out of range (bank has %lld)", slots[i], (long long)c->bank_slots);
+    return BUSCA_OK;
+}
+
+// bank <-> host, one copy per run of consecutive slots (alloc_slots hands out ascending runs, so a frame's crops are
+// usually a single DMA; with page-locked host memory it runs at PCIe speed)
+static int bank_copy_runs(busca_ctx *c, const int32_t *slots, int n, uint8_t *host, bool to_bank) {
+    int i = 0;
+    while (i < n) {
+        int j = i + 1;
+        while (j < n && slots[j] == slots[j - 1] + 1) ++j;
+        uint8_t *dev = c->bank + (size_t)slots[i] * PATCH_BYTES, *h = host + (size_t)i * PATCH_BYTES;
+        const size_t bytes = (size_t)(j - i) * PATCH_BYTES;
+        if (to_bank) CUDA_OK(cudaMemcpyAsync(dev, h, bytes, cudaMemcpyHostToDevice, c->stream));
+        else CUDA_OK(cudaMemcpyAsync(h, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        i = j;
+    }
     return BUSCA_OK;
 }
 
@@ -450,8 +494,8 @@ extern "C" int busca_crop(busca_ctx *c, const double *boxes, int32_t n, const in
     prof_reset(c);
     LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, dbox, n, dslots, c->bank, c->stream));
     if (host_out) {
-        for (int i = 0; i < n; ++i)
-            CUDA_OK(cudaMemcpyAsync(host_out + (size_t)i * PATCH_BYTES, c->bank + (size_t)slots[i] * PATCH_BYTES, PATCH_BYTES, cudaMemcpyDeviceToHost, c->stream));
+        int rc2 = bank_copy_runs(c, slots, n, host_out, false);
+        if (rc2) return rc2;
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     prof_collect(c);
@@ -463,8 +507,8 @@ extern "C" int busca_bank_upload(busca_ctx *c, const uint8_t *patches, int32_t n
     int rc = check_slots(c, slots, n, false);
     if (rc) return rc;
     CUDA_OK(cudaSetDevice(c->cfg.device));
-    for (int i = 0; i < n; ++i)
-        CUDA_OK(cudaMemcpyAsync(c->bank + (size_t)slots[i] * PATCH_BYTES, patches + (size_t)i * PATCH_BYTES, PATCH_BYTES, cudaMemcpyHostToDevice, c->stream));
+    rc = bank_copy_runs(c, slots, n, const_cast<uint8_t *>(patches), true);
+    if (rc) return rc;
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return BUSCA_OK;
 }
@@ -474,8 +518,8 @@ extern "C" int busca_bank_download(busca_ctx *c, const int32_t *slots, int32_t n
     int rc = check_slots(c, slots, n, false);
     if (rc) return rc;
     CUDA_OK(cudaSetDevice(c->cfg.device));
-    for (int i = 0; i < n; ++i)
-        CUDA_OK(cudaMemcpyAsync(host_out + (size_t)i * PATCH_BYTES, c->bank + (size_t)slots[i] * PATCH_BYTES, PATCH_BYTES, cudaMemcpyDeviceToHost, c->stream));
+    rc = bank_copy_runs(c, slots, n, host_out, false);
+    if (rc) return rc;
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return BUSCA_OK;
 }
@@ -577,21 +621,37 @@ extern "C" int busca_motion_proposals(busca_ctx *c, const double *mean, const ui
 // tcgen05 path (bf16): per bottleneck  conv1 -> conv2 -> conv3 (statistics only) [-> downsample (statistics only)] -> conv3 again
 // with BN3 + identity/downsample + ReLU in its epilogue.  BN + ReLU of conv1 / conv2 is applied to the consumer's A tile in
 // shared memory, so no elementwise pass and no raw conv3 / downsample tensor ever touches HBM.
-static int reid_forward_tc(busca_ctx *c, const int32_t *d_slots, int N, float *d_emb) {
+// One BatchNorm batch as the encoder runs it: the distinct images, their multiplicities, and the size of the batch the
+// reference stacks (the divisor of every batch statistic).
+struct ReidBatch {
+    const int32_t *slots = nullptr;   // device [n]
+    int n = 0;                        // images the encoder runs on
+    int n_total = 0;                  // images of the stacked batch
+    const float *weight = nullptr;    // device [n] multiplicities, null = all 1 (n == n_total)
+    const int32_t *map = nullptr;     // device [n_total]: row of slots[] / of the embeddings for every stacked image
+};
+
+static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
+    const int32_t *d_slots = rb.slots;
+    const int N = rb.n;
+    const long long NT = rb.n_total;
+    const float *img_w = rb.weight;
     const size_t big = (size_t)786432 * N * 2;
-    const size_t total = 3 * big + (size_t)393216 * N * 2 + (size_t)196608 * N * 2 + (size_t)N * 2048 * 4 + 1024;
+    const size_t total = 3 * big + (size_t)393216 * N * 2 + (size_t)196608 * N * 2 + (size_t)N * 2048 * 4 + (size_t)N * 512 * 4 + 2048;
     cudaError_t e = c->ws_reid.ensure(total);
     if (e != cudaSuccess) return set_err(BUSCA_ERR_NOMEM, "ReID workspace for %d patches (%.1f GB): %s", N, total / 1e9, cudaGetErrorString(e));
     char *base = (char *)c->ws_reid.p;
     void *X0 = base, *X1 = base + big, *RS = base + 2 * big;
     void *R1 = base + 3 * big, *R2 = (char *)R1 + (size_t)393216 * N * 2;
     float *pooled = (float *)((char *)R2 + (size_t)196608 * N * 2);
+    float *emb_u = rb.map ? pooled + (((size_t)N * 2048 + 63) & ~(size_t)63) : d_emb;      // embeddings of the distinct images
     cudaStream_t s = c->stream;
     CUDA_OK(cudaMemsetAsync(c->stats_pool, 0, c->stats_bytes, s));
     ConvLayer &stem = c->convs[0];
     if (stem_tc_scratch_bytes(N) > big) return set_err(BUSCA_ERR_STATE, "stem scratch does not fit");
-    LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, X1, RS, stem.stats, s));
-    LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, (long long)N * 192 * 64, s));
+    if (c->profiling) { c->next_flops = 2.0 * N * 192 * 64 * 64.0 * 147; c->next_kernel = "conv_tc_kernel<64, 64, 0>"; }
+    LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, X1, RS, stem.stats, img_w, s));
+    LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, NT * 192 * 64, s));
     LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(RS, X0, N, 192, 64, 64, stem.scale, stem.shift, 1, s));
     void *x = X0, *other = X1;
     int H = 96, W = 32;
@@ -599,9 +659,15 @@ static int reid_forward_tc(busca_ctx *c, const int32_t *d_slots, int N, float *d
     const int blocks[4] = {3, 4, 6, 3};
     auto conv = [&](ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, const char *name) -> int {
         char nm[96];
-        if (c->profiling)
+        if (c->profiling) {
             snprintf(nm, sizeof(nm), "%s_tc[%d>%d s%d %dx%d%s]", name, L.cin, L.cout, L.stride, a.H, a.W,
                      o.mode == TC_MODE_STATS ? " stats" : (o.mode == TC_MODE_FINAL ? (o.ds ? " final+ds" : " final") : ""));
+            const bool dual = o.mode == TC_MODE_FINAL && o.ds;
+            c->next_flops = 2.0 * a.N * a.Ho * a.Wo * (double)L.cout * ((double)L.cin * L.k * L.k + (dual ? (double)o.ds->cin : 0.0));
+            char kn[64];
+            snprintf(kn, sizeof(kn), "conv_tc_kernel<%d, 128, %d>", dual ? 128 : (L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64)), dual ? 1 : 0);
+            c->next_kernel = kn;
+        }
         LAUNCH(c, c->profiling ? nm : name, launch_conv_tc(L, a, o, s));
         return BUSCA_OK;
     };
@@ -614,26 +680,26 @@ static int reid_forward_tc(busca_ctx *c, const int32_t *d_slots, int N, float *d
             ConvTcOpts raw{}, stats{}, fin{};
             stats.mode = TC_MODE_STATS;
             fin.mode = TC_MODE_FINAL;
-            a.N = N;
+            a.N = N; a.img_w = img_w;
             a.in = x; a.out = R1; a.H = H; a.W = W; a.Ho = H; a.Wo = W; a.in_scale = nullptr; a.in_shift = nullptr;
             if ((rc = conv(c1, a, raw, "conv1x1"))) return rc;
-            LAUNCH(c, "bn_finalize", launch_bn_finalize(c1, (long long)N * H * W, s));
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c1, NT * H * W, s));
             LAUNCH(c, "bn_fold", launch_bn_fold(c1.scale, c1.shift, c2, s));
             a.in = R1; a.out = R2; a.Ho = Ho; a.Wo = Wo; a.in_xf = c2.xf;
             if ((rc = conv(c2, a, raw, "conv3x3"))) return rc;
-            LAUNCH(c, "bn_finalize", launch_bn_finalize(c2, (long long)N * Ho * Wo, s));
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c2, NT * Ho * Wo, s));
             LAUNCH(c, "bn_fold", launch_bn_fold(c2.scale, c2.shift, c3, s));
             ConvArgs a3{};
-            a3.N = N; a3.in = R2; a3.out = other; a3.H = Ho; a3.W = Wo; a3.Ho = Ho; a3.Wo = Wo; a3.in_xf = c3.xf;
+            a3.N = N; a3.img_w = img_w; a3.in = R2; a3.out = other; a3.H = Ho; a3.W = Wo; a3.Ho = Ho; a3.Wo = Wo; a3.in_xf = c3.xf;
             if ((rc = conv(c3, a3, stats, "conv1x1"))) return rc;
-            LAUNCH(c, "bn_finalize", launch_bn_finalize(c3, (long long)N * Ho * Wo, s));
+            LAUNCH(c, "bn_finalize", launch_bn_finalize(c3, NT * Ho * Wo, s));
             fin.e_scale = c3.scale; fin.e_shift = c3.shift;
             if (b == 0) {
                 ConvLayer &ds = c->convs[ci + 3];
                 ConvArgs ad{};
-                ad.N = N; ad.in = x; ad.out = other; ad.H = H; ad.W = W; ad.Ho = Ho; ad.Wo = Wo;
+                ad.N = N; ad.img_w = img_w; ad.in = x; ad.out = other; ad.H = H; ad.W = W; ad.Ho = Ho; ad.Wo = Wo;
                 if ((rc = conv(ds, ad, stats, "conv1x1"))) return rc;
-                LAUNCH(c, "bn_finalize", launch_bn_finalize(ds, (long long)N * Ho * Wo, s));
+                LAUNCH(c, "bn_finalize", launch_bn_finalize(ds, NT * Ho * Wo, s));
                 fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W; fin.ds_scale = ds.scale; fin.ds_shift = ds.shift;
                 ci += 4;
             } else {
@@ -646,15 +712,52 @@ static int reid_forward_tc(busca_ctx *c, const int32_t *d_slots, int N, float *d
         }
     LAUNCH(c, "global_maxpool", launch_global_maxpool(x, pooled, N, H * W, 2048, 1, s));
     LinearArgs la{};
-    la.A = pooled; la.W = c->red_w; la.bias = c->red_b; la.residual = nullptr; la.out = d_emb; la.M = N; la.N = 512; la.K = 2048; la.alpha = 1.f; la.act = 0;
+    la.A = pooled; la.W = c->red_w; la.bias = c->red_b; la.residual = nullptr; la.out = emb_u; la.M = N; la.N = 512; la.K = 2048; la.alpha = 1.f; la.act = 0;
     LAUNCH(c, "linear", launch_linear_f32(la, s));
-    LAUNCH(c, "l2norm", launch_l2norm_rows(d_emb, N, 512, s));
+    LAUNCH(c, "l2norm", launch_l2norm_rows(emb_u, N, 512, s));
+    if (rb.map) LAUNCH(c, "gather_rows", launch_gather_rows(emb_u, rb.map, d_emb, rb.n_total, 512, s));
+    c->reid_images_run += N;
+    c->reid_images_total += NT;
     return BUSCA_OK;
 }
 
-static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *d_emb) {
-    if (N <= 0) return BUSCA_OK;
-    if (c->use_tc) return reid_forward_tc(c, d_slots, N, d_emb);
+// Plan a batch: enqueue the duplicate elimination of `d_slots` (plan index 0 or 1) and the copy of the distinct count.
+// Without dedup (fp32 parity mode keeps the reference's summation over the stacked batch) the plan is the identity.
+static int reid_plan(busca_ctx *c, const int32_t *d_slots, int N, int which, ReidBatch *rb) {
+    *rb = ReidBatch{};
+    rb->slots = d_slots; rb->n = N; rb->n_total = N;
+    if (!(c->use_tc && c->dedup) || N <= 1) return BUSCA_OK;
+    const size_t per = (((size_t)N * 4 + 255) & ~(size_t)255);
+    CUDA_OK(c->ws_dedup[which].ensure(3 * per + 256));
+    char *b = (char *)c->ws_dedup[which].p;
+    int32_t *uniq = (int32_t *)b, *map = (int32_t *)(b + per);
+    float *w = (float *)(b + 2 * per);
+    int *nu = (int *)(b + 3 * per);
+    LAUNCH(c, "dedup_slots", launch_dedup_slots(d_slots, N, c->dedup_table, uniq, map, w, nu, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->h_nuniq + which, nu, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    rb->slots = uniq; rb->map = map; rb->weight = w; rb->n = -1 - which;      // resolved by reid_plan_wait
+    return BUSCA_OK;
+}
+// Wait (host) for the distinct counts of the planned batches; everything enqueued before the plans has then run.
+static int reid_plan_wait(busca_ctx *c, ReidBatch *a, ReidBatch *b) {
+    if ((a && a->n < 0) || (b && b->n < 0)) {
+        CUDA_OK(cudaEventRecord(c->ev_plan, c->stream));
+        CUDA_OK(cudaEventSynchronize(c->ev_plan));
+        for (ReidBatch *r : {a, b})
+            if (r && r->n < 0) {
+                r->n = c->h_nuniq[-1 - r->n];
+                if (r->n <= 0 || r->n > r->n_total) return set_err(BUSCA_ERR_STATE, "dedup returned %d distinct images of %d", r->n, r->n_total);
+                if (r->n == r->n_total) { r->weight = nullptr; r->map = nullptr; }   // nothing repeated: uniq == the stacked batch, in order
+            }
+    }
+    return BUSCA_OK;
+}
+
+static int reid_forward_dev(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
+    if (rb.n_total <= 0) return BUSCA_OK;
+    if (c->use_tc) return reid_forward_tc(c, rb, d_emb);
+    const int32_t *d_slots = rb.slots;
+    const int N = rb.n;
     const int bf16 = c->cfg.precision == BUSCA_PREC_BF16;
     const size_t es = bf16 ? 2 : 4;
     const size_t big = (size_t)786432 * N * es;
@@ -717,6 +820,8 @@ static int reid_forward_dev(busca_ctx *c, const int32_t *d_slots, int N, float *
     la.A = pooled; la.W = c->red_w; la.bias = c->red_b; la.residual = nullptr; la.out = d_emb; la.M = N; la.N = 512; la.K = 2048; la.alpha = 1.f; la.act = 0;
     LAUNCH(c, "linear", launch_linear_f32(la, s));
     LAUNCH(c, "l2norm", launch_l2norm_rows(d_emb, N, 512, s));
+    c->reid_images_run += N;
+    c->reid_images_total += N;
     return BUSCA_OK;
 }
 
@@ -732,7 +837,10 @@ extern "C" int busca_reid_embed(busca_ctx *c, const int32_t *slots, int32_t n, f
     float *demb = (float *)((char *)c->ws_io.p + (((size_t)n * 4 + 255) & ~(size_t)255));
     CUDA_OK(cudaMemcpyAsync(dsl, slots, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     prof_reset(c);
-    rc = reid_forward_dev(c, dsl, n, demb);
+    ReidBatch rb;
+    if ((rc = reid_plan(c, dsl, n, 0, &rb))) return rc;
+    if ((rc = reid_plan_wait(c, &rb, nullptr))) return rc;
+    rc = reid_forward_dev(c, rb, demb);
     if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(out, demb, (size_t)n * 512 * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -890,9 +998,13 @@ extern "C" int busca_associate(busca_ctx *c, const busca_assoc_args *a) {
                                                                  a->use_kalman ? (const int32_t *)(b + o_ks) : nullptr, (double *)(b + o_cb),
                                                                  (int32_t *)(b + o_cs), c->cfg.sentinel_fp64, s));
     LAUNCH(c, "pe_index", launch_pe_index((const double *)(b + o_mb), (const double *)(b + o_cb), T, L, C, c->cfg.sentinel_fp64, (int32_t *)(b + o_idx), s));
-    rc = reid_forward_dev(c, (const int32_t *)(b + o_ms), T * L, (float *)(b + o_me));
+    ReidBatch rb_mem, rb_can;
+    if ((rc = reid_plan(c, (const int32_t *)(b + o_ms), T * L, 0, &rb_mem))) return rc;
+    if ((rc = reid_plan(c, (const int32_t *)(b + o_cs), T * C, 1, &rb_can))) return rc;
+    if ((rc = reid_plan_wait(c, &rb_mem, &rb_can))) return rc;
+    rc = reid_forward_dev(c, rb_mem, (float *)(b + o_me));
     if (rc) return rc;
-    rc = reid_forward_dev(c, (const int32_t *)(b + o_cs), T * C, (float *)(b + o_ce));
+    rc = reid_forward_dev(c, rb_can, (float *)(b + o_ce));
     if (rc) return rc;
     TrOut o{(float *)(b + o_lg), (float *)(b + o_pr), a->cand_rows ? (float *)(b + o_cr) : nullptr, a->mem_logits ? (float *)(b + o_ml) : nullptr,
             a->input_seq ? (float *)(b + o_is) : nullptr};
@@ -957,9 +1069,14 @@ extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
                                                                  (const double *)(b + o_tlwh), a->kal_slots_dev, (double *)(b + o_cb), (int32_t *)(b + o_cs),
                                                                  c->cfg.sentinel_fp64, s));
     LAUNCH(c, "pe_index", launch_pe_index(a->mem_ltwh_dev, (const double *)(b + o_cb), T, L, C, c->cfg.sentinel_fp64, (int32_t *)(b + o_idx), s));
-    int rc = reid_forward_dev(c, a->mem_slots_dev, T * L, (float *)(b + o_me));
+    int rc;
+    ReidBatch rb_mem, rb_can;
+    if ((rc = reid_plan(c, a->mem_slots_dev, T * L, 0, &rb_mem))) return rc;
+    if ((rc = reid_plan(c, (const int32_t *)(b + o_cs), T * C, 1, &rb_can))) return rc;
+    if ((rc = reid_plan_wait(c, &rb_mem, &rb_can))) return rc;
+    rc = reid_forward_dev(c, rb_mem, (float *)(b + o_me));
     if (rc) return rc;
-    rc = reid_forward_dev(c, (const int32_t *)(b + o_cs), T * C, (float *)(b + o_ce));
+    rc = reid_forward_dev(c, rb_can, (float *)(b + o_ce));
     if (rc) return rc;
     TrOut o{(float *)(b + o_lg), a->probs_dev, nullptr, nullptr, nullptr};
     rc = transformer_dev(c, T, L, C, (const float *)(b + o_me), (const float *)(b + o_ce), (const int32_t *)(b + o_idx), o);
@@ -1048,7 +1165,7 @@ extern "C" int busca_debug_stem(busca_ctx *c, const int32_t *slots, int32_t N, i
     CUDA_OK(cudaMemcpyAsync(dsl, slots, (size_t)N * 4, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemsetAsync(L.stats, 0, 2 * 64 * sizeof(double), s));
     prof_reset(c);
-    if (use_tc) LAUNCH(c, "stem_tc", launch_stem_tc(c->bank, dsl, N, c->lut, L.w16, dscr, dout, L.stats, s));
+    if (use_tc) LAUNCH(c, "stem_tc", launch_stem_tc(c->bank, dsl, N, c->lut, L.w16, dscr, dout, L.stats, nullptr, s));
     else LAUNCH(c, "stem_simt", launch_stem(c->bank, dsl, N, c->lut, L, dout, 1, s));
     CUDA_OK(cudaMemcpyAsync(out_bf16, dout, out_b, cudaMemcpyDeviceToHost, s));
     if (stats_out) CUDA_OK(cudaMemcpyAsync(stats_out, L.stats, 2 * 64 * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1074,6 +1191,18 @@ extern "C" void *busca_dev_alloc(busca_ctx *c, int64_t bytes) {
     return p;
 }
 extern "C" void busca_dev_free(busca_ctx *c, void *p) { if (c && p) { cudaSetDevice(c->cfg.device); cudaFree(p); } }
+extern "C" void *busca_host_alloc(busca_ctx *c, int64_t bytes) {
+    if (!c || bytes <= 0) return nullptr;
+    cudaSetDevice(c->cfg.device);
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) { set_err(BUSCA_ERR_NOMEM, "cudaHostAlloc(%lld) failed", (long long)bytes); return nullptr; }
+    return p;
+}
+extern "C" void busca_host_free(busca_ctx *c, void *p) {      // ctx may be NULL (a block outliving its context)
+    if (!p) return;
+    if (c) cudaSetDevice(c->cfg.device);
+    cudaFreeHost(p);
+}
 extern "C" int busca_memcpy_h2d(busca_ctx *c, void *dst, const void *src, int64_t bytes) {
     if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
     CUDA_OK(cudaSetDevice(c->cfg.device));
@@ -1104,3 +1233,15 @@ extern "C" int busca_set_profiling(busca_ctx *c, int32_t on) {
     return BUSCA_OK;
 }
 extern "C" const char *busca_last_profile(busca_ctx *c) { return c ? c->prof_json.c_str() : "{}"; }
+extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
+    if (!c || !name) return set_err(BUSCA_ERR_ARG, "null argument");
+    if (strcmp(name, "dedup") == 0) { c->dedup = value != 0; return BUSCA_OK; }
+    return set_err(BUSCA_ERR_ARG, "unknown option '%s'", name);
+}
+extern "C" int64_t busca_counter(busca_ctx *c, const char *name) {
+    if (!c || !name) return -1;
+    if (strcmp(name, "reid_images_run") == 0) return c->reid_images_run;
+    if (strcmp(name, "reid_images_total") == 0) return c->reid_images_total;
+    if (strcmp(name, "kernel_launches") == 0) return c->launches;
+    return -1;
+}

@@ -73,6 +73,8 @@ struct TcParams {
     const float *residual;           // F32: float [M, Cout] or null
     float alpha;
     int act;                         // F32: 0 none, 1 relu, 2 gelu
+    const float *img_w;              // [Nimg] multiplicity of every image in the batch statistics, or null (= 1): see dedup_slots_kernel
+    int img_shift;                   // log2(BW*BH): tile row >> img_shift = image of the row within the tile
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -465,6 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         };
         const bool stats_t = BN == 256 && !DUAL && p.mode == MODE_STATS;
+        const bool weighted = want_stats && p.img_w != nullptr;
         int it = 0, gcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -475,6 +478,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (BN == 256 && !DUAL && p.mode == MODE_STATS) {
                 // transposed accumulator (see the MMA issuer): lane = channel, columns = pixels; this warp sums 64 of the 128 pixels
                 if (n_tile != stats_ntile) { flush_stats_t(); stats_ntile = n_tile; }
+                // multiplicity of the image each 16-column run of this warp's 64 pixels belongs to (an image is >= 16 pixels)
+                float wc[4] = {1.f, 1.f, 1.f, 1.f};
+                if (weighted) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) wc[u] = __ldg(p.img_w + min(n0 + ((half * 64 + u * 16) >> p.img_shift), p.Nimg - 1));
+                }
                 mbar_wait<0>(&tfull[acc], acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -486,13 +495,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         TMEM_LD_WAIT();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float x = __uint_as_float(r[j]);
-                            ts[h] += x;
-                            tq[h] = fmaf(x, x, tq[h]);
+                            const float x = __uint_as_float(r[j]), xw = x * wc[c2 * 2 + (j >> 4)];
+                            ts[h] += xw;
+                            tq[h] = fmaf(xw, x, tq[h]);
                         }
                     }
             } else if (p.mode == MODE_RAW || p.mode == MODE_STATS) {
                 if (want_stats && n_tile != stats_ntile) { flush_stats(); stats_ntile = n_tile; }
+                float wr[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};      // multiplicity of the image of each of this thread's 8 statistics rows
+                if (weighted) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wr[i] = __ldg(p.img_w + min(n0 + ((rsub + 16 * i) >> p.img_shift), p.Nimg - 1));
+                }
                 mbar_wait<0>(&tfull[acc], acc_phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -521,10 +535,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         for (int i = 0; i < 8; ++i) {
                             const uint2 v = lds64(st + st_off + (uint32_t)i * 2048);
                             const float x0 = bf_lo(v.x), x1 = bf_hi(v.x), x2 = bf_lo(v.y), x3 = bf_hi(v.y);
-                            acc_s[g][0] += x0; acc_q[g][0] = fmaf(x0, x0, acc_q[g][0]);
-                            acc_s[g][1] += x1; acc_q[g][1] = fmaf(x1, x1, acc_q[g][1]);
-                            acc_s[g][2] += x2; acc_q[g][2] = fmaf(x2, x2, acc_q[g][2]);
-                            acc_s[g][3] += x3; acc_q[g][3] = fmaf(x3, x3, acc_q[g][3]);
+                            const float w0 = x0 * wr[i], w1 = x1 * wr[i], w2 = x2 * wr[i], w3 = x3 * wr[i];
+                            acc_s[g][0] += w0; acc_q[g][0] = fmaf(w0, x0, acc_q[g][0]);
+                            acc_s[g][1] += w1; acc_q[g][1] = fmaf(w1, x1, acc_q[g][1]);
+                            acc_s[g][2] += w2; acc_q[g][2] = fmaf(w2, x2, acc_q[g][2]);
+                            acc_s[g][3] += w3; acc_q[g][3] = fmaf(w3, x3, acc_q[g][3]);
                         }
                     }
                 }
@@ -771,6 +786,10 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     p.a_xf = a.in_xf;
     p.e_scale = o.e_scale; p.e_shift = o.e_shift; p.d_scale = o.ds_scale; p.d_shift = o.ds_shift;
     p.out = a.out; p.stats = p.mode == MODE_FINAL ? nullptr : L.stats; p.bias = nullptr; p.residual = nullptr; p.alpha = 1.f; p.act = 0;
+    p.img_w = a.img_w;
+    p.img_shift = 0;
+    while ((1 << p.img_shift) < p.BW * p.BH) ++p.img_shift;
+    if ((1 << p.img_shift) != p.BW * p.BH || (a.img_w && p.BW * p.BH < 16)) return cudaErrorInvalidValue;
     TcMaps m;
     const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(a.in);
     const long long C = L.cin, W = a.W, H = a.H;
@@ -896,7 +915,7 @@ size_t stem_tc_scratch_bytes(int N) { return (size_t)N * PATCH_H * STEM_PITCH_PX
 
 // wstem: bf16 [64][7*32], element (ky, kx*4 + c_bgr) ; scratch: stem_tc_scratch_bytes(N); out: bf16 [N,192,64,64]
 cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem, void *scratch, void *out,
-                           double *stats, cudaStream_t s) {
+                           double *stats, const float *img_w, cudaStream_t s) {
     if (N <= 0) return cudaSuccess;
     const long long total_px = (long long)N * PATCH_H * STEM_PITCH_PX;
     long long blocks = (total_px + 255) / 256;
@@ -915,6 +934,7 @@ cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, con
     p.Ho = 192; p.Wo = 64; p.Nimg = N; p.Cout = 64; p.Hv = 192; p.Wv = 64;
     p.mode = MODE_RAW;
     p.out = out; p.stats = stats; p.alpha = 1.f;
+    p.img_w = img_w; p.img_shift = 7;                                 // BW*BH = 128 rows of one image
     const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(scratch);
     const long long pitch = (long long)STEM_PITCH_PX * 4;             // elements per padded row
     TcMaps m;

@@ -46,6 +46,7 @@ struct ConvArgs {
     int Ho, Wo;
     const float *in_scale, *in_shift;   // SIMT kernel: deferred BN+ReLU of the producer applied on load (null = identity)
     const uint16_t *in_xf;              // tensor-core kernel: the same as an exact max-transform (ConvLayer::xf), weights = w16s
+    const float *img_w;                 // tensor-core kernel: per-image multiplicity weighting the batch statistics (null = 1)
 };
 cudaError_t launch_stem(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const ConvLayer &L, void *out,
                         int bf16, cudaStream_t s);
@@ -71,7 +72,7 @@ struct ConvTcOpts {
 cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s);
 size_t stem_tc_scratch_bytes(int N);
 cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem_bf16, void *scratch, void *out,
-                           double *stats, cudaStream_t s);
+                           double *stats, const float *img_w, cudaStream_t s);
 // x = relu(x*scale + shift) in place (bf16 or float), rows x C
 cudaError_t launch_bn_relu_inplace(void *x, const float *scale, const float *shift, long long rows, int C, int bf16, cudaStream_t s);
 cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,
@@ -82,6 +83,9 @@ cudaError_t launch_bn_add_relu(const void *raw, const float *scale, const float 
                                cudaStream_t s);
 cudaError_t launch_global_maxpool(const void *x, float *out, int N, int HW, int C, int bf16, cudaStream_t s);
 cudaError_t launch_l2norm_rows(float *x, int rows, int cols, cudaStream_t s);
+// distinct bank slots of one BatchNorm batch + multiplicities (see reid.cu); table: [bank_slots + 1] ints, all 0x7f7f7f7f
+cudaError_t launch_dedup_slots(const int32_t *slots, int n, int *table, int32_t *uniq, int32_t *map, float *weight, int *n_uniq, cudaStream_t s);
+cudaError_t launch_gather_rows(const float *src, const int32_t *map, float *dst, int rows, int cols, cudaStream_t s);
 
 // ---------------------------------------------------------------- linear (reid.cu): out = act((A W^T + b) * alpha) + res
 struct LinearArgs {

@@ -643,6 +643,74 @@ cudaError_t launch_global_maxpool(const void *x, float *out, int N, int HW, int 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Duplicate elimination inside one BatchNorm batch.  The candidate patches of different tracks are the SAME detections
+// (T*C slots drawn from D + T crops) and every incomplete history is the same zero image, so the batch the reference
+// stacks (network.py:313-316, 383-386) holds many identical images.  An image's activations depend on the rest of the
+// batch only through the batch statistics, so the encoder runs once per DISTINCT bank slot and every statistic is
+// weighted by the slot's multiplicity: sum_i x_i over the stacked batch == sum_u w_u x_u over the distinct images.
+//   slots [n] (-1 = zero image)  ->  uniq [nu] (first occurrence order), map [n] (row of uniq), weight [nu], *nu
+// table [bank_slots + 1] must be all INT_MAX-like (0x7f7f7f7f) on entry and is restored on exit.  One CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) dedup_slots_kernel(const int32_t *__restrict__ slots, int n, int *__restrict__ table,
+                                                            int32_t *__restrict__ uniq, int32_t *__restrict__ map,
+                                                            float *__restrict__ weight, int *__restrict__ n_uniq) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + 1023) / 1024, lo = t * per, hi = min(n, lo + per);
+#define KEY(i) (max(slots[i], -1) + 1)                         /* every negative slot is the zero image */
+    for (int i = t; i < n; i += 1024) weight[i] = 0.f;
+    for (int i = lo; i < hi; ++i) atomicMin(&table[KEY(i)], i);
+    __syncthreads();
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += table[KEY(i)] == i;
+    part[t] = cnt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {              // inclusive scan of the per-thread counts
+        const int v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int rank = part[t] - cnt;
+    if (t == 1023) *n_uniq = part[1023];
+    __syncthreads();                                        // everyone has read table[] == first index
+    for (int i = lo; i < hi; ++i)
+        if (table[KEY(i)] == i) uniq[rank++] = slots[i];
+    __syncthreads();
+    rank = part[t] - cnt;
+    for (int i = lo; i < hi; ++i)                           // representatives publish their rank as -(rank + 1)
+        if (table[KEY(i)] == i) table[KEY(i)] = -(rank++ + 1);
+    __syncthreads();
+    for (int i = lo; i < hi; ++i) {
+        const int r = -table[KEY(i)] - 1;
+        map[i] = r;
+        atomicAdd(&weight[r], 1.f);
+    }
+    __syncthreads();
+    for (int i = lo; i < hi; ++i) table[KEY(i)] = 0x7f7f7f7f;
+#undef KEY
+}
+
+__global__ void gather_rows_kernel(const float4 *__restrict__ src, const int32_t *__restrict__ map, float4 *__restrict__ dst, int rows, int cols4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * cols4) return;
+    const int r = (int)(i / cols4), c = (int)(i % cols4);
+    dst[i] = src[(long long)map[r] * cols4 + c];
+}
+
+cudaError_t launch_dedup_slots(const int32_t *slots, int n, int *table, int32_t *uniq, int32_t *map, float *weight, int *n_uniq, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dedup_slots_kernel<<<1, 1024, 0, s>>>(slots, n, table, uniq, map, weight, n_uniq);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather_rows(const float *src, const int32_t *map, float *dst, int rows, int cols, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    const long long total = (long long)rows * (cols / 4);
+    gather_rows_kernel<<<ceil_div(total, 256), 256, 0, s>>>((const float4 *)src, map, (float4 *)dst, rows, cols / 4);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_l2norm_rows(float *x, int rows, int cols, cudaStream_t s) {
     if (rows <= 0) return cudaSuccess;
     l2norm_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, cols);

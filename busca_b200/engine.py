@@ -4,7 +4,9 @@ from __future__ import annotations
 
 import ctypes as C
 import json
-from typing import Dict, Iterable, Optional
+import os
+import weakref
+from typing import Dict, Iterable, List, Optional, Tuple
 
 import numpy as np
 
@@ -50,6 +52,17 @@ def pe_tables(d_model: int = 512):
             code(61)[:, : d_model - 2 * ch].to(torch.float16).numpy())
 
 
+class _PinnedBlock:
+    """Owner of one page-locked host allocation, visible to numpy through ``__array_interface__``.  Every array (and
+    every row view an adapter keeps in ``track.images_mem``) made from it holds a reference to it, so the memory goes
+    back to the engine's pool exactly when the last view dies."""
+    __slots__ = ("ptr", "nbytes", "__array_interface__", "__weakref__")
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
 class Engine:
     def __init__(self, device: int = 0, d_model: int = 512, nhead: int = 4, ff_size: int = 1024, num_layers: int = 4,
                  activation: str = "relu", precision: str = "fp32", sentinel_fp64: bool = True, bank_slots: int = 2048):
@@ -64,11 +77,45 @@ class Engine:
         self.d_model = d_model
         self._free = list(range(bank_slots - 1, -1, -1))
         self._cap = bank_slots
+        # page-locked pool for the crop arrays handed to the caller: size class (patches, power of two) -> free pointers
+        self._pin_free: Dict[int, List[int]] = {}
+        self._pin_total = 0
+        self._pin_max = int(float(os.environ.get("BUSCA_PINNED_MAX_GB", "8")) * (1 << 30))
 
     def close(self):
         if getattr(self, "h", None):
+            for ptrs in self._pin_free.values():
+                for p in ptrs:
+                    self.L.busca_host_free(self.h, p)
+            self._pin_free = {}
             self.L.busca_destroy(self.h)
             self.h = None
+
+    # ---- page-locked host pool ------------------------------------------------------------
+    def _pin_get(self, n_patches: int) -> Optional[_PinnedBlock]:
+        cls = 1 << max(0, int(n_patches - 1).bit_length())
+        nbytes = cls * PATCH_BYTES
+        free = self._pin_free.get(cls)
+        if free:
+            ptr = free.pop()
+        else:
+            if self._pin_total + nbytes > self._pin_max:
+                return None                                 # over the cap: the caller falls back to pageable memory
+            ptr = self.L.busca_host_alloc(self.h, nbytes)
+            if not ptr:
+                return None
+            self._pin_total += nbytes
+        blk = _PinnedBlock(ptr, nbytes)
+        weakref.finalize(blk, Engine._pin_release, weakref.ref(self), self.L, ptr, cls)
+        return blk
+
+    @staticmethod
+    def _pin_release(self_ref, lib, ptr, cls):
+        self = self_ref()
+        if self is not None and self.h is not None:
+            self._pin_free.setdefault(cls, []).append(ptr)
+        else:
+            lib.busca_host_free(None, ptr)
 
     def __del__(self):
         try:
@@ -125,6 +172,23 @@ class Engine:
         out = np.empty((len(boxes),) + PATCH_SHAPE, np.uint8) if to_host else None
         check(self.L.busca_crop(self.h, _ptr(boxes), len(boxes), _ptr(slots), _ptr(out)))
         return out
+
+    def crop_owned(self, boxes: np.ndarray, slots: np.ndarray) -> Tuple[np.ndarray, object]:
+        """Crops to bank slots AND to the host, into page-locked memory from the pool.  Returns ``(array, owner)``:
+        ``owner`` is the object that dies when the array and all of its views are gone (the pinned block, or the
+        array itself on the pageable fallback) - hang slot-recycling finalizers on it."""
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 4)
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        n = len(boxes)
+        blk = self._pin_get(n)
+        if blk is None:
+            out = np.empty((n,) + PATCH_SHAPE, np.uint8)
+            owner = out
+        else:
+            out = np.asarray(blk)[: n * PATCH_BYTES].reshape((n,) + PATCH_SHAPE)
+            owner = blk
+        check(self.L.busca_crop(self.h, _ptr(boxes), n, _ptr(slots), _ptr(out)))
+        return out, owner
 
     def bank_upload(self, patches: np.ndarray, slots: np.ndarray):
         patches = np.ascontiguousarray(patches, dtype=np.uint8).reshape(-1, *PATCH_SHAPE)
@@ -271,6 +335,12 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(self.L.busca_kernel_launches(self.h))
+
+    def set_option(self, name: str, value: int):
+        check(self.L.busca_set_option(self.h, name.encode(), int(value)))
+
+    def counter(self, name: str) -> int:
+        return int(self.L.busca_counter(self.h, name.encode()))
 
     def set_profiling(self, on: bool):
         check(self.L.busca_set_profiling(self.h, int(on)))

@@ -44,13 +44,16 @@ class _PatchRegistry:
     def __init__(self, engine: Engine):
         self.engine = engine
         self.slot_of: Dict[int, int] = {}
+        self._by_id: Dict[int, tuple] = {}
 
-    def register(self, arr: np.ndarray, slots: np.ndarray):
+    def register(self, arr: np.ndarray, slots: np.ndarray, owner=None):
+        """``owner``: the object that outlives every view of ``arr`` (the pinned block for pooled arrays; ``arr`` itself
+        when it owns its data - numpy points a row view's ``.base`` at the owner, not at ``arr``)."""
         base = arr.ctypes.data
-        keys = [base + i * PATCH_BYTES for i in range(len(slots))]
-        for k, s in zip(keys, slots):
-            self.slot_of[k] = int(s)
-        weakref.finalize(arr, _PatchRegistry._release, weakref.ref(self), keys, [int(s) for s in slots])
+        sl = slots.tolist()
+        keys = [base + i * PATCH_BYTES for i in range(len(sl))]
+        self.slot_of.update(zip(keys, sl))
+        weakref.finalize(arr if owner is None else owner, _PatchRegistry._release, weakref.ref(self), keys, sl)
 
     @staticmethod
     def _release(self_ref, keys, slots):
@@ -60,11 +63,27 @@ class _PatchRegistry:
         for k in keys:
             self.slot_of.pop(k, None)
         self.engine.free_slots(slots)
+        # (the per-object cache entries died with their arrays: the owner outlives every view)
 
     def lookup(self, patch: np.ndarray) -> Optional[int]:
         if patch.dtype != np.uint8 or patch.shape != PATCH_SHAPE or not patch.flags["C_CONTIGUOUS"]:
             return None
         return self.slot_of.get(patch.ctypes.data)
+
+    def lookup_cached(self, patch) -> Optional[int]:
+        """``lookup`` for the per-frame loops: adapters keep the SAME array objects in ``track.images_mem`` from frame
+        to frame, so the slot is remembered per object (id + weak reference, so a recycled id can never alias)."""
+        hit = self._by_id.get(id(patch))
+        if hit is not None and hit[0]() is patch:
+            return hit[1]
+        if not isinstance(patch, np.ndarray):
+            return None
+        s = self.lookup(patch)
+        if s is not None:
+            key = id(patch)
+            by_id = self._by_id
+            self._by_id[key] = (weakref.ref(patch, lambda _r, key=key, by_id=by_id: by_id.pop(key, None)), s)
+        return s
 
 
 class BUSCA:
@@ -148,14 +167,18 @@ class BUSCA:
             output_size = (self.expected_image_size[1], self.expected_image_size[0])
         if tuple(output_size) != (128, 384):
             raise NotImplementedError("crops are fixed at 128x384")
-        boxes = [np.asarray(b, dtype=np.float64).reshape(4) for b in bboxes]
+        if isinstance(bboxes, np.ndarray) and bboxes.ndim == 2 and bboxes.shape[1] == 4:
+            boxes = np.ascontiguousarray(bboxes, dtype=np.float64)
+        else:
+            rows = [np.asarray(b, dtype=np.float64).reshape(4) for b in bboxes]
+            boxes = np.stack(rows) if rows else np.zeros((0, 4))
         if len(boxes) == 0:
             return np.zeros([0, output_size[0], output_size[1], 3])       # float64, dims swapped - as network.py:503
         assert image is not None, "Image is None"
         self._ensure_frame(image)
         slots = self.engine.alloc_slots(len(boxes))
-        crops = self.engine.crop(np.stack(boxes), slots, to_host=True)
-        self._registry.register(crops, slots)
+        crops, owner = self.engine.crop_owned(boxes, slots)
+        self._registry.register(crops, slots, owner)
         if normalize:
             return np.stack([tracking.normalize_crop(c) for c in crops], axis=0)
         return crops
@@ -193,8 +216,14 @@ class BUSCA:
         temp_slots: List[int] = []
         pending = []                                       # (patch array, slot) uploads for arrays we have never seen
 
+        lookup = self._registry.lookup_cached
+        by_id = self._registry._by_id
+
         def slot_for(patch) -> int:
-            s = self._registry.lookup(patch) if isinstance(patch, np.ndarray) else None
+            hit = by_id.get(id(patch))                     # same array object as in an earlier frame: one dict probe
+            if hit is not None and hit[0]() is patch:
+                return hit[1]
+            s = lookup(patch)
             if s is None:
                 arr = np.ascontiguousarray(np.asarray(patch), dtype=np.uint8)
                 if arr.shape != PATCH_SHAPE:
@@ -212,23 +241,19 @@ class BUSCA:
                 sel = self._memory_indices(len(track.images_mem), L, use_broader_memory)
                 if len(sel) == L:
                     reliable[t] = True
-                    for i, j in enumerate(sel):
-                        mem_slots[t, i] = slot_for(track.images_mem[j])
-                        mem_ltwh[t, i] = np.asarray(track.tlwh_mem[j], np.float64) * track.scale
+                    ims, boxes = track.images_mem, track.tlwh_mem
+                    mem_slots[t] = [slot_for(ims[j]) for j in sel]
+                    mem_ltwh[t] = np.array([boxes[j] for j in sel], dtype=np.float64) * track.scale
                 else:                                      # incomplete history: zero images + filler box (network.py:304-308)
                     mem_ltwh[t] = np.array([250.0, 250.0, 500.0, 500.0])
-            det_slots = np.empty(D, np.int32)
-            det_ltwh = np.empty((D, 4), np.float64)
-            for j, det in enumerate(dets_embeddings):
-                det_slots[j] = slot_for(det.images_mem[-1])
-                det_ltwh[j] = np.asarray(det.tlwh_mem[-1], np.float64) * det.scale
+            det_slots = np.array([slot_for(det.images_mem[-1]) for det in dets_embeddings], np.int32).reshape(D)
+            det_ltwh = np.array([det.tlwh_mem[-1] for det in dets_embeddings], np.float64).reshape(D, 4) \
+                * np.array([det.scale for det in dets_embeddings], np.float64).reshape(D, 1)
             kal_slots = kal_ltwh = None
             if K:
-                kal_slots = np.empty(T, np.int32)
-                kal_ltwh = np.empty((T, 4), np.float64)
-                for t, kd in enumerate(extra_kalman_candidates):
-                    kal_slots[t] = slot_for(kd.images_mem[-1])
-                    kal_ltwh[t] = np.asarray(kd.tlwh, np.float64) * kd.scale
+                kal_slots = np.array([slot_for(kd.images_mem[-1]) for kd in extra_kalman_candidates], np.int32)
+                kal_ltwh = np.array([kd.tlwh for kd in extra_kalman_candidates], np.float64).reshape(T, 4) \
+                    * np.array([kd.scale for kd in extra_kalman_candidates], np.float64).reshape(T, 1)
             if pending:
                 self.engine.bank_upload(np.stack([p for p, _ in pending]), np.array([s for _, s in pending], np.int32))
             dists = np.asarray(dists_matrix, np.float64).reshape(T, D) if D else None
@@ -245,15 +270,17 @@ class BUSCA:
         # scatter into the global matrix (network.py:407-425)
         n_avail = min(D + 1, C) if K else min(D, C)
         probs_matrix = np.zeros([T, D + K])
-        for t in range(T):
-            p = probs[t]
-            if select_highest_candidate:
-                q = np.zeros_like(p)
-                thr = highest_candidate_minimum_thresh
-                if thr is None or thr == 0 or (thr > 0.0 and np.max(p) >= thr):
-                    q[np.argmax(p)] = np.max(p) if keep_highest_value else 1.0
-                p = q
-            probs_matrix[t, cand[t, :n_avail]] = p[:n_avail]
+        rows = np.arange(T)
+        if select_highest_candidate:
+            best = np.argmax(probs, axis=1)                     # first maximum, as np.argmax in the reference loop
+            top = probs[rows, best]
+            q = np.zeros_like(probs)
+            thr = highest_candidate_minimum_thresh
+            on = np.ones(T, bool) if (thr is None or thr == 0) else ((top >= thr) if thr > 0.0 else np.zeros(T, bool))
+            q[rows[on], best[on]] = top[on] if keep_highest_value else 1.0
+            probs = q
+        # the n_avail candidate columns of a track are distinct (detection ids + its own Kalman column)
+        probs_matrix[rows[:, None], cand[:, :n_avail]] = probs[:, :n_avail]
         return probs_matrix, reliable
 
     @staticmethod

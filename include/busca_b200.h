@@ -175,6 +175,10 @@ int busca_debug_stem(busca_ctx *ctx, const int32_t *slots, int32_t N, int32_t us
 /* ---- plumbing -------------------------------------------------------------------------------- */
 void *busca_dev_alloc(busca_ctx *ctx, int64_t bytes);
 void busca_dev_free(busca_ctx *ctx, void *p);
+/* page-locked host memory for the arrays get_image_crops hands to the caller (network.py:492-507): crops reach the
+ * host by ONE direct DMA per contiguous slot run instead of a staged pageable copy per crop */
+void *busca_host_alloc(busca_ctx *ctx, int64_t bytes);
+void busca_host_free(busca_ctx *ctx, void *p);
 int busca_memcpy_h2d(busca_ctx *ctx, void *dst_dev, const void *src, int64_t bytes);
 int busca_memcpy_d2h(busca_ctx *ctx, void *dst, const void *src_dev, int64_t bytes);
 int busca_sync(busca_ctx *ctx);
@@ -183,6 +187,12 @@ int64_t busca_kernel_launches(busca_ctx *ctx);    /* kernels launched by this co
 /* per-kernel device time of the most recent associate / step, name -> ms, as JSON (CUDA events) */
 int busca_set_profiling(busca_ctx *ctx, int32_t on);
 const char *busca_last_profile(busca_ctx *ctx);
+/* options: "dedup" (default 1, bf16 mode): run the ReID encoder once per DISTINCT patch of a BatchNorm batch and weight
+ * the batch statistics by the multiplicities - the batches the reference stacks (network.py:313-316, 383-386) repeat
+ * every detection crop for each track that lists it as a candidate, and every incomplete history is the same zero image */
+int busca_set_option(busca_ctx *ctx, const char *name, int64_t value);
+/* counters: "reid_images_run" / "reid_images_total" (encoder images executed / images of the stacked batches), "kernel_launches" */
+int64_t busca_counter(busca_ctx *ctx, const char *name);
 
 #ifdef __cplusplus
 }

@@ -338,3 +338,39 @@ def test_bf16_association_vs_reference(busca_bf16, golden_dir, name):
     srt = np.sort(ref_p, axis=1)
     clear_top = (srt[:, -1] - srt[:, -2]) > BF16_MARGIN
     assert np.array_equal(out["probs"].argmax(1)[clear_top], ref_p.argmax(1)[clear_top])
+
+
+def test_dedup_equals_stacked_batch(busca_bf16):
+    """Running the encoder once per DISTINCT patch with multiplicity-weighted batch statistics (the default in bf16
+    mode) is the same computation as running the stacked batch the reference builds (network.py:313-316, 383-386):
+    only the summation order of the statistics differs."""
+    m = busca_bf16
+    eng = m.engine
+    rng = np.random.default_rng(11)
+    frame = synth.make_frame(3)
+    H, W = frame.shape[:2]
+    boxes = synth.random_boxes(rng, 9, H, W)
+    boxes[:, 2:] += boxes[:, :2]
+    crops = m.get_image_crops(frame, boxes, normalize=False)
+    base = np.array([m._registry.lookup(c) for c in crops], np.int32)
+    # 40 stacked images: 9 distinct crops with multiplicities 1..8 and the zero image (-1) four times
+    slots = np.concatenate([np.repeat(base, [1, 2, 3, 4, 5, 6, 7, 7, 1]), np.full(4, -1, np.int32)])
+    rng.shuffle(slots)
+    run0, tot0 = eng.counter("reid_images_run"), eng.counter("reid_images_total")
+    on = eng.reid_embed(slots)
+    assert eng.counter("reid_images_run") - run0 == 10 and eng.counter("reid_images_total") - tot0 == len(slots)
+    eng.set_option("dedup", 0)
+    try:
+        run0 = eng.counter("reid_images_run")
+        off = eng.reid_embed(slots)
+        assert eng.counter("reid_images_run") - run0 == len(slots)
+    finally:
+        eng.set_option("dedup", 1)
+    cos = (on * off).sum(1) / (np.linalg.norm(on, axis=1) * np.linalg.norm(off, axis=1))
+    assert cos.min() > 0.999, cos.min()
+    assert np.abs(on - off).max() < 5e-3, np.abs(on - off).max()
+    # identical inputs -> identical rows, in both modes
+    for s in np.unique(slots):
+        rows = np.nonzero(slots == s)[0]
+        assert np.array_equal(on[rows], np.repeat(on[rows[:1]], len(rows), 0))
+        assert np.array_equal(off[rows], np.repeat(off[rows[:1]], len(rows), 0))

@@ -1,36 +1,75 @@
 #!/usr/bin/env python
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel (count, total ms, share).
+"""Summarise an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum,
+sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed] --csv` launch list by kernel:
+count, total ms, share of device time and - when captured - DRAM traffic per launch, the DRAM bandwidth that
+traffic means and the mean tensor-pipe activity.
 
-    python tools/ncu_launch_summary.py gpurun_out/launches.csv > profiles/rNN_launches_summary.md
+    python tools/ncu_launch_summary.py gpurun_out/launches.csv [--json profiles/ncu_traffic.json] > profiles/rNN_launches_summary.md
+
+--json writes {kernel: {dram_bytes_per_launch, launches, ...}}: bench.py reads it for `roofline.traffic`.
 """
 import collections
 import csv
+import json
 import re
 import sys
 
+UNIT = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6, "msecond": 1.0, "ms": 1.0, "s": 1e3, "second": 1e3}
+BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "bytes": 1.0}
 
-def main(path):
+
+def main(path, json_out=None):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
-    acc = collections.OrderedDict()
-    n = 0
+    per_id = collections.OrderedDict()
     for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
-            continue
         name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("<unnamed>::", "").replace("void ", "")
-        v = float(row["Metric Value"].replace(",", ""))
-        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[row["Metric Unit"]]
-        a = acc.setdefault(name, [0, 0.0])
-        a[0] += 1
-        a[1] += v
-        n += 1
-    tot = sum(a[1] for a in acc.values())
+        e = per_id.setdefault(row["ID"], {"name": name})
+        m, u = row.get("Metric Name"), row.get("Metric Unit")
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        if m == "gpu__time_duration.sum":
+            e["ms"] = v * UNIT.get(u, 1e-6)
+        elif m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            e["dram"] = e.get("dram", 0.0) + v * BYTES.get(u, 1.0)
+        elif m and m.startswith("sm__pipe_tensor_cycles_active"):
+            e["tensor"] = v
+    acc = collections.OrderedDict()
+    for e in per_id.values():
+        if "ms" not in e:
+            continue
+        a = acc.setdefault(e["name"], {"n": 0, "ms": 0.0, "dram": 0.0, "tensor_ms": 0.0, "has_dram": False, "has_tensor": False})
+        a["n"] += 1
+        a["ms"] += e["ms"]
+        if "dram" in e:
+            a["dram"] += e["dram"]
+            a["has_dram"] = True
+        if "tensor" in e:
+            a["tensor_ms"] += e["tensor"] * e["ms"]
+            a["has_tensor"] = True
+    tot = sum(a["ms"] for a in acc.values())
+    n = sum(a["n"] for a in acc.values())
     print(f"# ncu launch list summary: {path}\n")
     print(f"{n} launches, {tot:.3f} ms of device time (per-launch times are cold-cache and serialised: compare SHARES)\n")
-    print("| kernel | launches | total ms | share |\n|---|---:|---:|---:|")
-    for k, a in sorted(acc.items(), key=lambda kv: -kv[1][1]):
-        print(f"| `{k}` | {a[0]} | {a[1]:.3f} | {a[1] / tot * 100:.1f}% |")
+    print("| kernel | launches | total ms | share | DRAM MB / launch | DRAM GB/s | tensor pipe % (time-weighted) |\n|---|---:|---:|---:|---:|---:|---:|")
+    for k, a in sorted(acc.items(), key=lambda kv: -kv[1]["ms"]):
+        d = f"{a['dram'] / a['n'] / 1e6:.2f}" if a["has_dram"] else "-"
+        bw = f"{a['dram'] / (a['ms'] * 1e-3) / 1e9:.0f}" if a["has_dram"] and a["ms"] > 0 else "-"
+        tp = f"{a['tensor_ms'] / a['ms']:.1f}" if a["has_tensor"] and a["ms"] > 0 else "-"
+        print(f"| `{k}` | {a['n']} | {a['ms']:.3f} | {a['ms'] / tot * 100:.1f}% | {d} | {bw} | {tp} |")
+
+
+    if json_out:
+        out = {"source": path, "note": "ncu per-launch means; dram = dram__bytes_read.sum + dram__bytes_write.sum",
+               "kernels": {k: {"launches": a["n"], "dram_bytes_per_launch": round(a["dram"] / a["n"], 1) if a["has_dram"] else None,
+                               "ms_per_launch_under_ncu": round(a["ms"] / a["n"], 5),
+                               "tensor_pipe_pct": round(a["tensor_ms"] / a["ms"], 2) if a["has_tensor"] and a["ms"] > 0 else None}
+                           for k, a in acc.items()}}
+        with open(json_out, "w") as f:
+            json.dump(out, f, indent=1)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None)
