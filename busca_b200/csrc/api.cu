@@ -80,6 +80,7 @@ struct busca_ctx {
     // Transformer
     float *enc_w = nullptr, *enc_b = nullptr, *sep = nullptr, *non = nullptr, *bad = nullptr;
     void *enc_w16 = nullptr;
+    void *red_w16 = nullptr;                      // bf16 copy of red.weight: the 2048->512 reduction on the tensor cores (bf16 mode)
     std::vector<TLayer> layers;
     float *dec_g = nullptr, *dec_b = nullptr, *dec_w = nullptr, *dec_bias = nullptr;
     __half *pe_xy = nullptr, *pe_size = nullptr, *pe_t = nullptr;
@@ -373,6 +374,7 @@ extern "C" int busca_finalize(busca_ctx *c) {
     }
     NEED(c->red_w = upload_named(c, r + "red.weight", {512, 2048}));
     NEED(c->red_b = upload_named(c, r + "red.bias", {512}));
+    NEED(c->red_w16 = upload_named_bf16(c, r + "red.weight", {512, 2048}));
     NEED(c->lut = upload_named(c, "norm.lut", {256, 3}));
     const int d = c->cfg.d_model, ff = c->cfg.ff_size;
     NEED(c->enc_w = upload_named(c, "encoder.weight", {d, d}));
@@ -651,6 +653,7 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     if (stem_tc_scratch_bytes(N) > big) return set_err(BUSCA_ERR_STATE, "stem scratch does not fit");
     if (c->profiling) { c->next_flops = 2.0 * N * 192 * 64 * 64.0 * 147; c->next_kernel = "conv_tc_kernel<64, 64, 0>"; }
     LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, X1, RS, stem.stats, img_w, s));
+    if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();
     LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, NT * 192 * 64, s));
     LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(RS, X0, N, 192, 64, 64, stem.scale, stem.shift, 1, s));
     void *x = X0, *other = X1;
@@ -669,6 +672,7 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             c->next_kernel = kn;
         }
         LAUNCH(c, c->profiling ? nm : name, launch_conv_tc(L, a, o, s));
+        if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();   // the instantiation actually launched (resident weights or not)
         return BUSCA_OK;
     };
     int rc;
@@ -713,7 +717,14 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     LAUNCH(c, "global_maxpool", launch_global_maxpool(x, pooled, N, H * W, 2048, 1, s));
     LinearArgs la{};
     la.A = pooled; la.W = c->red_w; la.bias = c->red_b; la.residual = nullptr; la.out = emb_u; la.M = N; la.N = 512; la.K = 2048; la.alpha = 1.f; la.act = 0;
-    LAUNCH(c, "linear", launch_linear_f32(la, s));
+    static const bool red_tc = !(getenv("BUSCA_RED_TC") && getenv("BUSCA_RED_TC")[0] == '0');
+    if (red_tc) {
+        // the pooled features are maxima of bf16 activations, so the cast is exact; `other` is free after the last block
+        LAUNCH(c, "cast_bf16", launch_cast_bf16(pooled, other, (long long)N * 2048, s));
+        LAUNCH(c, "linear", launch_linear_tc(other, c->red_w16, la, s));
+    } else {
+        LAUNCH(c, "linear", launch_linear_f32(la, s));
+    }
     LAUNCH(c, "l2norm", launch_l2norm_rows(emb_u, N, 512, s));
     if (rb.map) LAUNCH(c, "gather_rows", launch_gather_rows(emb_u, rb.map, d_emb, rb.n_total, 512, s));
     c->reid_images_run += N;

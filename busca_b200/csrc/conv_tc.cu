@@ -39,6 +39,9 @@
 // quarter split a 64-channel group), warp 18 = identity-tile loader (FINAL mode).
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -83,16 +86,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint expires) instead of
+// returning after its short default window, so a waiting role issues a few instructions per wait rather than a
+// TRYWAIT/BRA/YIELD triple every ~40 cycles (profiles/r01f: 20-30 % of all issued instructions were such polls, and the
+// kernels with one k-iteration per tile are issue-bound).  Wake-up is by the barrier, not by the timer.
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
@@ -200,37 +207,70 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 #define TMEM_LD_WAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 #define EPI_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
 
-template <int BN, int KB, bool DUAL>
+// Coordinates of the tiles a persistent CTA visits (tile = blockIdx.x + j * gridDim.x; tile = m_tile * tiles_n + n_tile;
+// m_tile = image-group * h_tiles + row-group), stepped without the three integer divisions per tile.
+struct TileWalk {
+    int tile, n_tile, hi, ni;
+    int rn, qh, qi;
+    __device__ __forceinline__ explicit TileWalk(const TcParams &p) {
+        tile = blockIdx.x;
+        n_tile = tile % p.tiles_n;
+        const int m_tile = tile / p.tiles_n;
+        hi = m_tile % p.h_tiles;
+        ni = m_tile / p.h_tiles;
+        const int qn = (int)gridDim.x / p.tiles_n;
+        rn = (int)gridDim.x % p.tiles_n;
+        qh = qn % p.h_tiles;
+        qi = qn / p.h_tiles;
+    }
+    __device__ __forceinline__ void next(const TcParams &p) {
+        tile += gridDim.x;
+        n_tile += rn;
+        int e = 0;
+        if (n_tile >= p.tiles_n) { n_tile -= p.tiles_n; e = 1; }
+        hi += qh + e;                                   // < 2 * h_tiles: one carry is enough
+        ni += qi;
+        if (hi >= p.h_tiles) { hi -= p.h_tiles; ++ni; }
+    }
+};
+
+// RESB: the CTA's whole weight slab [BN x K] stays resident in shared memory (loaded once per launch; the host keeps a
+// CTA on one channel tile), so the ring only streams A boxes.  L2 -> SM delivery (~6300 B/clk chip-wide) is the bound of
+// every small-K convolution: with BN = 256 the weight tile is 2/3 of the bytes a k-iteration pulls.
+template <int BN, int KB, bool DUAL, bool RESB>
 struct TcCfg {
     static constexpr int BKE = KB / 2;                               // bf16 elements per K block
-    static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
+    static constexpr int STAGES = RESB ? 4 : (BN == 256 ? 3 : (BN == 128 ? 4 : 6));
     static constexpr int XBUF_BYTES = TC_BM * 128;                   // one 64-channel bf16 group of an output / identity tile
     static constexpr int A_BYTES = TC_BM * KB;                       // 16 KB (8 KB for the 64-byte stem rows)
     static constexpr int B_BYTES = BN * KB;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
+    static constexpr int RES_BYTES = RESB ? 65536 : 0;              // resident weight slab: k_iters * B_BYTES must fit
     static constexpr int PAR_FLOATS = DUAL ? 4 * 2048 : 2 * 2048;    // statistics (RAW/STATS) or epilogue BN parameters (FINAL)
     static constexpr int APAR_FLOATS = 512;                          // transform parameters: theta bf16 [512], sign mask u16 [512]
-    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + TC_XBUFS * XBUF_BYTES + (PAR_FLOATS + APAR_FLOATS) * 4 + 512;
+    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + RES_BYTES + TC_XBUFS * XBUF_BYTES + (PAR_FLOATS + APAR_FLOATS) * 4 + 512;
+    static_assert(SMEM <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
-template <int BN, int KB, bool DUAL>
+template <int BN, int KB, bool DUAL, bool RESB>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                                                                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                                                                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
                                                                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapIdt,
                                                                  const TcParams p) {
-    using Cfg = TcCfg<BN, KB, DUAL>;
+    using Cfg = TcCfg<BN, KB, DUAL, RESB>;
     constexpr int G = BN / 64;                                                            // 64-channel groups per tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t *tiles = smem;
-    uint8_t *xbuf = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                                // TC_XBUFS x [128 rows][128 B], swizzled
+    uint8_t *resb = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                                // RESB: k_iters x [BN rows][KB bytes], swizzled
+    uint8_t *xbuf = resb + Cfg::RES_BYTES;                                                // TC_XBUFS x [128 rows][128 B], swizzled
     float *s_par = reinterpret_cast<float *>(xbuf + TC_XBUFS * Cfg::XBUF_BYTES);
     float *s_apar = s_par + Cfg::PAR_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + Cfg::APAR_FLOATS);
     uint64_t *full = bars, *empty = full + Cfg::STAGES, *ready = empty + Cfg::STAGES, *tfull = ready + Cfg::STAGES, *tempty = tfull + 2;
-    uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(xfree + TC_XBUFS);
+    uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS, *bfull = xfree + TC_XBUFS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.tiles_m * p.tiles_n;
@@ -238,9 +278,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const bool want_stats = p.stats != nullptr && (p.mode == MODE_RAW || p.mode == MODE_STATS);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], (Cfg::STAGES % 2) == 0 ? 128 : 256); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         for (int b = 0; b < TC_XBUFS; ++b) { mbar_init(&xfull[b], 1); mbar_init(&xfree[b], 1); }
+        mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     }
@@ -272,6 +313,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if (RESB) {
+                // the weight slab of this CTA's channel tile (gridDim.x % tiles_n == 0: every tile of the CTA has the same n_tile)
+                const int n_tile = blockIdx.x % p.tiles_n;
+                mbar_expect_tx(bfull, (uint32_t)p.k_iters * Cfg::B_BYTES);
+                for (int kt = 0; kt < p.k_iters; ++kt) {
+                    if (!DUAL || kt < p.k1_iters) tma_load_2d(resb + kt * Cfg::B_BYTES, &mapB, bfull, kt * Cfg::BKE, n_tile * BN);
+                    else tma_load_2d(resb + kt * Cfg::B_BYTES, &mapB2, bfull, (kt - p.k1_iters) * Cfg::BKE, n_tile * BN);
+                }
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
                 const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
@@ -284,12 +334,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         const int m = p.tap_map[tap];
                         const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
                         tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                        tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
+                        if (!RESB) tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
                         if (++cb == p.cin_blocks) { cb = 0; ++tap; }
                     } else {                                     // downsample branch: 1x1 (strided view) on the block input
                         const int cb2 = kt - p.k1_iters;
                         tma_load_4d(a_dst, &mapA1, &full[stage], cb2 * Cfg::BKE, 0, h0, n0);
-                        tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
+                        if (!RESB) tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
                     }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -303,6 +353,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            if (RESB) mbar_wait<32>(bfull, 0);                   // the resident weight slab has landed
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
@@ -316,7 +367,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const uint32_t d_tmem = tmem_base + acc * 256 + (main_op ? 0 : BN);
                     const bool first = main_op ? kt == 0 : kt == p.k1_iters;
                     const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
-                    const uint64_t da = umma_desc<KB>(a_addr), db = umma_desc<KB>(a_addr + Cfg::A_BYTES);
+                    const uint64_t da = umma_desc<KB>(a_addr);
+                    const uint64_t db = umma_desc<KB>(RESB ? smem_u32(resb) + (uint32_t)kt * Cfg::B_BYTES : a_addr + Cfg::A_BYTES);
                     if (BN == 256 && !DUAL && p.mode == MODE_STATS) {
                         // statistics-only pass: D^T = W * A^T (operands swapped: M = 128 output channels, N = 128 pixels, two channel
                         // halves), so that TMEM lanes are CHANNELS and the per-channel sums over pixels are thread-local in the epilogue
@@ -339,13 +391,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
     } else if (warp < TC_EPI_WARP0) {
         // ===================================================== A-tile transform: a = max(x ^ signmask, theta); theta in the padding
+        // This role is a serial chain per stage (barrier wait -> 8 x 16 B per thread -> proxy fence -> arrive) and, for the
+        // convolutions with few k-iterations per tile, THE critical path of the kernel (profiles/r01f): nothing that can be
+        // hoisted out of the per-tile / per-k-iteration path is computed in it.
         if (xform) {
+            // With an even number of stages a group owns the stages of its own parity: every phase of those barriers is its own,
+            // so it never has to look at the other group's k-iterations.  With an odd number (3 stages of 48 KB, BN = 256) a
+            // group meets a stage on every second phase only; it then OBSERVES the other group's k-iterations too (see below).
+            constexpr bool EVEN = (Cfg::STAGES % 2) == 0;
             const int grp = (warp - TC_XF_WARP0) >> 2;        // this group handles k-iterations with (global index & 1) == grp
             const int tt = (threadIdx.x - TC_XF_WARP0 * 32) & 127;
             const int c = tt & 7, rb = tt >> 3;               // logical 16-byte chunk (8 channels), first row
             const uint32_t col_off = (uint32_t)((c ^ (rb & 7)) << 4);
             int r_hi[8], r_ni[8];
             uint32_t r_wb[8];                                 // bit (dw+1): column r_wi+dw is inside the (view of the) input
+            uint32_t mi9[8], alli = 0x1ffu;                   // masks of a tile that lies inside the image vertically, all images < N
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = rb + 16 * i;
@@ -353,37 +413,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 r_hi[i] = (r / p.BW) % p.BH;
                 r_ni[i] = r / (p.BW * p.BH);
                 r_wb[i] = ((unsigned)(wi - 1) < (unsigned)p.Wv ? 1u : 0u) | ((unsigned)wi < (unsigned)p.Wv ? 2u : 0u) | ((unsigned)(wi + 1) < (unsigned)p.Wv ? 4u : 0u);
+                mi9[i] = r_wb[i] | (r_wb[i] << 3) | (r_wb[i] << 6);
+                alli &= mi9[i];
             }
             const uint32_t par0 = smem_u32(s_apar) + (uint32_t)c * 16;
             const uint32_t tiles0 = smem_u32(tiles) + col_off + (uint32_t)rb * 128;
-            uint32_t ki = 0;                                  // global k-iteration counter (stage ring position)
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_tile = tile / p.tiles_n;
-                const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
+            uint32_t ki = 0;                                  // global k-iteration counter (stage ring position) at the start of the tile
+            TileWalk tw(p);
+            for (; tw.tile < total_tiles; tw.next(p), ki += (uint32_t)p.k_iters) {
+                const int kt0 = EVEN ? (int)((ki ^ (uint32_t)grp) & 1u) : 0;    // first k-iteration of this tile the group owns
+                if (EVEN && kt0 >= p.k_iters) continue;                         // single-k-iteration tile of the other group
+                const int h0 = tw.hi * p.BH, n0 = tw.ni * p.BI;
                 // per row: bit (dh+1)*3+(dw+1) = the tap reads inside the input; bit 9 = row of an image beyond N (stays all-zero, so
                 // its output is exactly 0 and drops out of the batch statistics, as with the TMA zero fill of the untransformed path)
-                uint32_t m9[8], all9 = 0x1ffu;
+                uint32_t m9[8], all9;
+                if (n0 + p.BI <= p.Nimg && (p.ntaps == 1 || (h0 >= 1 && h0 + p.BH < p.Hv))) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int hh = h0 + r_hi[i];
-                    uint32_t m = 0x200u;
-                    if (n0 + r_ni[i] < p.Nimg) {
-                        m = 0;
-                        if ((unsigned)(hh - 1) < (unsigned)p.Hv) m |= r_wb[i];
-                        if ((unsigned)hh < (unsigned)p.Hv) m |= r_wb[i] << 3;
-                        if ((unsigned)(hh + 1) < (unsigned)p.Hv) m |= r_wb[i] << 6;
+                    for (int i = 0; i < 8; ++i) m9[i] = mi9[i];
+                    all9 = alli;
+                } else {
+                    all9 = 0x1ffu;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int hh = h0 + r_hi[i];
+                        uint32_t m = 0x200u;
+                        if (n0 + r_ni[i] < p.Nimg) {
+                            m = 0;
+                            if ((unsigned)(hh - 1) < (unsigned)p.Hv) m |= r_wb[i];
+                            if ((unsigned)hh < (unsigned)p.Hv) m |= r_wb[i] << 3;
+                            if ((unsigned)(hh + 1) < (unsigned)p.Hv) m |= r_wb[i] << 6;
+                        }
+                        m9[i] = m;
+                        all9 &= m;
                     }
-                    m9[i] = m;
-                    all9 &= m;
                 }
-                int tap = 0, cb = 0;
-                for (int kt = 0; kt < p.k_iters; ++kt, ++ki) {
+                int tap = 0, cb = kt0;
+                while (cb >= p.cin_blocks) { cb -= p.cin_blocks; ++tap; }
+                for (int kt = kt0; kt < p.k_iters; kt += EVEN ? 2 : 1) {
                     const bool main_op = !DUAL || kt < p.k1_iters;
-                    const uint32_t stage = ki % Cfg::STAGES, phase = (ki / Cfg::STAGES) & 1;
-                    // BOTH groups observe every phase of every stage (with an odd number of stages a group would otherwise skip
-                    // every second phase of a stage, and a parity wait can only tell phases apart that are at most one apart)
-                    if ((int)(ki & 1) != grp) {
+                    const uint32_t kig = ki + (uint32_t)kt;
+                    const uint32_t stage = kig % Cfg::STAGES, phase = (kig / Cfg::STAGES) & 1;
+                    // odd number of stages: BOTH groups observe every phase of every stage (a parity wait can only tell phases
+                    // apart that are at most one apart) and BOTH arrive on ready[stage] (256 arrivals per phase): the observing
+                    // group is then part of the MMA's dependency chain, so it can never fall two phases of a stage behind the ring
+                    // (a late observer could otherwise miss a phase and wait for one that needs its own next arrival: deadlock).
+                    if (!EVEN && (int)(kig & 1) != grp) {
                         mbar_wait<0>(&full[stage], phase);
+                        mbar_arrive(&ready[stage]);
                     } else {
                         if (main_op) {
                             const int bit = p.tap_bit[tap];
@@ -420,7 +496,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         }
                         mbar_arrive(&ready[stage]);     // every k-iteration, so the barrier phase tracks the stage ring
                     }
-                    if (main_op && ++cb == p.cin_blocks) { cb = 0; ++tap; }
+                    if (main_op) {
+                        cb += EVEN ? 2 : 1;
+                        while (cb >= p.cin_blocks) { cb -= p.cin_blocks; ++tap; }
+                    }
                 }
             }
         }
@@ -469,11 +548,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const bool stats_t = BN == 256 && !DUAL && p.mode == MODE_STATS;
         const bool weighted = want_stats && p.img_w != nullptr;
         int it = 0, gcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        TileWalk tw(p);
+        for (; tw.tile < total_tiles; tw.next(p), ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
-            const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
+            const int n_tile = tw.n_tile;
+            const int h0 = tw.hi * p.BH, n0 = tw.ni * p.BI;
             const uint32_t t_acc = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
             if (BN == 256 && !DUAL && p.mode == MODE_STATS) {
                 // transposed accumulator (see the MMA issuer): lane = channel, columns = pixels; this warp sums 64 of the 128 pixels
@@ -493,11 +573,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         uint32_t r[32];
                         tmem_ld32(t_acc + h * 128 + half * 64 + c2 * 32, r);
                         TMEM_LD_WAIT();
+                        // two 16-column runs, each inside one image (constant multiplicity): two partial sums per run keep the
+                        // dependency chains short, the multiplicity is applied once per run
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float x = __uint_as_float(r[j]), xw = x * wc[c2 * 2 + (j >> 4)];
-                            ts[h] += xw;
-                            tq[h] = fmaf(xw, x, tq[h]);
+                        for (int u = 0; u < 2; ++u) {
+                            float ps0 = 0.f, ps1 = 0.f, pq0 = 0.f, pq1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                const float x0 = __uint_as_float(r[u * 16 + j]), x1 = __uint_as_float(r[u * 16 + j + 1]);
+                                ps0 += x0; pq0 = fmaf(x0, x0, pq0);
+                                ps1 += x1; pq1 = fmaf(x1, x1, pq1);
+                            }
+                            ts[h] = fmaf(ps0 + ps1, wc[c2 * 2 + u], ts[h]);
+                            tq[h] = fmaf(pq0 + pq1, wc[c2 * 2 + u], tq[h]);
                         }
                     }
             } else if (p.mode == MODE_RAW || p.mode == MODE_STATS) {
@@ -721,16 +809,28 @@ bool make_map2(CUtensorMap *m, const void *base, long long K, long long rows, in
 }
 
 int g_num_sms = 0;
+char g_last_kernel[64] = "";      // template instantiation of the last launch, spelled as ncu prints it
 
 struct TcMaps {
     CUtensorMap a[4], b, b2, out, idt;
 };
 
-template <int BN, int KB = 128, bool DUAL = false>
-cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
+// BUSCA_RESB=0 disables the resident-weight variant (A/B comparison on the GPU box)
+bool resb_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("BUSCA_RESB");
+        on = !(e && e[0] == '0');
+    }
+    return on != 0;
+}
+
+template <int BN, int KB, bool DUAL, bool RESB>
+cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
+    using Cfg = TcCfg<BN, KB, DUAL, RESB>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN, KB, DUAL>::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -741,13 +841,29 @@ cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     }
     const int total = p.tiles_m * p.tiles_n;
     int grid = total < g_num_sms ? total : g_num_sms;
-    // keep a CTA on one channel tile (its statistics accumulators stay in registers) when that costs < 3 % of the SMs
-    if (p.tiles_n > 1 && grid > p.tiles_n && grid % p.tiles_n != 0 && (grid % p.tiles_n) * 32 < grid) grid -= grid % p.tiles_n;
-    conv_tc_kernel<BN, KB, DUAL><<<grid, TC_THREADS, TcCfg<BN, KB, DUAL>::SMEM, s>>>(m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+    // keep a CTA on one channel tile (its statistics accumulators stay in registers) when that costs < 3 % of the SMs;
+    // with resident weights it is a requirement (total is a multiple of tiles_n, so grid >= tiles_n stays one)
+    if (p.tiles_n > 1 && grid > p.tiles_n && grid % p.tiles_n != 0 && (RESB || (grid % p.tiles_n) * 32 < grid)) grid -= grid % p.tiles_n;
+    conv_tc_kernel<BN, KB, DUAL, RESB><<<grid, TC_THREADS, Cfg::SMEM, s>>>(m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB);
     return cudaGetLastError();
 }
 
+template <int BN, int KB = 128, bool DUAL = false>
+cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
+    // resident weights whenever the CTA's slab [BN x K] fits and every CTA can stay on one channel tile
+    const int total = p.tiles_m * p.tiles_n;
+    // (only for tiles of one or two k-iterations: there the weight tile would otherwise be re-fetched for every 16 KB of A;
+    // longer k-loops keep the deeper ring, which hides the TMA + transform latency of a stage)
+    if (resb_enabled() && p.k_iters <= 2 && (long long)p.k_iters * TcCfg<BN, KB, DUAL, true>::B_BYTES <= TcCfg<BN, KB, DUAL, true>::RES_BYTES &&
+        total >= p.tiles_n)
+        return launch_tc_v<BN, KB, DUAL, true>(m, p, s);
+    return launch_tc_v<BN, KB, DUAL, false>(m, p, s);
+}
+
 }  // namespace
+
+const char *conv_tc_last_kernel() { return g_last_kernel; }
 
 // Output-tile geometry for an Ho x Wo output: BW = Wo (<= 32... or 128 for flat rows), BH | Ho, BI = 128 / (BW*BH).
 static bool tile_geometry(int Ho, int Wo, int &BW, int &BH, int &BI) {
