@@ -246,6 +246,41 @@ def test_associate_embeddings_vs_reference(busca, golden_dir, name):
     assert busca.associate_embeddings(case.tracks, [], np.zeros((T, 0)), L, C, True, False, normalize_ims=True) == (None, None)
 
 
+def test_long_history_config_vs_oracle(busca, weights):
+    """BASELINE.json configs[4] geometry at a size the CPU oracle finishes in seconds: seq_len 30, 10 candidates
+    (S = 54 tokens), histories longer than seq_len (the broader-memory sampling of network.py:247-279 picks
+    int(i*(len-1)/(L-1))), one track with a short history (zero images + filler box, unreliable), crops straddling the
+    border.  fp32 path against the oracle on the same seeded inputs; index work bit-exact."""
+    from busca_b200 import tracking
+    from oracle import crop as ocrop
+    from oracle import geometry as ogeo
+    from oracle import network as onet
+    T, D, L, C = 3, 14, 30, 10
+    mine = synth.make_assoc_case(23, T, D, L, crop_fn=lambda f, b: busca.get_image_crops(f, b, normalize=False),
+                                 hist_frames=37, short_history=1)
+    ref = synth.make_assoc_case(23, T, D, L, crop_fn=ocrop.get_image_crops, hist_frames=37, short_history=1)
+    for a, b in zip(mine.tracks, ref.tracks):
+        assert len(a.images_mem) == len(b.images_mem)
+        assert all(np.array_equal(x, y) for x, y in zip(a.images_mem, b.images_mem))
+    dists = tracking.center_distance(mine.tracks, mine.dets, engine=busca.engine)
+    assert np.array_equal(dists, ogeo.center_distance([t.tlbr for t in ref.tracks], [d.tlbr for d in ref.dets]))
+    pm, reliable = busca.associate_embeddings(mine.tracks, mine.dets, dists, L, C, use_broader_memory=True,
+                                              select_highest_candidate=False, extra_kalman_candidates=mine.kalman,
+                                              normalize_ims=True)
+    taps = {}
+    pm_ref, rel_ref = onet.associate(weights, ref.tracks, ref.dets, dists, L, C, True, kalman=ref.kalman, taps=taps)
+    assert pm.shape == (T, D + T) and np.array_equal(reliable, rel_ref) and not reliable.all() and reliable.any()
+    assert np.array_equal(pm > 0, pm_ref > 0)                 # same proposal table: 9 nearest detections + the Kalman slot
+    assert (pm > 0).sum(1).tolist() == [C] * T
+    assert np.abs(pm - pm_ref).max() < FP32_TOL, np.abs(pm - pm_ref).max()
+    assert busca.logits.shape == (T, C + 2, 512)
+    # history sampling: the device path read exactly the patches the reference's _get_track_mem picks
+    for t, tr in enumerate(mine.tracks):
+        sel = busca._memory_indices(len(tr.images_mem), L, True)
+        if len(sel) == L:
+            assert sel[0] == 0 and sel[-1] == len(tr.images_mem) - 1 and len(set(sel)) == L
+
+
 def test_stagewise_embeddings_vs_reference(busca, golden_dir):
     """ReID embeddings of the config-1 case against the reference's (accurate-kernel) run."""
     g = np.load(os.path.join(golden_dir, "assoc_cfg1.npz"))

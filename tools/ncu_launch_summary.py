@@ -6,6 +6,7 @@ traffic means and the mean tensor-pipe activity.
 
     python tools/ncu_launch_summary.py gpurun_out/launches.csv [--json profiles/ncu_traffic.json] > profiles/rNN_launches_summary.md
 
+--one-step keeps the first complete step of the list (period detected from the kernel-name sequence).
 --json writes {kernel: {dram_bytes_per_launch, launches, ...}}: bench.py reads it for `roofline.traffic`.
 """
 import collections
@@ -18,7 +19,19 @@ UNIT = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "nsecond": 1e-6, "msecond": 1.0
 BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "bytes": 1.0}
 
 
-def main(path, json_out=None):
+def one_step(per_id):
+    """Keep the launches of the first complete step: the list repeats with the step's period (a truncated capture would
+    otherwise weight the kernel classes by wherever the profiler was cut off)."""
+    ids = list(per_id)
+    names = [per_id[i]["name"] for i in ids]
+    for start in range(0, 8):                      # a few set-up launches may precede the first step
+        for period in range(50, len(names) - start - 20):
+            if names[start + period:start + period + 20] == names[start:start + 20]:
+                return collections.OrderedDict((i, per_id[i]) for i in ids[start:start + period]), period
+    return per_id, len(names)
+
+
+def main(path, json_out=None, first_step=False):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     per_id = collections.OrderedDict()
@@ -36,6 +49,9 @@ def main(path, json_out=None):
             e["dram"] = e.get("dram", 0.0) + v * BYTES.get(u, 1.0)
         elif m and m.startswith("sm__pipe_tensor_cycles_active"):
             e["tensor"] = v
+    captured = len(per_id)
+    if first_step:
+        per_id, period = one_step(per_id)
     acc = collections.OrderedDict()
     for e in per_id.values():
         if "ms" not in e:
@@ -52,6 +68,8 @@ def main(path, json_out=None):
     tot = sum(a["ms"] for a in acc.values())
     n = sum(a["n"] for a in acc.values())
     print(f"# ncu launch list summary: {path}\n")
+    if first_step:
+        print(f"(first complete step: {len(per_id)} of the {captured} captured launches)\n")
     print(f"{n} launches, {tot:.3f} ms of device time (per-launch times are cold-cache and serialised: compare SHARES)\n")
     print("| kernel | launches | total ms | share | DRAM MB / launch | DRAM GB/s | tensor pipe % (time-weighted) |\n|---|---:|---:|---:|---:|---:|---:|")
     for k, a in sorted(acc.items(), key=lambda kv: -kv[1]["ms"]):
@@ -72,4 +90,4 @@ def main(path, json_out=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None)
+    main(sys.argv[1], sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None, "--one-step" in sys.argv)
