@@ -1247,6 +1247,7 @@ extern "C" const char *busca_last_profile(busca_ctx *c) { return c ? c->prof_jso
 extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return set_err(BUSCA_ERR_ARG, "null argument");
     if (strcmp(name, "dedup") == 0) { c->dedup = value != 0; return BUSCA_OK; }
+    if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
     return set_err(BUSCA_ERR_ARG, "unknown option '%s'", name);
 }
 extern "C" int64_t busca_counter(busca_ctx *c, const char *name) {

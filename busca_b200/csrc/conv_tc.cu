@@ -768,6 +768,284 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 stride-1 convolution, HALO-BOX formulation (BUSCA_HALO=1).  EXPERIMENTAL: written after the GPU budget of round 1
+// was spent, compiled but not yet run on a B200 - off by default until tests/test_gpu_conv_tc.py has passed with it.
+//
+// Why (profiles/r01f_conv_ncu_source_summary.md): the tap-by-tap kernel above fetches and transforms nine shifted copies
+// of the same pixels per 64-channel block and is bound by shared-memory bandwidth.  Here ONE box per channel block is
+// loaded - the (R+2) x (W+2) halo of R output rows of one image - transformed ONCE, and the nine taps are nine tcgen05
+// A descriptors whose start address is shifted by (r*(W+2) + q) rows of 128 bytes inside that box: with the M index of
+// the MMA running over FLAT positions f = ho*(W+2) + wo of the halo grid, input pixel (ho+r-1, wo+q-1) of every output
+// pixel sits exactly (r*(W+2) + q) rows further.  Positions with wo >= W or ho >= R are junk rows of the accumulator
+// (75-87 % of the 128 rows are real outputs); they are neither stored nor counted in the statistics.  The row shift is
+// not a multiple of the 8-row swizzle atom, so the descriptor carries base_offset = (start >> 7) & 7 (PTX ISA, matrix
+// descriptor: start address not aligned to the 1024-byte repeat of SWIZZLE_128B).
+// Roles: warp 0 = weight-tile producer, warp 18 = halo producer, warp 1 = MMA, warps 2-9 = transform (one group of 256:
+// the transform runs once per nine taps and is off the critical path), warps 10-17 = epilogue (RAW mode only).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int HALO_STAGE_BYTES = 26624;          // 208 rows: <= 170 written by TMA, <= 2*(W+2)+2+128 = 198 addressed by the taps
+
+struct HaloParams {
+    int W, H, R, P;                  // output (= input) width / height, output rows per tile, halo pitch W + 2
+    int Nimg, cin_blocks, h_tiles;   // h_tiles = H / R
+    int total_tiles;                 // Nimg * h_tiles (Cout == BN: one channel tile)
+    int halo_rows;                   // (R + 2) * P rows of 128 B per box
+    int valid_rows;                  // R * W dense output rows per tile
+    const uint16_t *a_xf;            // [2*Cin] theta (bf16), sign masks
+    double *stats;                   // [2*Cout]
+    const float *img_w;              // [Nimg] multiplicities or null
+};
+
+template <int BN>
+struct HaloCfg {
+    static constexpr int SA = BN == 256 ? 3 : 4;                     // halo stages
+    static constexpr int SB = BN == 256 ? 3 : (BN == 128 ? 4 : 6);   // weight-tile stages
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int XBUF_BYTES = TC_BM * 128;
+    static constexpr int SMEM = 1024 + SA * HALO_STAGE_BYTES + SB * B_BYTES + 2 * XBUF_BYTES + (2 * 256 + 512) * 4 + 512;
+    static_assert(SMEM <= 232448, "shared memory budget (227 KB per CTA)");
+};
+
+// K-major SWIZZLE_128B descriptor whose start is a whole number of 128-byte rows into a 1024-byte-aligned tile
+__device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) {
+    return umma_desc<128>(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                      const __grid_constant__ CUtensorMap mapOut, const HaloParams p) {
+    using Cfg = HaloCfg<BN>;
+    constexpr int G = BN / 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *a_tiles = smem;
+    uint8_t *b_tiles = a_tiles + Cfg::SA * HALO_STAGE_BYTES;
+    uint8_t *xbuf = b_tiles + Cfg::SB * Cfg::B_BYTES;
+    float *s_par = reinterpret_cast<float *>(xbuf + 2 * Cfg::XBUF_BYTES);      // [2*BN] statistics
+    float *s_apar = s_par + 2 * 256;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + 512);
+    uint64_t *a_full = bars, *a_ready = a_full + Cfg::SA, *a_empty = a_ready + Cfg::SA, *b_full = a_empty + Cfg::SA, *b_empty = b_full + Cfg::SB;
+    uint64_t *tfull = b_empty + Cfg::SB, *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_ready[s], 256); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < Cfg::SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapOut);
+    }
+    for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) s_par[i] = 0.f;
+    {
+        const int cin = p.cin_blocks * 64;
+        uint16_t *sp = reinterpret_cast<uint16_t *>(s_apar);
+        for (int i = threadIdx.x; i < cin; i += TC_THREADS) { sp[i] = p.a_xf[i]; sp[512 + i] = p.a_xf[cin + i]; }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== weight tiles: (tap, channel block) in the order the MMA consumes them
+        if (lane == 0) {
+            int sb = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+                for (int cb = 0; cb < p.cin_blocks; ++cb)
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait<32>(&b_empty[sb], ph ^ 1);
+                        mbar_expect_tx(&b_full[sb], Cfg::B_BYTES);
+                        tma_load_2d(b_tiles + sb * Cfg::B_BYTES, &mapB, &b_full[sb], (tap * p.cin_blocks + cb) * 64, 0);
+                        if (++sb == Cfg::SB) { sb = 0; ph ^= 1; }
+                    }
+        }
+    } else if (warp == TC_IDT_WARP) {
+        // ===================================================== halo boxes: rows h0-1 .. h0+R, columns -1 .. W (zero fill outside)
+        if (lane == 0) {
+            int sa = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n = tile / p.h_tiles, h0 = (tile % p.h_tiles) * p.R;
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    mbar_wait<32>(&a_empty[sa], ph ^ 1);
+                    mbar_expect_tx(&a_full[sa], (uint32_t)p.halo_rows * 128u);
+                    tma_load_4d(a_tiles + sa * HALO_STAGE_BYTES, &mapA, &a_full[sa], cb * 64, -1, h0 - 1, n);
+                    if (++sa == Cfg::SA) { sa = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer: nine shifted views of one halo box per channel block
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int sa = 0, sb = 0, it = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait<32>(&tempty[acc], acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                    mbar_wait<0>(&a_ready[sa], pa);               // landed (the transform waited for a_full) and transformed
+                    const uint32_t a_base = smem_u32(a_tiles + sa * HALO_STAGE_BYTES);
+                    int r = 0, q = 0;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait<0>(&b_full[sb], pb);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t da = umma_desc_rowshift(a_base + (uint32_t)(r * p.P + q) * 128u);
+                        const uint64_t db = umma_desc<128>(smem_u32(b_tiles + sb * Cfg::B_BYTES));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(cb == 0 && tap == 0 && k == 0));
+                        umma_commit(&b_empty[sb]);
+                        if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
+                        if (++q == 3) { q = 0; ++r; }
+                    }
+                    umma_commit(&a_empty[sa]);                  // the nine taps have read the box
+                    if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp < TC_EPI_WARP0) {
+        // ===================================================== transform of the halo box, once per channel block
+        const int tt = threadIdx.x - TC_XF_WARP0 * 32;      // 0..255
+        const int c = tt & 7, rb = tt >> 3;                 // 16-byte chunk, first row; rows rb + 32*i (same swizzle phase)
+        const uint32_t col_off = (uint32_t)((c ^ (rb & 7)) << 4);
+        constexpr int NI = 6;                               // 6 * 32 = 192 >= 170 rows
+        int hr[NI];
+        bool in_box[NI], col_in[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int row = rb + 32 * i;
+            in_box[i] = row < p.halo_rows;
+            hr[i] = row / p.P;
+            const int wr = row % p.P;
+            col_in[i] = wr >= 1 && wr <= p.W;
+        }
+        const uint32_t par0 = smem_u32(s_apar) + (uint32_t)c * 16;
+        const uint32_t tiles0 = smem_u32(a_tiles) + col_off + (uint32_t)rb * 128;
+        int sa = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int h0 = (tile % p.h_tiles) * p.R;
+            const bool top_out = h0 == 0, bot_out = h0 + p.R == p.H;       // halo row 0 / R+1 lies outside the image
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+                const uint4 th = lds128(par0 + (uint32_t)cb * 128), sg = lds128(par0 + (uint32_t)cb * 128 + 1024);
+                mbar_wait<0>(&a_full[sa], ph);
+                const uint32_t base = tiles0 + sa * HALO_STAGE_BYTES;
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    if (!in_box[i]) continue;
+                    const uint32_t addr = base + (uint32_t)i * 4096;
+                    uint4 v = lds128(addr);
+                    const bool inside = col_in[i] && !(top_out && hr[i] == 0) && !(bot_out && hr[i] == p.R + 1);
+                    if (inside) {
+                        v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
+                        v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
+                    } else {
+                        v = th;                                  // padding reads theta: |s|*theta + t = 0 (see the header)
+                    }
+                    sts128(addr, v);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&a_ready[sa]);
+                if (++sa == Cfg::SA) { sa = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp < TC_IDT_WARP) {
+        // ===================================================== epilogue: real rows -> dense staging tile -> TMA store; statistics
+        const int e = threadIdx.x - TC_EPI_WARP0 * 32;   // 0..255
+        const int q = warp & 3;
+        const int half = (warp - TC_EPI_WARP0) >> 2;
+        const int f = q * 32 + lane;                     // accumulator row = flat halo position
+        const int ho = f / p.P, wo = f % p.P;
+        const bool real = ho < p.R && wo < p.W;
+        const int d = ho * p.W + wo;                     // dense row of the staging tile ([R][W] pixels)
+        const uint32_t xb0 = smem_u32(xbuf);
+        const int cq = e & 15, rsub = e >> 4;            // statistics: 4 channels x rows rsub + 16*i
+        const uint32_t st_off = (uint32_t)rsub * 128 + (uint32_t)((((cq >> 1) ^ (rsub & 7)) << 4) + (cq & 1) * 8);
+        float acc_s[G][4], acc_q[G][4];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc_s[g][j] = 0.f; acc_q[g][j] = 0.f; }
+        int it = 0, gcount = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int n = tile / p.h_tiles, h0 = (tile % p.h_tiles) * p.R;
+            const float wimg = p.img_w ? __ldg(p.img_w + n) : 1.f;
+            const uint32_t t_acc = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+            mbar_wait<0>(&tfull[acc], acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int g = 0; g < G; ++g, ++gcount) {
+                const uint32_t st = xb0 + (gcount & 1) * Cfg::XBUF_BYTES;
+                uint32_t r[32];
+                tmem_ld32(t_acc + g * 64 + half * 32, r);
+                TMEM_LD_WAIT();
+                if (real) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 w;
+                        w.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+                        w.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+                        w.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+                        w.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+                        sts128(st + (uint32_t)d * 128 + (uint32_t)(((half * 4 + j) ^ (d & 7)) << 4), w);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                EPI_BAR();
+                if (e == 0) tma_store_4d(xbuf + (gcount & 1) * Cfg::XBUF_BYTES, &mapOut, g * 64, 0, h0, n);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (rsub + 16 * i < p.valid_rows) {
+                        const uint2 v = lds64(st + st_off + (uint32_t)i * 2048);
+                        const float x0 = bf_lo(v.x), x1 = bf_hi(v.x), x2 = bf_lo(v.y), x3 = bf_hi(v.y);
+                        const float w0 = x0 * wimg, w1 = x1 * wimg, w2 = x2 * wimg, w3 = x3 * wimg;
+                        acc_s[g][0] += w0; acc_q[g][0] = fmaf(w0, x0, acc_q[g][0]);
+                        acc_s[g][1] += w1; acc_q[g][1] = fmaf(w1, x1, acc_q[g][1]);
+                        acc_s[g][2] += w2; acc_q[g][2] = fmaf(w2, x2, acc_q[g][2]);
+                        acc_s[g][3] += w3; acc_q[g][3] = fmaf(w3, x3, acc_q[g][3]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&s_par[g * 64 + cq * 4 + j], acc_s[g][j]);
+                atomicAdd(&s_par[BN + g * 64 + cq * 4 + j], acc_q[g][j]);
+            }
+        if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    __syncthreads();
+    if (p.stats)
+        for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) {
+            const float v = s_par[i];
+            if (v != 0.f) atomicAdd(p.stats + i, (double)v);
+        }
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -863,7 +1141,73 @@ cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
 
 }  // namespace
 
+namespace {
+// BUSCA_HALO=1 (or busca_set_option("halo", 1)) routes the stride-1 3x3 convolutions through conv3x3_halo_kernel
+// (experimental, see its header)
+int g_halo = -1;
+bool halo_enabled() {
+    if (g_halo < 0) {
+        const char *e = getenv("BUSCA_HALO");
+        g_halo = e && e[0] == '1';
+    }
+    return g_halo != 0;
+}
+
+template <int BN>
+cudaError_t launch_halo_v(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const HaloParams &p, cudaStream_t s) {
+    using Cfg = HaloCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+    conv3x3_halo_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, s>>>(ma, mb, mo, p);
+    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv3x3_halo_kernel<%d>", BN);
+    return cudaGetLastError();
+}
+
+// true if the shape is one the halo kernel covers (and it is enabled)
+bool halo_applies(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o) {
+    if (!halo_enabled() || L.k != 3 || L.stride != 1 || o.mode != TC_MODE_RAW || !a.in_xf || !L.w16s) return false;
+    if (L.cin % TC_BK != 0 || L.cin > 512 || (L.cout != 64 && L.cout != 128 && L.cout != 256)) return false;
+    if (a.Wo != a.W || a.Ho != a.H || (a.W != 32 && a.W != 16 && a.W != 8)) return false;
+    return true;
+}
+
+cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStream_t s) {
+    HaloParams p{};
+    p.W = a.W; p.H = a.H; p.P = a.W + 2;
+    p.R = 0;
+    for (int r = 128 / p.P; r >= 1; --r)
+        if (a.H % r == 0) { p.R = r; break; }
+    p.halo_rows = (p.R + 2) * p.P;
+    p.valid_rows = p.R * p.W;
+    if (p.R < 1 || p.halo_rows > 192 || 2 * p.P + 2 + 128 > HALO_STAGE_BYTES / 128 || p.valid_rows > 128) return cudaErrorInvalidValue;
+    p.Nimg = a.N; p.cin_blocks = L.cin / TC_BK; p.h_tiles = a.H / p.R; p.total_tiles = a.N * p.h_tiles;
+    p.a_xf = a.in_xf; p.stats = L.stats; p.img_w = a.img_w;
+    const long long C = L.cin, W = a.W, H = a.H;
+    CUtensorMap ma, mb, mo;
+    bool ok = make_map4(&ma, a.in, (int)C, a.W, a.H, a.N, C, W * C, H * W * C, p.P, p.R + 2, 1);
+    ok = ok && make_map2(&mb, L.w16s, 9LL * L.cin, L.cout, L.cout);
+    ok = ok && make_map4(&mo, a.out, L.cout, a.W, a.H, a.N, L.cout, W * L.cout, H * W * L.cout, a.W, p.R, 1);
+    if (!ok) return cudaErrorInvalidValue;
+    switch (L.cout) {
+        case 256: return launch_halo_v<256>(ma, mb, mo, p, s);
+        case 128: return launch_halo_v<128>(ma, mb, mo, p, s);
+        default: return launch_halo_v<64>(ma, mb, mo, p, s);
+    }
+}
+}  // namespace
+
 const char *conv_tc_last_kernel() { return g_last_kernel; }
+void conv_tc_set_halo(int on) { g_halo = on ? 1 : 0; }
 
 // Output-tile geometry for an Ho x Wo output: BW = Wo (<= 32... or 128 for flat rows), BH | Ho, BI = 128 / (BW*BH).
 static bool tile_geometry(int Ho, int Wo, int &BW, int &BH, int &BI) {
@@ -882,6 +1226,7 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     if (L.stride != 1 && L.stride != 2) return cudaErrorInvalidValue;
     if (L.stride == 2 && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
     if (a.in_xf && (L.cin > 512 || !L.w16s)) return cudaErrorInvalidValue;
+    if (halo_applies(L, a, o)) return launch_conv3x3_halo(L, a, s);
     const bool dual = o.mode == TC_MODE_FINAL && o.ds != nullptr;
     if (o.mode == TC_MODE_FINAL && (L.k != 1 || L.stride != 1 || !o.e_scale || !o.e_shift || (!dual && !o.idt))) return cudaErrorInvalidValue;
     if (dual && (o.ds->k != 1 || o.ds->cout != L.cout || o.ds->cin % TC_BK != 0 || !o.ds->w16 || !o.ds_in || !o.ds_scale || !o.ds_shift)) return cudaErrorInvalidValue;

@@ -189,7 +189,8 @@ int busca_set_profiling(busca_ctx *ctx, int32_t on);
 const char *busca_last_profile(busca_ctx *ctx);
 /* options: "dedup" (default 1, bf16 mode): run the ReID encoder once per DISTINCT patch of a BatchNorm batch and weight
  * the batch statistics by the multiplicities - the batches the reference stacks (network.py:313-316, 383-386) repeat
- * every detection crop for each track that lists it as a candidate, and every incomplete history is the same zero image */
+ * every detection crop for each track that lists it as a candidate, and every incomplete history is the same zero image;
+ * "halo" (default 0, process-wide): experimental halo-box kernel for the stride-1 3x3 convolutions (csrc/conv_tc.cu) */
 int busca_set_option(busca_ctx *ctx, const char *name, int64_t value);
 /* counters: "reid_images_run" / "reid_images_total" (encoder images executed / images of the stacked batches), "kernel_launches" */
 int64_t busca_counter(busca_ctx *ctx, const char *name);
