@@ -237,15 +237,31 @@ class BUSCA:
             mem_slots = np.full((T, L), -1, np.int32)
             mem_ltwh = np.empty((T, L, 4), np.float64)
             reliable = np.zeros(T, dtype=bool)
+            sel_cache = {}                                     # history length -> sampled indices (same L / flag for every track)
+            rel_rows, rel_boxes, rel_scales = [], [], []       # reliable tracks: one array build for all their boxes
             for t, track in enumerate(tracks_embeddings):
-                sel = self._memory_indices(len(track.images_mem), L, use_broader_memory)
+                ims = track.images_mem
+                n_obs = len(ims)
+                sel = sel_cache.get(n_obs)
+                if sel is None:
+                    sel = sel_cache[n_obs] = self._memory_indices(n_obs, L, use_broader_memory)
                 if len(sel) == L:
                     reliable[t] = True
-                    ims, boxes = track.images_mem, track.tlwh_mem
-                    mem_slots[t] = [slot_for(ims[j]) for j in sel]
-                    mem_ltwh[t] = np.array([boxes[j] for j in sel], dtype=np.float64) * track.scale
+                    boxes = track.tlwh_mem
+                    row = []
+                    for j in sel:
+                        patch = ims[j]
+                        hit = by_id.get(id(patch))             # same array object as in an earlier frame: one dict probe
+                        row.append(hit[1] if hit is not None and hit[0]() is patch else slot_for(patch))
+                    mem_slots[t] = row
+                    rel_rows.append(t)
+                    rel_boxes.extend([boxes[j] for j in sel])
+                    rel_scales.append(track.scale)
                 else:                                      # incomplete history: zero images + filler box (network.py:304-308)
                     mem_ltwh[t] = np.array([250.0, 250.0, 500.0, 500.0])
+            if rel_rows:
+                mem_ltwh[rel_rows] = np.array(rel_boxes, dtype=np.float64).reshape(len(rel_rows), L, 4) \
+                    * np.array(rel_scales, dtype=np.float64).reshape(-1, 1, 1)
             det_slots = np.array([slot_for(det.images_mem[-1]) for det in dets_embeddings], np.int32).reshape(D)
             det_ltwh = np.array([det.tlwh_mem[-1] for det in dets_embeddings], np.float64).reshape(D, 4) \
                 * np.array([det.scale for det in dets_embeddings], np.float64).reshape(D, 1)
