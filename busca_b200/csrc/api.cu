@@ -1164,6 +1164,19 @@ extern "C" int busca_debug_conv(busca_ctx *c, int32_t conv_index, const uint16_t
     d.out_bf16 = out_bf16; d.stats_out = stats_out;
     return busca_debug_conv_ex(c, &d);
 }
+// hardware probe: D = A(shifted by `shift_rows` rows inside a swizzled tile) * I, see umma_rowshift_probe_kernel (conv_tc.cu)
+extern "C" int busca_debug_umma_rowshift(busca_ctx *c, int32_t shift_rows, int32_t fill, int32_t use_base_offset, float *out) {
+    if (!c || !out) return set_err(BUSCA_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    CUDA_OK(c->ws_small.ensure(128 * 64 * 4));
+    float *d = (float *)c->ws_small.p;
+    CUDA_OK(cudaMemsetAsync(d, 0xff, 128 * 64 * 4, c->stream));
+    LAUNCH(c, "umma_rowshift_probe", launch_umma_rowshift_probe(shift_rows, fill, use_base_offset, d, c->stream));
+    CUDA_OK(cudaMemcpyAsync(out, d, 128 * 64 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BUSCA_OK;
+}
+
 extern "C" int busca_debug_stem(busca_ctx *c, const int32_t *slots, int32_t N, int32_t use_tc, uint16_t *out_bf16, double *stats_out) {
     if (!c || !c->finalized || !slots || N <= 0 || !out_bf16) return set_err(BUSCA_ERR_ARG, "bad argument");
     CUDA_OK(cudaSetDevice(c->cfg.device));

@@ -1046,6 +1046,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Probe of the one hardware assumption conv3x3_halo_kernel rests on (busca_debug_umma_rowshift, tests/probe_umma.py): an
+// A descriptor whose start address lies `shift` rows of 128 bytes into a 1024-byte-aligned SWIZZLE_128B tile.  One CTA,
+// A = 208 rows x 64 bf16 written with the TMA swizzle by ordinary stores, B = the 64 x 64 identity, so D[m][n] must be
+// A[m + shift][n]: fill 0 -> A[row][k] = row (which ROW each accumulator row read), fill 1 -> A[row][k] = k (whether the
+// 16-byte chunks are de-swizzled with the right phase).  use_base_offset selects descriptor bits 49-51 = (start >> 7) & 7
+// (PTX ISA) or 0.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_rowshift_probe_kernel(int shift, int fill, int use_base_offset, float *__restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *a_tile = smem;                              // 208 rows x 128 B
+    uint8_t *b_tile = smem + HALO_STAGE_BYTES;           // 64 rows x 128 B
+    uint64_t *bar = reinterpret_cast<uint64_t *>(b_tile + 64 * 128);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 208 * 64; i += 128) {
+        const int row = i >> 6, k = i & 63;
+        const float v = fill == 0 ? (float)row : (float)k;
+        *reinterpret_cast<__nv_bfloat16 *>(a_tile + row * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2) = __float2bfloat16(v);
+    }
+    for (int i = threadIdx.x; i < 64 * 64; i += 128) {
+        const int n = i >> 6, k = i & 63;
+        *reinterpret_cast<__nv_bfloat16 *>(b_tile + n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) = __float2bfloat16(n == k ? 1.f : 0.f);
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a_addr = smem_u32(a_tile) + (uint32_t)shift * 128u;
+        const uint64_t da = use_base_offset ? umma_desc_rowshift(a_addr) : umma_desc<128>(a_addr);
+        const uint64_t db = umma_desc<128>(smem_u32(b_tile));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, k != 0);
+        umma_commit(bar);
+    }
+    mbar_wait<32>(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = warp * 32 + lane;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + h * 32, r);
+        TMEM_LD_WAIT();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[m * 64 + h * 32 + j] = __uint_as_float(r[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1208,6 +1274,14 @@ cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStrea
 
 const char *conv_tc_last_kernel() { return g_last_kernel; }
 void conv_tc_set_halo(int on) { g_halo = on ? 1 : 0; }
+cudaError_t launch_umma_rowshift_probe(int shift, int fill, int use_base_offset, float *out_dev, cudaStream_t s) {
+    if (shift < 0 || shift + 128 > 208) return cudaErrorInvalidValue;
+    const int smem = 1024 + HALO_STAGE_BYTES + 64 * 128 + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_rowshift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    umma_rowshift_probe_kernel<<<1, 128, smem, s>>>(shift, fill, use_base_offset, out_dev);
+    return cudaGetLastError();
+}
 
 // Output-tile geometry for an Ho x Wo output: BW = Wo (<= 32... or 128 for flat rows), BH | Ho, BI = 128 / (BW*BH).
 static bool tile_geometry(int Ho, int Wo, int &BW, int &BH, int &BI) {

@@ -71,6 +71,7 @@ struct ConvTcOpts {
 };
 cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s);
 size_t stem_tc_scratch_bytes(int N);
+cudaError_t launch_umma_rowshift_probe(int shift, int fill, int use_base_offset, float *out_dev /* [128*64] */, cudaStream_t s);
 void conv_tc_set_halo(int on);       // experimental halo-box 3x3 kernel on/off (default: BUSCA_HALO env, off)
 const char *conv_tc_last_kernel();   // "conv_tc_kernel<BN, KB, DUAL, RESB>" of the last tensor-core launch (profiling labels)
 cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem_bf16, void *scratch, void *out,

@@ -169,6 +169,9 @@ typedef struct busca_debug_conv_args {
     double *stats_out;                       /* [2*cout] or NULL */
 } busca_debug_conv_args;
 int busca_debug_conv_ex(busca_ctx *ctx, const busca_debug_conv_args *args);
+/* hardware probe (tests/probe_umma.py): one tcgen05.mma whose A descriptor starts `shift_rows` rows of 128 B inside a
+ * SWIZZLE_128B tile, B = identity: out[128][64] must be A[m + shift_rows][n] (fill 0: A = row index, fill 1: A = column index) */
+int busca_debug_umma_rowshift(busca_ctx *ctx, int32_t shift_rows, int32_t fill, int32_t use_base_offset, float *out /* [128*64] */);
 int busca_debug_stem(busca_ctx *ctx, const int32_t *slots, int32_t N, int32_t use_tc, uint16_t *out_bf16 /* [N,192,64,64] */,
                      double *stats_out /* [128] or NULL */);
 
