@@ -1164,6 +1164,29 @@ extern "C" int busca_debug_conv(busca_ctx *c, int32_t conv_index, const uint16_t
     d.out_bf16 = out_bf16; d.stats_out = stats_out;
     return busca_debug_conv_ex(c, &d);
 }
+// test hook: relu(BN(x)) followed by the 3x3/2 max-pool of the ReID stem on a caller-provided bf16 NHWC tensor
+extern "C" int busca_debug_maxpool(busca_ctx *c, const uint16_t *in_bf16, int32_t N, int32_t H, int32_t W, int32_t Cc, const float *scale,
+                                   const float *shift, uint16_t *out_bf16) {
+    if (!c || !in_bf16 || !scale || !shift || !out_bf16 || N <= 0 || H <= 0 || W <= 0 || Cc <= 0 || Cc % 8 != 0 || ((H | W) & 1))
+        return set_err(BUSCA_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    Carver cv;
+    const size_t in_b = (size_t)N * H * W * Cc * 2, out_b = (size_t)N * (H / 2) * (W / 2) * Cc * 2;
+    size_t o_in = cv.take(in_b), o_out = cv.take(out_b), o_par = cv.take((size_t)2 * Cc * 4);
+    CUDA_OK(c->ws_io.ensure(cv.off));
+    char *b = (char *)c->ws_io.p;
+    cudaStream_t s = c->stream;
+    CUDA_OK(cudaMemcpyAsync(b + o_in, in_bf16, in_b, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b + o_par, scale, (size_t)Cc * 4, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(b + o_par + (size_t)Cc * 4, shift, (size_t)Cc * 4, cudaMemcpyHostToDevice, s));
+    prof_reset(c);
+    LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(b + o_in, b + o_out, N, H, W, Cc, (const float *)(b + o_par), (const float *)(b + o_par) + Cc, 1, s));
+    CUDA_OK(cudaMemcpyAsync(out_bf16, b + o_out, out_b, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
 // hardware probe: D = A(shifted by `shift_rows` rows inside a swizzled tile) * I, see umma_rowshift_probe_kernel (conv_tc.cu)
 extern "C" int busca_debug_umma_rowshift(busca_ctx *c, int32_t shift_rows, int32_t fill, int32_t use_base_offset, float *out) {
     if (!c || !out) return set_err(BUSCA_ERR_ARG, "bad argument");
@@ -1260,6 +1283,7 @@ extern "C" const char *busca_last_profile(busca_ctx *c) { return c ? c->prof_jso
 extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return set_err(BUSCA_ERR_ARG, "null argument");
     if (strcmp(name, "dedup") == 0) { c->dedup = value != 0; return BUSCA_OK; }
+    if (strcmp(name, "pool_mono") == 0) { reid_set_pool_mono(value); return BUSCA_OK; } // process-wide (experimental max-pool kernel)
     if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
     return set_err(BUSCA_ERR_ARG, "unknown option '%s'", name);
 }

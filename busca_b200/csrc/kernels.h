@@ -78,6 +78,7 @@ cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, con
                            double *stats, const float *img_w, cudaStream_t s);
 // x = relu(x*scale + shift) in place (bf16 or float), rows x C
 cudaError_t launch_bn_relu_inplace(void *x, const float *scale, const float *shift, long long rows, int C, int bf16, cudaStream_t s);
+void reid_set_pool_mono(int on);     // experimental monotone max-pool kernel on/off (default: BUSCA_POOL_MONO env, off)
 cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,
                                    const float *shift, int bf16, cudaStream_t s);
 // out = relu(raw*scale+shift + (idt_scale ? idt*idt_scale+idt_shift : idt)); out may alias idt

@@ -9,6 +9,8 @@
 // consumer applies y = relu(x*scale + shift) while loading its A operand ("deferred BN").  Residual joins are
 // materialised by bn_add_relu.
 #include "common.cuh"
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace {
@@ -587,13 +589,74 @@ static int ew_grid(long long total) {
     return (int)(b < 148 * 32 ? (b > 0 ? b : 1) : 148 * 32);
 }
 
+// EXPERIMENTAL variant (BUSCA_POOL_MONO=1 / busca_set_option("pool_mono", 1); off until its bitwise comparison on a B200,
+// tests/probe_pool.py): max-pooling commutes with the per-channel BN + ReLU because x -> fma(x, scale, shift) is monotone
+// (rounding included), so max_taps relu(fma(x_t)) = relu(fma(max_t x_t)) for scale >= 0 and relu(fma(min_t x_t)) for
+// scale < 0.  The nine taps cost one packed bf16 max and one packed min per two channels instead of unpack + fma + max per
+// channel (about 110 instead of 250 instructions per 8 channels; the kernel is latency / issue bound, not HBM bound).
+__global__ void __launch_bounds__(256) bn_relu_maxpool_bf16_mono_kernel(const uint4 *__restrict__ raw, uint4 *__restrict__ out, int N, int H, int W, int C8,
+                                                                         const float *__restrict__ scale, const float *__restrict__ shift) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)N * Ho * Wo * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        long long t = i / C8;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const long long n = t / Ho;
+        uint4 vmax, vmin;
+        bool first = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int iy = 2 * oy + dy;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int ix = 2 * ox + dx;
+                if (ix < 0 || ix >= W) continue;
+                const uint4 v = __ldg(raw + ((n * H + iy) * W + ix) * C8 + c8);
+                if (first) {
+                    vmax = v; vmin = v; first = false;
+                } else {
+                    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+                    __nv_bfloat162 *hx = reinterpret_cast<__nv_bfloat162 *>(&vmax), *hn = reinterpret_cast<__nv_bfloat162 *>(&vmin);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { hx[j] = __hmax2(hx[j], h[j]); hn[j] = __hmin2(hn[j], h[j]); }
+                }
+            }
+        }
+        float sc[8], sh[8], hi[8], lo[8], best[8];
+        load8(scale + c8 * 8, sc);
+        load8(shift + c8 * 8, sh);
+        unpack8(vmax, hi);
+        unpack8(vmin, lo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(0.f, fmaf(sc[j] < 0.f ? lo[j] : hi[j], sc[j], sh[j]));
+        out[i] = pack8(best);
+    }
+}
+
+int g_pool_mono = -1;
+void reid_set_pool_mono(int on) { g_pool_mono = on ? 1 : 0; }
+static bool pool_mono_enabled() {
+    if (g_pool_mono < 0) {
+        const char *e = getenv("BUSCA_POOL_MONO");
+        g_pool_mono = e && e[0] == '1';
+    }
+    return g_pool_mono != 0;
+}
+
 cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int W, int C, const float *scale,
                                    const float *shift, int bf16, cudaStream_t s) {
     long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
     if (total == 0) return cudaSuccess;
     if (bf16 && C % 8 == 0) {
         const long long t8 = (long long)N * (H / 2) * (W / 2) * (C / 8);
-        bn_relu_maxpool_bf16_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift);
+        if (pool_mono_enabled())
+            bn_relu_maxpool_bf16_mono_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift);
+        else
+            bn_relu_maxpool_bf16_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift);
     } else if (bf16)
         bn_relu_maxpool_kernel<__nv_bfloat16><<<ew_grid(total), 256, 0, s>>>((const __nv_bfloat16 *)raw, (__nv_bfloat16 *)out, N, H, W, C, scale, shift);
     else

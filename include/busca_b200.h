@@ -169,6 +169,9 @@ typedef struct busca_debug_conv_args {
     double *stats_out;                       /* [2*cout] or NULL */
 } busca_debug_conv_args;
 int busca_debug_conv_ex(busca_ctx *ctx, const busca_debug_conv_args *args);
+/* test hook: relu(x*scale + shift) followed by the 3x3 stride-2 max-pool (padding 1) of the ReID stem, bf16 NHWC in and out */
+int busca_debug_maxpool(busca_ctx *ctx, const uint16_t *in_bf16 /* [N,H,W,C] */, int32_t N, int32_t H, int32_t W, int32_t C,
+                        const float *scale, const float *shift, uint16_t *out_bf16 /* [N,H/2,W/2,C] */);
 /* hardware probe (tests/probe_umma.py): one tcgen05.mma whose A descriptor starts `shift_rows` rows of 128 B inside a
  * SWIZZLE_128B tile, B = identity: out[128][64] must be A[m + shift_rows][n] (fill 0: A = row index, fill 1: A = column index) */
 int busca_debug_umma_rowshift(busca_ctx *ctx, int32_t shift_rows, int32_t fill, int32_t use_base_offset, float *out /* [128*64] */);
@@ -193,7 +196,8 @@ const char *busca_last_profile(busca_ctx *ctx);
 /* options: "dedup" (default 1, bf16 mode): run the ReID encoder once per DISTINCT patch of a BatchNorm batch and weight
  * the batch statistics by the multiplicities - the batches the reference stacks (network.py:313-316, 383-386) repeat
  * every detection crop for each track that lists it as a candidate, and every incomplete history is the same zero image;
- * "halo" (default 0, process-wide): experimental halo-box kernel for the stride-1 3x3 convolutions (csrc/conv_tc.cu) */
+ * "halo" (default 0, process-wide): experimental halo-box kernel for the stride-1 3x3 convolutions (csrc/conv_tc.cu);
+ * "pool_mono" (default 0, process-wide): experimental max-pool kernel that pools before BN + ReLU (csrc/reid.cu) */
 int busca_set_option(busca_ctx *ctx, const char *name, int64_t value);
 /* counters: "reid_images_run" / "reid_images_total" (encoder images executed / images of the stacked batches), "kernel_launches" */
 int64_t busca_counter(busca_ctx *ctx, const char *name);
