@@ -316,6 +316,16 @@ def run_ours(args):
             scene.step_e2e(i)
         eng.sync()
         e2e_s = time.perf_counter() - t0
+        if args.profile_e2e and rank == 0:                    # where the host side of the plug-in path spends its time (stderr)
+            import cProfile
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            for i in range(args.steps):
+                scene.step_e2e(i)
+            eng.sync()
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(30)
 
     # NCCL only here: max over ranks of the device-timed regions, and the gather of the per-rank result tables
     ms_max, e2e_ms_max = sharding.reduce_max([ms, e2e_s * 1e3], dist, device=f"cuda:{local}")
@@ -464,6 +474,7 @@ if __name__ == "__main__":
     ap.add_argument("--cpu-tracks", type=int, default=16, help="size of the bounded CPU sample (unmatched tracks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the plug-in API leg (profiler runs)")
+    ap.add_argument("--profile-e2e", action="store_true", help="after the timed plug-in leg, cProfile the same loop to stderr")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
