@@ -1,9 +1,50 @@
-"""CPU check of the index arithmetic behind conv3x3_halo_kernel (busca_b200/csrc/conv_tc.cu): one (R+2) x (W+2) halo box per
+"""CPU checks of index arithmetic the CUDA kernels rely on, restated in numpy / plain Python.
+
+1. TileWalk (conv_tc.cu): the division-free stepping of a persistent CTA through its tiles.
+2. conv3x3_halo_kernel (busca_b200/csrc/conv_tc.cu): one (R+2) x (W+2) halo box per
 tile, output rows = FLAT positions f = ho*(W+2) + wo of the halo grid, tap (r, q) = the same box shifted by r*(W+2) + q rows.
 The numpy emulation below follows the kernel's loops (including the junk rows and the dense staging tile) and must equal a
 direct zero-padded 3x3 convolution."""
 import numpy as np
 import pytest
+
+
+def tile_walk(block, grid, tiles_n, h_tiles, total):
+    """TileWalk of conv_tc.cu, line for line."""
+    tile = block
+    n_tile = tile % tiles_n
+    m_tile = tile // tiles_n
+    hi, ni = m_tile % h_tiles, m_tile // h_tiles
+    qn, rn = grid // tiles_n, grid % tiles_n
+    qh, qi = qn % h_tiles, qn // h_tiles
+    while tile < total:
+        yield tile, n_tile, hi, ni
+        tile += grid
+        n_tile += rn
+        e = 0
+        if n_tile >= tiles_n:
+            n_tile -= tiles_n
+            e = 1
+        hi += qh + e
+        ni += qi
+        if hi >= h_tiles:
+            hi -= h_tiles
+            ni += 1
+
+
+@pytest.mark.parametrize("grid", [1, 3, 7, 64, 144, 148])
+@pytest.mark.parametrize("tiles_n", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("h_tiles", [1, 2, 3, 24, 96])
+def test_tile_walk_equals_division(grid, tiles_n, h_tiles):
+    tiles_m = 5 * h_tiles + 3                     # ragged: the last image group is partial
+    total = tiles_m * tiles_n
+    for block in {0, 1, grid // 2, grid - 1}:
+        seen = 0
+        for tile, n_tile, hi, ni in tile_walk(block, grid, tiles_n, h_tiles, total):
+            m_tile = tile // tiles_n
+            assert (n_tile, hi, ni) == (tile % tiles_n, m_tile % h_tiles, m_tile // h_tiles), (tile, grid, tiles_n, h_tiles)
+            seen += 1
+        assert seen == len(range(block, total, grid))
 
 
 def halo_geometry(H, W):
