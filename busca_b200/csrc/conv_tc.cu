@@ -779,8 +779,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // the MMA running over FLAT positions f = ho*(W+2) + wo of the halo grid, input pixel (ho+r-1, wo+q-1) of every output
 // pixel sits exactly (r*(W+2) + q) rows further.  Positions with wo >= W or ho >= R are junk rows of the accumulator
 // (75-87 % of the 128 rows are real outputs); they are neither stored nor counted in the statistics.  The row shift is
-// not a multiple of the 8-row swizzle atom, so the descriptor carries base_offset = (start >> 7) & 7 (PTX ISA, matrix
-// descriptor: start address not aligned to the 1024-byte repeat of SWIZZLE_128B).
+// not a multiple of the 8-row swizzle atom; the hardware de-swizzles by address bits, so the plain descriptor is right
+// (measured: tests/probe_umma.py, profiles/r02a_probe_umma.log - base_offset must stay 0).
 // Roles: warp 0 = weight-tile producer, warp 18 = halo producer, warp 1 = MMA, warps 2-9 = transform (one group of 256:
 // the transform runs once per nine taps and is off the critical path), warps 10-17 = epilogue (RAW mode only).
 // ---------------------------------------------------------------------------------------------------------------------
@@ -808,9 +808,9 @@ struct HaloCfg {
 };
 
 // K-major SWIZZLE_128B descriptor whose start is a whole number of 128-byte rows into a 1024-byte-aligned tile
-__device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) {
-    return umma_desc<128>(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
-}
+// (measured on a B200, profiles/r02a_probe_umma.log: the 16-byte-chunk XOR of SWIZZLE_128B is taken from the ADDRESS bits of
+// every row the tensor core reads, so a row-shifted start needs NO base_offset; setting bits 49-51 de-swizzles wrongly)
+__device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) { return umma_desc<128>(saddr); }
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -1087,7 +1087,7 @@ __global__ void __launch_bounds__(128, 1) umma_rowshift_probe_kernel(int shift, 
     if (threadIdx.x == 0) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t a_addr = smem_u32(a_tile) + (uint32_t)shift * 128u;
-        const uint64_t da = use_base_offset ? umma_desc_rowshift(a_addr) : umma_desc<128>(a_addr);
+        const uint64_t da = umma_desc<128>(a_addr) | (use_base_offset ? ((uint64_t)((a_addr >> 7) & 7u) << 49) : 0ull);
         const uint64_t db = umma_desc<128>(smem_u32(b_tile));
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, k != 0);

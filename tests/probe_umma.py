@@ -36,8 +36,10 @@ def main():
                               [(int(a), int(b), float(out[a, b]), float(want[a, b])) for a, b in d])
         verdict[use_bo] = (bad_rows, bad_cols)
         print(f"base_offset={'(start>>7)&7' if use_bo else '0'}: row mapping wrong at shifts {bad_rows or 'none'}; chunk de-swizzle wrong at shifts {bad_cols or 'none'}")
-    ok = not verdict[1][0] and not verdict[1][1]
-    print("conv3x3_halo_kernel's descriptor assumption", "HOLDS" if ok else "DOES NOT HOLD (see above; try base_offset 0 if that row is clean)")
+    # measured on a B200 (profiles/r02a_probe_umma.log): clean with base_offset 0, chunk order wrong with (start >> 7) & 7 -
+    # the swizzle XOR follows the address bits of each row, which is what conv3x3_halo_kernel now relies on
+    ok = not verdict[0][0] and not verdict[0][1]
+    print("conv3x3_halo_kernel's descriptor assumption (plain descriptor, base_offset 0)", "HOLDS" if ok else "DOES NOT HOLD (see above)")
     return 0 if ok else 1
 
 
