@@ -38,7 +38,8 @@ class StepArgs(C.Structure):
                 ("track_mean_dev", C.c_void_p), ("tracked_dev", C.c_void_p), ("det_tlbr_dev", C.c_void_p),
                 ("mem_slots_dev", C.c_void_p), ("mem_ltwh_dev", C.c_void_p), ("det_slots_dev", C.c_void_p),
                 ("kal_slots_dev", C.c_void_p), ("busca_thresh", C.c_float), ("reliable_dev", C.c_void_p),
-                ("probs_dev", C.c_void_p), ("keep_dev", C.c_void_p)]
+                ("probs_dev", C.c_void_p), ("keep_dev", C.c_void_p), ("cand_dev", C.c_void_p),
+                ("select_highest", C.c_int32), ("highest_min_thresh", C.c_float), ("keep_highest_value", C.c_int32)]
 
 
 class DebugConvArgs(C.Structure):

@@ -453,7 +453,8 @@ extern "C" int busca_bank_reserve(busca_ctx *c, int64_t n_slots) {
     if (c->dedup_table) cudaFree(c->dedup_table);
     c->dedup_table = nullptr;
     CUDA_OK(cudaMalloc((void **)&c->dedup_table, ((size_t)n_slots + 1) * sizeof(int)));
-    CUDA_OK(cudaMemset(c->dedup_table, 0x7f, ((size_t)n_slots + 1) * sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(c->dedup_table, 0x7f, ((size_t)n_slots + 1) * sizeof(int), c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
     return BUSCA_OK;
 }
 extern "C" int64_t busca_bank_capacity(busca_ctx *c) { return c ? c->bank_slots : 0; }
@@ -1092,7 +1093,10 @@ extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
     TrOut o{(float *)(b + o_lg), a->probs_dev, nullptr, nullptr, nullptr};
     rc = transformer_dev(c, T, L, C, (const float *)(b + o_me), (const float *)(b + o_ce), (const int32_t *)(b + o_idx), o);
     if (rc) return rc;
-    if (a->keep_dev) LAUNCH(c, "decide", launch_decide(a->probs_dev, (const int *)(b + o_cand), a->reliable_dev, T, D, C, a->busca_thresh, a->keep_dev, s));
+    if (a->keep_dev)
+        LAUNCH(c, "decide", launch_decide(a->probs_dev, (const int *)(b + o_cand), a->reliable_dev, T, D, C, a->busca_thresh, a->select_highest,
+                                          a->highest_min_thresh, a->keep_highest_value, a->keep_dev, s));
+    if (a->cand_dev) CUDA_OK(cudaMemcpyAsync(a->cand_dev, b + o_cand, (size_t)T * C * 4, cudaMemcpyDeviceToDevice, s));
     return BUSCA_OK;
 }
 

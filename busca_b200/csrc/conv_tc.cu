@@ -204,6 +204,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// one lane of a converged warp (the tcgen05 issue pattern: the WARP runs the role's loops with warp-uniform values, which the
+// compiler keeps in uniform registers, and only the instruction itself is predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 #define TMEM_LD_WAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 #define EPI_BAR() asm volatile("bar.sync 1, 256;" ::: "memory")
 
@@ -309,18 +322,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
-        if (lane == 0) {
+        // ===================================================== TMA producer (the warp walks the loops, one elected lane issues)
+        {
             int stage = 0;
             uint32_t phase = 0;
             if (RESB) {
                 // the weight slab of this CTA's channel tile (gridDim.x % tiles_n == 0: every tile of the CTA has the same n_tile)
                 const int n_tile = blockIdx.x % p.tiles_n;
-                mbar_expect_tx(bfull, (uint32_t)p.k_iters * Cfg::B_BYTES);
-                for (int kt = 0; kt < p.k_iters; ++kt) {
-                    if (!DUAL || kt < p.k1_iters) tma_load_2d(resb + kt * Cfg::B_BYTES, &mapB, bfull, kt * Cfg::BKE, n_tile * BN);
-                    else tma_load_2d(resb + kt * Cfg::B_BYTES, &mapB2, bfull, (kt - p.k1_iters) * Cfg::BKE, n_tile * BN);
+                if (elect_one()) {
+                    mbar_expect_tx(bfull, (uint32_t)p.k_iters * Cfg::B_BYTES);
+                    for (int kt = 0; kt < p.k_iters; ++kt) {
+                        if (!DUAL || kt < p.k1_iters) tma_load_2d(resb + kt * Cfg::B_BYTES, &mapB, bfull, kt * Cfg::BKE, n_tile * BN);
+                        else tma_load_2d(resb + kt * Cfg::B_BYTES, &mapB2, bfull, (kt - p.k1_iters) * Cfg::BKE, n_tile * BN);
+                    }
                 }
+                __syncwarp();
             }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
@@ -329,25 +345,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int kt = 0; kt < p.k_iters; ++kt) {
                     mbar_wait<32>(&empty[stage], phase ^ 1);
                     uint8_t *a_dst = tiles + stage * Cfg::STAGE_BYTES, *b_dst = a_dst + Cfg::A_BYTES;
-                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                    if (!DUAL || kt < p.k1_iters) {
-                        const int m = p.tap_map[tap];
-                        const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
-                        tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                        if (!RESB) tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
+                    const bool main_op = !DUAL || kt < p.k1_iters;
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        if (main_op) {
+                            const int m = p.tap_map[tap];
+                            const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
+                            tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+                            if (!RESB) tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
+                        } else {                                     // downsample branch: 1x1 (strided view) on the block input
+                            const int cb2 = kt - p.k1_iters;
+                            tma_load_4d(a_dst, &mapA1, &full[stage], cb2 * Cfg::BKE, 0, h0, n0);
+                            if (!RESB) tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
+                        }
+                    }
+                    __syncwarp();
+                    if (main_op) {
                         if (++cb == p.cin_blocks) { cb = 0; ++tap; }
-                    } else {                                     // downsample branch: 1x1 (strided view) on the block input
-                        const int cb2 = kt - p.k1_iters;
-                        tma_load_4d(a_dst, &mapA1, &full[stage], cb2 * Cfg::BKE, 0, h0, n0);
-                        if (!RESB) tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
                     }
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
+        // ===================================================== MMA issuer (the warp walks the loops, one elected lane issues: r02d)
+        {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
@@ -369,22 +391,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = umma_desc<KB>(a_addr);
                     const uint64_t db = umma_desc<KB>(RESB ? smem_u32(resb) + (uint32_t)kt * Cfg::B_BYTES : a_addr + Cfg::A_BYTES);
-                    if (BN == 256 && !DUAL && p.mode == MODE_STATS) {
-                        // statistics-only pass: D^T = W * A^T (operands swapped: M = 128 output channels, N = 128 pixels, two channel
-                        // halves), so that TMEM lanes are CHANNELS and the per-channel sums over pixels are thread-local in the epilogue
-                        const uint32_t idesc_t = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                    if (elect_one()) {
+                        if (BN == 256 && !DUAL && p.mode == MODE_STATS) {
+                            // statistics-only pass: D^T = W * A^T (operands swapped: M = 128 output channels, N = 128 pixels, two channel
+                            // halves), so that TMEM lanes are CHANNELS and the per-channel sums over pixels are thread-local in the epilogue
+                            const uint32_t idesc_t = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BM >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
+                            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                            for (int k = 0; k < Cfg::BKE / 16; ++k)
-                                umma_bf16(tmem_base + acc * 256 + h * 128, db + (uint64_t)(h * (128 * KB / 16)) + 2 * k, da + 2 * k, idesc_t, !(first && k == 0));
-                    } else {
+                                for (int k = 0; k < Cfg::BKE / 16; ++k)
+                                    umma_bf16(tmem_base + acc * 256 + h * 128, db + (uint64_t)(h * (128 * KB / 16)) + 2 * k, da + 2 * k, idesc_t, !(first && k == 0));
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
-                            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                            for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
+                                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
+                        }
+                        umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs retire
+                        if (kt == p.k_iters - 1) umma_commit(&tfull[acc]);
                     }
-                    umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs retire
-                    if (kt == p.k_iters - 1) umma_commit(&tfull[acc]);
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -739,7 +764,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
         // ===================================================== identity-tile loader (FINAL, single accumulator)
-        if (p.mode == MODE_FINAL && !DUAL && lane == 0) {
+        if (p.mode == MODE_FINAL && !DUAL) {
             int gcount = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
@@ -748,8 +773,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const int b = gcount % TC_XBUFS;
                     const uint32_t xph = (uint32_t)(gcount / TC_XBUFS) & 1;
                     mbar_wait<64>(&xfree[b], xph ^ 1);
-                    mbar_expect_tx(&xfull[b], Cfg::XBUF_BYTES);
-                    tma_load_4d(xbuf + b * Cfg::XBUF_BYTES, &mapIdt, &xfull[b], n_tile * BN + g * 64, 0, h0, n0);
+                    if (elect_one()) {
+                        mbar_expect_tx(&xfull[b], Cfg::XBUF_BYTES);
+                        tma_load_4d(xbuf + b * Cfg::XBUF_BYTES, &mapIdt, &xfull[b], n_tile * BN + g * 64, 0, h0, n0);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -784,27 +812,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // Roles: warp 0 = weight-tile producer, warp 18 = halo producer, warp 1 = MMA, warps 2-9 = transform (one group of 256:
 // the transform runs once per nine taps and is off the critical path), warps 10-17 = epilogue (RAW mode only).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int HALO_STAGE_BYTES = 26624;          // 208 rows: <= 170 written by TMA, <= 2*(W+2)+2+128 = 198 addressed by the taps
+constexpr int HALO_STAGE_BYTES = 26624;          // probe kernel: 208 rows
+constexpr int HALO_MAX_STAGES = 8;
 
+// Round-2 measurements (profiles/r02b_probe_halo.log) showed what really bounds the 3x3 kernels: not shared-memory bandwidth but
+// the WEIGHT tiles - re-fetched from L2 for every 128-pixel tile with only SB x B_BYTES in flight per SM against a ~1.6 us L2
+// round trip (64 KB in flight -> one 16 KB tile per ~750 cycles, while its MMAs need 256).  Hence
+//   RESW : the whole [Cout x 9 Cin] weight matrix stays resident in shared memory (64 -> 64: 72 KB), the ring streams halo boxes only;
+//   MT=2 : every weight tile is used for TWO pixel tiles (two halo boxes, two TMEM accumulators), halving the weight bytes per FLOP.
 struct HaloParams {
     int W, H, R, P;                  // output (= input) width / height, output rows per tile, halo pitch W + 2
     int Nimg, cin_blocks, h_tiles;   // h_tiles = H / R
     int total_tiles;                 // Nimg * h_tiles (Cout == BN: one channel tile)
+    int n_groups;                    // ceil(total_tiles / MT): a group = MT pixel tiles sharing every weight tile
     int halo_rows;                   // (R + 2) * P rows of 128 B per box
     int valid_rows;                  // R * W dense output rows per tile
+    int a_stage_bytes;               // bytes per halo stage: >= (2 P + 2 + 128) rows of 128 B (the taps address beyond the box), 1024-aligned
+    int SA, SB;                      // ring depths (halo boxes, weight tiles)
     const uint16_t *a_xf;            // [2*Cin] theta (bf16), sign masks
     double *stats;                   // [2*Cout]
     const float *img_w;              // [Nimg] multiplicities or null
-};
-
-template <int BN>
-struct HaloCfg {
-    static constexpr int SA = BN == 256 ? 3 : 4;                     // halo stages
-    static constexpr int SB = BN == 256 ? 3 : (BN == 128 ? 4 : 6);   // weight-tile stages
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int XBUF_BYTES = TC_BM * 128;
-    static constexpr int SMEM = 1024 + SA * HALO_STAGE_BYTES + SB * B_BYTES + 2 * XBUF_BYTES + (2 * 256 + 512) * 4 + 512;
-    static_assert(SMEM <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
 // K-major SWIZZLE_128B descriptor whose start is a whole number of 128-byte rows into a 1024-byte-aligned tile
@@ -812,28 +839,33 @@ struct HaloCfg {
 // every row the tensor core reads, so a row-shifted start needs NO base_offset; setting bits 49-51 de-swizzles wrongly)
 __device__ __forceinline__ uint64_t umma_desc_rowshift(uint32_t saddr) { return umma_desc<128>(saddr); }
 
-template <int BN>
+template <int BN, int MT, bool RESW>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                       const __grid_constant__ CUtensorMap mapOut, const HaloParams p) {
-    using Cfg = HaloCfg<BN>;
     constexpr int G = BN / 64;
+    constexpr int B_BYTES = BN * 128;
+    constexpr int XBUF_BYTES = TC_BM * 128;
+    constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;      // TMEM accumulator buffers (each MT x BN columns)
+    static_assert(MT * BN <= 512, "TMEM columns");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t *a_tiles = smem;
-    uint8_t *b_tiles = a_tiles + Cfg::SA * HALO_STAGE_BYTES;
-    uint8_t *xbuf = b_tiles + Cfg::SB * Cfg::B_BYTES;
-    float *s_par = reinterpret_cast<float *>(xbuf + 2 * Cfg::XBUF_BYTES);      // [2*BN] statistics
+    uint8_t *b_tiles = a_tiles + p.SA * p.a_stage_bytes;                        // RESW: 9 * cin_blocks tiles, loaded once
+    uint8_t *xbuf = b_tiles + (RESW ? 9 * p.cin_blocks : p.SB) * B_BYTES;
+    float *s_par = reinterpret_cast<float *>(xbuf + 2 * XBUF_BYTES);            // [2*BN] statistics
     float *s_apar = s_par + 2 * 256;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + 512);
-    uint64_t *a_full = bars, *a_ready = a_full + Cfg::SA, *a_empty = a_ready + Cfg::SA, *b_full = a_empty + Cfg::SA, *b_empty = b_full + Cfg::SB;
-    uint64_t *tfull = b_empty + Cfg::SB, *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *a_full = bars, *a_ready = a_full + HALO_MAX_STAGES, *a_empty = a_ready + HALO_MAX_STAGES, *b_full = a_empty + HALO_MAX_STAGES,
+             *b_empty = b_full + HALO_MAX_STAGES;
+    uint64_t *tfull = b_empty + HALO_MAX_STAGES, *tempty = tfull + 2, *bres = tempty + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_ready[s], 256); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < Cfg::SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < p.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_ready[s], 256); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < p.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+        mbar_init(bres, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapOut);
     }
@@ -853,65 +885,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================================================== weight tiles: (tap, channel block) in the order the MMA consumes them
-        if (lane == 0) {
+        // ===================================================== weight tiles: resident, or (tap, channel block) in the order the MMA consumes them
+        if (RESW) {
+            if (elect_one()) {
+                const int nb = 9 * p.cin_blocks;
+                mbar_expect_tx(bres, (uint32_t)nb * B_BYTES);
+                for (int i = 0; i < nb; ++i) tma_load_2d(b_tiles + i * B_BYTES, &mapB, bres, i * 64, 0);
+            }
+            __syncwarp();
+        } else {
             int sb = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x)
                 for (int cb = 0; cb < p.cin_blocks; ++cb)
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait<32>(&b_empty[sb], ph ^ 1);
-                        mbar_expect_tx(&b_full[sb], Cfg::B_BYTES);
-                        tma_load_2d(b_tiles + sb * Cfg::B_BYTES, &mapB, &b_full[sb], (tap * p.cin_blocks + cb) * 64, 0);
-                        if (++sb == Cfg::SB) { sb = 0; ph ^= 1; }
+                        if (elect_one()) {
+                            mbar_expect_tx(&b_full[sb], B_BYTES);
+                            tma_load_2d(b_tiles + sb * B_BYTES, &mapB, &b_full[sb], (tap * p.cin_blocks + cb) * 64, 0);
+                        }
+                        __syncwarp();
+                        if (++sb == p.SB) { sb = 0; ph ^= 1; }
                     }
         }
     } else if (warp == TC_IDT_WARP) {
         // ===================================================== halo boxes: rows h0-1 .. h0+R, columns -1 .. W (zero fill outside)
-        if (lane == 0) {
+        {
             int sa = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int n = tile / p.h_tiles, h0 = (tile % p.h_tiles) * p.R;
-                for (int cb = 0; cb < p.cin_blocks; ++cb) {
-                    mbar_wait<32>(&a_empty[sa], ph ^ 1);
-                    mbar_expect_tx(&a_full[sa], (uint32_t)p.halo_rows * 128u);
-                    tma_load_4d(a_tiles + sa * HALO_STAGE_BYTES, &mapA, &a_full[sa], cb * 64, -1, h0 - 1, n);
-                    if (++sa == Cfg::SA) { sa = 0; ph ^= 1; }
-                }
+            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+                const int nt = min(MT, p.total_tiles - grp * MT);
+                for (int cb = 0; cb < p.cin_blocks; ++cb)
+                    for (int m = 0; m < nt; ++m) {
+                        const int tile = grp * MT + m;
+                        const int n = tile / p.h_tiles, h0 = (tile % p.h_tiles) * p.R;
+                        mbar_wait<32>(&a_empty[sa], ph ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(&a_full[sa], (uint32_t)p.halo_rows * 128u);
+                            tma_load_4d(a_tiles + sa * p.a_stage_bytes, &mapA, &a_full[sa], cb * 64, -1, h0 - 1, n);
+                        }
+                        __syncwarp();
+                        if (++sa == p.SA) { sa = 0; ph ^= 1; }
+                    }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer: nine shifted views of one halo box per channel block
-        if (lane == 0) {
+        // ===================================================== MMA issuer: nine shifted views of each halo box per channel block
+        // The whole warp walks the loops (uniform values -> uniform registers, no per-instruction lane election code); one
+        // elected lane issues the tcgen05 instructions.  Measured (r02d): with an `if (lane == 0)` body the issue loop cost
+        // ~18 SASS instructions per MMA - as long as a 128x64 / 128x128 MMA itself.
+        {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int sa = 0, sb = 0, it = 0;
             uint32_t pa = 0, pb = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+            if (RESW) mbar_wait<32>(bres, 0);
+            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x, ++it) {
+                const int acc = NACC == 2 ? (it & 1) : 0;
+                const uint32_t acc_phase = NACC == 2 ? ((it >> 1) & 1) : (it & 1);
+                const int nt = min(MT, p.total_tiles - grp * MT);
                 mbar_wait<32>(&tempty[acc], acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + acc * 256;
+                const uint32_t d_tmem = tmem_base + acc * (MT * BN);
                 for (int cb = 0; cb < p.cin_blocks; ++cb) {
-                    mbar_wait<0>(&a_ready[sa], pa);               // landed (the transform waited for a_full) and transformed
-                    const uint32_t a_base = smem_u32(a_tiles + sa * HALO_STAGE_BYTES);
+                    uint32_t a_base[MT];
+                    int st[MT];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        a_base[m] = 0; st[m] = 0;
+                        if (m < nt) {
+                            st[m] = sa;
+                            mbar_wait<0>(&a_ready[sa], pa);           // landed (the transform waited for a_full) and transformed
+                            a_base[m] = smem_u32(a_tiles + sa * p.a_stage_bytes);
+                            if (++sa == p.SA) { sa = 0; pa ^= 1; }
+                        }
+                    }
                     int r = 0, q = 0;
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait<0>(&b_full[sb], pb);
+                        if (!RESW) mbar_wait<0>(&b_full[sb], pb);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t da = umma_desc_rowshift(a_base + (uint32_t)(r * p.P + q) * 128u);
-                        const uint64_t db = umma_desc<128>(smem_u32(b_tiles + sb * Cfg::B_BYTES));
+                        const uint64_t db = umma_desc<128>(smem_u32(b_tiles + (RESW ? (tap * p.cin_blocks + cb) : sb) * B_BYTES));
+                        const uint32_t shift = (uint32_t)(r * p.P + q) * 128u;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(cb == 0 && tap == 0 && k == 0));
-                        umma_commit(&b_empty[sb]);
-                        if (++sb == Cfg::SB) { sb = 0; pb ^= 1; }
+                            for (int m = 0; m < MT; ++m) {
+                                if (m < nt) {
+                                    const uint64_t da = umma_desc_rowshift(a_base[m] + shift);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem + m * BN, da + 2 * k, db + 2 * k, idesc, !(cb == 0 && tap == 0 && k == 0));
+                                }
+                            }
+                            if (!RESW) umma_commit(&b_empty[sb]);
+                        }
+                        __syncwarp();
+                        if (!RESW) {
+                            if (++sb == p.SB) { sb = 0; pb ^= 1; }
+                        }
                         if (++q == 3) { q = 0; ++r; }
                     }
-                    umma_commit(&a_empty[sa]);                  // the nine taps have read the box
-                    if (++sa == Cfg::SA) { sa = 0; pa ^= 1; }
+                    if (elect_one()) {
+#pragma unroll
+                        for (int m = 0; m < MT; ++m)
+                            if (m < nt) umma_commit(&a_empty[st[m]]);     // the nine taps have read the box
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&tfull[acc]);
+                if (elect_one()) umma_commit(&tfull[acc]);
+                __syncwarp();
             }
         }
     } else if (warp < TC_EPI_WARP0) {
@@ -934,30 +1013,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
         const uint32_t tiles0 = smem_u32(a_tiles) + col_off + (uint32_t)rb * 128;
         int sa = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int h0 = (tile % p.h_tiles) * p.R;
-            const bool top_out = h0 == 0, bot_out = h0 + p.R == p.H;       // halo row 0 / R+1 lies outside the image
+        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+            const int nt = min(MT, p.total_tiles - grp * MT);
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
                 const uint4 th = lds128(par0 + (uint32_t)cb * 128), sg = lds128(par0 + (uint32_t)cb * 128 + 1024);
-                mbar_wait<0>(&a_full[sa], ph);
-                const uint32_t base = tiles0 + sa * HALO_STAGE_BYTES;
+                for (int m = 0; m < nt; ++m) {
+                    const int h0 = ((grp * MT + m) % p.h_tiles) * p.R;
+                    const bool top_out = h0 == 0, bot_out = h0 + p.R == p.H;       // halo row 0 / R+1 lies outside the image
+                    mbar_wait<0>(&a_full[sa], ph);
+                    const uint32_t base = tiles0 + sa * p.a_stage_bytes;
 #pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    if (!in_box[i]) continue;
-                    const uint32_t addr = base + (uint32_t)i * 4096;
-                    uint4 v = lds128(addr);
-                    const bool inside = col_in[i] && !(top_out && hr[i] == 0) && !(bot_out && hr[i] == p.R + 1);
-                    if (inside) {
-                        v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
-                        v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
-                    } else {
-                        v = th;                                  // padding reads theta: |s|*theta + t = 0 (see the header)
+                    for (int i = 0; i < NI; ++i) {
+                        if (!in_box[i]) continue;
+                        const uint32_t addr = base + (uint32_t)i * 4096;
+                        uint4 v = lds128(addr);
+                        const bool inside = col_in[i] && !(top_out && hr[i] == 0) && !(bot_out && hr[i] == p.R + 1);
+                        if (inside) {
+                            v.x = max_bf16x2(v.x ^ sg.x, th.x); v.y = max_bf16x2(v.y ^ sg.y, th.y);
+                            v.z = max_bf16x2(v.z ^ sg.z, th.z); v.w = max_bf16x2(v.w ^ sg.w, th.w);
+                        } else {
+                            v = th;                                  // padding reads theta: |s|*theta + t = 0 (see the header)
+                        }
+                        sts128(addr, v);
                     }
-                    sts128(addr, v);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&a_ready[sa]);
+                    if (++sa == p.SA) { sa = 0; ph ^= 1; }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&a_ready[sa]);
-                if (++sa == Cfg::SA) { sa = 0; ph ^= 1; }
             }
         }
     } else if (warp < TC_IDT_WARP) {
@@ -978,45 +1060,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 4; ++j) { acc_s[g][j] = 0.f; acc_q[g][j] = 0.f; }
         int it = 0, gcount = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            const int n = tile / p.h_tiles, h0 = (tile % p.h_tiles) * p.R;
-            const float wimg = p.img_w ? __ldg(p.img_w + n) : 1.f;
-            const uint32_t t_acc = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x, ++it) {
+            const int acc = NACC == 2 ? (it & 1) : 0;
+            const uint32_t acc_phase = NACC == 2 ? ((it >> 1) & 1) : (it & 1);
+            const int nt = min(MT, p.total_tiles - grp * MT);
             mbar_wait<0>(&tfull[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int m = 0; m < nt; ++m) {
+                const int tile = grp * MT + m;
+                const int n = tile / p.h_tiles, h0 = (tile % p.h_tiles) * p.R;
+                const float wimg = p.img_w ? __ldg(p.img_w + n) : 1.f;
+                const uint32_t t_acc = tmem_base + acc * (MT * BN) + m * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-            for (int g = 0; g < G; ++g, ++gcount) {
-                const uint32_t st = xb0 + (gcount & 1) * Cfg::XBUF_BYTES;
-                uint32_t r[32];
-                tmem_ld32(t_acc + g * 64 + half * 32, r);
-                TMEM_LD_WAIT();
-                if (real) {
+                for (int g = 0; g < G; ++g, ++gcount) {
+                    const uint32_t st = xb0 + (gcount & 1) * XBUF_BYTES;
+                    uint32_t r[32];
+                    tmem_ld32(t_acc + g * 64 + half * 32, r);
+                    TMEM_LD_WAIT();
+                    if (real) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 w;
-                        w.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
-                        w.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
-                        w.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
-                        w.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
-                        sts128(st + (uint32_t)d * 128 + (uint32_t)(((half * 4 + j) ^ (d & 7)) << 4), w);
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 w;
+                            w.x = pack_bf16(__uint_as_float(r[j * 8 + 0]), __uint_as_float(r[j * 8 + 1]));
+                            w.y = pack_bf16(__uint_as_float(r[j * 8 + 2]), __uint_as_float(r[j * 8 + 3]));
+                            w.z = pack_bf16(__uint_as_float(r[j * 8 + 4]), __uint_as_float(r[j * 8 + 5]));
+                            w.w = pack_bf16(__uint_as_float(r[j * 8 + 6]), __uint_as_float(r[j * 8 + 7]));
+                            sts128(st + (uint32_t)d * 128 + (uint32_t)(((half * 4 + j) ^ (d & 7)) << 4), w);
+                        }
                     }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                EPI_BAR();
-                if (e == 0) tma_store_4d(xbuf + (gcount & 1) * Cfg::XBUF_BYTES, &mapOut, g * 64, 0, h0, n);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    EPI_BAR();
+                    if (e == 0) tma_store_4d(xbuf + (gcount & 1) * XBUF_BYTES, &mapOut, g * 64, 0, h0, n);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (rsub + 16 * i < p.valid_rows) {
-                        const uint2 v = lds64(st + st_off + (uint32_t)i * 2048);
-                        const float x0 = bf_lo(v.x), x1 = bf_hi(v.x), x2 = bf_lo(v.y), x3 = bf_hi(v.y);
-                        const float w0 = x0 * wimg, w1 = x1 * wimg, w2 = x2 * wimg, w3 = x3 * wimg;
-                        acc_s[g][0] += w0; acc_q[g][0] = fmaf(w0, x0, acc_q[g][0]);
-                        acc_s[g][1] += w1; acc_q[g][1] = fmaf(w1, x1, acc_q[g][1]);
-                        acc_s[g][2] += w2; acc_q[g][2] = fmaf(w2, x2, acc_q[g][2]);
-                        acc_s[g][3] += w3; acc_q[g][3] = fmaf(w3, x3, acc_q[g][3]);
+                    for (int i = 0; i < 8; ++i) {
+                        if (rsub + 16 * i < p.valid_rows) {
+                            const uint2 v = lds64(st + st_off + (uint32_t)i * 2048);
+                            const float x0 = bf_lo(v.x), x1 = bf_hi(v.x), x2 = bf_lo(v.y), x3 = bf_hi(v.y);
+                            const float w0 = x0 * wimg, w1 = x1 * wimg, w2 = x2 * wimg, w3 = x3 * wimg;
+                            acc_s[g][0] += w0; acc_q[g][0] = fmaf(w0, x0, acc_q[g][0]);
+                            acc_s[g][1] += w1; acc_q[g][1] = fmaf(w1, x1, acc_q[g][1]);
+                            acc_s[g][2] += w2; acc_q[g][2] = fmaf(w2, x2, acc_q[g][2]);
+                            acc_s[g][3] += w3; acc_q[g][3] = fmaf(w3, x3, acc_q[g][3]);
+                        }
                     }
                 }
             }
@@ -1214,28 +1300,44 @@ int g_halo = -1;
 bool halo_enabled() {
     if (g_halo < 0) {
         const char *e = getenv("BUSCA_HALO");
-        g_halo = e && e[0] == '1';
+        g_halo = !(e && e[0] == '0');            // on by default since round 2 (BUSCA_HALO=0: the tap-by-tap kernel)
     }
     return g_halo != 0;
 }
 
-template <int BN>
-cudaError_t launch_halo_v(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const HaloParams &p, cudaStream_t s) {
-    using Cfg = HaloCfg<BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+template <int BN, int MT, bool RESW>
+cudaError_t launch_halo_v(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, HaloParams p, cudaStream_t s) {
+    constexpr int B_BYTES = BN * 128;
+    const int fixed = 1024 + 2 * TC_BM * 128 + (2 * 256 + 512) * 4 + (5 * HALO_MAX_STAGES + 5) * 8 + 64;
+    const int budget = 232448 - fixed;
+    p.n_groups = (p.total_tiles + MT - 1) / MT;
+    if (RESW) {
+        const int wbytes = 9 * p.cin_blocks * B_BYTES;
+        p.SB = 1;
+        p.SA = (budget - wbytes) / p.a_stage_bytes;
+    } else {
+        // halo ring: the MT boxes the MMA is reading plus MT being filled / transformed; the rest of the budget goes to weight tiles in flight
+        p.SA = 2 * MT;
+        p.SB = (budget - p.SA * p.a_stage_bytes) / B_BYTES;
+    }
+    if (p.SA > HALO_MAX_STAGES) p.SA = HALO_MAX_STAGES;
+    if (p.SB > HALO_MAX_STAGES) p.SB = HALO_MAX_STAGES;
+    if (p.SA < 2 * MT || p.SB < 1 || (!RESW && p.SB < 2)) return cudaErrorInvalidValue;
+    const int smem = fixed + p.SA * p.a_stage_bytes + (RESW ? 9 * p.cin_blocks : p.SB) * B_BYTES;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<BN, MT, RESW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_smem = smem;
     }
     if (!g_num_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-    conv3x3_halo_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM, s>>>(ma, mb, mo, p);
-    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv3x3_halo_kernel<%d>", BN);
+    const int grid = p.n_groups < g_num_sms ? p.n_groups : g_num_sms;
+    conv3x3_halo_kernel<BN, MT, RESW><<<grid, TC_THREADS, smem, s>>>(ma, mb, mo, p);
+    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv3x3_halo_kernel<%d, %d, %d>", BN, MT, (int)RESW);
     return cudaGetLastError();
 }
 
@@ -1247,6 +1349,16 @@ bool halo_applies(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o) {
     return true;
 }
 
+// BUSCA_HALO_MT=1 forces one pixel tile per weight tile (A/B measurements)
+int halo_mt() {
+    static int mt = 0;
+    if (!mt) {
+        const char *e = getenv("BUSCA_HALO_MT");
+        mt = (e && e[0] == '1') ? 1 : 2;
+    }
+    return mt;
+}
+
 cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStream_t s) {
     HaloParams p{};
     p.W = a.W; p.H = a.H; p.P = a.W + 2;
@@ -1255,7 +1367,8 @@ cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStrea
         if (a.H % r == 0) { p.R = r; break; }
     p.halo_rows = (p.R + 2) * p.P;
     p.valid_rows = p.R * p.W;
-    if (p.R < 1 || p.halo_rows > 192 || 2 * p.P + 2 + 128 > HALO_STAGE_BYTES / 128 || p.valid_rows > 128) return cudaErrorInvalidValue;
+    p.a_stage_bytes = (((2 * p.P + 2 + 128) * 128) + 1023) & ~1023;
+    if (p.R < 1 || p.halo_rows > 192 || p.halo_rows * 128 > p.a_stage_bytes || p.valid_rows > 128) return cudaErrorInvalidValue;
     p.Nimg = a.N; p.cin_blocks = L.cin / TC_BK; p.h_tiles = a.H / p.R; p.total_tiles = a.N * p.h_tiles;
     p.a_xf = a.in_xf; p.stats = L.stats; p.img_w = a.img_w;
     const long long C = L.cin, W = a.W, H = a.H;
@@ -1264,10 +1377,13 @@ cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStrea
     ok = ok && make_map2(&mb, L.w16s, 9LL * L.cin, L.cout, L.cout);
     ok = ok && make_map4(&mo, a.out, L.cout, a.W, a.H, a.N, L.cout, W * L.cout, H * W * L.cout, a.W, p.R, 1);
     if (!ok) return cudaErrorInvalidValue;
+    const bool mt2 = halo_mt() == 2;
     switch (L.cout) {
-        case 256: return launch_halo_v<256>(ma, mb, mo, p, s);
-        case 128: return launch_halo_v<128>(ma, mb, mo, p, s);
-        default: return launch_halo_v<64>(ma, mb, mo, p, s);
+        case 256: return launch_halo_v<256, 1, false>(ma, mb, mo, p, s);      // measured (r02e): 0.112 ms vs 0.138 ms with MT = 2 (single TMEM buffer)
+        case 128: return mt2 ? launch_halo_v<128, 2, false>(ma, mb, mo, p, s) : launch_halo_v<128, 1, false>(ma, mb, mo, p, s);
+        default:
+            if (L.cin == 64) return launch_halo_v<64, 1, true>(ma, mb, mo, p, s);         // 72 KB of weights: resident
+            return launch_halo_v<64, 1, false>(ma, mb, mo, p, s);
     }
 }
 }  // namespace

@@ -122,4 +122,4 @@ cudaError_t launch_decoder(const float *x, int T, int S, int L, int C, const flo
                            const float *b, float *logits, float *probs, float *cand_rows, float *mem_logits,
                            cudaStream_t s);
 cudaError_t launch_decide(const float *probs, const int *cand, const uint8_t *reliable, int T, int D, int C, float thresh,
-                          uint8_t *keep, cudaStream_t s);
+                          int select_highest, float min_thresh, int keep_value, uint8_t *keep, cudaStream_t s);

@@ -589,7 +589,7 @@ static int ew_grid(long long total) {
     return (int)(b < 148 * 32 ? (b > 0 ? b : 1) : 148 * 32);
 }
 
-// EXPERIMENTAL variant (BUSCA_POOL_MONO=1 / busca_set_option("pool_mono", 1); off until its bitwise comparison on a B200,
+// Default variant (BUSCA_POOL_MONO=0 / busca_set_option("pool_mono", 0) selects the tap-by-tap kernel; compared bit for bit on a B200 by
 // tests/probe_pool.py): max-pooling commutes with the per-channel BN + ReLU because x -> fma(x, scale, shift) is monotone
 // (rounding included), so max_taps relu(fma(x_t)) = relu(fma(max_t x_t)) for scale >= 0 and relu(fma(min_t x_t)) for
 // scale < 0.  The nine taps cost one packed bf16 max and one packed min per two channels instead of unpack + fma + max per
@@ -642,7 +642,7 @@ void reid_set_pool_mono(int on) { g_pool_mono = on ? 1 : 0; }
 static bool pool_mono_enabled() {
     if (g_pool_mono < 0) {
         const char *e = getenv("BUSCA_POOL_MONO");
-        g_pool_mono = e && e[0] == '1';
+        g_pool_mono = !(e && e[0] == '0');      // on by default since round 2: bit-equal on a B200 (profiles/r02a_probe_pool.log)
     }
     return g_pool_mono != 0;
 }

@@ -283,13 +283,24 @@ __global__ void decoder_kernel(const float *__restrict__ x, int S, int L, int C,
     }
 }
 
-// decision: reliable[t] and p[t, kalman slot] > busca_thresh        byte_tracker.py:504-526
+// decision: reliable[t] and p'[t, kalman slot] > busca_thresh        byte_tracker.py:504-526
+// p' = p, or with select_highest_candidate (network.py:415-424) the one-hot of the FIRST maximum over all C+2 outputs (1.0, or the
+// maximum itself with keep_highest_value), all-zero when highest_candidate_minimum_thresh > 0 and the maximum is below it
 __global__ void decide_kernel(const float *__restrict__ probs, const uint8_t *__restrict__ reliable, int T, int D, int C, float thresh,
-                              uint8_t *__restrict__ keep) {
+                              int select_highest, float min_thresh, int keep_value, uint8_t *__restrict__ keep) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     const int kslot = min(D, C - 1);
-    keep[t] = (reliable ? reliable[t] != 0 : true) && probs[(size_t)t * (C + 2) + kslot] > thresh;
+    const float *p = probs + (size_t)t * (C + 2);
+    float pk = p[kslot];
+    if (select_highest) {
+        int best = 0;
+        for (int k = 1; k < C + 2; ++k)
+            if (p[k] > p[best]) best = k;
+        const bool on = min_thresh == 0.f || (min_thresh > 0.f && p[best] >= min_thresh);
+        pk = (on && best == kslot) ? (keep_value ? p[best] : 1.f) : 0.f;
+    }
+    keep[t] = (reliable ? reliable[t] != 0 : true) && pk > thresh;
 }
 
 }  // namespace
@@ -348,9 +359,9 @@ cudaError_t launch_decoder(const float *x, int T, int S, int L, int C, const flo
 }
 
 cudaError_t launch_decide(const float *probs, const int *cand, const uint8_t *reliable, int T, int D, int C, float thresh,
-                          uint8_t *keep, cudaStream_t s) {
+                          int select_highest, float min_thresh, int keep_value, uint8_t *keep, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
     (void)cand;
-    decide_kernel<<<ceil_div(T, 128), 128, 0, s>>>(probs, reliable, T, D, C, thresh, keep);
+    decide_kernel<<<ceil_div(T, 128), 128, 0, s>>>(probs, reliable, T, D, C, thresh, select_highest, min_thresh, keep_value, keep);
     return cudaGetLastError();
 }

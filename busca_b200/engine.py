@@ -63,6 +63,14 @@ class _PinnedBlock:
         self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
 
+_last_engine = None        # weak reference to the most recently created Engine (busca_b200.tracking.default_engine)
+
+
+def last_engine():
+    e = _last_engine() if _last_engine is not None else None
+    return e if e is not None and getattr(e, "h", None) else None
+
+
 class Engine:
     def __init__(self, device: int = 0, d_model: int = 512, nhead: int = 4, ff_size: int = 1024, num_layers: int = 4,
                  activation: str = "relu", precision: str = "fp32", sentinel_fp64: bool = True, bank_slots: int = 2048):
@@ -81,6 +89,9 @@ class Engine:
         self._pin_free: Dict[int, List[int]] = {}
         self._pin_total = 0
         self._pin_max = int(float(os.environ.get("BUSCA_PINNED_MAX_GB", "8")) * (1 << 30))
+        self.device = device
+        global _last_engine
+        _last_engine = weakref.ref(self)
 
     def close(self):
         if getattr(self, "h", None):

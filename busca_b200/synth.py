@@ -75,10 +75,29 @@ def reid_conv_specs():
     return specs
 
 
+# Knobs of the "conditioned" profile (designed with tests/analysis_weights.py, see make_weights)
+CONDITIONED = dict(bn3_gain=0.2, decoder_gain=6.0, decoder_seed=108, branch_gain=0.5)
+
+
 def make_weights(seed: int = 0, d_model: int = 512, ff: int = 1024, nlayer: int = 4,
-                 decoder_gain: float = 8.0, neg_bn_frac: float = 0.03) -> Dict[str, np.ndarray]:
+                 decoder_gain: float = 8.0, neg_bn_frac: float = 0.03, profile: str = "chaotic") -> Dict[str, np.ndarray]:
     """Random-init state dict with the reference's key names and shapes (fc.* omitted: the
-    reference drops them with ``ignore_reid_fc=True``, network.py:445-448)."""
+    reference drops them with ``ignore_reid_fc=True``, network.py:445-448).
+
+    ``profile="chaotic"`` (round-1 fixtures): plain random init.  An untrained batch-statistic-BN ResNet-50 with unit
+    residual-branch gains amplifies any perturbation ~50-100x over its 16 blocks, and a gain-8 decoder on random rows
+    makes one learned token win every row - good for stressing fp32 parity, useless for judging decisions or bf16.
+    ``profile="conditioned"``: the same draws, then (a) the last BatchNorm of every bottleneck gets a small gain
+    (|gamma| x 0.2: the residual branch perturbs the identity path instead of replacing it - what zero-init-residual
+    training produces, and what trained weights look like), (b) the Transformer's residual branches are damped (out_proj,
+    linear2 x 0.5), and (c) the decoder direction is the one of 4000 random draws (``decoder_seed``, gain 6; searched by
+    tests/analysis_weights.py --search on a calibration frame) for which the learned NON / BAD tokens do not dominate: the
+    C+2 logits then depend on the candidate embeddings, the winner varies from track to track and the Kalman-slot
+    probability falls on both sides of busca_thresh."""
+    if profile not in ("chaotic", "conditioned"):
+        raise ValueError(profile)
+    if profile == "conditioned":
+        decoder_gain = CONDITIONED["decoder_gain"]
     rng = np.random.default_rng(seed)
     sd: Dict[str, np.ndarray] = {}
     f32 = np.float32
@@ -127,6 +146,15 @@ def make_weights(seed: int = 0, d_model: int = 512, ff: int = 1024, nlayer: int 
         bn(f"{r}{bnn}", cout)
     sd[f"{r}red.weight"] = uniform((512, 2048), 1.0 / math.sqrt(2048))
     sd[f"{r}red.bias"] = uniform((512,), 1.0 / math.sqrt(2048))
+    if profile == "conditioned":
+        for k in list(sd):
+            if k.endswith(".bn3.weight"):
+                sd[k] = (sd[k] * CONDITIONED["bn3_gain"]).astype(f32)
+            elif k.endswith("self_attn.out_proj.weight") or k.endswith("linear2.weight"):
+                sd[k] = (sd[k] * CONDITIONED["branch_gain"]).astype(f32)
+        drng = np.random.default_rng(1_000_003 + CONDITIONED["decoder_seed"])
+        sd["decoder.1.weight"] = (drng.uniform(-1.0, 1.0, size=d_model).astype(f32) / f32(math.sqrt(d_model))
+                                  * f32(CONDITIONED["decoder_gain"])).reshape(1, d_model).astype(f32)
     return sd
 
 
@@ -246,3 +274,52 @@ def make_assoc_case(seed: int, T: int, D: int, L: int = 11, crop_fn=None, H: int
         k.images_mem.append(crop_fn(cur, [kb])[0])
         kalman.append(k)
     return AssocCase(frames=frames, tracks=tracks, dets=dets, kalman=kalman, frame=cur)
+
+
+# ----------------------------------------------------------------------------------------
+# detector output for a whole sequence (what a host tracker's update() receives per frame)
+# ----------------------------------------------------------------------------------------
+@dataclass
+class Sequence:
+    """frames[f]: uint8 BGR [H,W,3]; dets[f]: float32 [n_f,5] rows (x1, y1, x2, y2, score) in frame pixels."""
+    frames: List[np.ndarray]
+    dets: List[np.ndarray]
+    H: int
+    W: int
+
+
+def make_sequence(seed: int, n_frames: int, n_objects: int, H: int = 1080, W: int = 1920, warm: int = 13, miss: float = 0.2,
+                  low_score: float = 0.1, clutter: float = 0.5, frame_ring: int = 0) -> Sequence:
+    """``n_objects`` boxes on constant-velocity paths (+ jitter).  During the first ``warm`` frames every object is
+    detected with a high score (so every track collects >= seq_len confident observations); afterwards each object is
+    missed with probability ``miss``, detected with a low score (second-round material, 0.15..0.55) with probability
+    ``low_score``, and ``clutter`` false positives per frame (Poisson) are added.  ``frame_ring`` > 0 synthesises only
+    that many distinct frames and cycles through them (long benchmark sequences)."""
+    rng = np.random.default_rng(seed)
+    n_img = frame_ring if frame_ring else n_frames
+    frames = [make_frame(seed * 7919 + 1, H, W)]
+    for i in range(1, n_img):
+        frames.append(next_frame(frames[-1], seed * 7919 + 1 + i))
+    box = random_boxes(rng, n_objects, H, W, border_frac=0.0)
+    vel = rng.normal(0.0, 2.5, size=(n_objects, 2))
+    dets = []
+    for f in range(n_frames):
+        rows = []
+        for o in range(n_objects):
+            b = box[o].copy()
+            b[:2] += vel[o] * f + rng.normal(0.0, 0.7, 2)
+            b[2:] *= 1.0 + 0.01 * rng.standard_normal(2)
+            u = rng.uniform()
+            score = rng.uniform(0.75, 0.95)
+            if f >= warm:
+                if u < miss:
+                    continue
+                if u < miss + low_score:
+                    score = rng.uniform(0.15, 0.55)
+            rows.append([b[0], b[1], b[0] + b[2], b[1] + b[3], score])
+        if f >= warm:
+            for _ in range(rng.poisson(clutter)):
+                b = random_boxes(rng, 1, H, W, border_frac=0.0)[0]
+                rows.append([b[0], b[1], b[0] + b[2], b[1] + b[3], rng.uniform(0.15, 0.9)])
+        dets.append(np.asarray(rows, dtype=np.float32).reshape(-1, 5))
+    return Sequence(frames=[frames[f % n_img] for f in range(n_frames)], dets=dets, H=H, W=W)

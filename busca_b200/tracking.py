@@ -16,10 +16,17 @@ _default = None
 
 
 def default_engine() -> "_engine.Engine":
-    """Module-level functions have no BUSCA instance to hang on to, so they share one small context."""
+    """Module-level functions (the adapters call ``busca.tracking.center_distance(tracks, dets)`` with no handle,
+    byte_tracker.py:489) run on the context of the tracker's own BUSCA instance: the most recently constructed Engine of
+    this process.  Only if there is none a small context is created, on the GPU this process was given (LOCAL_RANK under
+    torchrun, else device 0) - never a second context on GPU 0 from every rank."""
     global _default
-    if _default is None:
-        _default = _engine.Engine(device=0, bank_slots=8)
+    live = _engine.last_engine()
+    if live is not None:
+        return live
+    if _default is None or _default.h is None:
+        import os
+        _default = _engine.Engine(device=int(os.environ.get("LOCAL_RANK", "0")), bank_slots=8)
     return _default
 
 

@@ -130,7 +130,9 @@ int busca_transformer(busca_ctx *ctx, int32_t T, int32_t L, int32_t C, const flo
                       const double *mem_ltwh, const double *can_ltwh, float *logits, float *probs, int32_t *pe_index,
                       float *cand_rows, float *input_seq);
 
-/* ---- device-resident step (bench `value`: inputs already in HBM) ------------------------------ */
+/* ---- device-resident step (bench `value`: inputs already in HBM) ------------------------------
+ * All boxes are FRAME coordinates, i.e. track.scale == 1 (CenterTrack / StrongSORT / GHOST pass the original frame; an
+ * adapter with a letter-boxed frame uses busca_crop + busca_associate, which take the scaled boxes the reference builds). */
 typedef struct busca_step_args {
     int32_t T, D, L, C;
     const double *track_mean_dev;   /* [T,8]  Kalman means BEFORE prediction */
@@ -144,7 +146,11 @@ typedef struct busca_step_args {
     const uint8_t *reliable_dev;    /* [T] */
     /* outputs (device) */
     float *probs_dev;               /* [T,C+2] */
-    uint8_t *keep_dev;              /* [T] decision: reliable && p[kalman slot] > thresh */
+    uint8_t *keep_dev;              /* [T] decision: reliable && p'[kalman slot] > busca_thresh, p' per the three fields below */
+    int32_t *cand_dev;              /* [T,C] proposal table (detection id, D+t for the Kalman slot, -1 = filler) or NULL */
+    int32_t select_highest;         /* select_highest_candidate (network.py:415-424): p' = one-hot of the argmax over the C+2 outputs */
+    float highest_min_thresh;       /* highest_candidate_minimum_thresh; 0 = none */
+    int32_t keep_highest_value;     /* keep_highest_value: the one-hot carries the maximum instead of 1.0 */
 } busca_step_args;
 /* One frame of the whole hot path with everything resident: motion proposals + geometry + crops of the
  * D detections and T proposals from the uploaded frame + ReID (2 batches) + Transformer + decision. */
@@ -196,8 +202,8 @@ const char *busca_last_profile(busca_ctx *ctx);
 /* options: "dedup" (default 1, bf16 mode): run the ReID encoder once per DISTINCT patch of a BatchNorm batch and weight
  * the batch statistics by the multiplicities - the batches the reference stacks (network.py:313-316, 383-386) repeat
  * every detection crop for each track that lists it as a candidate, and every incomplete history is the same zero image;
- * "halo" (default 0, process-wide): experimental halo-box kernel for the stride-1 3x3 convolutions (csrc/conv_tc.cu);
- * "pool_mono" (default 0, process-wide): experimental max-pool kernel that pools before BN + ReLU (csrc/reid.cu) */
+ * "halo" (default 1, process-wide): halo-box kernel for the stride-1 3x3 convolutions (csrc/conv_tc.cu), 0 = tap-by-tap kernel;
+ * "pool_mono" (default 1, process-wide): max-pool kernel that pools before BN + ReLU (csrc/reid.cu) */
 int busca_set_option(busca_ctx *ctx, const char *name, int64_t value);
 /* counters: "reid_images_run" / "reid_images_total" (encoder images executed / images of the stacked batches), "kernel_launches" */
 int64_t busca_counter(busca_ctx *ctx, const char *name);

@@ -42,19 +42,19 @@ def sha(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def build_reference(weights_seed=0):
+def build_reference(weights_seed=0, profile="chaotic"):
     targs, _ = load_args_from_config(os.path.join(REF, "config/ByteTrack/MOT20/config_bytetrack_mot20.yml"))
     a = targs.transformer
     a.device = torch.device("cpu")
     a.reid_weights_file = "no"
     model = ref_net.BUSCA(a).eval()
-    sd = synth.make_weights(weights_seed)
+    sd = synth.make_weights(weights_seed, profile=profile)
     ref_keys = {k for k in model.state_dict().keys() if ".fc." not in k}
     assert ref_keys == set(sd.keys()), (sorted(ref_keys - set(sd))[:5], sorted(set(sd) - ref_keys)[:5])
     for k, v in model.state_dict().items():
         if k in sd:
             assert tuple(v.shape) == tuple(sd[k].shape), (k, v.shape, sd[k].shape)
-    path = "/tmp/busca_golden_weights.pth"
+    path = "/tmp/busca_golden_weights_%s.pth" % profile
     torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, path)
     model.load_pretrained(path, ignore_reid_fc=True)
     return model, targs
@@ -310,8 +310,130 @@ def golden_pe(model):
     print("pe samples", vals.shape, vals[0, :4])
 
 
+def golden_assoc_cond(model):
+    """The plug-in call on the CONDITIONED weight set (synth.make_weights(profile="conditioned")): winners vary from track to
+    track and the Kalman-slot probabilities straddle busca_thresh, so decisions - and the bf16 path - are really tested."""
+    ref_crop = lambda frame, boxes: model.get_image_crops(frame, boxes, normalize=False)
+    cases = {"assoc_cfg1_cond": (101, 16, 40, 11, 5, 1), "assoc_fewdets_cond": (102, 5, 3, 11, 5, 2)}
+    for name, (seed, T, D, L, C, short) in cases.items():
+        case = synth.make_assoc_case(seed, T, D, L, crop_fn=ref_crop, short_history=short)
+        out = run_assoc(model, case, L, C, flavour64=True, select_highest_candidate=False)
+        store = {"meta": np.array([seed, T, D, L, C, short])}
+        for k in ("probs_matrix", "reliable", "mem_emb", "can_emb", "cand_rows", "logits", "probs", "mem_logits", "dists",
+                  "mem_xy", "mem_size", "can_xy", "can_size", "mem_t", "can_t"):
+            store["f64_" + k] = out[k]
+        o = run_assoc(model, case, L, C, flavour64=True, select_highest_candidate=True)
+        store["f64_probs_matrix_highest"] = o["probs_matrix"]
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **store)
+        p = out["probs"]
+        print(name, "winners", np.bincount(p.argmax(1), minlength=C + 2), "p_kalman", np.round(p[:, min(D, C - 1)], 3))
+
+
+def golden_scene(model, name, T, D, seed, emb_stride):
+    """One frame of busca_b200.scene.Scene (what bench.py times and busca_frame_step_dev consumes) through the reference's
+    associate_embeddings: the parity pin of the BENCHMARKED entry point at the benchmarked scale."""
+    from busca_b200.scene import Scene
+    L, C = 11, 5
+    sc = Scene(T, D, L, C, seed=seed)
+    ref_crop = lambda frame, boxes: model.get_image_crops(frame, boxes, normalize=False)
+    tracks, dets, kal = sc.objects(ref_crop)
+    case = SimpleCase(tracks, dets, kal)
+    import time
+    t0 = time.time()
+    out = run_assoc(model, case, L, C, flavour64=True, select_highest_candidate=False)
+    print(name, "reference run: %.1f s" % (time.time() - t0))
+    p = out["probs"]
+    kslot = min(D, C - 1)
+    store = {"meta": np.array([seed, T, D, L, C]), "emb_stride": emb_stride}
+    for k in ("probs_matrix", "reliable", "logits", "probs", "dists", "can_xy", "can_size", "mem_xy", "mem_size"):
+        store[k] = out[k]
+    store["mem_emb_sub"] = out["mem_emb"][::emb_stride]
+    store["can_emb_sub"] = out["can_emb"][::emb_stride]
+    store["cand_rows_sub"] = out["cand_rows"][::emb_stride]
+    store["crop_sha_kalman"] = np.array([sha(k.images_mem[-1]) for k in kal[:16]])
+    store["crop_sha_det"] = np.array([sha(d.images_mem[-1]) for d in dets[:16]])
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **store)
+    print(name, "winners", np.bincount(p.argmax(1), minlength=C + 2), "p_kalman>0.3:", int((p[:, kslot] > 0.3).sum()), "of", T,
+          "kept:", int((out["reliable"] & (p[:, kslot] > 0.3)).sum()))
+
+
+class SimpleCase:
+    def __init__(self, tracks, dets, kalman):
+        self.tracks, self.dets, self.kalman = tracks, dets, kalman
+
+
+def golden_adapter(weights_path):
+    """Drive the UNMODIFIED adapter (adapters/CenterTrack/src/lib/utils/byte_tracker.py, md5-identical to the ByteTrack copy)
+    over a synthetic sequence and record, per frame, the ids / boxes it outputs and what Step 3b decided.  Shims: lap, cython_bbox
+    (tests/golden/shims), np.float."""
+    import importlib
+    sys.path.insert(0, os.path.join(REF, "adapters/CenterTrack/src/lib"))
+    bt = importlib.import_module("utils.byte_tracker")
+    from utils.mot_online.basetrack import BaseTrack
+    n_frames, n_obj, seed = 36, 10, 5
+    seq = synth.make_sequence(seed, n_frames, n_obj, miss=0.25)
+    args, _ = load_args_from_config(os.path.join(REF, "config/ByteTrack/MOT20/config_bytetrack_mot20.yml"))
+    args.use_busca, args.device, args.busca_ckpt = True, "cpu", weights_path
+    args.track_thresh, args.track_buffer, args.match_thresh, args.mot20 = 0.6, 30, 0.9, True
+    args.transformer.reid_weights_file = "no"
+    BaseTrack._count = 0
+    tracker = bt.BYTETracker(args)
+    # accurate (NCHW) CPU batch-norm kernels, as for the other fixtures (see run_assoc)
+    enc_fwd = tracker.busca_tracker.reid_encoder.forward
+    tracker.busca_tracker.reid_encoder.forward = lambda x: enc_fwd(x.contiguous())
+    f64 = lambda seq_len=None, flavour="ltrb": ref_trk.missing_candidate_bbox(seq_len, flavour).astype(np.float64)
+    ref_enc.missing_candidate_bbox = f64
+    ref_net.missing_candidate_bbox = f64
+    tracker.busca_tracker.pos_encoder.distant_fake_bbox = torch.from_numpy(f64(flavour="ltwh"))
+    rec3 = {}
+    orig3 = tracker.third_round_association
+
+    def third(strack_pool, considered_dets, extra_kalman_candidates, asoc_thresh):
+        m, u = orig3(strack_pool=strack_pool, considered_dets=considered_dets, extra_kalman_candidates=extra_kalman_candidates, asoc_thresh=asoc_thresh)
+        rec3["pool_ids"] = [t.track_id for t in strack_pool]
+        rec3["matches"] = [(int(i), float(p)) for i, p in m]
+        rec3["n"] = len(strack_pool)
+        return m, u
+
+    tracker.third_round_association = third
+    ids, boxes, off, b3_ids, b3_keep, b3_prob, b3_off = [], [], [0], [], [], [], [0]
+    import time
+    t0 = time.time()
+    for f in range(n_frames):
+        rec3.clear()
+        out = tracker.update(seq.dets[f].copy(), [seq.H, seq.W], [seq.H, seq.W], current_frame=seq.frames[f])
+        ids += [t.track_id for t in out]
+        boxes += [t.tlwh for t in out]
+        off.append(len(ids))
+        if rec3.get("n"):
+            kept = {i: p for i, p in rec3["matches"]}
+            b3_ids += rec3["pool_ids"]
+            b3_keep += [i in kept for i in range(rec3["n"])]
+            b3_prob += [kept.get(i, -1.0) for i in range(rec3["n"])]
+        b3_off.append(len(b3_ids))
+        print("frame", f + 1, "ids", [t.track_id for t in out], "3b pool", rec3.get("pool_ids"), "kept", [rec3["pool_ids"][i] for i, _ in rec3.get("matches", [])],
+              "%.0f s" % (time.time() - t0), flush=True)
+    ref_enc.missing_candidate_bbox = ref_trk.missing_candidate_bbox
+    ref_net.missing_candidate_bbox = ref_trk.missing_candidate_bbox
+    np.savez_compressed(os.path.join(HERE, "adapter_seq.npz"), meta=np.array([seed, n_frames, n_obj]), miss=0.25,
+                        ids=np.array(ids), boxes=np.array(boxes).reshape(-1, 4), off=np.array(off),
+                        b3_ids=np.array(b3_ids), b3_keep=np.array(b3_keep, bool), b3_prob=np.array(b3_prob), b3_off=np.array(b3_off))
+    print("adapter: kept-alive decisions", int(np.sum(b3_keep)), "of", len(b3_keep))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["crops", "geometry", "pe", "assoc"]
+    if any(w in ("cond", "scene", "scene_mot20", "adapter") for w in which):
+        model, targs = build_reference(profile="conditioned")
+        if "cond" in which:
+            golden_assoc_cond(model)
+        if "scene" in which:
+            golden_scene(model, "scene_cfg1_cond", 16, 40, seed=11, emb_stride=1)
+        if "scene_mot20" in which:
+            golden_scene(model, "scene_mot20_cond", 200, 300, seed=0, emb_stride=8)
+        if "adapter" in which:
+            golden_adapter("/tmp/busca_golden_weights_conditioned.pth")
+        sys.exit(0)
     model, targs = build_reference()
     if "crops" in which:
         golden_crops(model)
