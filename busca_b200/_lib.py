@@ -39,7 +39,8 @@ class StepArgs(C.Structure):
                 ("mem_slots_dev", C.c_void_p), ("mem_ltwh_dev", C.c_void_p), ("det_slots_dev", C.c_void_p),
                 ("kal_slots_dev", C.c_void_p), ("busca_thresh", C.c_float), ("reliable_dev", C.c_void_p),
                 ("probs_dev", C.c_void_p), ("keep_dev", C.c_void_p), ("cand_dev", C.c_void_p),
-                ("select_highest", C.c_int32), ("highest_min_thresh", C.c_float), ("keep_highest_value", C.c_int32)]
+                ("select_highest", C.c_int32), ("highest_min_thresh", C.c_float), ("keep_highest_value", C.c_int32),
+                ("frame_dev", C.c_void_p), ("frame_H", C.c_int32), ("frame_W", C.c_int32)]
 
 
 class DebugConvArgs(C.Structure):
@@ -52,7 +53,7 @@ class DebugConvArgs(C.Structure):
 
 EXPORTS = [
     "busca_version", "busca_last_error", "busca_create", "busca_destroy", "busca_load_tensor", "busca_finalize",
-    "busca_upload_frame", "busca_bank_reserve", "busca_bank_capacity", "busca_crop", "busca_bank_upload",
+    "busca_upload_frame", "busca_sync_frame", "busca_bank_reserve", "busca_bank_capacity", "busca_crop", "busca_bank_upload",
     "busca_bank_download", "busca_center_distance", "busca_iou", "busca_motion_proposals", "busca_frame_geometry",
     "busca_reid_embed", "busca_associate", "busca_transformer", "busca_frame_step_dev", "busca_dev_alloc",
     "busca_dev_free", "busca_host_alloc", "busca_host_free", "busca_memcpy_h2d", "busca_memcpy_d2h", "busca_sync", "busca_stream", "busca_kernel_launches",
@@ -85,6 +86,7 @@ def load(build_if_missing: bool = True):
     L.busca_load_tensor.argtypes = [vp, C.c_char_p, vp, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
     L.busca_finalize.argtypes = [vp]
     L.busca_upload_frame.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int64]
+    L.busca_sync_frame.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int64, vp, C.c_int32, vp]
     L.busca_bank_reserve.argtypes = [vp, C.c_int64]
     L.busca_bank_capacity.argtypes = [vp]
     L.busca_bank_capacity.restype = C.c_int64

@@ -62,7 +62,8 @@ struct TLayer {
 struct ProfEntry {
     std::string name;
     cudaEvent_t a, b;
-    double flops;                                 // algorithmic FLOPs of the launch (convolutions; 0 = not tracked)
+    double flops;                                 // ALGORITHMIC FLOPs of the launch: every convolution counted once (statistics-only passes: 0)
+    double xflops;                                // FLOPs the launch executed (statistics-only passes included)
     std::string kernel;                           // the __global__ instantiation, as the ncu launch list names it
 };
 
@@ -86,6 +87,9 @@ struct busca_ctx {
     __half *pe_xy = nullptr, *pe_size = nullptr, *pe_t = nullptr;
     // frame + bank
     DevBuf frame;
+    uint8_t *mirror = nullptr;                    // page-locked host copy of the frame in HBM (busca_sync_frame)
+    size_t mirror_cap = 0;
+    bool mirror_valid = false;
     int fH = 0, fW = 0;
     int64_t fstride = 0;
     uint8_t *bank = nullptr;
@@ -109,7 +113,7 @@ struct busca_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::string prof_json;
-    double next_flops = 0.0;                      // consumed by the next prof_begin
+    double next_flops = 0.0, next_xflops = 0.0;   // consumed by the next prof_begin
     std::string next_kernel;
 };
 
@@ -123,8 +127,8 @@ static cudaEvent_t get_event(busca_ctx *c) {
 }
 static void prof_begin(busca_ctx *c, const char *name) {
     if (!c->profiling) return;
-    ProfEntry pe{name, get_event(c), get_event(c), c->next_flops, c->next_kernel};
-    c->next_flops = 0.0;
+    ProfEntry pe{name, get_event(c), get_event(c), c->next_flops, c->next_xflops > 0.0 ? c->next_xflops : c->next_flops, c->next_kernel};
+    c->next_flops = c->next_xflops = 0.0;
     c->next_kernel.clear();
     cudaEventRecord(pe.a, c->stream);
     c->prof.push_back(pe);
@@ -139,7 +143,7 @@ static void prof_reset(busca_ctx *c) {
 }
 static void prof_collect(busca_ctx *c) {
     if (!c->profiling) return;
-    struct Acc { double ms = 0, flops = 0; int n = 0; std::string kernel; };
+    struct Acc { double ms = 0, flops = 0, xflops = 0; int n = 0; std::string kernel; };
     std::map<std::string, Acc> acc;
     std::vector<std::string> order;
     for (auto &pe : c->prof) {
@@ -147,14 +151,14 @@ static void prof_collect(busca_ctx *c) {
         cudaEventElapsedTime(&ms, pe.a, pe.b);
         if (!acc.count(pe.name)) order.push_back(pe.name);
         Acc &a = acc[pe.name];
-        a.ms += ms; a.flops += pe.flops; a.n += 1; a.kernel = pe.kernel;
+        a.ms += ms; a.flops += pe.flops; a.xflops += pe.xflops; a.n += 1; a.kernel = pe.kernel;
     }
     std::string js = "{";
     for (size_t i = 0; i < order.size(); ++i) {
         char buf[512];
         const Acc &a = acc[order[i]];
-        snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d, \"flops\": %.6e, \"kernel\": \"%s\"}", i ? ", " : "", order[i].c_str(),
-                 a.ms, a.n, a.flops, a.kernel.c_str());
+        snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"launches\": %d, \"flops\": %.6e, \"xflops\": %.6e, \"kernel\": \"%s\"}", i ? ", " : "",
+                 order[i].c_str(), a.ms, a.n, a.flops, a.xflops, a.kernel.c_str());
         js += buf;
     }
     js += "}";
@@ -238,6 +242,7 @@ extern "C" void busca_destroy(busca_ctx *c) {
     c->ws_dedup[0].release();
     c->ws_dedup[1].release();
     c->frame.release();
+    if (c->mirror) cudaFreeHost(c->mirror);
     c->ws_reid.release();
     c->ws_tr.release();
     c->ws_io.release();
@@ -433,6 +438,52 @@ extern "C" int busca_upload_frame(busca_ctx *c, const uint8_t *bgr, int32_t H, i
     CUDA_OK(cudaMemcpy2DAsync(c->frame.p, (size_t)W * 3, bgr, (size_t)row_stride, (size_t)W * 3, H, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->fH = H; c->fW = W; c->fstride = (int64_t)W * 3;
+    c->mirror_valid = false;
+    return BUSCA_OK;
+}
+
+// Make the frame in HBM show, inside the given boxes (or everywhere), exactly the pixels of `bgr` - uploading only when they differ
+// from the page-locked host mirror of what is already there.  The adapters call get_image_crops 3 + T times per frame with the same
+// image (byte_tracker.py:278-282, 468-479); this keeps those calls at a memcmp of the rows they read.
+extern "C" int busca_sync_frame(busca_ctx *c, const uint8_t *bgr, int32_t H, int32_t W, int64_t row_stride, const double *boxes, int32_t n_boxes,
+                                int32_t *uploaded) {
+    if (!c || !bgr || H <= 0 || W <= 0 || row_stride < (int64_t)W * 3) return set_err(BUSCA_ERR_ARG, "bad frame");
+    if (uploaded) *uploaded = 0;
+    const size_t rowb = (size_t)W * 3;
+    if (c->mirror_valid && c->fH == H && c->fW == W) {
+        int y0 = 0, y1 = H, x0 = 0, x1 = W;
+        if (boxes && n_boxes > 0 && n_boxes <= 8) {
+            double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
+            for (int i = 0; i < n_boxes; ++i) {
+                bx0 = fmin(bx0, boxes[4 * i]); by0 = fmin(by0, boxes[4 * i + 1]);
+                bx1 = fmax(bx1, boxes[4 * i + 2]); by1 = fmax(by1, boxes[4 * i + 3]);
+            }
+            if (bx0 == bx0 && bx1 == bx1 && by0 == by0 && by1 == by1) {       // no NaN
+                x0 = (int)fmax(0.0, fmin((double)W, floor(bx0) - 1)); x1 = (int)fmax(0.0, fmin((double)W, ceil(bx1) + 1));
+                y0 = (int)fmax(0.0, fmin((double)H, floor(by0) - 1)); y1 = (int)fmax(0.0, fmin((double)H, ceil(by1) + 1));
+            }
+        }
+        bool same = true;
+        if (x1 > x0)
+            for (int y = y0; y < y1 && same; ++y)
+                same = memcmp(bgr + (size_t)y * row_stride + (size_t)x0 * 3, c->mirror + (size_t)y * rowb + (size_t)x0 * 3, (size_t)(x1 - x0) * 3) == 0;
+        if (same) return BUSCA_OK;
+    }
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t bytes = (size_t)H * rowb;
+    if (bytes > c->mirror_cap) {
+        if (c->mirror) cudaFreeHost(c->mirror);
+        c->mirror = nullptr; c->mirror_cap = 0;
+        CUDA_OK(cudaHostAlloc((void **)&c->mirror, bytes, cudaHostAllocPortable));
+        c->mirror_cap = bytes;
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));                 // an earlier upload may still be reading the mirror
+    for (int y = 0; y < H; ++y) memcpy(c->mirror + (size_t)y * rowb, bgr + (size_t)y * row_stride, rowb);
+    CUDA_OK(c->frame.ensure(bytes + 64));
+    CUDA_OK(cudaMemcpyAsync(c->frame.p, c->mirror, bytes, cudaMemcpyHostToDevice, c->stream));     // page-locked source: a plain DMA, stream ordered
+    c->fH = H; c->fW = W; c->fstride = (int64_t)rowb;
+    c->mirror_valid = true;
+    if (uploaded) *uploaded = 1;
     return BUSCA_OK;
 }
 
@@ -488,14 +539,22 @@ extern "C" int busca_crop(busca_ctx *c, const double *boxes, int32_t n, const in
     int rc = check_slots(c, slots, n, false);
     if (rc) return rc;
     CUDA_OK(cudaSetDevice(c->cfg.device));
-    size_t bb = (size_t)n * 4 * sizeof(double), sb = (size_t)n * sizeof(int32_t);
-    CUDA_OK(c->ws_small.ensure(bb + sb + 64));
-    double *dbox = (double *)c->ws_small.p;
-    int32_t *dslots = (int32_t *)((char *)c->ws_small.p + bb);
-    CUDA_OK(cudaMemcpyAsync(dbox, boxes, bb, cudaMemcpyHostToDevice, c->stream));
-    CUDA_OK(cudaMemcpyAsync(dslots, slots, sb, cudaMemcpyHostToDevice, c->stream));
     prof_reset(c);
-    LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, dbox, n, dslots, c->bank, c->stream));
+    if (n <= 4) {
+        CropSmall sm{};
+        sm.n = n;
+        memcpy(sm.boxes, boxes, (size_t)n * 4 * sizeof(double));
+        memcpy(sm.slots, slots, (size_t)n * sizeof(int32_t));
+        LAUNCH(c, "crop_resize", launch_crop_resize_small((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, sm, c->bank, c->stream));
+    } else {
+        size_t bb = (size_t)n * 4 * sizeof(double), sb = (size_t)n * sizeof(int32_t);
+        CUDA_OK(c->ws_small.ensure(bb + sb + 64));
+        double *dbox = (double *)c->ws_small.p;
+        int32_t *dslots = (int32_t *)((char *)c->ws_small.p + bb);
+        CUDA_OK(cudaMemcpyAsync(dbox, boxes, bb, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(dslots, slots, sb, cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, dbox, n, dslots, c->bank, c->stream));
+    }
     if (host_out) {
         int rc2 = bank_copy_runs(c, slots, n, host_out, false);
         if (rc2) return rc2;
@@ -667,7 +726,8 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             snprintf(nm, sizeof(nm), "%s_tc[%d>%d s%d %dx%d%s]", name, L.cin, L.cout, L.stride, a.H, a.W,
                      o.mode == TC_MODE_STATS ? " stats" : (o.mode == TC_MODE_FINAL ? (o.ds ? " final+ds" : " final") : ""));
             const bool dual = o.mode == TC_MODE_FINAL && o.ds;
-            c->next_flops = 2.0 * a.N * a.Ho * a.Wo * (double)L.cout * ((double)L.cin * L.k * L.k + (dual ? (double)o.ds->cin : 0.0));
+            c->next_xflops = 2.0 * a.N * a.Ho * a.Wo * (double)L.cout * ((double)L.cin * L.k * L.k + (dual ? (double)o.ds->cin : 0.0));
+            c->next_flops = o.mode == TC_MODE_STATS ? 0.0 : c->next_xflops;     // a statistics-only pass recomputes a GEMM the FINAL pass is credited for
             char kn[64];
             snprintf(kn, sizeof(kn), "conv_tc_kernel<%d, 128, %d>", dual ? 128 : (L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64)), dual ? 1 : 0);
             c->next_kernel = kn;
@@ -688,24 +748,20 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             a.N = N; a.img_w = img_w;
             a.in = x; a.out = R1; a.H = H; a.W = W; a.Ho = H; a.Wo = W; a.in_scale = nullptr; a.in_shift = nullptr;
             if ((rc = conv(c1, a, raw, "conv1x1"))) return rc;
-            LAUNCH(c, "bn_finalize", launch_bn_finalize(c1, NT * H * W, s));
-            LAUNCH(c, "bn_fold", launch_bn_fold(c1.scale, c1.shift, c2, s));
+            LAUNCH(c, "bn_finalize_fold", launch_bn_finalize_fold(c1, NT * H * W, c2, s));
             a.in = R1; a.out = R2; a.Ho = Ho; a.Wo = Wo; a.in_xf = c2.xf;
             if ((rc = conv(c2, a, raw, "conv3x3"))) return rc;
-            LAUNCH(c, "bn_finalize", launch_bn_finalize(c2, NT * Ho * Wo, s));
-            LAUNCH(c, "bn_fold", launch_bn_fold(c2.scale, c2.shift, c3, s));
+            LAUNCH(c, "bn_finalize_fold", launch_bn_finalize_fold(c2, NT * Ho * Wo, c3, s));
             ConvArgs a3{};
             a3.N = N; a3.img_w = img_w; a3.in = R2; a3.out = other; a3.H = Ho; a3.W = Wo; a3.Ho = Ho; a3.Wo = Wo; a3.in_xf = c3.xf;
             if ((rc = conv(c3, a3, stats, "conv1x1"))) return rc;
-            LAUNCH(c, "bn_finalize", launch_bn_finalize(c3, NT * Ho * Wo, s));
-            fin.e_scale = c3.scale; fin.e_shift = c3.shift;
+            fin.bn_count = NT * Ho * Wo;                        // BN3 (and the downsample BN) are finalised in the FINAL kernel's prologue
             if (b == 0) {
                 ConvLayer &ds = c->convs[ci + 3];
                 ConvArgs ad{};
                 ad.N = N; ad.img_w = img_w; ad.in = x; ad.out = other; ad.H = H; ad.W = W; ad.Ho = Ho; ad.Wo = Wo;
                 if ((rc = conv(ds, ad, stats, "conv1x1"))) return rc;
-                LAUNCH(c, "bn_finalize", launch_bn_finalize(ds, NT * Ho * Wo, s));
-                fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W; fin.ds_scale = ds.scale; fin.ds_shift = ds.shift;
+                fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W;
                 ci += 4;
             } else {
                 fin.idt = x;
@@ -1053,7 +1109,10 @@ extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
     if (!c->finalized) return set_err(BUSCA_ERR_STATE, "weights not finalized");
     const int T = a->T, D = a->D, L = a->L, C = a->C;
     if (T <= 0 || D <= 0 || L < 1 || C < 1 || C + 2 > 30 || L + 2 * (C + 2) > 64) return set_err(BUSCA_ERR_ARG, "unsupported sizes");
-    if (!c->frame.p) return set_err(BUSCA_ERR_STATE, "no frame uploaded");
+    const uint8_t *frame = a->frame_dev ? a->frame_dev : (const uint8_t *)c->frame.p;
+    const int fH = a->frame_dev ? a->frame_H : c->fH, fW = a->frame_dev ? a->frame_W : c->fW;
+    const int64_t fstride = a->frame_dev ? (int64_t)a->frame_W * 3 : c->fstride;
+    if (!frame || fH <= 0 || fW <= 0) return set_err(BUSCA_ERR_STATE, "no frame uploaded");
     CUDA_OK(cudaSetDevice(c->cfg.device));
     const int S = L + 2 * (C + 2), nc = C + 2;
     Carver cv;
@@ -1071,8 +1130,8 @@ extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
     p.dist_out = (double *)(b + o_dist); p.iou_out = (double *)(b + o_iou); p.cand_out = (int *)(b + o_cand);
     LAUNCH(c, "frame_geometry", launch_frame_geometry(p, s));
     // crops of the D detections and the T motion proposals, straight from the resident frame
-    LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, a->det_tlbr_dev, D, a->det_slots_dev, c->bank, s));
-    LAUNCH(c, "crop_resize", launch_crop_resize((const uint8_t *)c->frame.p, c->fH, c->fW, c->fstride, (const double *)(b + o_tlbr), T, a->kal_slots_dev, c->bank, s));
+    LAUNCH(c, "crop_resize", launch_crop_resize(frame, fH, fW, fstride, a->det_tlbr_dev, D, a->det_slots_dev, c->bank, s));
+    LAUNCH(c, "crop_resize", launch_crop_resize(frame, fH, fW, fstride, (const double *)(b + o_tlbr), T, a->kal_slots_dev, c->bank, s));
     prof_begin(c, "tlbr_to_ltwh");
     tlbr_to_ltwh_kernel<<<ceil_div(D, 128), 128, 0, s>>>(a->det_tlbr_dev, (double *)(b + o_dl), D);
     prof_end(c);

@@ -70,6 +70,10 @@ struct TcParams {
     const uint16_t *a_xf;            // [2*Cin] theta (bf16) then sign masks: transform of the A tile in shared memory, or null
     const float *e_scale, *e_shift;  // FINAL: BN of this conv           [Cout]
     const float *d_scale, *d_shift;  // FINAL + DUAL: BN of the downsample conv
+    // FINAL, alternative to e_scale / d_scale: finalise the batch statistics in the prologue (saves one launch per BatchNorm)
+    const double *e_stats, *d_stats; // [2*Cout] sum, sum of squares
+    const float *e_gamma, *e_beta, *d_gamma, *d_beta;
+    double inv_count;                // 1 / (stacked batch size * Ho * Wo)
     void *out;                       // F32: float [M, Cout]
     double *stats;                   // [2*Cout] or null
     const float *bias;               // F32: [Cout] or null
@@ -302,9 +306,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int i = threadIdx.x; i < 2 * p.Cout; i += TC_THREADS) s_par[i] = 0.f;
     if (p.mode == MODE_FINAL) {
         for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
-            s_par[i] = p.e_scale[i];
-            s_par[p.Cout + i] = p.e_shift[i];
-            if (DUAL) { s_par[2 * p.Cout + i] = p.d_scale[i]; s_par[3 * p.Cout + i] = p.d_shift[i]; }
+            if (p.e_stats) {
+                // the arithmetic of bn_finalize_kernel (reid.cu), in fp64: biased variance, eps 1e-5
+                const double mean = p.e_stats[i] * p.inv_count;
+                double var = p.e_stats[p.Cout + i] * p.inv_count - mean * mean;
+                var = var > 0.0 ? var : 0.0;
+                const double a = (double)p.e_gamma[i] / sqrt(var + 1e-5);
+                s_par[i] = (float)a;
+                s_par[p.Cout + i] = (float)((double)p.e_beta[i] - mean * a);
+            } else {
+                s_par[i] = p.e_scale[i];
+                s_par[p.Cout + i] = p.e_shift[i];
+            }
+            if (DUAL) {
+                if (p.d_stats) {
+                    const double mean = p.d_stats[i] * p.inv_count;
+                    double var = p.d_stats[p.Cout + i] * p.inv_count - mean * mean;
+                    var = var > 0.0 ? var : 0.0;
+                    const double a = (double)p.d_gamma[i] / sqrt(var + 1e-5);
+                    s_par[2 * p.Cout + i] = (float)a;
+                    s_par[3 * p.Cout + i] = (float)((double)p.d_beta[i] - mean * a);
+                } else {
+                    s_par[2 * p.Cout + i] = p.d_scale[i];
+                    s_par[3 * p.Cout + i] = p.d_shift[i];
+                }
+            }
         }
     }
     if (xform) {
@@ -624,7 +650,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int g = 0; g < G; ++g, ++gcount) {
-                    const uint32_t st = xb0 + (gcount & 1) * Cfg::XBUF_BYTES;
+                    // three staging tiles in rotation: the store of group g-1 may still be reading its tile while group g is packed and
+                    // handed to the TMA engine (wait_group.read 1 only retires the stores up to g-2, whose tile group g+1 overwrites)
+                    const int xb = gcount % TC_XBUFS;
+                    const uint32_t st = xb0 + xb * Cfg::XBUF_BYTES;
                     uint32_t r[32];
                     tmem_ld32(t_acc + g * 64 + half * 32, r);
                     TMEM_LD_WAIT();
@@ -639,10 +668,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                     if (p.mode == MODE_RAW) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // store(g-1) has released the buffer group g+1 will overwrite
+                        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store(g-2) has released the tile group g+1 will overwrite
                     }
                     EPI_BAR();
-                    if (p.mode == MODE_RAW && e == 0) tma_store_4d(xbuf + (gcount & 1) * Cfg::XBUF_BYTES, &mapOut, n_tile * BN + g * 64, 0, h0, n0);
+                    if (p.mode == MODE_RAW && e == 0) tma_store_4d(xbuf + xb * Cfg::XBUF_BYTES, &mapOut, n_tile * BN + g * 64, 0, h0, n0);
                     if (want_stats) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -852,7 +881,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
     uint8_t *a_tiles = smem;
     uint8_t *b_tiles = a_tiles + p.SA * p.a_stage_bytes;                        // RESW: 9 * cin_blocks tiles, loaded once
     uint8_t *xbuf = b_tiles + (RESW ? 9 * p.cin_blocks : p.SB) * B_BYTES;
-    float *s_par = reinterpret_cast<float *>(xbuf + 2 * XBUF_BYTES);            // [2*BN] statistics
+    float *s_par = reinterpret_cast<float *>(xbuf + TC_XBUFS * XBUF_BYTES);     // [2*BN] statistics
     float *s_apar = s_par + 2 * 256;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + 512);
     uint64_t *a_full = bars, *a_ready = a_full + HALO_MAX_STAGES, *a_empty = a_ready + HALO_MAX_STAGES, *b_full = a_empty + HALO_MAX_STAGES,
@@ -1073,7 +1102,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
                 const uint32_t t_acc = tmem_base + acc * (MT * BN) + m * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
                 for (int g = 0; g < G; ++g, ++gcount) {
-                    const uint32_t st = xb0 + (gcount & 1) * XBUF_BYTES;
+                    const int xb = gcount % TC_XBUFS;          // three staging tiles in rotation (see conv_tc_kernel)
+                    const uint32_t st = xb0 + xb * XBUF_BYTES;
                     uint32_t r[32];
                     tmem_ld32(t_acc + g * 64 + half * 32, r);
                     TMEM_LD_WAIT();
@@ -1089,9 +1119,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     EPI_BAR();
-                    if (e == 0) tma_store_4d(xbuf + (gcount & 1) * XBUF_BYTES, &mapOut, g * 64, 0, h0, n);
+                    if (e == 0) tma_store_4d(xbuf + xb * XBUF_BYTES, &mapOut, g * 64, 0, h0, n);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         if (rsub + 16 * i < p.valid_rows) {
@@ -1308,7 +1338,7 @@ bool halo_enabled() {
 template <int BN, int MT, bool RESW>
 cudaError_t launch_halo_v(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, HaloParams p, cudaStream_t s) {
     constexpr int B_BYTES = BN * 128;
-    const int fixed = 1024 + 2 * TC_BM * 128 + (2 * 256 + 512) * 4 + (5 * HALO_MAX_STAGES + 5) * 8 + 64;
+    const int fixed = 1024 + TC_XBUFS * TC_BM * 128 + (2 * 256 + 512) * 4 + (5 * HALO_MAX_STAGES + 5) * 8 + 64;
     const int budget = 232448 - fixed;
     p.n_groups = (p.total_tiles + MT - 1) / MT;
     if (RESW) {
@@ -1418,8 +1448,9 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     if (a.in_xf && (L.cin > 512 || !L.w16s)) return cudaErrorInvalidValue;
     if (halo_applies(L, a, o)) return launch_conv3x3_halo(L, a, s);
     const bool dual = o.mode == TC_MODE_FINAL && o.ds != nullptr;
-    if (o.mode == TC_MODE_FINAL && (L.k != 1 || L.stride != 1 || !o.e_scale || !o.e_shift || (!dual && !o.idt))) return cudaErrorInvalidValue;
-    if (dual && (o.ds->k != 1 || o.ds->cout != L.cout || o.ds->cin % TC_BK != 0 || !o.ds->w16 || !o.ds_in || !o.ds_scale || !o.ds_shift)) return cudaErrorInvalidValue;
+    const bool from_stats = o.mode == TC_MODE_FINAL && o.bn_count > 0;     // finalise the BatchNorms in the kernel prologue
+    if (o.mode == TC_MODE_FINAL && (L.k != 1 || L.stride != 1 || (!from_stats && (!o.e_scale || !o.e_shift)) || (!dual && !o.idt))) return cudaErrorInvalidValue;
+    if (dual && (o.ds->k != 1 || o.ds->cout != L.cout || o.ds->cin % TC_BK != 0 || !o.ds->w16 || !o.ds_in || (!from_stats && (!o.ds_scale || !o.ds_shift)))) return cudaErrorInvalidValue;
     TcParams p{};
     if (!tile_geometry(a.Ho, a.Wo, p.BW, p.BH, p.BI)) return cudaErrorInvalidValue;
     const int BN = dual ? 128 : (L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64));
@@ -1436,6 +1467,10 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     p.mode = o.mode == TC_MODE_FINAL ? MODE_FINAL : (o.mode == TC_MODE_STATS ? MODE_STATS : MODE_RAW);
     p.a_xf = a.in_xf;
     p.e_scale = o.e_scale; p.e_shift = o.e_shift; p.d_scale = o.ds_scale; p.d_shift = o.ds_shift;
+    if (from_stats) {
+        p.e_stats = L.stats; p.e_gamma = L.gamma; p.e_beta = L.beta; p.inv_count = 1.0 / (double)o.bn_count;
+        if (dual) { p.d_stats = o.ds->stats; p.d_gamma = o.ds->gamma; p.d_beta = o.ds->beta; }
+    }
     p.out = a.out; p.stats = p.mode == MODE_FINAL ? nullptr : L.stats; p.bias = nullptr; p.residual = nullptr; p.alpha = 1.f; p.act = 0;
     p.img_w = a.img_w;
     p.img_shift = 0;

@@ -30,10 +30,8 @@ __device__ __forceinline__ int clamp_coord(double v) {
     return (int)v;
 }
 
-__global__ void __launch_bounds__(CROP_THREADS) crop_resize_kernel(const uint8_t *__restrict__ frame, int H, int W,
-                                                                   long long row_stride, const double *__restrict__ boxes,
-                                                                   int n, const int32_t *__restrict__ slots,
-                                                                   uint8_t *__restrict__ bank) {
+__device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int H, int W, long long row_stride, const double *b,
+                                          int slot, uint8_t *__restrict__ bank) {
     __shared__ CropWin win;
     __shared__ unsigned long long ssum[CROP_THREADS / 32];
     __shared__ int xs0[PATCH_W], xs1[PATCH_W];
@@ -41,15 +39,11 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_resize_kernel(const uint8_t
     __shared__ int yr0[PATCH_H], yr1[PATCH_H];
     __shared__ short yb0[PATCH_H], yb1[PATCH_H];
 
-    const int i = blockIdx.x;
-    if (i >= n) return;
-    const int slot = slots[i];
     if (slot < 0) return;
     const int tid = threadIdx.x;
     uint8_t *out = bank + (size_t)slot * PATCH_BYTES;
 
     if (tid == 0) {
-        const double *b = boxes + 4 * (size_t)i;
         CropWin w;
         int X1 = clamp_coord(floor(b[0])), Y1 = clamp_coord(floor(b[1]));
         int X2 = clamp_coord(ceil(b[2])), Y2 = clamp_coord(ceil(b[3]));
@@ -178,7 +172,31 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_resize_kernel(const uint8_t
     }
 }
 
+__global__ void __launch_bounds__(CROP_THREADS) crop_resize_kernel(const uint8_t *__restrict__ frame, int H, int W,
+                                                                   long long row_stride, const double *__restrict__ boxes,
+                                                                   int n, const int32_t *__restrict__ slots,
+                                                                   uint8_t *__restrict__ bank) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    crop_body(frame, H, W, row_stride, boxes + 4 * (size_t)i, slots[i], bank);
+}
+
+// up to 4 boxes passed BY VALUE in the kernel parameters: the adapters crop the Kalman proposal of every unmatched track with
+// one single-box call each (byte_tracker.py:468-479) - no host->device copy of boxes / slots for those calls
+__global__ void __launch_bounds__(CROP_THREADS) crop_resize_small_kernel(const uint8_t *__restrict__ frame, int H, int W, long long row_stride,
+                                                                         const __grid_constant__ CropSmall s, uint8_t *__restrict__ bank) {
+    const int i = blockIdx.x;
+    if (i >= s.n) return;
+    crop_body(frame, H, W, row_stride, &s.boxes[4 * i], s.slots[i], bank);
+}
+
 }  // namespace
+
+cudaError_t launch_crop_resize_small(const uint8_t *frame, int H, int W, int64_t row_stride, const CropSmall &sm, uint8_t *bank, cudaStream_t s) {
+    if (sm.n <= 0) return cudaSuccess;
+    crop_resize_small_kernel<<<sm.n, CROP_THREADS, 0, s>>>(frame, H, W, (long long)row_stride, sm, bank);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_crop_resize(const uint8_t *frame, int H, int W, int64_t row_stride, const double *boxes, int n,
                                const int32_t *slots, uint8_t *bank, cudaStream_t s) {

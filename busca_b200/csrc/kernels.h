@@ -27,6 +27,9 @@ cudaError_t launch_pair_matrix(const double *a, int na, const double *b, int nb,
 cudaError_t launch_crop_resize(const uint8_t *frame, int H, int W, int64_t row_stride, const double *boxes, int n,
                                const int32_t *slots, uint8_t *bank, cudaStream_t s);
 
+struct CropSmall { double boxes[16]; int32_t slots[4]; int32_t n; };
+cudaError_t launch_crop_resize_small(const uint8_t *frame, int H, int W, int64_t row_stride, const CropSmall &sm, uint8_t *bank, cudaStream_t s);
+
 // ---------------------------------------------------------------- reid.cu
 struct ConvLayer {
     int cin, cout, k, stride;
@@ -55,6 +58,8 @@ cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t
 // Fold relu(scale*x + shift) of the producing BN ([consumer.cin] values) into the consumer conv for the tensor-core kernel:
 // consumer.xf = {bf16(-shift/|scale|), sign masks}, consumer.w16s = bf16(consumer.w32m * |scale|)    (see conv_tc.cu)
 cudaError_t launch_bn_fold(const float *scale, const float *shift, const ConvLayer &consumer, cudaStream_t s);
+// bn_finalize of `producer` (count elements per channel) and bn_fold into `consumer` as ONE launch
+cudaError_t launch_bn_finalize_fold(const ConvLayer &producer, long long count, const ConvLayer &consumer, cudaStream_t s);
 // conv_tc.cu: tcgen05 / TMEM / TMA implicit GEMM on bf16 NHWC activations.  ConvArgs::in_scale/in_shift (the BN + ReLU
 // of the producing conv) are applied to the A tile in shared memory.
 enum { TC_MODE_RAW = 0,      // raw bf16 output + batch statistics
@@ -68,6 +73,8 @@ struct ConvTcOpts {
     const void *ds_in = nullptr;                           //        its input [N, ds_H, ds_W, ds->cin] bf16 (activated)
     int ds_H = 0, ds_W = 0;
     const float *ds_scale = nullptr, *ds_shift = nullptr;  //        its finalised BN
+    long long bn_count = 0;                                // FINAL: > 0 = finalise this conv's (and ds's) BatchNorm from L.stats / gamma / beta in the
+                                                           //        kernel prologue with this element count (no bn_finalize launch, e_scale etc. unused)
 };
 cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s);
 size_t stem_tc_scratch_bytes(int N);

@@ -345,6 +345,39 @@ __global__ void __launch_bounds__(256) bn_fold_kernel(const float *__restrict__ 
     }
 }
 
+// bn_finalize_kernel + bn_fold_kernel in one launch: every block finalises all C (<= 512) channels of the producer redundantly
+// (same fp64 arithmetic, so scale / shift are bit-equal to the two-launch path), block 0 publishes them, all blocks fold.
+__global__ void __launch_bounds__(256) bn_finalize_fold_kernel(const double *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                int C, double inv_count, float *__restrict__ scale, float *__restrict__ shift,
+                                                                const float4 *__restrict__ w32, uint2 *__restrict__ w16s, uint16_t *__restrict__ xf, long long total4) {
+    __shared__ float sabs[512];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double mean = stats[c] * inv_count;
+        double var = stats[C + c] * inv_count - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const double a64 = (double)gamma[c] / sqrt(var + 1e-5);
+        float sc = (float)a64;
+        const float sh = (float)((double)beta[c] - mean * a64);
+        if (blockIdx.x == 0) { scale[c] = sc; shift[c] = sh; }
+        if (!(fabsf(sc) >= 1e-20f)) sc = 1e-20f;
+        const float a = fabsf(sc);
+        sabs[c] = a;
+        if (blockIdx.x == 0) {
+            const __nv_bfloat16 th = __float2bfloat16_rn(-sh / a);
+            xf[c] = *reinterpret_cast<const uint16_t *>(&th);
+            xf[C + c] = sc < 0.f ? 0x8000u : 0u;
+        }
+    }
+    __syncthreads();
+    const int C4 = C / 4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        const float4 w = w32[i];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(w.x * sabs[c], w.y * sabs[c + 1]), hi = __floats2bfloat162_rn(w.z * sabs[c + 2], w.w * sabs[c + 3]);
+        w16s[i] = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+    }
+}
+
 // relu(bn(x)) followed by MaxPool2d(3, stride 2, pad 1)           resnet.py:271-272
 template <typename T>
 __global__ void bn_relu_maxpool_kernel(const T *__restrict__ raw, T *__restrict__ out, int N, int H, int W, int C,
@@ -581,6 +614,16 @@ cudaError_t launch_bn_fold(const float *scale, const float *shift, const ConvLay
     long long blocks = (total4 + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
     bn_fold_kernel<<<(int)blocks, 256, 0, s>>>(scale, shift, L.cin, (const float4 *)L.w32m, (uint2 *)L.w16s, L.xf, total4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bn_finalize_fold(const ConvLayer &P, long long count, const ConvLayer &L, cudaStream_t s) {
+    if (P.cout != L.cin || L.cin > 512 || L.cin % 4 != 0 || !L.w32m || !L.w16s || !L.xf) return cudaErrorInvalidValue;
+    const long long total4 = (long long)L.cout * L.k * L.k * L.cin / 4;
+    long long blocks = (total4 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    bn_finalize_fold_kernel<<<(int)blocks, 256, 0, s>>>(P.stats, P.gamma, P.beta, P.cout, 1.0 / (double)count, P.scale, P.shift, (const float4 *)L.w32m,
+                                                        (uint2 *)L.w16s, L.xf, total4);
     return cudaGetLastError();
 }
 

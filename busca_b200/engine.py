@@ -71,6 +71,20 @@ def last_engine():
     return e if e is not None and getattr(e, "h", None) else None
 
 
+class _PinnedSlice:
+    """A few patches carved out of a page-locked arena.  It is the ``base`` of the array handed to the caller (and of every row
+    view of it), so it dies exactly when the last view dies; it keeps its arena alive, and the arena goes back to the pool when
+    its last slice is gone."""
+    __slots__ = ("arena", "__array_interface__", "__weakref__")
+
+    def __init__(self, arena: _PinnedBlock, offset: int, nbytes: int):
+        self.arena = arena
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (arena.ptr + offset, False), "version": 3}
+
+
+ARENA_PATCHES = 64      # single-box crop calls (byte_tracker.py:468-479) are served from 9.4 MB arenas instead of one cudaHostAlloc each
+
+
 class Engine:
     def __init__(self, device: int = 0, d_model: int = 512, nhead: int = 4, ff_size: int = 1024, num_layers: int = 4,
                  activation: str = "relu", precision: str = "fp32", sentinel_fp64: bool = True, bank_slots: int = 2048):
@@ -88,7 +102,12 @@ class Engine:
         # page-locked pool for the crop arrays handed to the caller: size class (patches, power of two) -> free pointers
         self._pin_free: Dict[int, List[int]] = {}
         self._pin_total = 0
-        self._pin_max = int(float(os.environ.get("BUSCA_PINNED_MAX_GB", "8")) * (1 << 30))
+        # page-locking costs ~0.75 ms per MB (measured on the B200 host, r02n), more than a pageable D2H of the same bytes: blocks are
+        # recycled through the pool, and NEW ones are only locked below this cap (adapters keep rows of the big per-frame arrays alive
+        # for the life of a track, so those blocks rarely come back)
+        self._pin_max = int(float(os.environ.get("BUSCA_PINNED_MAX_GB", "1")) * (1 << 30))
+        self._arena: Optional[_PinnedBlock] = None
+        self._arena_used = 0
         self.device = device
         global _last_engine
         _last_engine = weakref.ref(self)
@@ -177,6 +196,18 @@ class Engine:
             image = np.ascontiguousarray(image)
         check(self.L.busca_upload_frame(self.h, _ptr(image), image.shape[0], image.shape[1], image.strides[0]))
 
+    def sync_frame(self, image: np.ndarray, boxes: Optional[np.ndarray] = None) -> bool:
+        """Upload ``image`` unless the pixels ``boxes`` read (all pixels without boxes) already are in HBM (busca_sync_frame)."""
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise ValueError("frame must be uint8 [H,W,3] BGR")
+        if image.strides[2] != 1 or image.strides[1] != 3:
+            image = np.ascontiguousarray(image)
+        up = C.c_int32(0)
+        nb = 0 if boxes is None else len(boxes)
+        check(self.L.busca_sync_frame(self.h, _ptr(image), image.shape[0], image.shape[1], image.strides[0],
+                                      _ptr(boxes) if nb else None, nb, C.byref(up)))
+        return bool(up.value)
+
     def crop(self, boxes: np.ndarray, slots: np.ndarray, to_host: bool = True) -> Optional[np.ndarray]:
         boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 4)
         slots = np.ascontiguousarray(slots, dtype=np.int32)
@@ -191,7 +222,15 @@ class Engine:
         boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 4)
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         n = len(boxes)
-        blk = self._pin_get(n)
+        blk = None
+        if n * 8 <= ARENA_PATCHES:                          # small call: a slice of the current arena
+            if self._arena is None or self._arena_used + n > ARENA_PATCHES:
+                self._arena, self._arena_used = self._pin_get(ARENA_PATCHES), 0
+            if self._arena is not None:
+                blk = _PinnedSlice(self._arena, self._arena_used * PATCH_BYTES, n * PATCH_BYTES)
+                self._arena_used += n
+        else:
+            blk = self._pin_get(n)
         if blk is None:
             out = np.empty((n,) + PATCH_SHAPE, np.uint8)
             owner = out

@@ -9,11 +9,14 @@ numeric runs in libbusca_b200.so on the B200 (no CPU fallback).
 Patches never have to leave the GPU: ``get_image_crops`` returns a real numpy array (adapters store its rows in
 ``track.images_mem``) AND remembers which patch-bank slot holds each row; ``associate_embeddings`` resolves every
 ``images_mem`` entry back to its slot by host address and only uploads arrays it has never seen.
+
+Contract inherited from the adapters (byte_tracker.py:40-42, 117-121: crops are appended, never edited): a crop row handed
+out by ``get_image_crops`` is IMMUTABLE - the registry maps its address to the device patch, so writing into the row
+afterwards would not reach the GPU.  Copy the row (a copy is an unknown array and is uploaded) to change pixels.
 """
 from __future__ import annotations
 
 import weakref
-import zlib
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -104,7 +107,6 @@ class BUSCA:
                              bank_slots=int(getattr(args, "bank_slots", 2048)))
         self.expected_image_size = (384, 128)           # ReID_Encoder.PRETRAINED_SIZE (network.py:512)
         self._registry = _PatchRegistry(self.engine)
-        self._frame_key = None
         self.attentions = None
         self.logits = None
         self.mem_logits = None
@@ -148,19 +150,19 @@ class BUSCA:
         self.engine.load_state_dict(keep)
 
     # ---- crops: get_image_crops (network.py:492-507) ----------------------------------------------------
-    def _ensure_frame(self, image: np.ndarray):
-        # The adapters call this 3 + T times per frame with the same image (byte_tracker.py:278-282, 468-479);
-        # re-uploading 6 MB each time would dominate.  A sampled CRC guards against address reuse.
-        sample = np.ascontiguousarray(image.reshape(-1)[::97]) if image.flags["C_CONTIGUOUS"] else np.ascontiguousarray(image[::7, ::11])
-        key = (image.ctypes.data, image.shape, image.strides, zlib.crc32(sample))
-        if key != self._frame_key:
-            self.engine.upload_frame(image)
-            self._frame_key = key
+    def _ensure_frame(self, image: np.ndarray, boxes: Optional[np.ndarray] = None):
+        """Make sure the frame in HBM shows, inside ``boxes``, exactly the pixels of ``image``.
+
+        The adapters call get_image_crops 3 + T times per frame with the same image (byte_tracker.py:278-282, 468-479);
+        re-uploading 6 MB each time would dominate.  The library keeps a page-locked host mirror of the frame it holds and
+        compares, byte for byte, the rows the crops read (the union of the boxes for a single-box call, else the whole
+        frame): equal -> the device frame is valid for these crops by construction (no sampling, no reliance on buffer
+        identity); different -> upload."""
+        self.engine.sync_frame(image, boxes if boxes is not None and 0 < len(boxes) <= 8 else None)
 
     def set_frame(self, image: np.ndarray):
         """Explicitly (re)upload the current frame."""
         self.engine.upload_frame(image)
-        self._frame_key = None
 
     def get_image_crops(self, image, bboxes, output_size=None, normalize=True):
         if output_size is None:
@@ -175,7 +177,7 @@ class BUSCA:
         if len(boxes) == 0:
             return np.zeros([0, output_size[0], output_size[1], 3])       # float64, dims swapped - as network.py:503
         assert image is not None, "Image is None"
-        self._ensure_frame(image)
+        self._ensure_frame(image, boxes)
         slots = self.engine.alloc_slots(len(boxes))
         crops, owner = self.engine.crop_owned(boxes, slots)
         self._registry.register(crops, slots, owner)

@@ -33,13 +33,20 @@ def predict_boxes(mean: np.ndarray, tracked: np.ndarray):
     return m, tlwh, tlbr
 
 
+def scene_frames(seed: int, n_frames: int = 3):
+    frames = [synth.make_frame(seed * 10 + 1)]
+    for i in range(1, n_frames):
+        frames.append(synth.next_frame(frames[-1], seed * 10 + 1 + i))
+    return frames
+
+
 class Scene:
-    def __init__(self, T: int, D: int, L: int, C: int, seed: int, n_frames: int = 3, short_frac: float = 0.05):
+    def __init__(self, T: int, D: int, L: int, C: int, seed: int, n_frames: int = 3, short_frac: float = 0.05, frames=None):
+        """``frames``: optional list of frames to use instead of synthesising ``make_frame(seed*10+1)``, ... (benchmarks with
+        many sequences share a few frame sets; boxes, histories and detections still follow ``seed``)."""
         rng = np.random.default_rng(seed)
         self.T, self.D, self.L, self.C, self.seed = T, D, L, C, seed
-        self.frames = [synth.make_frame(seed * 10 + 1)]
-        for i in range(1, n_frames):
-            self.frames.append(synth.next_frame(self.frames[-1], seed * 10 + 1 + i))
+        self.frames = list(frames) if frames is not None else scene_frames(seed, n_frames)
         H, W = self.frames[0].shape[:2]
         box = synth.random_boxes(rng, T, H, W)                     # ltwh
         vel = rng.normal(0, 3, (T, 2))
@@ -102,7 +109,8 @@ class Scene:
         return tracks, dets, kal
 
     # ---- device-resident path ----------------------------------------------------------------------------------
-    def setup_resident(self, model, busca_thresh: float = 0.3, select_highest: bool = False):
+    def setup_resident(self, model, busca_thresh: float = 0.3, select_highest: bool = False, own_frame: bool = False):
+        """``own_frame``: keep this scene's frame in its own HBM buffer (several scenes sharing one context)."""
         from ._lib import StepArgs
         self.model = model
         eng = model.engine
@@ -131,6 +139,10 @@ class Scene:
         a.probs_dev = self.probs_dev
         a.keep_dev = self.keep_dev
         a.cand_dev = self.cand_dev
+        if own_frame:
+            f = np.ascontiguousarray(self.frames[0])
+            a.frame_dev = eng.to_dev(f)
+            a.frame_H, a.frame_W = f.shape[0], f.shape[1]
         self.step_args = a
 
     def step_resident(self):

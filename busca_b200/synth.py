@@ -40,7 +40,7 @@ def make_frame(seed: int, H: int = 1080, W: int = 1920, noise: float = 8.0) -> n
     lr = rng.uniform(20.0, 235.0, size=(32, 32, 3))
     img = _upsample_linear(lr, H, W)
     img += rng.normal(0.0, noise, size=img.shape)
-    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))     # C order, as cv2 / a detector hands frames over
 
 
 def next_frame(prev: np.ndarray, seed: int, noise: float = 4.0) -> np.ndarray:
@@ -48,7 +48,7 @@ def next_frame(prev: np.ndarray, seed: int, noise: float = 4.0) -> np.ndarray:
     rng = np.random.default_rng(seed)
     out = np.roll(prev, 1, axis=1).astype(np.int16)
     out += np.rint(rng.normal(0.0, noise, size=out.shape)).astype(np.int16)
-    return np.clip(out, 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(out, 0, 255).astype(np.uint8))
 
 
 # ----------------------------------------------------------------------------------------

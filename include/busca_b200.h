@@ -65,6 +65,11 @@ int busca_finalize(busca_ctx *ctx);
 /* ---- frame + patch bank --------------------------------------------------------------------- */
 /* the `image` argument of get_image_crops: uint8 BGR HWC, row stride in bytes      network.py:492 */
 int busca_upload_frame(busca_ctx *ctx, const uint8_t *bgr, int32_t H, int32_t W, int64_t row_stride);
+/* Upload only if needed: compares the pixels the given boxes read (all pixels when boxes == NULL or n_boxes > 8) with a page-locked
+ * host mirror of the frame already in HBM; *uploaded = 1 if a new frame went up.  For callers that pass the same image to several
+ * crop calls per frame without saying so (get_image_crops, network.py:492-507; byte_tracker.py:278-282, 468-479). */
+int busca_sync_frame(busca_ctx *ctx, const uint8_t *bgr, int32_t H, int32_t W, int64_t row_stride, const double *boxes, int32_t n_boxes,
+                     int32_t *uploaded);
 int busca_bank_reserve(busca_ctx *ctx, int64_t n_slots);
 int64_t busca_bank_capacity(busca_ctx *ctx);
 /* get_image_crops -> get_bbox_crop -> _cutout_with_pad + cv2.resize     network.py:492-507; tracking.py:62-113
@@ -151,6 +156,9 @@ typedef struct busca_step_args {
     int32_t select_highest;         /* select_highest_candidate (network.py:415-424): p' = one-hot of the argmax over the C+2 outputs */
     float highest_min_thresh;       /* highest_candidate_minimum_thresh; 0 = none */
     int32_t keep_highest_value;     /* keep_highest_value: the one-hot carries the maximum instead of 1.0 */
+    const uint8_t *frame_dev;       /* optional: this sequence's current frame, uint8 BGR [frame_H, frame_W, 3] packed, resident in HBM
+                                       (several sequences share one context); NULL = the frame of busca_upload_frame */
+    int32_t frame_H, frame_W;
 } busca_step_args;
 /* One frame of the whole hot path with everything resident: motion proposals + geometry + crops of the
  * D detections and T proposals from the uploaded frame + ReID (2 batches) + Transformer + decision. */
