@@ -48,7 +48,7 @@ class DebugConvArgs(C.Structure):
                 ("mode", C.c_int32), ("in_bf16", C.c_void_p), ("in_scale", C.c_void_p), ("in_shift", C.c_void_p),
                 ("e_scale", C.c_void_p), ("e_shift", C.c_void_p), ("idt_bf16", C.c_void_p), ("ds_index", C.c_int32),
                 ("ds_H", C.c_int32), ("ds_W", C.c_int32), ("ds_in_bf16", C.c_void_p), ("ds_scale", C.c_void_p),
-                ("ds_shift", C.c_void_p), ("out_bf16", C.c_void_p), ("stats_out", C.c_void_p)]
+                ("ds_shift", C.c_void_p), ("out_bf16", C.c_void_p), ("stats_out", C.c_void_p), ("img_w", C.c_void_p)]
 
 
 EXPORTS = [
@@ -57,7 +57,7 @@ EXPORTS = [
     "busca_bank_download", "busca_center_distance", "busca_iou", "busca_motion_proposals", "busca_frame_geometry",
     "busca_reid_embed", "busca_associate", "busca_transformer", "busca_frame_step_dev", "busca_dev_alloc",
     "busca_dev_free", "busca_host_alloc", "busca_host_free", "busca_memcpy_h2d", "busca_memcpy_d2h", "busca_sync", "busca_stream", "busca_kernel_launches",
-    "busca_set_profiling", "busca_last_profile", "busca_set_option", "busca_counter", "busca_debug_conv", "busca_debug_conv_ex", "busca_conv_info", "busca_debug_stem", "busca_debug_umma_rowshift", "busca_debug_maxpool",
+    "busca_set_profiling", "busca_last_profile", "busca_set_option", "busca_counter", "busca_debug_conv", "busca_debug_conv_ex", "busca_conv_info", "busca_debug_stem", "busca_debug_umma_rowshift", "busca_debug_maxpool", "busca_debug_gram",
 ]
 
 
@@ -127,6 +127,7 @@ def load(build_if_missing: bool = True):
     L.busca_conv_info.argtypes = [vp, C.c_int32, vp]
     L.busca_debug_stem.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp]
     L.busca_debug_umma_rowshift.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.busca_debug_gram.argtypes = [vp, vp, C.c_int32, vp]
     L.busca_debug_maxpool.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
     _lib = L
     return L

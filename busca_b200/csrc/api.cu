@@ -95,7 +95,8 @@ struct busca_ctx {
     uint8_t *bank = nullptr;
     int64_t bank_slots = 0;
     // scratch
-    DevBuf ws_reid, ws_tr, ws_io, ws_small;
+    DevBuf ws_reid, ws_tr, ws_io, ws_small, ws_gram;
+    bool gram = true;                             // Gram-matrix statistics for the 1x1 convolutions with Cin <= 256 (BUSCA_GRAM=0 / option "gram")
     void *pinned = nullptr;
     size_t pinned_cap = 0;
     int64_t launches = 0;
@@ -222,6 +223,8 @@ extern "C" int busca_create(const busca_config *cfg, busca_ctx **out) {
     c->use_tc = cfg->precision == BUSCA_PREC_BF16 && !(cm && strcmp(cm, "simt") == 0);
     const char *dd = getenv("BUSCA_DEDUP");
     c->dedup = !(dd && strcmp(dd, "0") == 0);
+    const char *gg = getenv("BUSCA_GRAM");
+    c->gram = !(gg && strcmp(gg, "0") == 0);
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_OK(cudaHostAlloc((void **)&c->h_nuniq, 4 * sizeof(int), cudaHostAllocPortable));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming));
@@ -247,6 +250,7 @@ extern "C" void busca_destroy(busca_ctx *c) {
     c->ws_tr.release();
     c->ws_io.release();
     c->ws_small.release();
+    c->ws_gram.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -691,6 +695,7 @@ struct ReidBatch {
     int n_total = 0;                  // images of the stacked batch
     const float *weight = nullptr;    // device [n] multiplicities, null = all 1 (n == n_total)
     const int32_t *map = nullptr;     // device [n_total]: row of slots[] / of the embeddings for every stacked image
+    int n_single = 0;                 // the first n_single images have multiplicity 1 (dedup_partition_kernel); == n without weights
 };
 
 static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
@@ -737,6 +742,45 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
         return BUSCA_OK;
     };
     int rc;
+    // Batch statistics of a 1x1 convolution whose output is never stored (conv3, downsample): the Gram matrix of its input for the images
+    // of multiplicity 1 (Cin <= 256), the weighted statistics-only GEMM pass for the repeated ones (and for Cin > 256).
+    const int n_gram = c->gram ? (rb.n_single / 8) * 8 : 0;                // whole pixel tiles (a tile holds up to 8 images)
+    auto stats_pass = [&](ConvLayer &Lc, const ConvArgs &a, const void *w_gram, const char *name) -> int {
+        int ng = (Lc.k == 1 && (Lc.cin == 64 || Lc.cin == 128 || Lc.cin == 256)) ? n_gram : 0;
+        if (ng > 0) {
+            const size_t C2 = (size_t)Lc.cin * Lc.cin;
+            const int maxg = gram_max_ctas();
+            const size_t o_sp = (C2 * 4 + 255) & ~(size_t)255, o_g64 = o_sp + (((size_t)Lc.cin * 4 + 255) & ~(size_t)255),
+                         o_s64 = o_g64 + C2 * 8;
+            CUDA_OK(c->ws_gram.ensure(o_s64 + (size_t)Lc.cin * 8 + 256));
+            char *gb = (char *)c->ws_gram.p;
+            ConvArgs ag = a;
+            ag.N = ng; ag.img_w = nullptr;
+            int grid = 0;
+            if (c->profiling) {
+                c->next_xflops = 2.0 * ng * a.Ho * a.Wo * (double)Lc.cin * (Lc.cin + 16.0) + 2.0 * (double)Lc.cout * Lc.cin * Lc.cin;
+                c->next_flops = 0.0;
+            }
+            char nm[96];
+            snprintf(nm, sizeof(nm), "gram_stats[%d>%d s%d %dx%d]", Lc.cin, Lc.cout, Lc.stride, a.H, a.W);
+            CUDA_OK(cudaMemsetAsync(gb, 0, o_sp + (size_t)Lc.cin * 4, s));
+            LAUNCH(c, c->profiling ? nm : "gram_stats", launch_gram_stats(Lc, ag, (float *)gb, (float *)(gb + o_sp), &grid, s));
+            if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();
+            LAUNCH(c, "gram_finalize", launch_gram_finalize((const float *)gb, (const float *)(gb + o_sp), grid, Lc.cin, w_gram, Lc.cout, (double *)(gb + o_g64),
+                                                            (double *)(gb + o_s64), Lc.stats, s));
+        }
+        if (a.N - ng > 0) {
+            ConvArgs as = a;
+            as.N = a.N - ng;
+            as.in = (const char *)a.in + (size_t)ng * a.H * a.W * Lc.cin * 2;
+            as.img_w = a.img_w ? a.img_w + ng : nullptr;
+            ConvTcOpts st{};
+            st.mode = TC_MODE_STATS;
+            int rc2 = conv(Lc, as, st, name);
+            if (rc2) return rc2;
+        }
+        return BUSCA_OK;
+    };
     for (int li = 0; li < 4; ++li)
         for (int b = 0; b < blocks[li]; ++b) {
             ConvLayer &c1 = c->convs[ci], &c2 = c->convs[ci + 1], &c3 = c->convs[ci + 2];
@@ -754,13 +798,13 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             LAUNCH(c, "bn_finalize_fold", launch_bn_finalize_fold(c2, NT * Ho * Wo, c3, s));
             ConvArgs a3{};
             a3.N = N; a3.img_w = img_w; a3.in = R2; a3.out = other; a3.H = Ho; a3.W = Wo; a3.Ho = Ho; a3.Wo = Wo; a3.in_xf = c3.xf;
-            if ((rc = conv(c3, a3, stats, "conv1x1"))) return rc;
+            if ((rc = stats_pass(c3, a3, c3.w16s, "conv1x1"))) return rc;
             fin.bn_count = NT * Ho * Wo;                        // BN3 (and the downsample BN) are finalised in the FINAL kernel's prologue
             if (b == 0) {
                 ConvLayer &ds = c->convs[ci + 3];
                 ConvArgs ad{};
                 ad.N = N; ad.img_w = img_w; ad.in = x; ad.out = other; ad.H = H; ad.W = W; ad.Ho = Ho; ad.Wo = Wo;
-                if ((rc = conv(ds, ad, stats, "conv1x1"))) return rc;
+                if ((rc = stats_pass(ds, ad, ds.w16, "conv1x1"))) return rc;
                 fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W;
                 ci += 4;
             } else {
@@ -793,16 +837,20 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
 // Without dedup (fp32 parity mode keeps the reference's summation over the stacked batch) the plan is the identity.
 static int reid_plan(busca_ctx *c, const int32_t *d_slots, int N, int which, ReidBatch *rb) {
     *rb = ReidBatch{};
-    rb->slots = d_slots; rb->n = N; rb->n_total = N;
+    rb->slots = d_slots; rb->n = N; rb->n_total = N; rb->n_single = N;
     if (!(c->use_tc && c->dedup) || N <= 1) return BUSCA_OK;
     const size_t per = (((size_t)N * 4 + 255) & ~(size_t)255);
-    CUDA_OK(c->ws_dedup[which].ensure(3 * per + 256));
+    CUDA_OK(c->ws_dedup[which].ensure(6 * per + 256));
     char *b = (char *)c->ws_dedup[which].p;
     int32_t *uniq = (int32_t *)b, *map = (int32_t *)(b + per);
     float *w = (float *)(b + 2 * per);
-    int *nu = (int *)(b + 3 * per);
+    int32_t *tmp_u = (int32_t *)(b + 3 * per), *newpos = (int32_t *)(b + 5 * per);
+    float *tmp_w = (float *)(b + 4 * per);
+    int *nu = (int *)(b + 6 * per);
     LAUNCH(c, "dedup_slots", launch_dedup_slots(d_slots, N, c->dedup_table, uniq, map, w, nu, c->stream));
-    CUDA_OK(cudaMemcpyAsync(c->h_nuniq + which, nu, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // multiplicity-1 images first: they take the unweighted Gram-matrix statistics path, the repeated ones the weighted pass
+    LAUNCH(c, "dedup_partition", launch_dedup_partition(uniq, w, map, N, nu, tmp_u, tmp_w, newpos, nu + 1, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->h_nuniq + 2 * which, nu, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     rb->slots = uniq; rb->map = map; rb->weight = w; rb->n = -1 - which;      // resolved by reid_plan_wait
     return BUSCA_OK;
 }
@@ -813,9 +861,12 @@ static int reid_plan_wait(busca_ctx *c, ReidBatch *a, ReidBatch *b) {
         CUDA_OK(cudaEventSynchronize(c->ev_plan));
         for (ReidBatch *r : {a, b})
             if (r && r->n < 0) {
-                r->n = c->h_nuniq[-1 - r->n];
-                if (r->n <= 0 || r->n > r->n_total) return set_err(BUSCA_ERR_STATE, "dedup returned %d distinct images of %d", r->n, r->n_total);
-                if (r->n == r->n_total) { r->weight = nullptr; r->map = nullptr; }   // nothing repeated: uniq == the stacked batch, in order
+                const int which = -1 - r->n;
+                r->n = c->h_nuniq[2 * which];
+                r->n_single = c->h_nuniq[2 * which + 1];
+                if (r->n <= 0 || r->n > r->n_total || r->n_single < 0 || r->n_single > r->n)
+                    return set_err(BUSCA_ERR_STATE, "dedup returned %d distinct images (%d single) of %d", r->n, r->n_single, r->n_total);
+                if (r->n == r->n_total) { r->weight = nullptr; r->map = nullptr; r->n_single = r->n; }   // nothing repeated: uniq == the stacked batch, in order
             }
     }
     return BUSCA_OK;
@@ -1165,6 +1216,7 @@ extern "C" int busca_frame_step_dev(busca_ctx *c, const busca_step_args *a) {
 extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d) {
     if (!c || !d || !c->finalized || d->conv_index < 1 || d->conv_index >= (int)c->convs.size() || !d->in_bf16) return set_err(BUSCA_ERR_ARG, "bad argument");
     if (!d->use_tc && d->mode != 0) return set_err(BUSCA_ERR_ARG, "the SIMT kernel only has the raw mode");
+    if (d->mode == 3 && !d->use_tc) return set_err(BUSCA_ERR_ARG, "mode 3 (Gram-matrix statistics) is a tensor-core mode");
     CUDA_OK(cudaSetDevice(c->cfg.device));
     ConvLayer &L = c->convs[d->conv_index];
     const int N = d->N, H = d->H, W = d->W, Ho = H / L.stride, Wo = W / L.stride;
@@ -1172,7 +1224,8 @@ extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d)
     Carver cv;
     const size_t in_b = (size_t)N * H * W * L.cin * 2, out_b = (size_t)N * Ho * Wo * L.cout * 2;
     const size_t ds_b = DS ? (size_t)N * d->ds_H * d->ds_W * DS->cin * 2 : 0;
-    size_t o_in = cv.take(in_b), o_out = cv.take(out_b), o_idt = cv.take(out_b), o_ds = cv.take(ds_b + 16), o_par = cv.take((size_t)(2 * L.cin + 4 * L.cout) * 4);
+    size_t o_in = cv.take(in_b), o_out = cv.take(out_b), o_idt = cv.take(out_b), o_ds = cv.take(ds_b + 16), o_par = cv.take((size_t)(2 * L.cin + 4 * L.cout) * 4),
+           o_w = cv.take((size_t)N * 4 + 16);
     CUDA_OK(c->ws_reid.ensure(cv.off + 512));
     char *b = (char *)c->ws_reid.p;
     float *par = (float *)(b + o_par);
@@ -1183,6 +1236,10 @@ extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d)
     CUDA_OK(cudaMemsetAsync(L.stats, 0, 2 * (size_t)L.cout * sizeof(double), s));
     ConvArgs a{};
     a.in = b + o_in; a.out = b + o_out; a.N = N; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo;
+    if (d->img_w && d->use_tc) {
+        CUDA_OK(cudaMemcpyAsync(b + o_w, d->img_w, (size_t)N * 4, cudaMemcpyHostToDevice, s));
+        a.img_w = (const float *)(b + o_w);
+    }
     if (d->in_scale) {
         CUDA_OK(cudaMemcpyAsync(in_sc, d->in_scale, (size_t)L.cin * 4, cudaMemcpyHostToDevice, s));
         CUDA_OK(cudaMemcpyAsync(in_sh, d->in_shift, (size_t)L.cin * 4, cudaMemcpyHostToDevice, s));
@@ -1212,7 +1269,19 @@ extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d)
         }
     }
     prof_reset(c);
-    if (d->use_tc) LAUNCH(c, "conv_tc", launch_conv_tc(L, a, o, s));
+    if (d->mode == 3) {
+        // Gram-matrix statistics of this (1x1) convolution on the given input: stats_out must equal mode 1's
+        const size_t C2 = (size_t)L.cin * L.cin;
+        const int maxg = gram_max_ctas();
+        const size_t o_sp = (C2 * 4 + 255) & ~(size_t)255, o_g64 = o_sp + (((size_t)L.cin * 4 + 255) & ~(size_t)255), o_s64 = o_g64 + C2 * 8;
+        CUDA_OK(c->ws_gram.ensure(o_s64 + (size_t)L.cin * 8 + 256));
+        char *gb = (char *)c->ws_gram.p;
+        int grid = 0;
+        CUDA_OK(cudaMemsetAsync(gb, 0, o_sp + (size_t)L.cin * 4, s));
+        LAUNCH(c, "gram_stats", launch_gram_stats(L, a, (float *)gb, (float *)(gb + o_sp), &grid, s));
+        LAUNCH(c, "gram_finalize", launch_gram_finalize((const float *)gb, (const float *)(gb + o_sp), grid, L.cin, a.in_xf ? L.w16s : L.w16, L.cout,
+                                                        (double *)(gb + o_g64), (double *)(gb + o_s64), L.stats, s));
+    } else if (d->use_tc) LAUNCH(c, "conv_tc", launch_conv_tc(L, a, o, s));
     else LAUNCH(c, "conv_simt", launch_conv_simt(L, a, 1, s));
     if (d->out_bf16) CUDA_OK(cudaMemcpyAsync(d->out_bf16, b + o_out, out_b, cudaMemcpyDeviceToHost, s));
     if (d->stats_out) CUDA_OK(cudaMemcpyAsync(d->stats_out, L.stats, 2 * (size_t)L.cout * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1259,6 +1328,22 @@ extern "C" int busca_debug_umma_rowshift(busca_ctx *c, int32_t shift_rows, int32
     CUDA_OK(cudaMemsetAsync(d, 0xff, 128 * 64 * 4, c->stream));
     LAUNCH(c, "umma_rowshift_probe", launch_umma_rowshift_probe(shift_rows, fill, use_base_offset, d, c->stream));
     CUDA_OK(cudaMemcpyAsync(out, d, 128 * 64 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return BUSCA_OK;
+}
+
+// hardware probe: Gram matrix A^T A of nb pixel tiles through MN-major operand descriptors (umma_gram_probe_kernel, conv_tc.cu)
+extern "C" int busca_debug_gram(busca_ctx *c, const uint16_t *a_bf16, int32_t nb, float *out) {
+    if (!c || !a_bf16 || !out || (nb != 1 && nb != 2 && nb != 4)) return set_err(BUSCA_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t C = 64 * (size_t)nb, in_b = 128 * C * 2, out_b = C * C * 4;
+    CUDA_OK(c->ws_small.ensure(in_b + out_b + 512));
+    uint16_t *da = (uint16_t *)c->ws_small.p;
+    float *dout = (float *)((char *)c->ws_small.p + ((in_b + 255) & ~(size_t)255));
+    CUDA_OK(cudaMemcpyAsync(da, a_bf16, in_b, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(dout, 0xff, out_b, c->stream));
+    LAUNCH(c, "umma_gram_probe", launch_umma_gram_probe(da, nb, dout, c->stream));
+    CUDA_OK(cudaMemcpyAsync(out, dout, out_b, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return BUSCA_OK;
 }
@@ -1346,6 +1431,7 @@ extern "C" const char *busca_last_profile(busca_ctx *c) { return c ? c->prof_jso
 extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return set_err(BUSCA_ERR_ARG, "null argument");
     if (strcmp(name, "dedup") == 0) { c->dedup = value != 0; return BUSCA_OK; }
+    if (strcmp(name, "gram") == 0) { c->gram = value != 0; return BUSCA_OK; }
     if (strcmp(name, "pool_mono") == 0) { reid_set_pool_mono(value); return BUSCA_OK; } // process-wide (experimental max-pool kernel)
     if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
     return set_err(BUSCA_ERR_ARG, "unknown option '%s'", name);

@@ -1228,6 +1228,292 @@ __global__ void __launch_bounds__(128, 1) umma_rowshift_probe_kernel(int shift, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Batch statistics of a 1x1 convolution WITHOUT computing it: the Gram matrix of its input.
+//   y[p][c] = sum_k W[c][k] a[p][k]   =>   sum_p y[p][c] = W[c] . m,   sum_p y[p][c]^2 = W[c]^T G W[c],   m = sum_p a[p], G = sum_p a[p] a[p]^T
+// A bottleneck's last convolution has Cout = 4 Cin, so G (Cin x Cin) costs a quarter of the FLOPs of the statistics-only pass it
+// replaces and needs no per-tile epilogue at all: the accumulator stays in TMEM for the whole launch.  The pixel tiles are the same
+// K-major, 128-byte-swizzled [128 pixels x 64 channels] TMA boxes conv_tc_kernel consumes (and the same in-place max-transform of the
+// producing BN + ReLU); they are read MN-major by BOTH tcgen05 operands (probe: umma_gram_probe_kernel), the column sums m come from
+// a second MMA against an all-ones B tile.  NB = Cin / 64 in {1, 2, 4}: one stage holds all NB channel tiles of a pixel tile, 16 KB
+// apart (= the LBO of the MN-major descriptors).  TMEM: NB=1 G[64x64] | m ; NB=2 G[128x128] | m ; NB=4 rows 0-127 x 256 | rows 128-255 x
+// columns 128-255 | m, m (the missing quadrant is the transpose of a computed one).  At the end every CTA adds its partial to G / m in
+// global memory (fp32 reductions); the quadratic forms are gram_quadform_kernel (reid.cu), in fp64.
+// Images are not weighted here: the host sends images with multiplicity 1 (the vast majority) through this path and the few repeated
+// ones through the weighted statistics-only pass of conv_tc_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+// four consecutive floats added with one reduction (REDG.E.ADD.F32x4): a quarter of the atomic operations of a TMEM dump
+__device__ __forceinline__ void red_add_v4(float *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)),
+                 "f"(__uint_as_float(d))
+                 : "memory");
+}
+// MN-major SWIZZLE_128B operand: 64 channels per 128-byte row, LBO between 64-channel groups, SBO = 1 KB between 8-pixel groups
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+constexpr int GRAM_THREADS = 448;          // warp 0 TMA, warp 1 MMA, warps 2-9 transform, warps 10-13 final TMEM dump
+constexpr int GRAM_DUMP_WARP0 = 10;
+
+struct GramParams {
+    int tiles_m, h_tiles, BH, BI, Nimg, img_shift;
+    const uint16_t *a_xf;            // [2*Cin] theta (bf16), sign masks - or null (input already activated)
+    float *gpart;                    // [C*C] fp32, zero on entry: every CTA adds its partial G (all four quadrants)
+    float *spart;                    // [C]   fp32, zero on entry: column sums m
+};
+
+template <int NB>
+__global__ void __launch_bounds__(GRAM_THREADS, 1) gram_stats_kernel(const __grid_constant__ CUtensorMap mapA, const GramParams p) {
+    constexpr int STAGES = NB == 1 ? 8 : (NB == 2 ? 5 : 3);
+    constexpr int STAGE_BYTES = NB * 16384;
+    constexpr int C = NB * 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *tiles = smem;
+    uint8_t *ones = tiles + STAGES * STAGE_BYTES;                 // 2 KB of bf16 1.0
+    uint16_t *s_apar = reinterpret_cast<uint16_t *>(ones + 2048); // theta [512], sign [512]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ones + 2048 + 2048);
+    uint64_t *full = bars, *ready = full + STAGES, *empty = ready + STAGES, *done = empty + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool xform = p.a_xf != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 256); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&mapA);
+    }
+    for (int i = threadIdx.x; i < 1024; i += GRAM_THREADS) reinterpret_cast<uint16_t *>(ones)[i] = 0x3F80;     // bf16 1.0
+    if (xform)
+        for (int i = threadIdx.x; i < C; i += GRAM_THREADS) { s_apar[i] = p.a_xf[i]; s_apar[512 + i] = p.a_xf[C + i]; }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the ones tile is read by the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr uint32_t COL_S0 = NB == 1 ? 64 : (NB == 2 ? 128 : 384), COL_S1 = 400, COL_G1 = 256;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer: the NB channel tiles of one pixel tile per stage
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x) {
+            const int h0 = (tile % p.h_tiles) * p.BH, n0 = (tile / p.h_tiles) * p.BI;
+            mbar_wait<32>(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+                mbar_expect_tx(&full[stage], STAGE_BYTES);
+#pragma unroll
+                for (int cb = 0; cb < NB; ++cb) tma_load_4d(tiles + stage * STAGE_BYTES + cb * 16384, &mapA, &full[stage], cb * 64, 0, h0, n0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer: G += T^T T, m += T^T 1 for every pixel tile T; one commit at the end
+        constexpr int M = NB == 1 ? 64 : 128;
+        constexpr uint32_t ID_MN = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(M >> 4) << 24);   // A, B MN-major
+        constexpr uint32_t ID_ONES = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // B K-major
+        const uint64_t d_ones = umma_desc<128>(smem_u32(ones));
+        int stage = 0;
+        uint32_t phase = 0;
+        bool first = true;
+        for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x) {
+            mbar_wait<0>(xform ? &ready[stage] : &full[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = smem_u32(tiles + stage * STAGE_BYTES);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {                        // 16 pixels per step = two 8-pixel groups = 2 KB
+                    const uint32_t acc = !(first && ks == 0);
+                    const uint64_t d0 = umma_desc_mn(base + ks * 2048, 16384);
+                    if (NB == 4) {
+                        const uint64_t d1 = umma_desc_mn(base + 2 * 16384 + ks * 2048, 16384);
+                        umma_bf16(tmem_base, d0, d0, ID_MN | ((uint32_t)(256 >> 3) << 17), acc);
+                        umma_bf16(tmem_base + COL_G1, d1, d1, ID_MN | ((uint32_t)(128 >> 3) << 17), acc);
+                        umma_bf16(tmem_base + COL_S0, d0, d_ones, ID_ONES, acc);
+                        umma_bf16(tmem_base + COL_S1, d1, d_ones, ID_ONES, acc);
+                    } else {
+                        umma_bf16(tmem_base, d0, d0, ID_MN | ((uint32_t)(C >> 3) << 17), acc);
+                        umma_bf16(tmem_base + COL_S0, d0, d_ones, ID_ONES, acc);
+                    }
+                }
+                umma_commit(&empty[stage]);
+            }
+            __syncwarp();
+            first = false;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(done);
+        __syncwarp();
+    } else if (warp < GRAM_DUMP_WARP0) {
+        // ===================================================== transform: a = max(x ^ signmask, theta) in place; rows of images beyond N stay 0
+        if (xform) {
+            const int tt = threadIdx.x - 64;                    // 0..255
+            const int c = tt & 7, rb = tt >> 3;                 // 16-byte chunk, rows rb + 32 i
+            const uint32_t col_off = (uint32_t)((c ^ (rb & 7)) << 4);
+            const uint32_t par0 = smem_u32(s_apar) + (uint32_t)c * 16;
+            const uint32_t tiles0 = smem_u32(tiles) + col_off + (uint32_t)rb * 128;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x) {
+                const int n0 = (tile / p.h_tiles) * p.BI;
+                const bool all_in = n0 + p.BI <= p.Nimg;
+                mbar_wait<0>(&full[stage], phase);
+                const uint32_t base = tiles0 + stage * STAGE_BYTES;
+#pragma unroll
+                for (int cb = 0; cb < NB; ++cb) {
+                    const uint4 th = lds128(par0 + (uint32_t)cb * 128), sg = lds128(par0 + (uint32_t)cb * 128 + 1024);
+                    uint4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = lds128(base + cb * 16384 + (uint32_t)i * 4096);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (all_in || n0 + ((rb + 32 * i) >> p.img_shift) < p.Nimg) {
+                            v[i].x = max_bf16x2(v[i].x ^ sg.x, th.x); v[i].y = max_bf16x2(v[i].y ^ sg.y, th.y);
+                            v[i].z = max_bf16x2(v[i].z ^ sg.z, th.z); v[i].w = max_bf16x2(v[i].w ^ sg.w, th.w);
+                        } else {
+                            v[i] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        sts128(base + cb * 16384 + (uint32_t)i * 4096, v[i]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&ready[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================== final dump: TMEM -> G and m in global memory (fp32 reductions, no return value)
+        const int qq = warp & 3;                                // TMEM lane quarter this warp may read
+        mbar_wait<64>(done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float *g = p.gpart, *sv = p.spart;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(qq * 32) << 16);
+        if (NB == 1) {
+            const int row = qq * 16 + lane;                     // M = 64: rows in lanes 0..15 of every quarter
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_lane + c0, r);
+                TMEM_LD_WAIT();
+                if (lane < 16)
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) red_add_v4(&g[row * C + c0 + j], r[j], r[j + 1], r[j + 2], r[j + 3]);
+            }
+            uint32_t r16[16];
+            tmem_ld16(t_lane + COL_S0, r16);
+            TMEM_LD_WAIT();
+            if (lane < 16) atomicAdd(&sv[row], __uint_as_float(r16[0]));
+        } else {
+            const int row = qq * 32 + lane;
+            for (int c0 = 0; c0 < (NB == 4 ? 256 : C); c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_lane + c0, r);
+                TMEM_LD_WAIT();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) red_add_v4(&g[row * C + c0 + j], r[j], r[j + 1], r[j + 2], r[j + 3]);
+                if (NB == 4 && c0 >= 128)                       // the quadrant that is not computed: its transpose (consecutive lanes = consecutive addresses)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(&g[(c0 + j) * C + row], __uint_as_float(r[j]));
+            }
+            uint32_t r16[16];
+            tmem_ld16(t_lane + COL_S0, r16);
+            TMEM_LD_WAIT();
+            atomicAdd(&sv[row], __uint_as_float(r16[0]));
+            if (NB == 4) {
+                for (int c0 = 0; c0 < 128; c0 += 32) {          // rows 128..255, columns 128..255
+                    uint32_t r[32];
+                    tmem_ld32(t_lane + COL_G1 + c0, r);
+                    TMEM_LD_WAIT();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) red_add_v4(&g[(128 + row) * C + 128 + c0 + j], r[j], r[j + 1], r[j + 2], r[j + 3]);
+                }
+                tmem_ld16(t_lane + COL_S1, r16);
+                TMEM_LD_WAIT();
+                atomicAdd(&sv[128 + row], __uint_as_float(r16[0]));
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Probe of the operand form the Gram-matrix statistics rest on (busca_debug_gram, tests/probe_gram.py): D = A^T A with BOTH operands
+// read MN-major from the same K-major-stored pixel tiles.  nb tiles of [128 pixels x 64 channels] bf16 (128-byte rows, SWIZZLE_128B,
+// 16 KB apart) are exactly the canonical MN-major SW128 layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units with the channel
+// dimension as M/N (64 channels = one 128-byte row), LBO = 16 KB between 64-channel groups and SBO = 1 KB between 8-pixel groups.
+//   nb = 1: M = 64  (TMEM rows in lanes (r % 16) + 32 * (r / 16)), N = 64
+//   nb = 2: M = 128, N = 128;   nb = 4: two M halves of 128 channels, N = 256
+// ---------------------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128, 1) umma_gram_probe_kernel(const uint16_t *__restrict__ a /* [128][64*nb] */, int nb, float *__restrict__ out /* [64nb][64nb] */) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 4 * 16384);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = 64 * nb;
+    for (int i = threadIdx.x; i < 128 * C; i += 128) {
+        const int row = i / C, ch = i % C, t = ch >> 6, k = ch & 63;
+        *reinterpret_cast<uint16_t *>(smem + t * 16384 + row * 128 + (((k >> 3) ^ (row & 7)) << 4) + (k & 7) * 2) = a[i];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int M = nb == 1 ? 64 : 128, N = C, halves = nb == 4 ? 2 : 1;
+    if (threadIdx.x == 0) {
+        // both operands MN-major (bits 15, 16)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const uint32_t base = smem_u32(smem);
+        for (int h = 0; h < halves; ++h)
+            for (int ks = 0; ks < 8; ++ks) {                       // 16 pixels per step = two 8-pixel groups = 2 KB
+                const uint64_t da = umma_desc_mn(base + h * 2 * 16384 + ks * 2048, 16384);
+                const uint64_t db = umma_desc_mn(base + ks * 2048, 16384);
+                umma_bf16(tmem_base + h * 256, da, db, idesc, ks != 0);
+            }
+        umma_commit(bar);
+    }
+    mbar_wait<32>(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int h = 0; h < halves; ++h)
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + h * 256 + c0, r);
+            TMEM_LD_WAIT();
+            int row;
+            bool valid = true;
+            if (M == 64) { row = warp * 16 + lane; valid = lane < 16; }
+            else row = h * 128 + warp * 32 + lane;
+            if (valid)
+                for (int j = 0; j < 32; ++j) out[(size_t)row * C + c0 + j] = __uint_as_float(r[j]);
+        }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1420,6 +1706,67 @@ cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStrea
 
 const char *conv_tc_last_kernel() { return g_last_kernel; }
 void conv_tc_set_halo(int on) { g_halo = on ? 1 : 0; }
+static bool tile_geometry(int Ho, int Wo, int &BW, int &BH, int &BI);
+namespace {
+template <int NB>
+cudaError_t launch_gram_v(const CUtensorMap &ma, const GramParams &p, int grid, cudaStream_t s) {
+    constexpr int STAGES = NB == 1 ? 8 : (NB == 2 ? 5 : 3);
+    const int smem = 1024 + STAGES * NB * 16384 + 4096 + (3 * STAGES + 2) * 8 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gram_stats_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    gram_stats_kernel<NB><<<grid, GRAM_THREADS, smem, s>>>(ma, p);
+    snprintf(g_last_kernel, sizeof(g_last_kernel), "gram_stats_kernel<%d>", NB);
+    return cudaGetLastError();
+}
+}  // namespace
+
+int gram_max_ctas() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_num_sms;
+}
+
+// Gram matrix / column sums of the (transformed) input of the 1x1 convolution L over images [0, a.N), ADDED to gpart [C*C], spart [C]
+// (zero them first); returns the grid size used in *grid_out.
+cudaError_t launch_gram_stats(const ConvLayer &L, const ConvArgs &a, float *gpart, float *spart, int *grid_out, cudaStream_t s) {
+    if (L.k != 1 || (L.cin != 64 && L.cin != 128 && L.cin != 256) || (L.stride != 1 && L.stride != 2)) return cudaErrorInvalidValue;
+    GramParams p{};
+    int BW;
+    if (!tile_geometry(a.Ho, a.Wo, BW, p.BH, p.BI)) return cudaErrorInvalidValue;
+    p.h_tiles = a.Ho / p.BH;
+    p.tiles_m = ((a.N + p.BI - 1) / p.BI) * p.h_tiles;
+    p.Nimg = a.N;
+    p.img_shift = 0;
+    while ((1 << p.img_shift) < BW * p.BH) ++p.img_shift;
+    if ((1 << p.img_shift) != BW * p.BH) return cudaErrorInvalidValue;
+    p.a_xf = a.in_xf; p.gpart = gpart; p.spart = spart;
+    const long long C = L.cin, W = a.W, H = a.H, st = L.stride;
+    CUtensorMap ma;
+    if (!make_map4(&ma, a.in, (int)C, (int)(W / st), (int)(H / st), a.N, st * C, st * W * C, H * W * C, BW, p.BH, p.BI)) return cudaErrorInvalidValue;
+    const int grid = p.tiles_m < gram_max_ctas() ? p.tiles_m : gram_max_ctas();
+    *grid_out = grid;
+    switch (L.cin) {
+        case 64: return launch_gram_v<1>(ma, p, grid, s);
+        case 128: return launch_gram_v<2>(ma, p, grid, s);
+        default: return launch_gram_v<4>(ma, p, grid, s);
+    }
+}
+
+cudaError_t launch_umma_gram_probe(const uint16_t *a_dev, int nb, float *out_dev, cudaStream_t s) {
+    if (nb != 1 && nb != 2 && nb != 4) return cudaErrorInvalidValue;
+    const int smem = 1024 + 4 * 16384 + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_gram_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    umma_gram_probe_kernel<<<1, 128, smem, s>>>(a_dev, nb, out_dev);
+    return cudaGetLastError();
+}
 cudaError_t launch_umma_rowshift_probe(int shift, int fill, int use_base_offset, float *out_dev, cudaStream_t s) {
     if (shift < 0 || shift + 128 > 208) return cudaErrorInvalidValue;
     const int smem = 1024 + HALO_STAGE_BYTES + 64 * 128 + 64;

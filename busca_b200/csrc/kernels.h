@@ -78,6 +78,13 @@ struct ConvTcOpts {
 };
 cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s);
 size_t stem_tc_scratch_bytes(int N);
+// Gram-matrix statistics of a 1x1 convolution (conv_tc.cu / reid.cu): partials by the tensor-core kernel, then the fp64 reduction and the
+// quadratic forms  stats[c] += W[c].m,  stats[Cout + c] += W[c]^T G W[c]  (W bf16 [Cout][Cin])
+int gram_max_ctas();
+cudaError_t launch_gram_stats(const ConvLayer &L, const ConvArgs &a, float *gpart, float *spart, int *grid_out, cudaStream_t s);
+cudaError_t launch_gram_finalize(const float *gpart, const float *spart, int grid, int C, const void *w_bf16, int Cout, double *G64, double *s64,
+                                 double *stats, cudaStream_t s);
+cudaError_t launch_umma_gram_probe(const uint16_t *a_dev /* [128][64*nb] bf16 */, int nb, float *out_dev /* [64nb][64nb] */, cudaStream_t s);
 cudaError_t launch_umma_rowshift_probe(int shift, int fill, int use_base_offset, float *out_dev /* [128*64] */, cudaStream_t s);
 void conv_tc_set_halo(int on);       // experimental halo-box 3x3 kernel on/off (default: BUSCA_HALO env, off)
 const char *conv_tc_last_kernel();   // "conv_tc_kernel<BN, KB, DUAL, RESB>" of the last tensor-core launch (profiling labels)
@@ -96,6 +103,8 @@ cudaError_t launch_global_maxpool(const void *x, float *out, int N, int HW, int 
 cudaError_t launch_l2norm_rows(float *x, int rows, int cols, cudaStream_t s);
 // distinct bank slots of one BatchNorm batch + multiplicities (see reid.cu); table: [bank_slots + 1] ints, all 0x7f7f7f7f
 cudaError_t launch_dedup_slots(const int32_t *slots, int n, int *table, int32_t *uniq, int32_t *map, float *weight, int *n_uniq, cudaStream_t s);
+cudaError_t launch_dedup_partition(int32_t *uniq, float *weight, int32_t *map, int n, const int *n_uniq, int32_t *tmp_u, float *tmp_w, int32_t *newpos,
+                                   int *n_single, cudaStream_t s);
 cudaError_t launch_gather_rows(const float *src, const int32_t *map, float *dst, int rows, int cols, cudaStream_t s);
 
 // ---------------------------------------------------------------- linear (reid.cu): out = act((A W^T + b) * alpha) + res

@@ -805,6 +805,98 @@ __global__ void gather_rows_kernel(const float4 *__restrict__ src, const int32_t
     dst[i] = src[(long long)map[r] * cols4 + c];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Gram-matrix statistics, second half (first half: gram_stats_kernel, conv_tc.cu, which leaves G [C*C] and m [C] in fp32): the
+// quadratic forms, in fp64.
+// ---------------------------------------------------------------------------------------------------------------------
+// 4 output channels per block: stats[o] += W[o] . m ; stats[Cout + o] += W[o]^T G W[o]   (thread i owns row i of G W[o]^T, read through G's symmetry
+// so that consecutive threads read consecutive addresses)
+__global__ void __launch_bounds__(256) gram_quadform_kernel(const float *__restrict__ G64, const float *__restrict__ s64, int C,
+                                                            const __nv_bfloat16 *__restrict__ w, int Cout, double *__restrict__ stats) {
+    __shared__ double sw[4][256];
+    __shared__ double red[8][8];
+    const int o0 = blockIdx.x * 4, i = threadIdx.x;
+    for (int q = 0; q < 4; ++q)
+        if (i < C) sw[q][i] = (o0 + q < Cout) ? (double)__bfloat162float(w[(size_t)(o0 + q) * C + i]) : 0.0;
+    __syncthreads();
+    double r[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+    if (i < C) {
+        for (int j = 0; j < C; ++j) {
+            const double gji = (double)G64[(size_t)j * C + i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[q] = fma(gji, sw[q][j], r[q]);
+        }
+        const double mi = (double)s64[i];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { r[q] *= sw[q][i]; s1[q] = sw[q][i] * mi; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            r[q] += __shfl_xor_sync(0xffffffffu, r[q], o);
+            s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
+        }
+    if ((i & 31) == 0)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { red[i >> 5][q] = r[q]; red[i >> 5][4 + q] = s1[q]; }
+    __syncthreads();
+    if (i < 8) {
+        double acc = 0.0;
+        for (int wv = 0; wv < 8; ++wv) acc += red[wv][i];
+        const int q = i & 3;
+        if (o0 + q < Cout) atomicAdd(stats + (i < 4 ? Cout : 0) + o0 + q, acc);
+    }
+}
+
+cudaError_t launch_gram_finalize(const float *gpart, const float *spart, int grid, int C, const void *w_bf16, int Cout, double *G64, double *s64,
+                                 double *stats, cudaStream_t s) {
+    if (C > 256 || C % 64 != 0) return cudaErrorInvalidValue;
+    (void)grid; (void)G64; (void)s64;
+    gram_quadform_kernel<<<ceil_div(Cout, 4), 256, 0, s>>>(gpart, spart, C, (const __nv_bfloat16 *)w_bf16, Cout, stats);
+    return cudaGetLastError();
+}
+
+// Stable partition of the distinct images of a BatchNorm batch: multiplicity 1 first, repeated images last (uniq / weight / map are
+// rewritten in place through the scratch arrays; one CTA).  *n_single = number of images with multiplicity 1.
+__global__ void __launch_bounds__(1024) dedup_partition_kernel(int32_t *__restrict__ uniq, float *__restrict__ weight, int32_t *__restrict__ map, int n,
+                                                                const int *__restrict__ n_uniq, int32_t *__restrict__ tmp_u, float *__restrict__ tmp_w,
+                                                                int32_t *__restrict__ newpos, int *__restrict__ n_single) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x, nu = *n_uniq;
+    const int per = (nu + 1023) / 1024, lo = min(nu, t * per), hi = min(nu, lo + per);
+    int cnt = 0;
+    for (int r = lo; r < hi; ++r) cnt += weight[r] == 1.f;
+    part[t] = cnt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const int v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const int ns = part[1023];
+    int rs = part[t] - cnt, rm = ns + (lo - rs);               // singles before this chunk; multiples before it = lo - singles
+    for (int r = lo; r < hi; ++r) {
+        const bool single = weight[r] == 1.f;
+        const int pos = single ? rs++ : rm++;
+        newpos[r] = pos;
+        tmp_u[pos] = uniq[r];
+        tmp_w[pos] = weight[r];
+    }
+    if (t == 0) *n_single = ns;
+    __syncthreads();
+    for (int r = t; r < nu; r += 1024) { uniq[r] = tmp_u[r]; weight[r] = tmp_w[r]; }
+    for (int i = t; i < n; i += 1024) map[i] = newpos[map[i]];
+}
+
+cudaError_t launch_dedup_partition(int32_t *uniq, float *weight, int32_t *map, int n, const int *n_uniq, int32_t *tmp_u, float *tmp_w, int32_t *newpos,
+                                   int *n_single, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    dedup_partition_kernel<<<1, 1024, 0, s>>>(uniq, weight, map, n, n_uniq, tmp_u, tmp_w, newpos, n_single);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dedup_slots(const int32_t *slots, int n, int *table, int32_t *uniq, int32_t *map, float *weight, int *n_uniq, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     dedup_slots_kernel<<<1, 1024, 0, s>>>(slots, n, table, uniq, map, weight, n_uniq);

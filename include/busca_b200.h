@@ -181,6 +181,7 @@ typedef struct busca_debug_conv_args {
     const float *ds_scale, *ds_shift;        /* [cout] */
     uint16_t *out_bf16;                      /* [N,Ho,Wo,cout] or NULL */
     double *stats_out;                       /* [2*cout] or NULL */
+    const float *img_w;                      /* tensor-core kernel: [N] multiplicity of every image in the batch statistics, or NULL (= 1) */
 } busca_debug_conv_args;
 int busca_debug_conv_ex(busca_ctx *ctx, const busca_debug_conv_args *args);
 /* test hook: relu(x*scale + shift) followed by the 3x3 stride-2 max-pool (padding 1) of the ReID stem, bf16 NHWC in and out */
@@ -189,6 +190,9 @@ int busca_debug_maxpool(busca_ctx *ctx, const uint16_t *in_bf16 /* [N,H,W,C] */,
 /* hardware probe (tests/probe_umma.py): one tcgen05.mma whose A descriptor starts `shift_rows` rows of 128 B inside a
  * SWIZZLE_128B tile, B = identity: out[128][64] must be A[m + shift_rows][n] (fill 0: A = row index, fill 1: A = column index) */
 int busca_debug_umma_rowshift(busca_ctx *ctx, int32_t shift_rows, int32_t fill, int32_t use_base_offset, float *out /* [128*64] */);
+/* hardware probe (tests/probe_gram.py): out[64nb][64nb] = A^T A of A[128][64nb] (bf16), both tcgen05 operands read MN-major from the
+ * K-major-stored SWIZZLE_128B pixel tiles - the operand form of the Gram-matrix batch statistics */
+int busca_debug_gram(busca_ctx *ctx, const uint16_t *a_bf16, int32_t nb, float *out);
 int busca_debug_stem(busca_ctx *ctx, const int32_t *slots, int32_t N, int32_t use_tc, uint16_t *out_bf16 /* [N,192,64,64] */,
                      double *stats_out /* [128] or NULL */);
 

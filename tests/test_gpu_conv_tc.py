@@ -120,7 +120,7 @@ def _ptr(a):
 
 
 def run_conv(engine, idx, xb, N, H, W, use_tc, mode=0, in_scale=None, in_shift=None, e_scale=None, e_shift=None, idt=None,
-             ds_index=-1, ds_in=None, ds_H=0, ds_W=0, ds_scale=None, ds_shift=None):
+             ds_index=-1, ds_in=None, ds_H=0, ds_W=0, ds_scale=None, ds_shift=None, img_w=None):
     from busca_b200._lib import DebugConvArgs
     L = engine.L
     info = (C.c_int32 * 4)()
@@ -129,10 +129,10 @@ def run_conv(engine, idx, xb, N, H, W, use_tc, mode=0, in_scale=None, in_shift=N
     Ho, Wo = H // stride, W // stride
     out = np.full((N, Ho, Wo, cout), 0xAAAA, np.uint16)
     st = np.zeros(2 * cout, np.float64)
-    keep = [np.ascontiguousarray(a, np.float32) if a is not None else None for a in (in_scale, in_shift, e_scale, e_shift, ds_scale, ds_shift)]
+    keep = [np.ascontiguousarray(a, np.float32) if a is not None else None for a in (in_scale, in_shift, e_scale, e_shift, ds_scale, ds_shift, img_w)]
     d = DebugConvArgs(conv_index=idx, N=N, H=H, W=W, use_tc=use_tc, mode=mode, in_bf16=_ptr(xb), in_scale=_ptr(keep[0]), in_shift=_ptr(keep[1]),
                       e_scale=_ptr(keep[2]), e_shift=_ptr(keep[3]), idt_bf16=_ptr(idt), ds_index=ds_index, ds_H=ds_H, ds_W=ds_W,
-                      ds_in_bf16=_ptr(ds_in), ds_scale=_ptr(keep[4]), ds_shift=_ptr(keep[5]), out_bf16=_ptr(out), stats_out=_ptr(st))
+                      ds_in_bf16=_ptr(ds_in), ds_scale=_ptr(keep[4]), ds_shift=_ptr(keep[5]), out_bf16=_ptr(out), stats_out=_ptr(st), img_w=_ptr(keep[6]))
     rc = L.busca_debug_conv_ex(engine.h, C.byref(d))
     assert rc == 0, L.busca_last_error().decode()
     return out, st, (cin, cout, k, stride)
@@ -243,3 +243,86 @@ def test_conv_tc_final_epilogue(engine, weights, name, idx, H, W, N):
     err = np.abs(got - want).max() / np.abs(want).max()
     assert err < 2e-2, (name, err)                                  # raw3/rawd reference values are bf16-rounded, the kernel's are fp32
     assert np.abs(got - want).mean() / np.abs(want).mean() < 5e-3
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# independent references: torch.nn.functional.conv2d on the CPU, and stacked-vs-deduplicated statistics
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("idx,H,W", SHAPES)
+def test_conv_tc_matches_torch_conv2d(engine, weights, idx, H, W):
+    """Every distinct convolution shape of the ReID network on the tensor cores against F.conv2d (fp32, CPU) on the SAME bf16-rounded
+    input and bf16-rounded weights: the only differences left are the fp32 accumulation order and the final rounding to bf16."""
+    import torch
+    import torch.nn.functional as F
+    name, _bn, cin, cout, k, stride = synth.reid_conv_specs()[idx]
+    N = 3
+    rng = np.random.default_rng(idx * 31 + 7)
+    x = np.maximum(rng.standard_normal((N, H, W, cin)).astype(np.float32), 0) + 0.1 * rng.standard_normal((N, H, W, cin)).astype(np.float32)
+    xb, xr = bf16_round(x)
+    _wb, wr = bf16_round(np.asarray(weights["reid_encoder.model." + name + ".weight"], np.float32))
+    ref = F.conv2d(torch.from_numpy(np.ascontiguousarray(xr.transpose(0, 3, 1, 2))).double(), torch.from_numpy(wr).double(), stride=stride, padding=k // 2)
+    ref = ref.permute(0, 2, 3, 1).numpy()                                     # fp64 accumulate: the exact value of the bf16 x bf16 products' sum
+    out, st, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1)
+    tc = bf16_to_f32(out).astype(np.float64)
+    assert np.isfinite(tc).all()
+    _rb, ref16 = bf16_round(ref.astype(np.float32))
+    scale = np.abs(ref).max()
+    assert np.abs(tc - ref).max() / scale < 4e-3                              # half a bf16 ulp of the largest value, plus accumulation noise
+    assert np.mean(tc != ref16) < 0.03                                        # same bf16 value except where the fp32 sum sits on a rounding boundary
+    want = np.concatenate([tc.reshape(-1, cout).sum(0), (tc.reshape(-1, cout) ** 2).sum(0)])
+    assert np.allclose(st, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())   # statistics of exactly the stored values
+
+
+@pytest.mark.parametrize("name,idx,H,W", [r for r in XFORM if r[0].startswith("layer1.0") or r[0].startswith("layer3.0")])
+def test_statistics_of_a_deduplicated_batch(engine, name, idx, H, W):
+    """The duplicate elimination of a BatchNorm batch: running each DISTINCT image once with its multiplicity as
+    the weight of its rows gives the per-channel sums of the stacked batch - here checked at fp32 rounding (1e-5 relative) on the first
+    convolutions after a transform, RAW and statistics-only modes."""
+    rng = np.random.default_rng(idx)
+    info = (C.c_int32 * 4)()
+    engine.L.busca_conv_info(engine.h, idx, info)
+    cin, cout = info[0], info[1]
+    mult = np.array([1, 3, 2, 5, 1], np.int64)
+    U = len(mult)
+    xb, _ = bf16_round(rng.standard_normal((U, H, W, cin)).astype(np.float32))
+    sc, sh = bn_params(rng, cin)
+    stacked = np.repeat(xb, mult, axis=0)
+    for mode in (0, 1):
+        _o, st_stacked, _ = run_conv(engine, idx, stacked, int(mult.sum()), H, W, use_tc=1, mode=mode, in_scale=sc, in_shift=sh)
+        _o, st_dedup, _ = run_conv(engine, idx, xb, U, H, W, use_tc=1, mode=mode, in_scale=sc, in_shift=sh, img_w=mult.astype(np.float32))
+        ref = np.abs(st_stacked).reshape(2, cout).max(axis=1).repeat(cout)
+        assert np.abs(st_dedup - st_stacked).max() < 1e-5 * ref.max(), (mode, np.abs(st_dedup - st_stacked).max() / ref.max())
+        assert np.all(np.abs(st_dedup - st_stacked) < 2e-5 * ref)
+
+
+GRAM = [(n, i, h, w) for n, i, h, w in ROLES if (n.endswith("conv3") or "downsample" in n) and n.split(".")[1] == "0"
+        and synth.reid_conv_specs()[i][2] <= 256]
+
+
+@pytest.mark.parametrize("name,idx,H,W", GRAM)
+@pytest.mark.parametrize("N", [2, 8, 21])
+def test_gram_matrix_statistics(engine, name, idx, H, W, N):
+    """Batch statistics of a 1x1 convolution from the Gram matrix of its (transformed) input - sum_p y = W m, sum_p y^2 = W^T G W, G on the
+    tensor cores with MN-major operands, quadratic forms in fp64 - against the statistics-only GEMM pass they replace (mode 1), for the
+    last convolution of a bottleneck (input transformed in shared memory) and the strided downsample convolution (no transform)."""
+    rng = np.random.default_rng(idx * 13 + N)
+    info = (C.c_int32 * 4)()
+    engine.L.busca_conv_info(engine.h, idx, info)
+    cin, cout, k, stride = list(info)
+    assert k == 1
+    xb, _ = bf16_round(rng.standard_normal((N, H, W, cin)).astype(np.float32) + (0.3 if "downsample" in name else 0.0))
+    kw = {}
+    if "downsample" not in name:
+        sc, sh = bn_params(rng, cin)
+        kw = dict(in_scale=sc, in_shift=sh)
+    _o, st_direct, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=1, **kw)
+    _o, st_gram, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=3, **kw)
+    s_ref, q_ref = st_direct[:cout], st_direct[cout:]
+    assert np.isfinite(st_gram).all()
+    assert np.abs(st_gram[:cout] - s_ref).max() < 2e-4 * np.abs(s_ref).max() + 1e-3
+    assert np.abs(st_gram[cout:] - q_ref).max() < 2e-4 * np.abs(q_ref).max()
+    # what BatchNorm makes of them: mean and variance per channel
+    cnt = N * (H // stride) * (W // stride)
+    var_d = q_ref / cnt - (s_ref / cnt) ** 2
+    var_g = st_gram[cout:] / cnt - (st_gram[:cout] / cnt) ** 2
+    assert np.abs(var_g - var_d).max() < 1e-3 * np.abs(var_d).max()

@@ -182,3 +182,30 @@ def test_association_conditioned_weights(models, golden_dir, name, precision):
     if precision == "fp32":
         pm2, _ = m.associate_embeddings(case.tracks, case.dets, dists, L, C, True, True, extra_kalman_candidates=case.kalman, normalize_ims=True)
         assert np.array_equal(pm2, g["f64_probs_matrix_highest"])
+
+
+def test_dedup_equals_stacked_batch_conditioned(models):
+    """End of the network, conditioned weights: embeddings of a batch with repeated images, duplicate elimination on vs off.  Same
+    maths, different summation order of the statistics (and Gram-matrix vs direct statistics for the repeated images): the bf16 rounding
+    of activations turns 1e-7 differences of a BatchNorm scale into an occasional different bf16 value, so the embeddings agree to the
+    level of the bf16 path's own error, not bit for bit.  The statistics themselves are compared at 1e-5 in
+    tests/test_gpu_conv_tc.py::test_statistics_of_a_deduplicated_batch."""
+    m = models("bf16")
+    eng = m.engine
+    rng = np.random.default_rng(11)
+    frame = synth.make_frame(3)
+    boxes = synth.random_boxes(rng, 9, *frame.shape[:2])
+    boxes[:, 2:] += boxes[:, :2]
+    crops = m.get_image_crops(frame, boxes, normalize=False)
+    base = np.array([m._registry.lookup(c) for c in crops], np.int32)
+    slots = np.concatenate([np.repeat(base, [1, 2, 3, 4, 5, 6, 7, 7, 1]), np.full(4, -1, np.int32)])
+    rng.shuffle(slots)
+    on = eng.reid_embed(slots)
+    eng.set_option("dedup", 0)
+    try:
+        off = eng.reid_embed(slots)
+    finally:
+        eng.set_option("dedup", 1)
+    cos = (on * off).sum(1) / (np.linalg.norm(on, axis=1) * np.linalg.norm(off, axis=1))
+    assert cos.min() > 0.9998, cos.min()                       # measured 0.99990: the size of the bf16 path's own distance to fp32
+    assert np.abs(on - off).max() / np.abs(off).max() < 5e-2
