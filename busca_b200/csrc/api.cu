@@ -338,13 +338,13 @@ extern "C" int busca_finalize(busca_ctx *c) {
                             re[(((size_t)o * sp.k + ky) * sp.k + kx) * sp.cin + ci] = w->f[(((size_t)o * sp.cin + ci) * sp.k + ky) * sp.k + kx];
         }
         if (sp.cin == 3) {
-            // tensor-core stem weights: bf16 [cout][ky][kx*4 + c_bgr] with kx padded to 8 and c to 4 (zeros)
-            std::vector<__nv_bfloat16> h((size_t)64 * 7 * 32, __float2bfloat16(0.f));
+            // tensor-core stem weights: bf16 [cout][row pair p][kx*8 + r*4 + c_bgr] = W[o][c][2p+r][kx], zeros for kx = 7, ky = 7, c = 3
+            std::vector<__nv_bfloat16> h((size_t)64 * 4 * 64, __float2bfloat16(0.f));
             for (int o = 0; o < 64; ++o)
                 for (int ci = 0; ci < 3; ++ci)
                     for (int ky = 0; ky < 7; ++ky)
                         for (int kx = 0; kx < 7; ++kx)
-                            h[((size_t)o * 7 + ky) * 32 + kx * 4 + (2 - ci)] = __float2bfloat16(w->f[(((size_t)o * 3 + ci) * 7 + ky) * 7 + kx]);
+                            h[((size_t)o * 4 + ky / 2) * 64 + kx * 8 + (ky & 1) * 4 + (2 - ci)] = __float2bfloat16(w->f[(((size_t)o * 3 + ci) * 7 + ky) * 7 + kx]);
             L.w16 = upload(c, h.data(), h.size());
             NEED(L.w16);
         }
@@ -716,7 +716,7 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     CUDA_OK(cudaMemsetAsync(c->stats_pool, 0, c->stats_bytes, s));
     ConvLayer &stem = c->convs[0];
     if (stem_tc_scratch_bytes(N) > big) return set_err(BUSCA_ERR_STATE, "stem scratch does not fit");
-    if (c->profiling) { c->next_flops = 2.0 * N * 192 * 64 * 64.0 * 147; c->next_kernel = "conv_tc_kernel<64, 64, 0>"; }
+    if (c->profiling) { c->next_flops = 2.0 * N * 192 * 64 * 64.0 * 147; c->next_kernel = "conv_tc_kernel<64, 128, 0>"; }
     LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, X1, RS, stem.stats, img_w, s));
     if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();
     LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, NT * 192 * 64, s));

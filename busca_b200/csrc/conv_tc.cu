@@ -1907,78 +1907,85 @@ cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const Linea
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Stem on tensor cores.  The 7x7 stride-2 convolution over 3 channels becomes a GEMM with K = 7 tap-rows x 32:
-// a pre-pass writes the normalised patch as bf16 with 4 channels per pixel (B,G,R,0) and 3+5 zero pixels of horizontal
-// padding per row; then, for one tap-row ky, the 7x4 (+4 zero) window of output pixel ox is 32 CONTIGUOUS elements
-// starting 16 bytes after the window of ox-1.  An overlapping-stride tensor map {32 el, 64 ox (stride 16 B), rows of
-// one parity (stride 2 rows), N} therefore delivers the im2col tile directly; vertical padding is TMA zero fill.
+// Stem on tensor cores.  The 7x7 stride-2 convolution over 3 channels becomes a GEMM with K = 4 row-PAIRS x 64:
+// a pre-pass writes the normalised patch as bf16 with, per pixel, the 4 channels (B,G,R,0) of input row y followed by the 4
+// channels of row y+1 (16 bytes), 3+5 zero pixels of horizontal padding per row and 3+4 zero rows of vertical padding; then,
+// for the tap rows (2p, 2p+1), the 7x8 (+8 zero) window of output pixel ox is 64 CONTIGUOUS elements (128 bytes) starting
+// 32 bytes after the window of ox-1.  An overlapping-stride tensor map {64 el, 64 ox (stride 32 B), row pairs (stride 2 rows), N}
+// therefore delivers the im2col tile directly, as ordinary 128-byte-swizzled rows.  (Round 1 used one tap row = 64 bytes per
+// request and was bound by the TMA request rate: 896 requests per 128-pixel tile; row pairs make it 512.)
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr int STEM_PITCH_PX = 136;                       // 3 zero px + 128 px + 5 zero px
+constexpr int STEM_ROWS = PATCH_H + 7;                   // 3 zero rows + 384 rows + 4 zero rows: entry yy holds rows (yy-3, yy-2)
 __global__ void __launch_bounds__(256) stem_prepass_kernel(const uint8_t *__restrict__ bank, const int32_t *__restrict__ slots,
-                                                           const float *__restrict__ lut, uint2 *__restrict__ out, long long total_px) {
+                                                           const float *__restrict__ lut, uint4 *__restrict__ out, long long total_px) {
     __shared__ float slut[768];
     for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_px; i += (long long)gridDim.x * blockDim.x) {
         const int px = (int)(i % STEM_PITCH_PX);
         const long long t = i / STEM_PITCH_PX;
-        const int y = (int)(t % PATCH_H);
-        const int n = (int)(t / PATCH_H);
-        uint2 v = make_uint2(0u, 0u);
+        const int yy = (int)(t % STEM_ROWS);
+        const int n = (int)(t / STEM_ROWS);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
         const int x = px - 3;
         if (x >= 0 && x < PATCH_W) {
             const int slot = slots[n];
-            int b = 0, g = 0, r = 0;
-            if (slot >= 0) {
-                const uint8_t *p = bank + (size_t)slot * PATCH_BYTES + ((size_t)y * PATCH_W + x) * 3;
-                b = p[0]; g = p[1]; r = p[2];
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int y = yy - 3 + r;
+                if (y >= 0 && y < PATCH_H) {
+                    int b = 0, g = 0, rr = 0;
+                    if (slot >= 0) {
+                        const uint8_t *p = bank + (size_t)slot * PATCH_BYTES + ((size_t)y * PATCH_W + x) * 3;
+                        b = p[0]; g = p[1]; rr = p[2];
+                    }
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(slut[b * 3 + 0], slut[g * 3 + 1]);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(slut[rr * 3 + 2], 0.f);
+                    w[2 * r] = *reinterpret_cast<uint32_t *>(&lo);
+                    w[2 * r + 1] = *reinterpret_cast<uint32_t *>(&hi);
+                }
             }
-            __nv_bfloat162 lo = __floats2bfloat162_rn(slut[b * 3 + 0], slut[g * 3 + 1]);
-            __nv_bfloat162 hi = __floats2bfloat162_rn(slut[r * 3 + 2], 0.f);
-            v.x = *reinterpret_cast<uint32_t *>(&lo);
-            v.y = *reinterpret_cast<uint32_t *>(&hi);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
         out[i] = v;
     }
 }
 }  // namespace
 
-size_t stem_tc_scratch_bytes(int N) { return (size_t)N * PATCH_H * STEM_PITCH_PX * 4 * 2; }
+size_t stem_tc_scratch_bytes(int N) { return (size_t)N * STEM_ROWS * STEM_PITCH_PX * 16; }
 
-// wstem: bf16 [64][7*32], element (ky, kx*4 + c_bgr) ; scratch: stem_tc_scratch_bytes(N); out: bf16 [N,192,64,64]
+// wstem: bf16 [64][4 row pairs][64], element (p, kx*8 + r*4 + c_bgr) = W[o][c][2p+r][kx]; scratch: stem_tc_scratch_bytes(N); out: bf16 [N,192,64,64]
 cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem, void *scratch, void *out,
                            double *stats, const float *img_w, cudaStream_t s) {
     if (N <= 0) return cudaSuccess;
-    const long long total_px = (long long)N * PATCH_H * STEM_PITCH_PX;
+    const long long total_px = (long long)N * STEM_ROWS * STEM_PITCH_PX;
     long long blocks = (total_px + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    stem_prepass_kernel<<<(int)blocks, 256, 0, s>>>(bank, slots, lut, (uint2 *)scratch, total_px);
+    stem_prepass_kernel<<<(int)blocks, 256, 0, s>>>(bank, slots, lut, (uint4 *)scratch, total_px);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     TcParams p{};
     p.BW = 64; p.BH = 2; p.BI = 1;
     p.tiles_n = 1; p.h_tiles = 192 / 2; p.tiles_m = N * p.h_tiles;
-    p.cin_blocks = 1; p.ntaps = 7; p.k_iters = p.k1_iters = 7;
-    for (int ky = 0; ky < 7; ++ky) {
-        const int oy = ky - 3, ph = oy & 1;
-        p.tap_map[ky] = ph; p.tap_dh[ky] = (oy - ph) / 2; p.tap_dw[ky] = 0;
-    }
+    p.cin_blocks = 1; p.ntaps = 4; p.k_iters = p.k1_iters = 4;
+    for (int pr = 0; pr < 4; ++pr) { p.tap_map[pr] = 0; p.tap_dh[pr] = pr; p.tap_dw[pr] = 0; }    // row pair p of output row oy starts at entry 2 (oy + p)
     p.Ho = 192; p.Wo = 64; p.Nimg = N; p.Cout = 64; p.Hv = 192; p.Wv = 64;
     p.mode = MODE_RAW;
     p.out = out; p.stats = stats; p.alpha = 1.f;
     p.img_w = img_w; p.img_shift = 7;                                 // BW*BH = 128 rows of one image
     const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(scratch);
-    const long long pitch = (long long)STEM_PITCH_PX * 4;             // elements per padded row
+    const long long pitch = (long long)STEM_PITCH_PX * 8;             // elements per padded row entry
     TcMaps m;
-    bool ok = true;
-    for (int ph = 0; ph < 2; ++ph)      // dims {32 window elements, 64 ox (stride 8 el = 16 B), 192 rows of this parity, N}
-        ok = ok && make_map4(&m.a[ph], in + ph * pitch, 32, 64, 192, N, 8, 2 * pitch, (long long)PATCH_H * pitch, 64, 2, 1, 32);
-    m.a[2] = m.a[3] = m.a[0];
-    ok = ok && make_map2(&m.b, wstem, 7 * 32, 64, 64, 32);
+    // dims {64 window elements, 64 ox (stride 16 el = 32 B), 196 even entries (stride 2 entries), N}
+    bool ok = make_map4(&m.a[0], in, 64, 64, 196, N, 16, 2 * pitch, (long long)STEM_ROWS * pitch, 64, 2, 1);
+    m.a[1] = m.a[2] = m.a[3] = m.a[0];
+    ok = ok && make_map2(&m.b, wstem, 4 * 64, 64, 64);
     ok = ok && make_map4(&m.out, out, 64, 64, 192, N, 64, 64 * 64, 192LL * 64 * 64, 64, 2, 1);
     if (!ok) return cudaErrorInvalidValue;
     m.b2 = m.b;
     m.idt = m.out;
-    return launch_tc<64, 64>(m, p, s);
+    return launch_tc<64>(m, p, s);
 }
