@@ -680,6 +680,63 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bf16_mono_kernel(const ui
     }
 }
 
+// Strip variant of the kernel above for the stem's shape (Wo * C/8 == 256): one block walks R output rows of one image downwards, a
+// thread owns one (ox, 8-channel chunk) column.  Input row 2oy+1 of output row oy is input row 2(oy+1)-1 of the next one, so only the
+// horizontal 3-max / 3-min of TWO new input rows are computed per output row (6 loads instead of 9), and horizontally adjacent
+// windows share their edge pixel inside the block (L1).  The tensor is then read from L2 about once instead of 2.25 times.
+constexpr int POOL_STRIP_ROWS = 12;
+__global__ void __launch_bounds__(256) bn_relu_maxpool_bf16_strip_kernel(const uint4 *__restrict__ raw, uint4 *__restrict__ out, int N, int H, int W, int C8,
+                                                                          const float *__restrict__ scale, const float *__restrict__ shift, int strips) {
+    const int Ho = H / 2, Wo = W / 2;
+    const int n = blockIdx.x / strips, oy0 = (blockIdx.x % strips) * POOL_STRIP_ROWS;
+    const int c8 = threadIdx.x % C8, ox = threadIdx.x / C8;
+    float sc[8], sh[8];
+    load8(scale + c8 * 8, sc);
+    load8(shift + c8 * 8, sh);
+    const uint4 *img = raw + (size_t)n * H * W * C8;
+    auto hrow = [&](int iy, uint4 &mx, uint4 &mn) {             // horizontal max / min of input row iy over ix = 2ox-1 .. 2ox+1
+        const uint4 *r = img + ((size_t)iy * W + 2 * ox) * C8 + c8;
+        const uint4 b = __ldg(r), c = __ldg(r + C8);
+        mx = b; mn = b;
+        __nv_bfloat162 *hx = reinterpret_cast<__nv_bfloat162 *>(&mx), *hn = reinterpret_cast<__nv_bfloat162 *>(&mn);
+        const __nv_bfloat162 *hc = reinterpret_cast<const __nv_bfloat162 *>(&c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { hx[j] = __hmax2(hx[j], hc[j]); hn[j] = __hmin2(hn[j], hc[j]); }
+        if (ox > 0) {
+            const uint4 a = __ldg(r - C8);
+            const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hx[j] = __hmax2(hx[j], ha[j]); hn[j] = __hmin2(hn[j], ha[j]); }
+        }
+    };
+    uint4 pmx, pmn;                                             // row 2oy-1 (the previous iteration's row 2oy+1)
+    bool have_prev = false;
+    if (oy0 > 0) { hrow(2 * oy0 - 1, pmx, pmn); have_prev = true; }
+    const int oy1 = min(Ho, oy0 + POOL_STRIP_ROWS);
+    for (int oy = oy0; oy < oy1; ++oy) {
+        uint4 amx, amn, bmx, bmn;
+        hrow(2 * oy, amx, amn);
+        hrow(2 * oy + 1, bmx, bmn);                             // 2oy+1 <= H-1 always (H even)
+        uint4 vmax = amx, vmin = amn;
+        __nv_bfloat162 *hx = reinterpret_cast<__nv_bfloat162 *>(&vmax), *hn = reinterpret_cast<__nv_bfloat162 *>(&vmin);
+        const __nv_bfloat162 *bx = reinterpret_cast<const __nv_bfloat162 *>(&bmx), *bn = reinterpret_cast<const __nv_bfloat162 *>(&bmn);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { hx[j] = __hmax2(hx[j], bx[j]); hn[j] = __hmin2(hn[j], bn[j]); }
+        if (have_prev) {
+            const __nv_bfloat162 *px = reinterpret_cast<const __nv_bfloat162 *>(&pmx), *pn = reinterpret_cast<const __nv_bfloat162 *>(&pmn);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { hx[j] = __hmax2(hx[j], px[j]); hn[j] = __hmin2(hn[j], pn[j]); }
+        }
+        float hi[8], lo[8], best[8];
+        unpack8(vmax, hi);
+        unpack8(vmin, lo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(0.f, fmaf(sc[j] < 0.f ? lo[j] : hi[j], sc[j], sh[j]));
+        out[(((size_t)n * Ho + oy) * Wo + ox) * C8 + c8] = pack8(best);
+        pmx = bmx; pmn = bmn; have_prev = true;
+    }
+}
+
 int g_pool_mono = -1;
 void reid_set_pool_mono(int on) { g_pool_mono = on ? 1 : 0; }
 static bool pool_mono_enabled() {
@@ -696,7 +753,10 @@ cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int
     if (total == 0) return cudaSuccess;
     if (bf16 && C % 8 == 0) {
         const long long t8 = (long long)N * (H / 2) * (W / 2) * (C / 8);
-        if (pool_mono_enabled())
+        if (pool_mono_enabled() && (W / 2) * (C / 8) == 256 && (H / 2) % POOL_STRIP_ROWS == 0) {
+            const int strips = (H / 2) / POOL_STRIP_ROWS;
+            bn_relu_maxpool_bf16_strip_kernel<<<N * strips, 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift, strips);
+        } else if (pool_mono_enabled())
             bn_relu_maxpool_bf16_mono_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift);
         else
             bn_relu_maxpool_bf16_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift);

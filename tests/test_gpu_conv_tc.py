@@ -326,3 +326,31 @@ def test_gram_matrix_statistics(engine, name, idx, H, W, N):
     var_d = q_ref / cnt - (s_ref / cnt) ** 2
     var_g = st_gram[cout:] / cnt - (st_gram[:cout] / cnt) ** 2
     assert np.abs(var_g - var_d).max() < 1e-3 * np.abs(var_d).max()
+
+
+@pytest.mark.parametrize("shape", [(3, 192, 64, 64), (2, 16, 8, 32), (1, 192, 64, 64)])
+def test_bn_relu_maxpool_kernels_agree(engine, shape):
+    """relu(BN(x)) + 3x3/2 max-pool of the stem: the strip kernel (row reuse, stem shape) and the monotone kernel (pool the packed bf16
+    max / min first, one fma per channel) against the tap-by-tap kernel - equal values - and against numpy on the same bf16 input."""
+    N, H, W, Cc = shape
+    rng = np.random.default_rng(H + Cc)
+    xb, xr = bf16_round(rng.standard_normal(shape).astype(np.float32) * 3)
+    scale = (rng.uniform(0.2, 2.0, Cc) * np.where(rng.uniform(size=Cc) < 0.3, -1, 1)).astype(np.float32)
+    scale[1] = 0.0
+    shift = (0.5 * rng.standard_normal(Cc)).astype(np.float32)
+    outs = []
+    for mono in (0, 1):
+        out = np.empty((N, H // 2, W // 2, Cc), np.uint16)
+        engine.set_option("pool_mono", mono)
+        rc = engine.L.busca_debug_maxpool(engine.h, _ptr(xb), N, H, W, Cc, _ptr(scale), _ptr(shift), _ptr(out))
+        engine.set_option("pool_mono", 1)
+        assert rc == 0, engine.L.busca_last_error().decode()
+        outs.append(bf16_to_f32(out))
+    assert np.array_equal(outs[0], outs[1])
+    act = np.maximum(np.float32(xr * scale + shift), 0)            # fp32 fma vs mul+add can differ in the last bit before the bf16 rounding
+    pad = np.full((N, H + 2, W + 2, Cc), -np.inf, np.float32)
+    pad[:, 1:-1, 1:-1] = act
+    want = np.max(np.stack([pad[:, dy:dy + H:2, dx:dx + W:2] for dy in range(3) for dx in range(3)]), axis=0)
+    _b, want16 = bf16_round(want)
+    assert np.mean(outs[1] != want16) < 2e-3
+    assert np.abs(outs[1] - want16).max() <= 2.0 ** -7 * np.abs(want16).max()
