@@ -166,6 +166,17 @@ static void prof_collect(busca_ctx *c) {
     c->prof_json = js;
 }
 
+// programmatic dependent launch of the ReID kernel chain (common.cuh); BUSCA_PDL=1 enables
+static int g_pdl = -1;
+int pdl_enabled() {
+    if (g_pdl < 0) {
+        const char *e = getenv("BUSCA_PDL");
+        g_pdl = (e && e[0] == '1');          // off by default: measured 47.1 ms/frame without, 48.0 with (profiles/r02u)
+    }
+    return g_pdl;
+}
+void pdl_set(int on) { g_pdl = on ? 1 : 0; }
+
 // BUSCA_TRACE=1: print every kernel name and synchronise after it (attributing a hang or a fault to one launch)
 static const bool g_trace = getenv("BUSCA_TRACE") != nullptr;
 #define LAUNCH(ctx, name, call)                                                                            \
@@ -362,6 +373,12 @@ extern "C" int busca_finalize(busca_ctx *c) {
                 std::vector<uint16_t> z(2 * (size_t)sp.cin, 0);
                 L.xf = upload(c, z.data(), z.size());
                 NEED(L.xf);
+            }
+            if (c->cfg.precision == BUSCA_PREC_BF16 && sp.k == 1 && sp.cout >= 256 && sp.cout > sp.cin) {
+                // last conv of a bottleneck / downsample conv: weights of the FINAL pass (times the scale of the conv's own BatchNorm)
+                if (!L.w32m) { L.w32m = upload(c, re.data(), re.size()); NEED(L.w32m); }
+                L.w16f = upload(c, h.data(), h.size());
+                NEED(L.w16f);
             }
             // bf16 mode: the SIMT kernel multiplies by the same bf16-rounded weights as the tensor-core kernel
             if (c->cfg.precision == BUSCA_PREC_BF16)
@@ -714,6 +731,13 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     float *emb_u = rb.map ? pooled + (((size_t)N * 2048 + 63) & ~(size_t)63) : d_emb;      // embeddings of the distinct images
     cudaStream_t s = c->stream;
     CUDA_OK(cudaMemsetAsync(c->stats_pool, 0, c->stats_bytes, s));
+    // Gram-matrix partials of the (at most 20) statistics passes of one call: one arena, zeroed once
+    const size_t gram_arena = c->gram ? 20 * ((size_t)256 * 256 * 4 + 1024) : 0;
+    size_t gram_cursor = 0;
+    if (gram_arena) {
+        CUDA_OK(c->ws_gram.ensure(gram_arena));
+        CUDA_OK(cudaMemsetAsync(c->ws_gram.p, 0, gram_arena, s));
+    }
     ConvLayer &stem = c->convs[0];
     if (stem_tc_scratch_bytes(N) > big) return set_err(BUSCA_ERR_STATE, "stem scratch does not fit");
     if (c->profiling) { c->next_flops = 2.0 * N * 192 * 64 * 64.0 * 147; c->next_kernel = "conv_tc_kernel<64, 128, 0>"; }
@@ -734,7 +758,7 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             c->next_xflops = 2.0 * a.N * a.Ho * a.Wo * (double)L.cout * ((double)L.cin * L.k * L.k + (dual ? (double)o.ds->cin : 0.0));
             c->next_flops = o.mode == TC_MODE_STATS ? 0.0 : c->next_xflops;     // a statistics-only pass recomputes a GEMM the FINAL pass is credited for
             char kn[64];
-            snprintf(kn, sizeof(kn), "conv_tc_kernel<%d, 128, %d>", dual ? 128 : (L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64)), dual ? 1 : 0);
+            snprintf(kn, sizeof(kn), "conv_tc_kernel<%d, 128, %d>", L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64), dual ? 1 : 0);
             c->next_kernel = kn;
         }
         LAUNCH(c, c->profiling ? nm : name, launch_conv_tc(L, a, o, s));
@@ -748,12 +772,12 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     auto stats_pass = [&](ConvLayer &Lc, const ConvArgs &a, const void *w_gram, const char *name) -> int {
         int ng = (Lc.k == 1 && (Lc.cin == 64 || Lc.cin == 128 || Lc.cin == 256)) ? n_gram : 0;
         if (ng > 0) {
+            // partial G [C*C] and m [C] of this pass: a fresh, zeroed slice of the Gram arena (one memset per ReID call, above)
             const size_t C2 = (size_t)Lc.cin * Lc.cin;
-            const int maxg = gram_max_ctas();
-            const size_t o_sp = (C2 * 4 + 255) & ~(size_t)255, o_g64 = o_sp + (((size_t)Lc.cin * 4 + 255) & ~(size_t)255),
-                         o_s64 = o_g64 + C2 * 8;
-            CUDA_OK(c->ws_gram.ensure(o_s64 + (size_t)Lc.cin * 8 + 256));
-            char *gb = (char *)c->ws_gram.p;
+            const size_t o_sp = (C2 * 4 + 255) & ~(size_t)255, slice = o_sp + (((size_t)Lc.cin * 4 + 255) & ~(size_t)255);
+            if (gram_cursor + slice > gram_arena) return set_err(BUSCA_ERR_STATE, "Gram arena exhausted");
+            char *gb = (char *)c->ws_gram.p + gram_cursor;
+            gram_cursor += slice;
             ConvArgs ag = a;
             ag.N = ng; ag.img_w = nullptr;
             int grid = 0;
@@ -763,11 +787,9 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             }
             char nm[96];
             snprintf(nm, sizeof(nm), "gram_stats[%d>%d s%d %dx%d]", Lc.cin, Lc.cout, Lc.stride, a.H, a.W);
-            CUDA_OK(cudaMemsetAsync(gb, 0, o_sp + (size_t)Lc.cin * 4, s));
             LAUNCH(c, c->profiling ? nm : "gram_stats", launch_gram_stats(Lc, ag, (float *)gb, (float *)(gb + o_sp), &grid, s));
             if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();
-            LAUNCH(c, "gram_finalize", launch_gram_finalize((const float *)gb, (const float *)(gb + o_sp), grid, Lc.cin, w_gram, Lc.cout, (double *)(gb + o_g64),
-                                                            (double *)(gb + o_s64), Lc.stats, s));
+            LAUNCH(c, "gram_finalize", launch_gram_finalize((const float *)gb, (const float *)(gb + o_sp), grid, Lc.cin, w_gram, Lc.cout, nullptr, nullptr, Lc.stats, s));
         }
         if (a.N - ng > 0) {
             ConvArgs as = a;
@@ -799,18 +821,22 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             ConvArgs a3{};
             a3.N = N; a3.img_w = img_w; a3.in = R2; a3.out = other; a3.H = Ho; a3.W = Wo; a3.Ho = Ho; a3.Wo = Wo; a3.in_xf = c3.xf;
             if ((rc = stats_pass(c3, a3, c3.w16s, "conv1x1"))) return rc;
-            fin.bn_count = NT * Ho * Wo;                        // BN3 (and the downsample BN) are finalised in the FINAL kernel's prologue
+            FoldFinalArgs ff{};                                  // BN3 (and the downsample BN): scales into the FINAL pass's weights
+            ff.L = &c3; ff.in_scale = c2.scale; ff.count = NT * Ho * Wo; ff.shift_out = c3.shift;
+            fin.e_shift = c3.shift;
             if (b == 0) {
                 ConvLayer &ds = c->convs[ci + 3];
                 ConvArgs ad{};
                 ad.N = N; ad.img_w = img_w; ad.in = x; ad.out = other; ad.H = H; ad.W = W; ad.Ho = Ho; ad.Wo = Wo;
                 if ((rc = stats_pass(ds, ad, ds.w16, "conv1x1"))) return rc;
                 fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W;
+                ff.ds = &ds;
                 ci += 4;
             } else {
                 fin.idt = x;
                 ci += 3;
             }
+            LAUNCH(c, "bn_fold_final", launch_bn_fold_final(ff, s));
             if ((rc = conv(c3, a3, fin, "conv1x1"))) return rc;
             void *t = x; x = other; other = t;
             H = Ho; W = Wo;
@@ -1255,18 +1281,22 @@ extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d)
         if (!d->e_scale || !d->e_shift) return set_err(BUSCA_ERR_ARG, "final mode needs e_scale / e_shift");
         CUDA_OK(cudaMemcpyAsync(e_sc, d->e_scale, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
         CUDA_OK(cudaMemcpyAsync(e_sh, d->e_shift, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
-        o.e_scale = e_sc; o.e_shift = e_sh;
+        FoldFinalArgs ff{};
+        ff.L = &L; ff.in_scale = d->in_scale ? in_sc : nullptr; ff.scale = e_sc; ff.shift = e_sh; ff.shift_out = L.shift;
+        o.e_shift = L.shift;
         if (DS) {
             if (!d->ds_in_bf16 || !d->ds_scale || !d->ds_shift) return set_err(BUSCA_ERR_ARG, "downsample inputs missing");
             CUDA_OK(cudaMemcpyAsync(b + o_ds, d->ds_in_bf16, ds_b, cudaMemcpyHostToDevice, s));
             CUDA_OK(cudaMemcpyAsync(d_sc, d->ds_scale, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
             CUDA_OK(cudaMemcpyAsync(d_sh, d->ds_shift, (size_t)L.cout * 4, cudaMemcpyHostToDevice, s));
-            o.ds = DS; o.ds_in = b + o_ds; o.ds_H = d->ds_H; o.ds_W = d->ds_W; o.ds_scale = d_sc; o.ds_shift = d_sh;
+            o.ds = DS; o.ds_in = b + o_ds; o.ds_H = d->ds_H; o.ds_W = d->ds_W;
+            ff.ds = DS; ff.ds_scale = d_sc; ff.ds_shift = d_sh;
         } else {
             if (!d->idt_bf16) return set_err(BUSCA_ERR_ARG, "final mode needs an identity tensor or a downsample conv");
             CUDA_OK(cudaMemcpyAsync(b + o_idt, d->idt_bf16, out_b, cudaMemcpyHostToDevice, s));
             o.idt = b + o_idt;
         }
+        LAUNCH(c, "bn_fold_final", launch_bn_fold_final(ff, s));
     }
     prof_reset(c);
     if (d->mode == 3) {
@@ -1434,6 +1464,7 @@ extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (strcmp(name, "gram") == 0) { c->gram = value != 0; return BUSCA_OK; }
     if (strcmp(name, "pool_mono") == 0) { reid_set_pool_mono(value); return BUSCA_OK; } // process-wide (experimental max-pool kernel)
     if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
+    if (strcmp(name, "pdl") == 0) { pdl_set(value != 0); return BUSCA_OK; }          // process-wide (programmatic dependent launch)
     return set_err(BUSCA_ERR_ARG, "unknown option '%s'", name);
 }
 extern "C" int64_t busca_counter(busca_ctx *c, const char *name) {

@@ -33,6 +33,28 @@ static __device__ __forceinline__ float warp_max(float v) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (PDL): a kernel launched through launch_pdl may become resident while its predecessor in the stream is
+// still draining; it runs its private prologue (barrier init, TMEM allocation, tensor-map prefetch), then pdl_wait() blocks until the
+// predecessor has COMPLETED and its memory is visible.  Every kernel launched this way calls pdl_wait() before its first access to
+// global memory another kernel may write (or still read), and pdl_trigger() at its start so that its own successor may be scheduled
+// as SMs free up.  OFF by default (BUSCA_PDL=1 / busca_set_option("pdl", 1) enables it): on a B200 the chain of persistent one-CTA-per-SM
+// kernels ran 2 % SLOWER with it (profiles/r02u: 48.0 vs 47.1 ms/frame) - a successor CTA cannot become resident before its
+// predecessor's CTA on that SM has exited (shared memory), so only the launch latency is hidden, and griddepcontrol.wait costs more.
+static __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+int pdl_enabled();              // api.cu
+void pdl_set(int on);
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Activation storage types of the ReID path: float (fp32 mode) or __nv_bfloat16 (bf16 mode).
 template <typename T> struct ActIO;
 template <> struct ActIO<float> {

@@ -25,10 +25,10 @@
 //            (bf16-rounded) output are read back from the staging tile with 64-bit shared loads into per-thread
 //            register accumulators that live across tiles (no shuffles, no atomics in the loop).
 //     STATS  the same without the store: the statistics-only first pass of a bottleneck's last 1x1 convolution.
-//     FINAL  second pass of that convolution: out = relu(acc*s3 + t3 + identity) where the identity tile is TMA-
-//            loaded into the staging buffer the result is then stored from; with DUAL the downsample 1x1 conv is
-//            accumulated in a second TMEM accumulator by the same kernel: relu(acc*s3+t3 + acc_ds*s_ds+t_ds).
-//            The raw output of conv3 / downsample is therefore NEVER written to HBM.
+//     FINAL  second pass of that convolution, with the scale of ITS OWN BatchNorm folded into the weights as well (bn_fold_final,
+//            reid.cu): out = relu(acc + t3 + identity), the identity tile TMA-loaded into the staging buffer the result is then
+//            stored from; with DUAL the downsample 1x1 conv (weights times ITS BN scale) accumulates into the SAME TMEM tile
+//            and the shift is t3 + t_ds.  The raw output of conv3 / downsample is therefore NEVER written to HBM.
 //     F32    fp32 output with bias / scale / activation / residual (Transformer linears).
 // * Persistent: one CTA per SM, static round-robin over (pixel-tile, channel-tile) pairs, channel-tile fastest so
 //   CTAs running concurrently share the same A boxes through L2.
@@ -69,12 +69,7 @@ struct TcParams {
     int Hv, Wv;                      // extent of the (parity view of the) input the taps index: padding mask of the transform
     int mode;
     const uint16_t *a_xf;            // [2*Cin] theta (bf16) then sign masks: transform of the A tile in shared memory, or null
-    const float *e_scale, *e_shift;  // FINAL: BN of this conv           [Cout]
-    const float *d_scale, *d_shift;  // FINAL + DUAL: BN of the downsample conv
-    // FINAL, alternative to e_scale / d_scale: finalise the batch statistics in the prologue (saves one launch per BatchNorm)
-    const double *e_stats, *d_stats; // [2*Cout] sum, sum of squares
-    const float *e_gamma, *e_beta, *d_gamma, *d_beta;
-    double inv_count;                // 1 / (stacked batch size * Ho * Wo)
+    const float *e_shift;            // FINAL: shift of this conv's BN (+ shift of the downsample BN) [Cout]; the scales are in the weights
     void *out;                       // F32: float [M, Cout]
     double *stats;                   // [2*Cout] or null
     const float *bias;               // F32: [Cout] or null
@@ -124,7 +119,7 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * KB;
     static constexpr int STAGE_BYTES = RESB ? A_BYTES : A_BYTES + B_BYTES;
     static constexpr int RES_BYTES = RESB ? 65536 : 0;              // resident weight slab: k_iters * B_BYTES must fit
-    static constexpr int PAR_FLOATS = DUAL ? 4 * 2048 : 2 * 2048;    // statistics (RAW/STATS) or epilogue BN parameters (FINAL)
+    static constexpr int PAR_FLOATS = 2 * 2048;                      // statistics (RAW/STATS: 2 Cout) or the epilogue shift (FINAL: Cout)
     static constexpr int APAR_FLOATS = 512;                          // transform parameters: theta bf16 [512], sign mask u16 [512]
     static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + RES_BYTES + TC_XBUFS * XBUF_BYTES + (PAR_FLOATS + APAR_FLOATS) * 4 + 512;
     static_assert(SMEM <= 232448, "shared memory budget (227 KB per CTA)");
@@ -155,6 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const bool xform = p.a_xf != nullptr;
     const bool want_stats = p.stats != nullptr && (p.mode == MODE_RAW || p.mode == MODE_STATS);
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], (Cfg::STAGES % 2) == 0 ? 128 : 256); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
@@ -165,43 +161,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (want_stats)
         for (int i = threadIdx.x; i < 2 * p.Cout; i += TC_THREADS) s_par[i] = 0.f;
-    if (p.mode == MODE_FINAL) {
-        for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) {
-            if (p.e_stats) {
-                // the arithmetic of bn_finalize_kernel (reid.cu), in fp64: biased variance, eps 1e-5
-                const double mean = p.e_stats[i] * p.inv_count;
-                double var = p.e_stats[p.Cout + i] * p.inv_count - mean * mean;
-                var = var > 0.0 ? var : 0.0;
-                const double a = (double)p.e_gamma[i] / sqrt(var + 1e-5);
-                s_par[i] = (float)a;
-                s_par[p.Cout + i] = (float)((double)p.e_beta[i] - mean * a);
-            } else {
-                s_par[i] = p.e_scale[i];
-                s_par[p.Cout + i] = p.e_shift[i];
-            }
-            if (DUAL) {
-                if (p.d_stats) {
-                    const double mean = p.d_stats[i] * p.inv_count;
-                    double var = p.d_stats[p.Cout + i] * p.inv_count - mean * mean;
-                    var = var > 0.0 ? var : 0.0;
-                    const double a = (double)p.d_gamma[i] / sqrt(var + 1e-5);
-                    s_par[2 * p.Cout + i] = (float)a;
-                    s_par[3 * p.Cout + i] = (float)((double)p.d_beta[i] - mean * a);
-                } else {
-                    s_par[2 * p.Cout + i] = p.d_scale[i];
-                    s_par[3 * p.Cout + i] = p.d_shift[i];
-                }
-            }
-        }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();              // everything above is private to this CTA; from here on the predecessor's results are read
+    if (p.mode == MODE_FINAL)
+        for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) s_par[i] = p.e_shift[i];
     if (xform) {
         const int cin = p.cin_blocks * Cfg::BKE;
         uint16_t *sp = reinterpret_cast<uint16_t *>(s_apar);
         for (int i = threadIdx.x; i < cin; i += TC_THREADS) { sp[i] = p.a_xf[i]; sp[512 + i] = p.a_xf[cin + i]; }
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -269,12 +239,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 mbar_wait<32>(&tempty[acc], acc_phase ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kt = 0; kt < p.k_iters; ++kt) {
-                    const bool main_op = !DUAL || kt < p.k1_iters;
                     mbar_wait<0>(&full[stage], phase);
                     if (xform) mbar_wait<0>(&ready[stage], phase);      // the transform warps have rewritten the A tile
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_tmem = tmem_base + acc * 256 + (main_op ? 0 : BN);
-                    const bool first = main_op ? kt == 0 : kt == p.k1_iters;
+                    const uint32_t d_tmem = tmem_base + acc * 256;        // DUAL: the downsample conv accumulates into the same tile
+                    const bool first = kt == 0;
                     const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
                     const uint64_t da = umma_desc<KB>(a_addr);
                     const uint64_t db = umma_desc<KB>(RESB ? smem_u32(resb) + (uint32_t)kt * Cfg::B_BYTES : a_addr + Cfg::A_BYTES);
@@ -555,38 +524,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     const uint32_t xph = (uint32_t)(gcount / TC_XBUFS) & 1;
                     const uint32_t st = xb0 + b * Cfg::XBUF_BYTES;
                     const int col0 = n_tile * BN + g * 64 + half * 32;
-                    uint32_t r[32];                             // accumulator, then (in place) the BN-applied value as float bits
+                    // shift of this thread's 32 channels first (shared-memory latency overlaps the TMEM load), then the accumulator
+                    const uint32_t pt = smem_u32(s_par) + (uint32_t)col0 * 4;
+                    float4 t4[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t4[j] = lds128f(pt + j * 16);
+                    uint32_t r[32];                             // accumulator, then (in place) acc + shift as float bits
                     tmem_ld32(t_acc + g * 64 + half * 32, r);
                     TMEM_LD_WAIT();
-                    const uint32_t ps = smem_u32(s_par) + (uint32_t)col0 * 4, pt = ps + (uint32_t)p.Cout * 4;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float4 s4 = lds128f(ps + j * 16), t4 = lds128f(pt + j * 16);
-                        r[4 * j + 0] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 0]), s4.x, t4.x));
-                        r[4 * j + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 1]), s4.y, t4.y));
-                        r[4 * j + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 2]), s4.z, t4.z));
-                        r[4 * j + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * j + 3]), s4.w, t4.w));
+                        r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + t4[j].x);
+                        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + t4[j].y);
+                        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + t4[j].z);
+                        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t4[j].w);
                     }
-                    if (DUAL) {
-                        const uint32_t ds = ps + (uint32_t)p.Cout * 8, dt = ps + (uint32_t)p.Cout * 12;
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {         // downsample accumulator, 16 columns at a time (register budget)
-                            uint32_t r2[16];
-                            tmem_ld16(t_acc + BN + g * 64 + half * 32 + hh * 16, r2);
-                            TMEM_LD_WAIT();
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 s4 = lds128f(ds + (hh * 4 + j) * 16), t4 = lds128f(dt + (hh * 4 + j) * 16);
-                                const int o = hh * 16 + 4 * j;
-                                r[o + 0] = __float_as_uint(__uint_as_float(r[o + 0]) + fmaf(__uint_as_float(r2[4 * j + 0]), s4.x, t4.x));
-                                r[o + 1] = __float_as_uint(__uint_as_float(r[o + 1]) + fmaf(__uint_as_float(r2[4 * j + 1]), s4.y, t4.y));
-                                r[o + 2] = __float_as_uint(__uint_as_float(r[o + 2]) + fmaf(__uint_as_float(r2[4 * j + 2]), s4.z, t4.z));
-                                r[o + 3] = __float_as_uint(__uint_as_float(r[o + 3]) + fmaf(__uint_as_float(r2[4 * j + 3]), s4.w, t4.w));
-                            }
-                        }
-                    } else {
-                        mbar_wait<0>(&xfull[b], xph);           // identity tile of this group has landed in the staging buffer
-                    }
+                    if (!DUAL) mbar_wait<0>(&xfull[b], xph);    // identity tile of this group has landed in the staging buffer
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t addr = st + row_off + (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
@@ -594,22 +547,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         uint4 w;
                         if (!DUAL) {
                             const uint4 d = lds128(addr);
-                            w.x = pack_bf16(fmaxf(v[0] + bf_lo(d.x), 0.f), fmaxf(v[1] + bf_hi(d.x), 0.f));
-                            w.y = pack_bf16(fmaxf(v[2] + bf_lo(d.y), 0.f), fmaxf(v[3] + bf_hi(d.y), 0.f));
-                            w.z = pack_bf16(fmaxf(v[4] + bf_lo(d.z), 0.f), fmaxf(v[5] + bf_hi(d.z), 0.f));
-                            w.w = pack_bf16(fmaxf(v[6] + bf_lo(d.w), 0.f), fmaxf(v[7] + bf_hi(d.w), 0.f));
+                            // ReLU after the rounding (one packed max per two channels): rounding is monotone and keeps 0, so it commutes
+                            w.x = max_bf16x2(pack_bf16(v[0] + bf_lo(d.x), v[1] + bf_hi(d.x)), 0u);
+                            w.y = max_bf16x2(pack_bf16(v[2] + bf_lo(d.y), v[3] + bf_hi(d.y)), 0u);
+                            w.z = max_bf16x2(pack_bf16(v[4] + bf_lo(d.z), v[5] + bf_hi(d.z)), 0u);
+                            w.w = max_bf16x2(pack_bf16(v[6] + bf_lo(d.w), v[7] + bf_hi(d.w)), 0u);
                         } else {
-                            w.x = pack_bf16(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
-                            w.y = pack_bf16(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-                            w.z = pack_bf16(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f));
-                            w.w = pack_bf16(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
+                            w.x = max_bf16x2(pack_bf16(v[0], v[1]), 0u);
+                            w.y = max_bf16x2(pack_bf16(v[2], v[3]), 0u);
+                            w.z = max_bf16x2(pack_bf16(v[4], v[5]), 0u);
+                            w.w = max_bf16x2(pack_bf16(v[6], v[7]), 0u);
                         }
                         sts128(addr, w);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (e == 0) {
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // every earlier store has finished reading its buffer
-                        if (gcount > 0) mbar_arrive(&xfree[(gcount - 1) % TC_XBUFS]);
+                        if (DUAL) {
+                            // no identity loader: the three staging tiles only rotate between the stores (as in the RAW epilogue)
+                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        } else {
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // every earlier store has finished reading its buffer
+                            if (gcount > 0) mbar_arrive(&xfree[(gcount - 1) % TC_XBUFS]);
+                        }
                     }
                     EPI_BAR();
                     if (e == 0) tma_store_4d(xbuf + b * Cfg::XBUF_BYTES, &mapOut, n_tile * BN + g * 64, 0, h0, n0);
@@ -751,6 +710,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bres + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_ready[s], 256); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < p.SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -760,14 +720,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv3x3_halo_kernel(const __gri
         prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapOut);
     }
     for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) s_par[i] = 0.f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_wait();
     {
         const int cin = p.cin_blocks * 64;
         uint16_t *sp = reinterpret_cast<uint16_t *>(s_apar);
         for (int i = threadIdx.x; i < cin; i += TC_THREADS) { sp[i] = p.a_xf[i]; sp[512 + i] = p.a_xf[cin + i]; }
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1139,6 +1100,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_stats_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool xform = p.a_xf != nullptr;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 256); mbar_init(&empty[s], 1); }
         mbar_init(done, 1);
@@ -1146,12 +1108,13 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1) gram_stats_kernel(const __gri
         prefetch_tmap(&mapA);
     }
     for (int i = threadIdx.x; i < 1024; i += GRAM_THREADS) reinterpret_cast<uint16_t *>(ones)[i] = 0x3F80;     // bf16 1.0
-    if (xform)
-        for (int i = threadIdx.x; i < C; i += GRAM_THREADS) { s_apar[i] = p.a_xf[i]; s_apar[512 + i] = p.a_xf[C + i]; }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();
+    if (xform)
+        for (int i = threadIdx.x; i < C; i += GRAM_THREADS) { s_apar[i] = p.a_xf[i]; s_apar[512 + i] = p.a_xf[C + i]; }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the ones tile is read by the tensor core (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -1451,7 +1414,8 @@ cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     // keep a CTA on one channel tile (its statistics accumulators stay in registers) when that costs < 3 % of the SMs;
     // with resident weights it is a requirement (total is a multiple of tiles_n, so grid >= tiles_n stays one)
     if (p.tiles_n > 1 && grid > p.tiles_n && grid % p.tiles_n != 0 && (RESB || (grid % p.tiles_n) * 32 < grid)) grid -= grid % p.tiles_n;
-    conv_tc_kernel<BN, KB, DUAL, RESB><<<grid, TC_THREADS, Cfg::SMEM, s>>>(m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+    cudaError_t le = launch_pdl(conv_tc_kernel<BN, KB, DUAL, RESB>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+    if (le != cudaSuccess) return le;
     snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB);
     return cudaGetLastError();
 }
@@ -1513,7 +1477,8 @@ cudaError_t launch_halo_v(const CUtensorMap &ma, const CUtensorMap &mb, const CU
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int grid = p.n_groups < g_num_sms ? p.n_groups : g_num_sms;
-    conv3x3_halo_kernel<BN, MT, RESW><<<grid, TC_THREADS, smem, s>>>(ma, mb, mo, p);
+    cudaError_t le = launch_pdl(conv3x3_halo_kernel<BN, MT, RESW>, dim3(grid), dim3(TC_THREADS), (size_t)smem, s, ma, mb, mo, p);
+    if (le != cudaSuccess) return le;
     snprintf(g_last_kernel, sizeof(g_last_kernel), "conv3x3_halo_kernel<%d, %d, %d>", BN, MT, (int)RESW);
     return cudaGetLastError();
 }
@@ -1579,7 +1544,8 @@ cudaError_t launch_gram_v(const CUtensorMap &ma, const GramParams &p, int grid, 
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    gram_stats_kernel<NB><<<grid, GRAM_THREADS, smem, s>>>(ma, p);
+    cudaError_t le = launch_pdl(gram_stats_kernel<NB>, dim3(grid), dim3(GRAM_THREADS), (size_t)smem, s, ma, p);
+    if (le != cudaSuccess) return le;
     snprintf(g_last_kernel, sizeof(g_last_kernel), "gram_stats_kernel<%d>", NB);
     return cudaGetLastError();
 }
@@ -1656,12 +1622,12 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     if (a.in_xf && (L.cin > 512 || !L.w16s)) return cudaErrorInvalidValue;
     if (halo_applies(L, a, o)) return launch_conv3x3_halo(L, a, s);
     const bool dual = o.mode == TC_MODE_FINAL && o.ds != nullptr;
-    const bool from_stats = o.mode == TC_MODE_FINAL && o.bn_count > 0;     // finalise the BatchNorms in the kernel prologue
-    if (o.mode == TC_MODE_FINAL && (L.k != 1 || L.stride != 1 || (!from_stats && (!o.e_scale || !o.e_shift)) || (!dual && !o.idt))) return cudaErrorInvalidValue;
-    if (dual && (o.ds->k != 1 || o.ds->cout != L.cout || o.ds->cin % TC_BK != 0 || !o.ds->w16 || !o.ds_in || (!from_stats && (!o.ds_scale || !o.ds_shift)))) return cudaErrorInvalidValue;
+    if (o.mode == TC_MODE_FINAL && (L.k != 1 || L.stride != 1 || !o.e_shift || !L.w16f || (!dual && !o.idt))) return cudaErrorInvalidValue;
+    if (dual && (o.ds->k != 1 || o.ds->cout != L.cout || o.ds->cin % TC_BK != 0 || !o.ds->w16f || !o.ds_in)) return cudaErrorInvalidValue;
     TcParams p{};
     if (!tile_geometry(a.Ho, a.Wo, p.BW, p.BH, p.BI)) return cudaErrorInvalidValue;
-    const int BN = dual ? 128 : (L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64));
+    const int BN = L.cout >= 256 ? 256 : (L.cout >= 128 ? 128 : 64);
+    if (dual && BN != 256) return cudaErrorInvalidValue;
     if (L.cout % BN != 0) return cudaErrorInvalidValue;
     p.tiles_n = L.cout / BN;
     p.h_tiles = a.Ho / p.BH;
@@ -1674,11 +1640,7 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     p.Hv = a.H / L.stride; p.Wv = a.W / L.stride;
     p.mode = o.mode == TC_MODE_FINAL ? MODE_FINAL : (o.mode == TC_MODE_STATS ? MODE_STATS : MODE_RAW);
     p.a_xf = a.in_xf;
-    p.e_scale = o.e_scale; p.e_shift = o.e_shift; p.d_scale = o.ds_scale; p.d_shift = o.ds_shift;
-    if (from_stats) {
-        p.e_stats = L.stats; p.e_gamma = L.gamma; p.e_beta = L.beta; p.inv_count = 1.0 / (double)o.bn_count;
-        if (dual) { p.d_stats = o.ds->stats; p.d_gamma = o.ds->gamma; p.d_beta = o.ds->beta; }
-    }
+    p.e_shift = o.e_shift;
     p.out = a.out; p.stats = p.mode == MODE_FINAL ? nullptr : L.stats; p.bias = nullptr; p.residual = nullptr; p.alpha = 1.f; p.act = 0;
     p.img_w = a.img_w;
     p.img_shift = 0;
@@ -1713,7 +1675,8 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
                 p.tap_bit[r * L.k + q] = (p.tap_dh[r * L.k + q] + 1) * 3 + (p.tap_dw[r * L.k + q] + 1);
             }
     }
-    ok = ok && make_map2(&m.b, a.in_xf ? L.w16s : L.w16, (long long)p.ntaps * L.cin, L.cout, BN);   // w16s = bf16(W * |scale_in|)
+    // w16s = bf16(W * |scale_in|); FINAL: w16f = bf16(W * |scale_in| * scale of this conv's BN)
+    ok = ok && make_map2(&m.b, p.mode == MODE_FINAL ? L.w16f : (a.in_xf ? L.w16s : L.w16), (long long)p.ntaps * L.cin, L.cout, BN);
     m.b2 = m.b;
     if (dual) {
         // downsample branch: 1x1 conv (stride ds->stride) on the block input [N, ds_H, ds_W, ds->cin]; view (0,0) for stride 2
@@ -1721,7 +1684,7 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
         const int sd = o.ds->stride;
         if (Hd / sd != a.Ho || Wd / sd != a.Wo) return cudaErrorInvalidValue;
         ok = ok && make_map4(&m.a[1], o.ds_in, (int)Cd, (int)(Wd / sd), (int)(Hd / sd), a.N, sd * Cd, sd * Wd * Cd, Hd * Wd * Cd, p.BW, p.BH, p.BI);
-        ok = ok && make_map2(&m.b2, o.ds->w16, Cd, L.cout, BN);
+        ok = ok && make_map2(&m.b2, o.ds->w16f, Cd, L.cout, BN);
     }
     // output [N][Ho][Wo][Cout] bf16, stored one 64-channel group of a tile at a time; images beyond N are clipped by TMA
     ok = ok && make_map4(&m.out, a.out, L.cout, a.Wo, a.Ho, a.N, L.cout, (long long)a.Wo * L.cout, (long long)a.Ho * a.Wo * L.cout, p.BW, p.BH, p.BI);
@@ -1729,7 +1692,7 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     if (p.mode == MODE_FINAL && !dual)
         ok = ok && make_map4(&m.idt, o.idt, L.cout, a.Wo, a.Ho, a.N, L.cout, (long long)a.Wo * L.cout, (long long)a.Ho * a.Wo * L.cout, p.BW, p.BH, p.BI);
     if (!ok) return cudaErrorInvalidValue;
-    if (dual) return launch_tc<128, 128, true>(m, p, s);
+    if (dual) return launch_tc<256, 128, true>(m, p, s);
     switch (BN) {
         case 256: return launch_tc<256>(m, p, s);
         case 128: return launch_tc<128>(m, p, s);
@@ -1782,6 +1745,8 @@ constexpr int STEM_ROWS = PATCH_H + 7;                   // 3 zero rows + 384 ro
 __global__ void __launch_bounds__(256) stem_prepass_kernel(const uint8_t *__restrict__ bank, const int32_t *__restrict__ slots,
                                                            const float *__restrict__ lut, uint4 *__restrict__ out, long long total_px) {
     __shared__ float slut[768];
+    pdl_trigger();
+    pdl_wait();
     for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_px; i += (long long)gridDim.x * blockDim.x) {
@@ -1825,8 +1790,7 @@ cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, con
     const long long total_px = (long long)N * STEM_ROWS * STEM_PITCH_PX;
     long long blocks = (total_px + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    stem_prepass_kernel<<<(int)blocks, 256, 0, s>>>(bank, slots, lut, (uint4 *)scratch, total_px);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(stem_prepass_kernel, dim3((int)blocks), dim3(256), 0, s, bank, slots, lut, (uint4 *)scratch, total_px);
     if (e != cudaSuccess) return e;
     TcParams p{};
     p.BW = 64; p.BH = 2; p.BI = 1;

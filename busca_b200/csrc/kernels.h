@@ -37,6 +37,8 @@ struct ConvLayer {
     float *w32m;                // unrounded fp32 master of the same layout (source of the folded weights)
     void *w16;                  // same layout, bf16
     void *w16s;                 // bf16(W * |scale of the input BN|): rewritten by launch_bn_fold on every call
+    void *w16f;                 // last 1x1 conv of a bottleneck / downsample conv: bf16(W * |scale of the input BN| * scale of ITS OWN BN), the
+                                // weights of the FINAL pass (launch_bn_fold_final)
     uint16_t *xf;               // [2*cin] transform of this conv's input: theta = -shift/|scale| (bf16), then sign masks
     float *gamma, *beta;        // BatchNorm affine
     double *stats;              // [2*cout] sum, sum of squares of the raw conv output (this batch)
@@ -67,15 +69,28 @@ enum { TC_MODE_RAW = 0,      // raw bf16 output + batch statistics
        TC_MODE_FINAL = 2 };  // out = relu(acc*e_scale + e_shift + identity), identity = idt tensor or BN(downsample conv)
 struct ConvTcOpts {
     int mode = TC_MODE_RAW;
-    const float *e_scale = nullptr, *e_shift = nullptr;    // FINAL: this conv's finalised BN
-    const void *idt = nullptr;                             // FINAL: identity tensor [M, cout] bf16 (no downsample)
-    const ConvLayer *ds = nullptr;                         // FINAL: downsample 1x1 conv accumulated by the same kernel
-    const void *ds_in = nullptr;                           //        its input [N, ds_H, ds_W, ds->cin] bf16 (activated)
+    // FINAL: out = relu(acc + e_shift + identity).  The BN scales of this conv (and of the downsample conv) are folded into the weights
+    // L.w16f / ds->w16f by launch_bn_fold_final, which also writes e_shift = shift of this BN (+ shift of the downsample BN); with `ds`
+    // the downsample 1x1 conv accumulates into the SAME TMEM accumulator and replaces the identity tensor.
+    const float *e_shift = nullptr;                        // [cout]
+    const void *idt = nullptr;                             // identity tensor [M, cout] bf16 (no downsample)
+    const ConvLayer *ds = nullptr;                         // downsample 1x1 conv accumulated by the same kernel
+    const void *ds_in = nullptr;                           //   its input [N, ds_H, ds_W, ds->cin] bf16 (activated)
     int ds_H = 0, ds_W = 0;
-    const float *ds_scale = nullptr, *ds_shift = nullptr;  //        its finalised BN
-    long long bn_count = 0;                                // FINAL: > 0 = finalise this conv's (and ds's) BatchNorm from L.stats / gamma / beta in the
-                                                           //        kernel prologue with this element count (no bn_finalize launch, e_scale etc. unused)
 };
+// Weights and shift of a FINAL pass.  BN of L (and of ds): from the batch statistics (count > 0: L.stats / gamma / beta, as bn_finalize) or
+// explicit (scale / shift, ds_scale / ds_shift).  in_scale: scale of the BN whose ReLU output is L's input (|.| is folded, as in bn_fold;
+// null = none).  Writes L.w16f = bf16(W |in_scale| s_L), ds->w16f = bf16(W_ds s_ds), shift_out = t_L (+ t_ds), and L.scale / ds->scale.
+struct FoldFinalArgs {
+    const ConvLayer *L = nullptr;
+    const float *in_scale = nullptr;
+    long long count = 0;
+    const float *scale = nullptr, *shift = nullptr;
+    const ConvLayer *ds = nullptr;
+    const float *ds_scale = nullptr, *ds_shift = nullptr;
+    float *shift_out = nullptr;
+};
+cudaError_t launch_bn_fold_final(const FoldFinalArgs &a, cudaStream_t s);
 cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s);
 size_t stem_tc_scratch_bytes(int N);
 // Gram-matrix statistics of a 1x1 convolution (conv_tc.cu / reid.cu): partials by the tensor-core kernel, then the fp64 reduction and the

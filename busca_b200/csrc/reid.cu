@@ -309,6 +309,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const uint8_t *__restrict__ b
 __global__ void bn_finalize_kernel(const double *__restrict__ stats, const float *__restrict__ gamma,
                                    const float *__restrict__ beta, int C, double inv_count, float *__restrict__ scale,
                                    float *__restrict__ shift) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double mean = stats[c] * inv_count;
@@ -351,6 +353,8 @@ __global__ void __launch_bounds__(256) bn_finalize_fold_kernel(const double *__r
                                                                 int C, double inv_count, float *__restrict__ scale, float *__restrict__ shift,
                                                                 const float4 *__restrict__ w32, uint2 *__restrict__ w16s, uint16_t *__restrict__ xf, long long total4) {
     __shared__ float sabs[512];
+    pdl_trigger();
+    pdl_wait();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const double mean = stats[c] * inv_count;
         double var = stats[C + c] * inv_count - mean * mean;
@@ -459,6 +463,8 @@ __global__ void bn_relu_inplace_kernel(T *x, const float *__restrict__ scale, co
 
 // fp32 -> bf16 copy (A operand of the tensor-core linears)
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4 *__restrict__ in, uint2 *__restrict__ out, long long n4) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 v = in[i];
         __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
@@ -468,6 +474,8 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4 *__restrict
 
 template <typename T>
 __global__ void global_maxpool_kernel(const T *__restrict__ x, float *__restrict__ out, int N, int HW, int C) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)N * C) return;
     const int c = (int)(i % C);
@@ -479,6 +487,8 @@ __global__ void global_maxpool_kernel(const T *__restrict__ x, float *__restrict
 
 // F.normalize(x, p=2, dim=1): x / max(||x||_2, 1e-12)              resnet.py:319-322
 __global__ void l2norm_rows_kernel(float *x, int rows, int cols) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -604,8 +614,7 @@ cudaError_t launch_linear_f32(const LinearArgs &a, cudaStream_t s) {
 }
 
 cudaError_t launch_bn_finalize(const ConvLayer &L, long long count, cudaStream_t s) {
-    bn_finalize_kernel<<<ceil_div(L.cout, 128), 128, 0, s>>>(L.stats, L.gamma, L.beta, L.cout, 1.0 / (double)count, L.scale, L.shift);
-    return cudaGetLastError();
+    return launch_pdl(bn_finalize_kernel, dim3(ceil_div(L.cout, 128)), dim3(128), 0, s, L.stats, L.gamma, L.beta, L.cout, 1.0 / (double)count, L.scale, L.shift);
 }
 
 cudaError_t launch_bn_fold(const float *scale, const float *shift, const ConvLayer &L, cudaStream_t s) {
@@ -622,9 +631,79 @@ cudaError_t launch_bn_finalize_fold(const ConvLayer &P, long long count, const C
     const long long total4 = (long long)L.cout * L.k * L.k * L.cin / 4;
     long long blocks = (total4 + 255) / 256;
     if (blocks > 148 * 4) blocks = 148 * 4;
-    bn_finalize_fold_kernel<<<(int)blocks, 256, 0, s>>>(P.stats, P.gamma, P.beta, P.cout, 1.0 / (double)count, P.scale, P.shift, (const float4 *)L.w32m,
-                                                        (uint2 *)L.w16s, L.xf, total4);
-    return cudaGetLastError();
+    return launch_pdl(bn_finalize_fold_kernel, dim3((int)blocks), dim3(256), 0, s, P.stats, P.gamma, P.beta, P.cout, 1.0 / (double)count, P.scale, P.shift,
+                      (const float4 *)L.w32m, (uint2 *)L.w16s, L.xf, total4);
+}
+
+// FINAL-pass weights (kernels.h: FoldFinalArgs).  One block per output channel: the channel's BN scale / shift (fp64 from the batch
+// statistics, the arithmetic of bn_finalize_kernel, or given), then its weight row(s) times that scale (and |scale| of the input BN),
+// rounded to bf16 ONCE from the fp32 master.
+__global__ void __launch_bounds__(128) bn_fold_final_kernel(const double *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                             const float *__restrict__ scale_in, const float *__restrict__ shift_in, double inv_count, int Cout,
+                                                             const float *__restrict__ in_scale, const float *__restrict__ w32, __nv_bfloat16 *__restrict__ w16f,
+                                                             int Cin, float *__restrict__ scale_out,
+                                                             const double *__restrict__ d_stats, const float *__restrict__ d_gamma, const float *__restrict__ d_beta,
+                                                             const float *__restrict__ d_scale_in, const float *__restrict__ d_shift_in,
+                                                             const float *__restrict__ dw32, __nv_bfloat16 *__restrict__ dw16f, int dCin,
+                                                             float *__restrict__ d_scale_out, float *__restrict__ shift_out) {
+    pdl_trigger();
+    pdl_wait();
+    const int c = blockIdx.x;
+    float sc, sh;
+    if (stats) {
+        const double mean = stats[c] * inv_count;
+        double var = stats[Cout + c] * inv_count - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const double a = (double)gamma[c] / sqrt(var + 1e-5);
+        sc = (float)a;
+        sh = (float)((double)beta[c] - mean * a);
+    } else {
+        sc = scale_in[c];
+        sh = shift_in[c];
+    }
+    float dsc = 0.f, dsh = 0.f;
+    if (dw32) {
+        if (d_stats) {
+            const double mean = d_stats[c] * inv_count;
+            double var = d_stats[Cout + c] * inv_count - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const double a = (double)d_gamma[c] / sqrt(var + 1e-5);
+            dsc = (float)a;
+            dsh = (float)((double)d_beta[c] - mean * a);
+        } else {
+            dsc = d_scale_in[c];
+            dsh = d_shift_in[c];
+        }
+    }
+    if (threadIdx.x == 0) {
+        shift_out[c] = sh + dsh;
+        if (scale_out) scale_out[c] = sc;
+        if (dw32 && d_scale_out) d_scale_out[c] = dsc;
+    }
+    for (int k = threadIdx.x; k < Cin; k += blockDim.x) {
+        float a = 1.f;
+        if (in_scale) {                                         // the clamp of bn_fold_kernel: the transform parameters were derived with it
+            a = fabsf(in_scale[k]);
+            if (!(a >= 1e-20f)) a = 1e-20f;
+        }
+        w16f[(size_t)c * Cin + k] = __float2bfloat16_rn(w32[(size_t)c * Cin + k] * a * sc);
+    }
+    if (dw32)
+        for (int k = threadIdx.x; k < dCin; k += blockDim.x) dw16f[(size_t)c * dCin + k] = __float2bfloat16_rn(dw32[(size_t)c * dCin + k] * dsc);
+}
+
+cudaError_t launch_bn_fold_final(const FoldFinalArgs &a, cudaStream_t s) {
+    const ConvLayer *L = a.L, *D = a.ds;
+    if (!L || L->k != 1 || !L->w32m || !L->w16f || !a.shift_out) return cudaErrorInvalidValue;
+    if (a.count <= 0 && (!a.scale || !a.shift)) return cudaErrorInvalidValue;
+    if (D && (D->k != 1 || D->cout != L->cout || !D->w32m || !D->w16f || (a.count <= 0 && (!a.ds_scale || !a.ds_shift)))) return cudaErrorInvalidValue;
+    const bool from_stats = a.count > 0;
+    return launch_pdl(bn_fold_final_kernel, dim3(L->cout), dim3(128), 0, s, from_stats ? (const double *)L->stats : (const double *)nullptr,
+                      (const float *)L->gamma, (const float *)L->beta, a.scale, a.shift, from_stats ? 1.0 / (double)a.count : 0.0, L->cout, a.in_scale,
+                      (const float *)L->w32m, (__nv_bfloat16 *)L->w16f, L->cin, L->scale,
+                      (D && from_stats) ? (const double *)D->stats : (const double *)nullptr, D ? (const float *)D->gamma : (const float *)nullptr,
+                      D ? (const float *)D->beta : (const float *)nullptr, a.ds_scale, a.ds_shift, D ? (const float *)D->w32m : (const float *)nullptr,
+                      D ? (__nv_bfloat16 *)D->w16f : (__nv_bfloat16 *)nullptr, D ? D->cin : 0, D ? D->scale : (float *)nullptr, a.shift_out);
 }
 
 static int ew_grid(long long total) {
@@ -687,6 +766,8 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_bf16_mono_kernel(const ui
 constexpr int POOL_STRIP_ROWS = 12;
 __global__ void __launch_bounds__(256) bn_relu_maxpool_bf16_strip_kernel(const uint4 *__restrict__ raw, uint4 *__restrict__ out, int N, int H, int W, int C8,
                                                                           const float *__restrict__ scale, const float *__restrict__ shift, int strips) {
+    pdl_trigger();
+    pdl_wait();
     const int Ho = H / 2, Wo = W / 2;
     const int n = blockIdx.x / strips, oy0 = (blockIdx.x % strips) * POOL_STRIP_ROWS;
     const int c8 = threadIdx.x % C8, ox = threadIdx.x / C8;
@@ -755,7 +836,7 @@ cudaError_t launch_bn_relu_maxpool(const void *raw, void *out, int N, int H, int
         const long long t8 = (long long)N * (H / 2) * (W / 2) * (C / 8);
         if (pool_mono_enabled() && (W / 2) * (C / 8) == 256 && (H / 2) % POOL_STRIP_ROWS == 0) {
             const int strips = (H / 2) / POOL_STRIP_ROWS;
-            bn_relu_maxpool_bf16_strip_kernel<<<N * strips, 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift, strips);
+            return launch_pdl(bn_relu_maxpool_bf16_strip_kernel, dim3(N * strips), dim3(256), 0, s, (const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift, strips);
         } else if (pool_mono_enabled())
             bn_relu_maxpool_bf16_mono_kernel<<<ew_grid(t8), 256, 0, s>>>((const uint4 *)raw, (uint4 *)out, N, H, W, C / 8, scale, shift);
         else
@@ -795,7 +876,7 @@ cudaError_t launch_bn_relu_inplace(void *x, const float *scale, const float *shi
 cudaError_t launch_cast_bf16(const float *in, void *out, long long n, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     if (n % 4 != 0) return cudaErrorInvalidValue;
-    cast_bf16_kernel<<<ew_grid(n / 4), 256, 0, s>>>((const float4 *)in, (uint2 *)out, n / 4);
+    return launch_pdl(cast_bf16_kernel, dim3(ew_grid(n / 4)), dim3(256), 0, s, (const float4 *)in, (uint2 *)out, n / 4);
     return cudaGetLastError();
 }
 
@@ -803,7 +884,7 @@ cudaError_t launch_global_maxpool(const void *x, float *out, int N, int HW, int 
     long long total = (long long)N * C;
     if (total == 0) return cudaSuccess;
     if (bf16)
-        global_maxpool_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, s>>>((const __nv_bfloat16 *)x, out, N, HW, C);
+        return launch_pdl(global_maxpool_kernel<__nv_bfloat16>, dim3(ceil_div(total, 256)), dim3(256), 0, s, (const __nv_bfloat16 *)x, out, N, HW, C);
     else
         global_maxpool_kernel<float><<<ceil_div(total, 256), 256, 0, s>>>((const float *)x, out, N, HW, C);
     return cudaGetLastError();
@@ -859,6 +940,8 @@ __global__ void __launch_bounds__(1024) dedup_slots_kernel(const int32_t *__rest
 }
 
 __global__ void gather_rows_kernel(const float4 *__restrict__ src, const int32_t *__restrict__ map, float4 *__restrict__ dst, int rows, int cols4) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)rows * cols4) return;
     const int r = (int)(i / cols4), c = (int)(i % cols4);
@@ -869,27 +952,36 @@ __global__ void gather_rows_kernel(const float4 *__restrict__ src, const int32_t
 // Gram-matrix statistics, second half (first half: gram_stats_kernel, conv_tc.cu, which leaves G [C*C] and m [C] in fp32): the
 // quadratic forms, in fp64.
 // ---------------------------------------------------------------------------------------------------------------------
-// 4 output channels per block: stats[o] += W[o] . m ; stats[Cout + o] += W[o]^T G W[o]   (thread i owns row i of G W[o]^T, read through G's symmetry
-// so that consecutive threads read consecutive addresses)
+// 4 output channels per block: stats[o] += W[o] . m ; stats[Cout + o] += W[o]^T G W[o].  Thread (i, part) owns row i of G W[o]^T over the
+// part-th slice of the j range (256 / C slices; G is read through its symmetry so that consecutive threads read consecutive addresses),
+// eight loads in flight per thread; the partial quadratic forms are reduced in fp64 through warp shuffles and one shared array.
 __global__ void __launch_bounds__(256) gram_quadform_kernel(const float *__restrict__ G64, const float *__restrict__ s64, int C,
                                                             const __nv_bfloat16 *__restrict__ w, int Cout, double *__restrict__ stats) {
     __shared__ double sw[4][256];
     __shared__ double red[8][8];
-    const int o0 = blockIdx.x * 4, i = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    const int o0 = blockIdx.x * 4, t = threadIdx.x;
+    const int parts = 256 / C, i = t % C, part = t / C;          // C in {64, 128, 256}
+    const int jlen = C / parts, j0 = part * jlen;
     for (int q = 0; q < 4; ++q)
-        if (i < C) sw[q][i] = (o0 + q < Cout) ? (double)__bfloat162float(w[(size_t)(o0 + q) * C + i]) : 0.0;
+        if (t < C) sw[q][t] = (o0 + q < Cout) ? (double)__bfloat162float(w[(size_t)(o0 + q) * C + t]) : 0.0;
     __syncthreads();
     double r[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
-    if (i < C) {
-        for (int j = 0; j < C; ++j) {
-            const double gji = (double)G64[(size_t)j * C + i];
+    for (int jb = j0; jb < j0 + jlen; jb += 8) {
+        float g[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) r[q] = fma(gji, sw[q][j], r[q]);
+        for (int u = 0; u < 8; ++u) g[u] = __ldg(G64 + (size_t)(jb + u) * C + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double gji = (double)g[u];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[q] = fma(gji, sw[q][jb + u], r[q]);
         }
-        const double mi = (double)s64[i];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { r[q] *= sw[q][i]; s1[q] = sw[q][i] * mi; }
     }
+    const double mi = part == 0 ? (double)s64[i] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { r[q] *= sw[q][i]; s1[q] = sw[q][i] * mi; }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -897,24 +989,23 @@ __global__ void __launch_bounds__(256) gram_quadform_kernel(const float *__restr
             r[q] += __shfl_xor_sync(0xffffffffu, r[q], o);
             s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
         }
-    if ((i & 31) == 0)
+    if ((t & 31) == 0)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { red[i >> 5][q] = r[q]; red[i >> 5][4 + q] = s1[q]; }
+        for (int q = 0; q < 4; ++q) { red[t >> 5][q] = r[q]; red[t >> 5][4 + q] = s1[q]; }
     __syncthreads();
-    if (i < 8) {
+    if (t < 8) {
         double acc = 0.0;
-        for (int wv = 0; wv < 8; ++wv) acc += red[wv][i];
-        const int q = i & 3;
-        if (o0 + q < Cout) atomicAdd(stats + (i < 4 ? Cout : 0) + o0 + q, acc);
+        for (int wv = 0; wv < 8; ++wv) acc += red[wv][t];
+        const int q = t & 3;
+        if (o0 + q < Cout) atomicAdd(stats + (t < 4 ? Cout : 0) + o0 + q, acc);
     }
 }
 
 cudaError_t launch_gram_finalize(const float *gpart, const float *spart, int grid, int C, const void *w_bf16, int Cout, double *G64, double *s64,
                                  double *stats, cudaStream_t s) {
-    if (C > 256 || C % 64 != 0) return cudaErrorInvalidValue;
+    if (C != 64 && C != 128 && C != 256) return cudaErrorInvalidValue;
     (void)grid; (void)G64; (void)s64;
-    gram_quadform_kernel<<<ceil_div(Cout, 4), 256, 0, s>>>(gpart, spart, C, (const __nv_bfloat16 *)w_bf16, Cout, stats);
-    return cudaGetLastError();
+    return launch_pdl(gram_quadform_kernel, dim3(ceil_div(Cout, 4)), dim3(256), 0, s, gpart, spart, C, (const __nv_bfloat16 *)w_bf16, Cout, stats);
 }
 
 // Stable partition of the distinct images of a BatchNorm batch: multiplicity 1 first, repeated images last (uniq / weight / map are
@@ -965,12 +1056,12 @@ cudaError_t launch_dedup_slots(const int32_t *slots, int n, int *table, int32_t 
 cudaError_t launch_gather_rows(const float *src, const int32_t *map, float *dst, int rows, int cols, cudaStream_t s) {
     if (rows <= 0) return cudaSuccess;
     const long long total = (long long)rows * (cols / 4);
-    gather_rows_kernel<<<ceil_div(total, 256), 256, 0, s>>>((const float4 *)src, map, (float4 *)dst, rows, cols / 4);
+    return launch_pdl(gather_rows_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, s, (const float4 *)src, map, (float4 *)dst, rows, cols / 4);
     return cudaGetLastError();
 }
 
 cudaError_t launch_l2norm_rows(float *x, int rows, int cols, cudaStream_t s) {
     if (rows <= 0) return cudaSuccess;
-    l2norm_rows_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(x, rows, cols);
+    return launch_pdl(l2norm_rows_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, s, x, rows, cols);
     return cudaGetLastError();
 }
