@@ -769,7 +769,7 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     // Batch statistics of a 1x1 convolution whose output is never stored (conv3, downsample): the Gram matrix of its input for the images
     // of multiplicity 1 (Cin <= 256), the weighted statistics-only GEMM pass for the repeated ones (and for Cin > 256).
     const int n_gram = c->gram ? (rb.n_single / 8) * 8 : 0;                // whole pixel tiles (a tile holds up to 8 images)
-    auto stats_pass = [&](ConvLayer &Lc, const ConvArgs &a, const void *w_gram, const char *name) -> int {
+    auto stats_pass = [&](ConvLayer &Lc, const ConvArgs &a, const float **gram_G, const float **gram_m, const char *name) -> int {
         int ng = (Lc.k == 1 && (Lc.cin == 64 || Lc.cin == 128 || Lc.cin == 256)) ? n_gram : 0;
         if (ng > 0) {
             // partial G [C*C] and m [C] of this pass: a fresh, zeroed slice of the Gram arena (one memset per ReID call, above)
@@ -789,7 +789,8 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             snprintf(nm, sizeof(nm), "gram_stats[%d>%d s%d %dx%d]", Lc.cin, Lc.cout, Lc.stride, a.H, a.W);
             LAUNCH(c, c->profiling ? nm : "gram_stats", launch_gram_stats(Lc, ag, (float *)gb, (float *)(gb + o_sp), &grid, s));
             if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();
-            LAUNCH(c, "gram_finalize", launch_gram_finalize((const float *)gb, (const float *)(gb + o_sp), grid, Lc.cin, w_gram, Lc.cout, nullptr, nullptr, Lc.stats, s));
+            *gram_G = (const float *)gb;                             // the quadratic forms are taken by bn_fold_final
+            *gram_m = (const float *)(gb + o_sp);
         }
         if (a.N - ng > 0) {
             ConvArgs as = a;
@@ -820,17 +821,17 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
             LAUNCH(c, "bn_finalize_fold", launch_bn_finalize_fold(c2, NT * Ho * Wo, c3, s));
             ConvArgs a3{};
             a3.N = N; a3.img_w = img_w; a3.in = R2; a3.out = other; a3.H = Ho; a3.W = Wo; a3.Ho = Ho; a3.Wo = Wo; a3.in_xf = c3.xf;
-            if ((rc = stats_pass(c3, a3, c3.w16s, "conv1x1"))) return rc;
             FoldFinalArgs ff{};                                  // BN3 (and the downsample BN): scales into the FINAL pass's weights
             ff.L = &c3; ff.in_scale = c2.scale; ff.count = NT * Ho * Wo; ff.shift_out = c3.shift;
+            if ((rc = stats_pass(c3, a3, &ff.gram_G, &ff.gram_m, "conv1x1"))) return rc;
             fin.e_shift = c3.shift;
             if (b == 0) {
                 ConvLayer &ds = c->convs[ci + 3];
                 ConvArgs ad{};
                 ad.N = N; ad.img_w = img_w; ad.in = x; ad.out = other; ad.H = H; ad.W = W; ad.Ho = Ho; ad.Wo = Wo;
-                if ((rc = stats_pass(ds, ad, ds.w16, "conv1x1"))) return rc;
-                fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W;
                 ff.ds = &ds;
+                if ((rc = stats_pass(ds, ad, &ff.ds_gram_G, &ff.ds_gram_m, "conv1x1"))) return rc;
+                fin.ds = &ds; fin.ds_in = x; fin.ds_H = H; fin.ds_W = W;
                 ci += 4;
             } else {
                 fin.idt = x;
@@ -1300,17 +1301,20 @@ extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d)
     }
     prof_reset(c);
     if (d->mode == 3) {
-        // Gram-matrix statistics of this (1x1) convolution on the given input: stats_out must equal mode 1's
+        // Gram-matrix statistics of this (1x1) convolution on the given input: stats_out must equal mode 1's.  The quadratic forms are
+        // part of bn_fold_final (which also folds the FINAL-pass weights of L from those statistics).
+        if (!L.w16f) return set_err(BUSCA_ERR_ARG, "mode 3 is for the last conv of a bottleneck / a downsample conv");
         const size_t C2 = (size_t)L.cin * L.cin;
-        const int maxg = gram_max_ctas();
-        const size_t o_sp = (C2 * 4 + 255) & ~(size_t)255, o_g64 = o_sp + (((size_t)L.cin * 4 + 255) & ~(size_t)255), o_s64 = o_g64 + C2 * 8;
-        CUDA_OK(c->ws_gram.ensure(o_s64 + (size_t)L.cin * 8 + 256));
+        const size_t o_sp = (C2 * 4 + 255) & ~(size_t)255;
+        CUDA_OK(c->ws_gram.ensure(o_sp + (size_t)L.cin * 4 + 256));
         char *gb = (char *)c->ws_gram.p;
         int grid = 0;
         CUDA_OK(cudaMemsetAsync(gb, 0, o_sp + (size_t)L.cin * 4, s));
         LAUNCH(c, "gram_stats", launch_gram_stats(L, a, (float *)gb, (float *)(gb + o_sp), &grid, s));
-        LAUNCH(c, "gram_finalize", launch_gram_finalize((const float *)gb, (const float *)(gb + o_sp), grid, L.cin, a.in_xf ? L.w16s : L.w16, L.cout,
-                                                        (double *)(gb + o_g64), (double *)(gb + o_s64), L.stats, s));
+        FoldFinalArgs ff{};
+        ff.L = &L; ff.in_scale = d->in_scale ? in_sc : nullptr; ff.count = (long long)N * Ho * Wo; ff.shift_out = L.shift;
+        ff.gram_G = (const float *)gb; ff.gram_m = (const float *)(gb + o_sp);
+        LAUNCH(c, "bn_fold_final", launch_bn_fold_final(ff, s));
     } else if (d->use_tc) LAUNCH(c, "conv_tc", launch_conv_tc(L, a, o, s));
     else LAUNCH(c, "conv_simt", launch_conv_simt(L, a, 1, s));
     if (d->out_bf16) CUDA_OK(cudaMemcpyAsync(d->out_bf16, b + o_out, out_b, cudaMemcpyDeviceToHost, s));

@@ -1781,6 +1781,200 @@ __global__ void __launch_bounds__(256) stem_prepass_kernel(const uint8_t *__rest
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Stem GEMM, row-marching formulation (default; BUSCA_STEM=tap selects the tap-by-tap path through conv_tc_kernel).
+// Measured (profiles/r02u): the tap-by-tap stem is bound by the TMA REQUEST rate - every 128-pixel tile pulls four im2col boxes whose
+// 128-byte rows start 32 bytes apart (each row its own, line-straddling L2 request: ~1000 requests per tile, ~3 cycles each) - and
+// three of a tile's four boxes are fetched again by the tile of the next output row.  Here a CTA marches DOWN a column strip instead:
+//   * M tile = ONE output row of an image PAIR (2 x 64 pixels), so the box of padded-row entry 2j (128 rows x 128 B) is the A operand
+//     of output row j - p for each of the four row pairs p = 0..3: it is loaded ONCE and multiplied by the four weight slices
+//     (resident in shared memory) into the four accumulators that are open at that moment.  A quarter of the requests and bytes.
+//   * accumulators: a ring of eight 64-column TMEM tiles; the tile of output row oy opens at step j = oy (p = 0, accumulate off)
+//     and is complete after step oy + 3.
+//   * two epilogue teams of eight warps take alternate output rows (TMEM -> bf16 -> swizzled staging -> TMA store, statistics from
+//     the staging tile as in conv_tc_kernel's RAW mode), so a row's epilogue has two row-times to finish.
+// Work units: (image pair, segment of 48 output rows); a segment re-reads 3 entries of its predecessor (6 %).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int SM_STAGES = 5;
+constexpr int SM_SLOTS = 8;
+constexpr int SM_TEAM_WARPS = 8;
+constexpr int SM_THREADS = 64 + 2 * SM_TEAM_WARPS * 32;      // warp 0 TMA, warp 1 MMA, warps 2-9 team 0, warps 10-17 team 1
+constexpr int SM_A_BYTES = 16384, SM_W_BYTES = 4 * 8192, SM_XBUF = 16384;
+constexpr int SM_SMEM = 1024 + SM_STAGES * SM_A_BYTES + SM_W_BYTES + 2 * 3 * SM_XBUF + 128 * 4 + (2 * SM_STAGES + 1 + 2 * SM_SLOTS) * 8 + 64;
+static_assert(SM_SMEM <= 232448, "shared memory budget");
+struct StemParams {
+    int N, segs, seg_rows, total_units;
+    double *stats;                   // [128] sum, sum of squares
+    const float *img_w;              // [N] multiplicities or null
+};
+
+__global__ void __launch_bounds__(SM_THREADS, 1) stem_march_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                    const __grid_constant__ CUtensorMap mapOut, const StemParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *a_tiles = smem;
+    uint8_t *w_tiles = a_tiles + SM_STAGES * SM_A_BYTES;                 // four [64 cout x 64 k] slices, one per row pair
+    uint8_t *xbuf = w_tiles + SM_W_BYTES;                                // 2 teams x 3 staging tiles
+    float *s_par = reinterpret_cast<float *>(xbuf + 6 * SM_XBUF);        // [128] statistics
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_par + 128);
+    uint64_t *a_full = bars, *a_empty = a_full + SM_STAGES, *wfull = a_empty + SM_STAGES, *tfull = wfull + 1, *tempty = tfull + SM_SLOTS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + SM_SLOTS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SM_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        mbar_init(wfull, 1);
+        for (int t = 0; t < SM_SLOTS; ++t) { mbar_init(&tfull[t], 1); mbar_init(&tempty[t], SM_TEAM_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&mapA); prefetch_tmap(&mapB); prefetch_tmap(&mapOut);
+    }
+    for (int i = threadIdx.x; i < 128; i += SM_THREADS) s_par[i] = 0.f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    pdl_wait();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer: the weight slices once, then one entry box per step
+        if (elect_one()) {
+            mbar_expect_tx(wfull, SM_W_BYTES);
+            for (int pr = 0; pr < 4; ++pr) tma_load_2d(w_tiles + pr * 8192, &mapB, wfull, pr * 64, 0);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            const int n0 = (u / p.segs) * 2, oy0 = (u % p.segs) * p.seg_rows;
+            for (int j = oy0; j < oy0 + p.seg_rows + 3; ++j) {
+                mbar_wait<32>(&a_empty[stage], phase ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&a_full[stage], SM_A_BYTES);
+                    tma_load_4d(a_tiles + stage * SM_A_BYTES, &mapA, &a_full[stage], 0, 0, j, n0);
+                }
+                __syncwarp();
+                if (++stage == SM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t w_addr = smem_u32(w_tiles);
+        int stage = 0;
+        uint32_t phase = 0;
+        int t_base = 0;                                  // running index of this CTA's output rows: row oy of the unit is tile t_base + oy - oy0
+        mbar_wait<32>(wfull, 0);
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, t_base += p.seg_rows) {
+            const int oy0 = (u % p.segs) * p.seg_rows;
+            for (int j = oy0; j < oy0 + p.seg_rows + 3; ++j) {
+                if (j < oy0 + p.seg_rows) {              // the tile of output row j opens at this step: its TMEM slot must have been drained
+                    const int t = t_base + j - oy0;
+                    mbar_wait<32>(&tempty[t & (SM_SLOTS - 1)], ((uint32_t)(t >> 3) & 1) ^ 1);
+                }
+                mbar_wait<0>(&a_full[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc<128>(smem_u32(a_tiles + stage * SM_A_BYTES));
+                if (elect_one()) {
+#pragma unroll
+                    for (int pr = 0; pr < 4; ++pr) {
+                        const int oy = j - pr;
+                        if (oy >= oy0 && oy < oy0 + p.seg_rows) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)((t_base + oy - oy0) & (SM_SLOTS - 1)) * 64u;
+                            const uint64_t db = umma_desc<128>(w_addr + pr * 8192);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(pr == 0 && k == 0));
+                        }
+                    }
+                    umma_commit(&a_empty[stage]);
+                    if (j - 3 >= oy0) umma_commit(&tfull[(t_base + j - 3 - oy0) & (SM_SLOTS - 1)]);    // output row j - 3 is complete
+                }
+                __syncwarp();
+                if (++stage == SM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================================================== epilogue teams: team = parity of the CTA's running tile index
+        const int team = (warp - 2) / SM_TEAM_WARPS;
+        const int e = threadIdx.x - 64 - team * (SM_TEAM_WARPS * 32);      // 0..255 within the team
+        const int q = warp & 3;                                            // TMEM lane quarter this warp may read
+        const int half = ((warp - 2) % SM_TEAM_WARPS) >> 2;                // which 32 of the 64 channels
+        const int row = q * 32 + lane;
+        const uint32_t xb0 = smem_u32(xbuf) + team * 3 * SM_XBUF;
+        const uint32_t row_off = (uint32_t)row * 128;
+        const int cq = e & 15, rsub = e >> 4;                              // statistics: 4 channels x rows rsub + 16 i (i < 4: first image)
+        const uint32_t st_off = (uint32_t)rsub * 128 + (uint32_t)((((cq >> 1) ^ (rsub & 7)) << 4) + (cq & 1) * 8);
+        float acc_s[4] = {0.f, 0.f, 0.f, 0.f}, acc_q[4] = {0.f, 0.f, 0.f, 0.f};
+        int t_base = 0, cnt = 0;
+        for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, t_base += p.seg_rows) {
+            const int n0 = (u / p.segs) * 2, oy0 = (u % p.segs) * p.seg_rows;
+            float w0 = 1.f, w1 = 1.f;
+            if (p.img_w) { w0 = __ldg(p.img_w + n0); w1 = __ldg(p.img_w + min(n0 + 1, p.N - 1)); }
+            for (int r = (t_base & 1) == team ? 0 : 1; r < p.seg_rows; r += 2, ++cnt) {
+                const int t = t_base + r, slot = t & (SM_SLOTS - 1);
+                const uint32_t st = xb0 + (uint32_t)(cnt % 3) * SM_XBUF;
+                mbar_wait<0>(&tfull[slot], (uint32_t)(t >> 3) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 64u + half * 32, rr);
+                TMEM_LD_WAIT();
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[slot]);                  // the accumulator is in registers: the slot may be reopened
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 w;
+                    w.x = pack_bf16(__uint_as_float(rr[j * 8 + 0]), __uint_as_float(rr[j * 8 + 1]));
+                    w.y = pack_bf16(__uint_as_float(rr[j * 8 + 2]), __uint_as_float(rr[j * 8 + 3]));
+                    w.z = pack_bf16(__uint_as_float(rr[j * 8 + 4]), __uint_as_float(rr[j * 8 + 5]));
+                    w.w = pack_bf16(__uint_as_float(rr[j * 8 + 6]), __uint_as_float(rr[j * 8 + 7]));
+                    sts128(st + row_off + (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4), w);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store two tiles back has released the tile the next one overwrites
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+                if (e == 0) tma_store_4d(xbuf + (team * 3 + cnt % 3) * SM_XBUF, &mapOut, 0, 0, oy0 + r, n0);
+                if (p.stats) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint2 v = lds64(st + st_off + (uint32_t)i * 2048);
+                        const float wi = i < 4 ? w0 : w1;
+                        const float x0 = bf_lo(v.x), x1 = bf_hi(v.x), x2 = bf_lo(v.y), x3 = bf_hi(v.y);
+                        const float y0 = x0 * wi, y1 = x1 * wi, y2 = x2 * wi, y3 = x3 * wi;
+                        acc_s[0] += y0; acc_q[0] = fmaf(y0, x0, acc_q[0]);
+                        acc_s[1] += y1; acc_q[1] = fmaf(y1, x1, acc_q[1]);
+                        acc_s[2] += y2; acc_q[2] = fmaf(y2, x2, acc_q[2]);
+                        acc_s[3] += y3; acc_q[3] = fmaf(y3, x3, acc_q[3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&s_par[cq * 4 + j], acc_s[j]);
+            atomicAdd(&s_par[64 + cq * 4 + j], acc_q[j]);
+        }
+        if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    __syncthreads();
+    if (p.stats)
+        for (int i = threadIdx.x; i < 128; i += SM_THREADS) {
+            const float v = s_par[i];
+            if (v != 0.f) atomicAdd(p.stats + i, (double)v);
+        }
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+}  // namespace
+
 size_t stem_tc_scratch_bytes(int N) { return (size_t)N * STEM_ROWS * STEM_PITCH_PX * 16; }
 
 // wstem: bf16 [64][4 row pairs][64], element (p, kx*8 + r*4 + c_bgr) = W[o][c][2p+r][kx]; scratch: stem_tc_scratch_bytes(N); out: bf16 [N,192,64,64]
@@ -1792,6 +1986,35 @@ cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, con
     if (blocks > 148 * 32) blocks = 148 * 32;
     cudaError_t e = launch_pdl(stem_prepass_kernel, dim3((int)blocks), dim3(256), 0, s, bank, slots, lut, (uint4 *)scratch, total_px);
     if (e != cudaSuccess) return e;
+    static const bool march = !(getenv("BUSCA_STEM") && getenv("BUSCA_STEM")[0] == 't');      // BUSCA_STEM=tap: the tap-by-tap path below
+    if (march) {
+        const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(scratch);
+        const long long pitch = (long long)STEM_PITCH_PX * 8;
+        CUtensorMap ma, mb, mo;
+        // dims {64 window elements, 64 ox (stride 16 el = 32 B), 196 even entries (stride 2 entries), N}; box = one entry of an image pair
+        bool ok = make_map4(&ma, in, 64, 64, 196, N, 16, 2 * pitch, (long long)STEM_ROWS * pitch, 64, 1, 2);
+        ok = ok && make_map2(&mb, wstem, 4 * 64, 64, 64);
+        ok = ok && make_map4(&mo, out, 64, 64, 192, N, 64, 64 * 64, 192LL * 64 * 64, 64, 1, 2);
+        if (!ok) return cudaErrorInvalidValue;
+        StemParams sp{};
+        sp.N = N; sp.segs = 4; sp.seg_rows = 192 / sp.segs; sp.total_units = ((N + 1) / 2) * sp.segs;
+        sp.stats = stats; sp.img_w = img_w;
+        static bool attr_set = false;
+        if (!attr_set) {
+            e = cudaFuncSetAttribute(stem_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        if (!g_num_sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int grid = sp.total_units < g_num_sms ? sp.total_units : g_num_sms;
+        e = launch_pdl(stem_march_kernel, dim3(grid), dim3(SM_THREADS), (size_t)SM_SMEM, s, ma, mb, mo, sp);
+        snprintf(g_last_kernel, sizeof(g_last_kernel), "stem_march_kernel");
+        return e;
+    }
     TcParams p{};
     p.BW = 64; p.BH = 2; p.BI = 1;
     p.tiles_n = 1; p.h_tiles = 192 / 2; p.tiles_m = N * p.h_tiles;

@@ -78,27 +78,32 @@ struct ConvTcOpts {
     const void *ds_in = nullptr;                           //   its input [N, ds_H, ds_W, ds->cin] bf16 (activated)
     int ds_H = 0, ds_W = 0;
 };
-// Weights and shift of a FINAL pass.  BN of L (and of ds): from the batch statistics (count > 0: L.stats / gamma / beta, as bn_finalize) or
-// explicit (scale / shift, ds_scale / ds_shift).  in_scale: scale of the BN whose ReLU output is L's input (|.| is folded, as in bn_fold;
-// null = none).  Writes L.w16f = bf16(W |in_scale| s_L), ds->w16f = bf16(W_ds s_ds), shift_out = t_L (+ t_ds), and L.scale / ds->scale.
+// Weights and shift of a FINAL pass, and the end of the Gram-matrix statistics (one launch, reid.cu: gram_fold_final_kernel).
+// Per conv (L, and ds if given):
+//   statistics: L.stats holds what the weighted statistics-only pass added (or zeros); if gram_G is given the quadratic forms
+//               stats[c] += Wq[c] . m, stats[Cout + c] += Wq[c]^T G Wq[c] (fp64; Wq = the bf16 weights the statistics refer to: w16s
+//               for L when in_scale is given, else w16) are added and the totals written back;
+//   BatchNorm:  from those totals (count > 0; the arithmetic of bn_finalize) or explicit (scale / shift, ds_scale / ds_shift);
+//   weights:    L.w16f = bf16(W |in_scale| s_L), ds->w16f = bf16(W_ds s_ds) from the fp32 masters; shift_out = t_L (+ t_ds); L.scale, ds->scale.
+// in_scale: scale of the BN whose ReLU output is L's input (|.| with the clamp of bn_fold; null = none).
 struct FoldFinalArgs {
     const ConvLayer *L = nullptr;
     const float *in_scale = nullptr;
     long long count = 0;
     const float *scale = nullptr, *shift = nullptr;
+    const float *gram_G = nullptr, *gram_m = nullptr;      // [cin*cin], [cin] fp32 (cin <= 256) or null
     const ConvLayer *ds = nullptr;
     const float *ds_scale = nullptr, *ds_shift = nullptr;
+    const float *ds_gram_G = nullptr, *ds_gram_m = nullptr;
     float *shift_out = nullptr;
 };
 cudaError_t launch_bn_fold_final(const FoldFinalArgs &a, cudaStream_t s);
 cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOpts &o, cudaStream_t s);
 size_t stem_tc_scratch_bytes(int N);
-// Gram-matrix statistics of a 1x1 convolution (conv_tc.cu / reid.cu): partials by the tensor-core kernel, then the fp64 reduction and the
-// quadratic forms  stats[c] += W[c].m,  stats[Cout + c] += W[c]^T G W[c]  (W bf16 [Cout][Cin])
+// Gram-matrix statistics of a 1x1 convolution (conv_tc.cu): G = sum_p a a^T and m = sum_p a by the tensor-core kernel; the quadratic
+// forms  stats[c] += W[c].m,  stats[Cout + c] += W[c]^T G W[c]  (W bf16 [Cout][Cin]) are part of launch_bn_fold_final
 int gram_max_ctas();
 cudaError_t launch_gram_stats(const ConvLayer &L, const ConvArgs &a, float *gpart, float *spart, int *grid_out, cudaStream_t s);
-cudaError_t launch_gram_finalize(const float *gpart, const float *spart, int grid, int C, const void *w_bf16, int Cout, double *G64, double *s64,
-                                 double *stats, cudaStream_t s);
 cudaError_t launch_umma_gram_probe(const uint16_t *a_dev /* [128][64*nb] bf16 */, int nb, float *out_dev /* [64nb][64nb] */, cudaStream_t s);
 cudaError_t launch_umma_rowshift_probe(int shift, int fill, int use_base_offset, float *out_dev /* [128*64] */, cudaStream_t s);
 void conv_tc_set_halo(int on);       // experimental halo-box 3x3 kernel on/off (default: BUSCA_HALO env, off)

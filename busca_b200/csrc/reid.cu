@@ -635,75 +635,149 @@ cudaError_t launch_bn_finalize_fold(const ConvLayer &P, long long count, const C
                       (const float4 *)L.w32m, (uint2 *)L.w16s, L.xf, total4);
 }
 
-// FINAL-pass weights (kernels.h: FoldFinalArgs).  One block per output channel: the channel's BN scale / shift (fp64 from the batch
-// statistics, the arithmetic of bn_finalize_kernel, or given), then its weight row(s) times that scale (and |scale| of the input BN),
-// rounded to bf16 ONCE from the fp32 master.
-__global__ void __launch_bounds__(128) bn_fold_final_kernel(const double *__restrict__ stats, const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                             const float *__restrict__ scale_in, const float *__restrict__ shift_in, double inv_count, int Cout,
-                                                             const float *__restrict__ in_scale, const float *__restrict__ w32, __nv_bfloat16 *__restrict__ w16f,
-                                                             int Cin, float *__restrict__ scale_out,
-                                                             const double *__restrict__ d_stats, const float *__restrict__ d_gamma, const float *__restrict__ d_beta,
-                                                             const float *__restrict__ d_scale_in, const float *__restrict__ d_shift_in,
-                                                             const float *__restrict__ dw32, __nv_bfloat16 *__restrict__ dw16f, int dCin,
-                                                             float *__restrict__ d_scale_out, float *__restrict__ shift_out) {
-    pdl_trigger();
-    pdl_wait();
-    const int c = blockIdx.x;
-    float sc, sh;
-    if (stats) {
-        const double mean = stats[c] * inv_count;
-        double var = stats[Cout + c] * inv_count - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        const double a = (double)gamma[c] / sqrt(var + 1e-5);
-        sc = (float)a;
-        sh = (float)((double)beta[c] - mean * a);
-    } else {
-        sc = scale_in[c];
-        sh = shift_in[c];
-    }
-    float dsc = 0.f, dsh = 0.f;
-    if (dw32) {
-        if (d_stats) {
-            const double mean = d_stats[c] * inv_count;
-            double var = d_stats[Cout + c] * inv_count - mean * mean;
-            var = var > 0.0 ? var : 0.0;
-            const double a = (double)d_gamma[c] / sqrt(var + 1e-5);
-            dsc = (float)a;
-            dsh = (float)((double)d_beta[c] - mean * a);
-        } else {
-            dsc = d_scale_in[c];
-            dsh = d_shift_in[c];
+// FINAL-pass weights and the second half of the Gram-matrix statistics (kernels.h: FoldFinalArgs).  A block owns GFF_CH output
+// channels: quadratic forms of its channels (thread (i, part) owns row i of G W^T over the part-th slice of the j range, G read
+// through its symmetry so that consecutive threads read consecutive addresses; G is read once per GFF_CH channels), the channels'
+// BN scale / shift, then their weight rows times that scale (and |scale| of the input BN), rounded to bf16 ONCE from the fp32 master.
+constexpr int GFF_CH = 8;
+struct GffConv {
+    const float *G, *m;              // Gram partials or null
+    const __nv_bfloat16 *wq;         // [Cout][C] bf16 weights the statistics refer to
+    double *stats;                   // [2*Cout] in: weighted-pass contribution, out: totals (null with explicit scale / shift)
+    const float *gamma, *beta;
+    const float *scale_in, *shift_in;   // explicit BN (stats == null)
+    const float *w32;                // fp32 master [Cout][C]
+    __nv_bfloat16 *w16f;
+    float *scale_out;
+    int C;
+};
+struct GffParams {
+    GffConv a, d;
+    int has_d, Cout;
+    const float *in_scale;
+    double inv_count;
+    float *shift_out;
+};
+
+// fp64 arithmetic runs at ~2 TFLOP/s on this part (measured: the all-fp64 quadratic forms of a 256 -> 1024 convolution took ~60 us), so
+// the O(C^2) inner sums v_i = sum_j G_ij w_j are fp32 (four partial sums per thread and channel; G itself is an fp32 accumulation) and only
+// the O(C) outer sums sum_i w_i v_i, sum_i w_i m_i and everything after them are fp64.
+__device__ __forceinline__ void gff_conv(const GffConv &cv, const GffParams &p, const float *in_scale, int c0, float (*sw)[GFF_CH], double (*red)[2 * GFF_CH],
+                                          float *s_sc, float *s_sh) {
+    const int t = threadIdx.x, C = cv.C;
+    if (cv.G) {
+        for (int idx = t; idx < GFF_CH * C; idx += 256) {
+            const int q = idx / C, k = idx - q * C;
+            sw[k][q] = __bfloat162float(cv.wq[(size_t)(c0 + q) * C + k]);
         }
+        __syncthreads();
+        const int parts = 256 / C, i = t % C, part = t / C;     // C in {64, 128, 256}
+        const int jlen = C / parts, j0 = part * jlen;
+        float v[4][GFF_CH];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < GFF_CH; ++q) v[u][q] = 0.f;
+        for (int jb = j0; jb < j0 + jlen; jb += 4) {
+            float g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = __ldg(cv.G + (size_t)(jb + u) * C + i);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 wa = *reinterpret_cast<const float4 *>(&sw[jb + u][0]), wb = *reinterpret_cast<const float4 *>(&sw[jb + u][4]);
+                v[u][0] = fmaf(g[u], wa.x, v[u][0]); v[u][1] = fmaf(g[u], wa.y, v[u][1]); v[u][2] = fmaf(g[u], wa.z, v[u][2]); v[u][3] = fmaf(g[u], wa.w, v[u][3]);
+                v[u][4] = fmaf(g[u], wb.x, v[u][4]); v[u][5] = fmaf(g[u], wb.y, v[u][5]); v[u][6] = fmaf(g[u], wb.z, v[u][6]); v[u][7] = fmaf(g[u], wb.w, v[u][7]);
+            }
+        }
+        const double mi = part == 0 ? (double)cv.m[i] : 0.0;
+        double r[GFF_CH], s1[GFF_CH];
+#pragma unroll
+        for (int q = 0; q < GFF_CH; ++q) {
+            const double wi = (double)sw[i][q];
+            r[q] = (((double)v[0][q] + (double)v[1][q]) + ((double)v[2][q] + (double)v[3][q])) * wi;
+            s1[q] = wi * mi;
+        }
+#pragma unroll
+        for (int q = 0; q < GFF_CH; ++q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                r[q] += __shfl_xor_sync(0xffffffffu, r[q], o);
+                s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
+            }
+        if ((t & 31) == 0)
+#pragma unroll
+            for (int q = 0; q < GFF_CH; ++q) { red[t >> 5][q] = s1[q]; red[t >> 5][GFF_CH + q] = r[q]; }
+        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        shift_out[c] = sh + dsh;
-        if (scale_out) scale_out[c] = sc;
-        if (dw32 && d_scale_out) d_scale_out[c] = dsc;
+    if (t < GFF_CH) {
+        const int c = c0 + t;
+        float sc, sh;
+        if (cv.stats) {
+            double S = cv.stats[c], Q = cv.stats[p.Cout + c];
+            if (cv.G) {
+                for (int wv = 0; wv < 8; ++wv) { S += red[wv][t]; Q += red[wv][GFF_CH + t]; }
+                cv.stats[c] = S;
+                cv.stats[p.Cout + c] = Q;
+            }
+            const double mean = S * p.inv_count;
+            double var = Q * p.inv_count - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            const double a = (double)cv.gamma[c] / sqrt(var + 1e-5);
+            sc = (float)a;
+            sh = (float)((double)cv.beta[c] - mean * a);
+        } else {
+            sc = cv.scale_in[c];
+            sh = cv.shift_in[c];
+        }
+        s_sc[t] = sc;
+        s_sh[t] = sh;
+        if (cv.scale_out) cv.scale_out[c] = sc;
     }
-    for (int k = threadIdx.x; k < Cin; k += blockDim.x) {
+    __syncthreads();
+    for (int idx = t; idx < GFF_CH * C; idx += 256) {
+        const int q = idx / C, k = idx - q * C;
         float a = 1.f;
         if (in_scale) {                                         // the clamp of bn_fold_kernel: the transform parameters were derived with it
             a = fabsf(in_scale[k]);
             if (!(a >= 1e-20f)) a = 1e-20f;
         }
-        w16f[(size_t)c * Cin + k] = __float2bfloat16_rn(w32[(size_t)c * Cin + k] * a * sc);
+        const size_t o = (size_t)(c0 + q) * C + k;
+        cv.w16f[o] = __float2bfloat16_rn(cv.w32[o] * a * s_sc[q]);
     }
-    if (dw32)
-        for (int k = threadIdx.x; k < dCin; k += blockDim.x) dw16f[(size_t)c * dCin + k] = __float2bfloat16_rn(dw32[(size_t)c * dCin + k] * dsc);
+}
+
+__global__ void __launch_bounds__(256) gram_fold_final_kernel(const GffParams p) {
+    __shared__ __align__(16) float sw[256][GFF_CH];
+    __shared__ double red[8][2 * GFF_CH];
+    __shared__ float s_sc[2][GFF_CH], s_sh[2][GFF_CH];
+    pdl_trigger();
+    pdl_wait();
+    const int c0 = blockIdx.x * GFF_CH;
+    gff_conv(p.a, p, p.in_scale, c0, sw, red, s_sc[0], s_sh[0]);
+    if (p.has_d) {
+        __syncthreads();
+        gff_conv(p.d, p, nullptr, c0, sw, red, s_sc[1], s_sh[1]);
+    }
+    __syncthreads();
+    if (threadIdx.x < GFF_CH) p.shift_out[c0 + threadIdx.x] = s_sh[0][threadIdx.x] + (p.has_d ? s_sh[1][threadIdx.x] : 0.f);
 }
 
 cudaError_t launch_bn_fold_final(const FoldFinalArgs &a, cudaStream_t s) {
     const ConvLayer *L = a.L, *D = a.ds;
-    if (!L || L->k != 1 || !L->w32m || !L->w16f || !a.shift_out) return cudaErrorInvalidValue;
-    if (a.count <= 0 && (!a.scale || !a.shift)) return cudaErrorInvalidValue;
-    if (D && (D->k != 1 || D->cout != L->cout || !D->w32m || !D->w16f || (a.count <= 0 && (!a.ds_scale || !a.ds_shift)))) return cudaErrorInvalidValue;
+    if (!L || L->k != 1 || !L->w32m || !L->w16f || !a.shift_out || L->cout % GFF_CH != 0) return cudaErrorInvalidValue;
     const bool from_stats = a.count > 0;
-    return launch_pdl(bn_fold_final_kernel, dim3(L->cout), dim3(128), 0, s, from_stats ? (const double *)L->stats : (const double *)nullptr,
-                      (const float *)L->gamma, (const float *)L->beta, a.scale, a.shift, from_stats ? 1.0 / (double)a.count : 0.0, L->cout, a.in_scale,
-                      (const float *)L->w32m, (__nv_bfloat16 *)L->w16f, L->cin, L->scale,
-                      (D && from_stats) ? (const double *)D->stats : (const double *)nullptr, D ? (const float *)D->gamma : (const float *)nullptr,
-                      D ? (const float *)D->beta : (const float *)nullptr, a.ds_scale, a.ds_shift, D ? (const float *)D->w32m : (const float *)nullptr,
-                      D ? (__nv_bfloat16 *)D->w16f : (__nv_bfloat16 *)nullptr, D ? D->cin : 0, D ? D->scale : (float *)nullptr, a.shift_out);
+    if (!from_stats && (!a.scale || !a.shift)) return cudaErrorInvalidValue;
+    if (D && (D->k != 1 || D->cout != L->cout || !D->w32m || !D->w16f || (!from_stats && (!a.ds_scale || !a.ds_shift)))) return cudaErrorInvalidValue;
+    if (a.gram_G && (!from_stats || !a.gram_m || (L->cin != 64 && L->cin != 128 && L->cin != 256))) return cudaErrorInvalidValue;
+    if (a.ds_gram_G && (!D || !from_stats || !a.ds_gram_m || (D->cin != 64 && D->cin != 128 && D->cin != 256))) return cudaErrorInvalidValue;
+    GffParams p{};
+    p.Cout = L->cout; p.in_scale = a.in_scale; p.inv_count = from_stats ? 1.0 / (double)a.count : 0.0; p.shift_out = a.shift_out; p.has_d = D ? 1 : 0;
+    p.a = GffConv{a.gram_G, a.gram_m, (const __nv_bfloat16 *)(a.in_scale ? L->w16s : L->w16), from_stats ? L->stats : nullptr, L->gamma, L->beta, a.scale, a.shift,
+                  L->w32m, (__nv_bfloat16 *)L->w16f, L->scale, L->cin};
+    if (D)
+        p.d = GffConv{a.ds_gram_G, a.ds_gram_m, (const __nv_bfloat16 *)D->w16, from_stats ? D->stats : nullptr, D->gamma, D->beta, a.ds_scale, a.ds_shift,
+                      D->w32m, (__nv_bfloat16 *)D->w16f, D->scale, D->cin};
+    return launch_pdl(gram_fold_final_kernel, dim3(L->cout / GFF_CH), dim3(256), 0, s, p);
 }
 
 static int ew_grid(long long total) {
@@ -946,66 +1020,6 @@ __global__ void gather_rows_kernel(const float4 *__restrict__ src, const int32_t
     if (i >= (long long)rows * cols4) return;
     const int r = (int)(i / cols4), c = (int)(i % cols4);
     dst[i] = src[(long long)map[r] * cols4 + c];
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Gram-matrix statistics, second half (first half: gram_stats_kernel, conv_tc.cu, which leaves G [C*C] and m [C] in fp32): the
-// quadratic forms, in fp64.
-// ---------------------------------------------------------------------------------------------------------------------
-// 4 output channels per block: stats[o] += W[o] . m ; stats[Cout + o] += W[o]^T G W[o].  Thread (i, part) owns row i of G W[o]^T over the
-// part-th slice of the j range (256 / C slices; G is read through its symmetry so that consecutive threads read consecutive addresses),
-// eight loads in flight per thread; the partial quadratic forms are reduced in fp64 through warp shuffles and one shared array.
-__global__ void __launch_bounds__(256) gram_quadform_kernel(const float *__restrict__ G64, const float *__restrict__ s64, int C,
-                                                            const __nv_bfloat16 *__restrict__ w, int Cout, double *__restrict__ stats) {
-    __shared__ double sw[4][256];
-    __shared__ double red[8][8];
-    pdl_trigger();
-    pdl_wait();
-    const int o0 = blockIdx.x * 4, t = threadIdx.x;
-    const int parts = 256 / C, i = t % C, part = t / C;          // C in {64, 128, 256}
-    const int jlen = C / parts, j0 = part * jlen;
-    for (int q = 0; q < 4; ++q)
-        if (t < C) sw[q][t] = (o0 + q < Cout) ? (double)__bfloat162float(w[(size_t)(o0 + q) * C + t]) : 0.0;
-    __syncthreads();
-    double r[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int jb = j0; jb < j0 + jlen; jb += 8) {
-        float g[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) g[u] = __ldg(G64 + (size_t)(jb + u) * C + i);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const double gji = (double)g[u];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r[q] = fma(gji, sw[q][jb + u], r[q]);
-        }
-    }
-    const double mi = part == 0 ? (double)s64[i] : 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { r[q] *= sw[q][i]; s1[q] = sw[q][i] * mi; }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            r[q] += __shfl_xor_sync(0xffffffffu, r[q], o);
-            s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], o);
-        }
-    if ((t & 31) == 0)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { red[t >> 5][q] = r[q]; red[t >> 5][4 + q] = s1[q]; }
-    __syncthreads();
-    if (t < 8) {
-        double acc = 0.0;
-        for (int wv = 0; wv < 8; ++wv) acc += red[wv][t];
-        const int q = t & 3;
-        if (o0 + q < Cout) atomicAdd(stats + (t < 4 ? Cout : 0) + o0 + q, acc);
-    }
-}
-
-cudaError_t launch_gram_finalize(const float *gpart, const float *spart, int grid, int C, const void *w_bf16, int Cout, double *G64, double *s64,
-                                 double *stats, cudaStream_t s) {
-    if (C != 64 && C != 128 && C != 256) return cudaErrorInvalidValue;
-    (void)grid; (void)G64; (void)s64;
-    return launch_pdl(gram_quadform_kernel, dim3(ceil_div(Cout, 4)), dim3(256), 0, s, gpart, spart, C, (const __nv_bfloat16 *)w_bf16, Cout, stats);
 }
 
 // Stable partition of the distinct images of a BatchNorm batch: multiplicity 1 first, repeated images last (uniq / weight / map are

@@ -8,7 +8,9 @@
 
 Tolerances (stated once, used everywhere below):
   fp32: probabilities / embeddings within 1e-3 (north_star), decisions identical outside 2e-3 near-ties.
-  bf16: embedding cosine >= 0.999 and rel-L2 <= 2.5e-2; probabilities: max |dp| <= 3e-2 and 95 % of them within 1e-2; decisions
+  bf16: embedding cosine >= 0.999 and rel-L2 <= 2.5e-2; probabilities: max |dp| <= 3e-2, 95 % of them within 1.5e-2 and half of them
+        within 4e-3 (measured on a B200, 200 tracks / 1400 probabilities: max 2.0-2.5e-2, 95th percentile 0.9-1.05e-2 from run to run -
+        the fp32 reductions are atomics - median 1.6e-3); decisions
         identical outside 3e-2 near-ties of the threshold (arg-max: outside 6e-2 top-1/top-2 margins, two probabilities being involved).  (CPU emulation of the bf16 roundings, tests/analysis_weights.py, 24 tracks: cosine
         0.9998, rel-L2 <= 2.0e-2, max |dp| 1.3e-2, median 1.6e-3; measured on a B200 at 200 tracks / 1400 probabilities: max 2.03e-2.)"""
 import os
@@ -21,7 +23,7 @@ pytestmark = pytest.mark.gpu
 from busca_b200 import synth
 from busca_b200.scene import Scene
 
-TOL = {"fp32": dict(prob=1e-3, p95=1e-3, tie=2e-3, rows=1e-3), "bf16": dict(prob=3e-2, p95=1e-2, tie=3e-2, rows=6e-2)}
+TOL = {"fp32": dict(prob=1e-3, p95=1e-3, p50=1e-3, tie=2e-3, rows=1e-3), "bf16": dict(prob=3e-2, p95=1.5e-2, p50=4e-3, tie=3e-2, rows=6e-2)}
 BF16_COS, BF16_L2 = 0.999, 2.5e-2
 THRESH = 0.3                      # busca_thresh of config_bytetrack_mot20.yml
 
@@ -57,6 +59,7 @@ def check_decisions(probs, reliable, ref_probs, ref_reliable, kslot, tol, min_cl
     dp = np.abs(probs - ref_probs)
     assert dp.max() < tol["prob"], dp.max()
     assert np.percentile(dp, 95) < tol["p95"], np.percentile(dp, 95)
+    assert np.percentile(dp, 50) < tol["p50"], np.percentile(dp, 50)
     clear = np.abs(ref_probs[:, kslot] - THRESH) > tol["tie"]
     keep, ref_keep = reliable & (probs[:, kslot] > THRESH), ref_reliable & (ref_probs[:, kslot] > THRESH)
     assert clear.mean() > min_clear, clear.mean()
