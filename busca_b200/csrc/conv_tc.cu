@@ -1732,41 +1732,40 @@ cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const Linea
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Stem on tensor cores.  The 7x7 stride-2 convolution over 3 channels becomes a GEMM with K = 4 row-PAIRS x 64:
-// a pre-pass writes the normalised patch as bf16 with, per pixel, the 4 channels (B,G,R,0) of input row y followed by the 4
-// channels of row y+1 (16 bytes), 3+5 zero pixels of horizontal padding per row and 3+4 zero rows of vertical padding; then,
-// for the tap rows (2p, 2p+1), the 7x8 (+8 zero) window of output pixel ox is 64 CONTIGUOUS elements (128 bytes) starting
-// 32 bytes after the window of ox-1.  An overlapping-stride tensor map {64 el, 64 ox (stride 32 B), row pairs (stride 2 rows), N}
-// therefore delivers the im2col tile directly, as ordinary 128-byte-swizzled rows.  (Round 1 used one tap row = 64 bytes per
-// request and was bound by the TMA request rate: 896 requests per 128-pixel tile; row pairs make it 512.)
+// a pre-pass writes the normalised patch as bf16 "entries": entry e of an image holds, per pixel, the 4 channels (B,G,R,0) of input
+// row 2e-3 followed by the 4 channels of row 2e-2 (16 bytes), with 3+5 zero pixels of horizontal padding per row (rows outside the
+// image are zero).  For output row oy and row pair p (filter rows 2p, 2p+1) the 7x8 (+8 zero) window of output pixel ox is then 64
+// CONTIGUOUS elements (128 bytes) of entry oy + p, starting 32 bytes after the window of ox-1: an overlapping-stride tensor map
+// {64 el, 64 ox (stride 32 B), 196 entries, N} delivers the im2col tile directly, as ordinary 128-byte-swizzled rows.
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
 constexpr int STEM_PITCH_PX = 136;                       // 3 zero px + 128 px + 5 zero px
-constexpr int STEM_ROWS = PATCH_H + 7;                   // 3 zero rows + 384 rows + 4 zero rows: entry yy holds rows (yy-3, yy-2)
+constexpr int STEM_ENTRIES = PATCH_H / 2 + 4;            // 196: entry e = rows (2e-3, 2e-2), e = 0 .. 195 covers rows -3 .. 388
+constexpr int STEM_EPB = 4;                              // entries per block of the pre-pass
 __global__ void __launch_bounds__(256) stem_prepass_kernel(const uint8_t *__restrict__ bank, const int32_t *__restrict__ slots,
-                                                           const float *__restrict__ lut, uint4 *__restrict__ out, long long total_px) {
+                                                           const float *__restrict__ lut, uint4 *__restrict__ out) {
     __shared__ float slut[768];
     pdl_trigger();
     pdl_wait();
     for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_px; i += (long long)gridDim.x * blockDim.x) {
-        const int px = (int)(i % STEM_PITCH_PX);
-        const long long t = i / STEM_PITCH_PX;
-        const int yy = (int)(t % STEM_ROWS);
-        const int n = (int)(t / STEM_ROWS);
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        const int x = px - 3;
+    const int n = blockIdx.y, e0 = blockIdx.x * STEM_EPB;
+    const int slot = slots[n];
+    const uint8_t *img = bank + (size_t)(slot < 0 ? 0 : slot) * PATCH_BYTES;
+    uint4 *dst = out + ((size_t)n * STEM_ENTRIES + e0) * STEM_PITCH_PX;
+    for (int i = threadIdx.x; i < STEM_EPB * STEM_PITCH_PX; i += 256) {
+        const int el = i / STEM_PITCH_PX, px = i - el * STEM_PITCH_PX;
+        const int x = px - 3, y0 = 2 * (e0 + el) - 3;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (x >= 0 && x < PATCH_W) {
-            const int slot = slots[n];
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const int y = yy - 3 + r;
+                const int y = y0 + r;
                 if (y >= 0 && y < PATCH_H) {
                     int b = 0, g = 0, rr = 0;
                     if (slot >= 0) {
-                        const uint8_t *p = bank + (size_t)slot * PATCH_BYTES + ((size_t)y * PATCH_W + x) * 3;
-                        b = p[0]; g = p[1]; rr = p[2];
+                        const uint8_t *q = img + ((size_t)y * PATCH_W + x) * 3;
+                        b = q[0]; g = q[1]; rr = q[2];
                     }
                     __nv_bfloat162 lo = __floats2bfloat162_rn(slut[b * 3 + 0], slut[g * 3 + 1]);
                     __nv_bfloat162 hi = __floats2bfloat162_rn(slut[rr * 3 + 2], 0.f);
@@ -1774,23 +1773,26 @@ __global__ void __launch_bounds__(256) stem_prepass_kernel(const uint8_t *__rest
                     w[2 * r + 1] = *reinterpret_cast<uint32_t *>(&hi);
                 }
             }
-            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        out[i] = v;
+        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Stem GEMM, row-marching formulation (default; BUSCA_STEM=tap selects the tap-by-tap path through conv_tc_kernel).
-// Measured (profiles/r02u): the tap-by-tap stem is bound by the TMA REQUEST rate - every 128-pixel tile pulls four im2col boxes whose
+// Stem GEMM, row-marching formulation.
+// Measured (profiles/r02u): a tap-by-tap stem (one im2col box per row pair and tile through conv_tc_kernel) is bound by the TMA REQUEST rate - every 128-pixel tile pulls four im2col boxes whose
 // 128-byte rows start 32 bytes apart (each row its own, line-straddling L2 request: ~1000 requests per tile, ~3 cycles each) - and
 // three of a tile's four boxes are fetched again by the tile of the next output row.  Here a CTA marches DOWN a column strip instead:
 //   * M tile = ONE output row of an image PAIR (2 x 64 pixels), so the box of padded-row entry 2j (128 rows x 128 B) is the A operand
 //     of output row j - p for each of the four row pairs p = 0..3: it is loaded ONCE and multiplied by the four weight slices
 //     (resident in shared memory) into the four accumulators that are open at that moment.  A quarter of the requests and bytes.
-//   * accumulators: a ring of eight 64-column TMEM tiles; the tile of output row oy opens at step j = oy (p = 0, accumulate off)
-//     and is complete after step oy + 3.
+//   * accumulators: a ring of eight 64-column TMEM tiles; the tile of output row oy opens at step j = oy and is complete after step
+//     oy + 3.  The (up to) four tiles open at a step are ADJACENT in TMEM and the weight slices are stored in the order p = 3, 2, 1, 0,
+//     so ONE tcgen05.mma with N = 256 updates all four (two instructions where the ring wraps).  Measured (profiles/r02x): an M = 128
+//     MMA costs about 64 + N/2 cycles per K = 16 step - operand fetch, the A tile is re-read by every instruction - i.e. 96 cycles at
+//     N = 64 but 192 at N = 256: half the tensor-pipe time of four N = 64 instructions.  Since every instruction accumulates, a tile
+//     must be ZERO when it opens: the epilogue warps clear a tile (tcgen05.st) right after reading it, and all of TMEM at the start.
 //   * two epilogue teams of eight warps take alternate output rows (TMEM -> bf16 -> swizzled staging -> TMA store, statistics from
 //     the staging tile as in conv_tc_kernel's RAW mode), so a row's epilogue has two row-times to finish.
 // Work units: (image pair, segment of 48 output rows); a segment re-reads 3 entries of its predecessor (6 %).
@@ -1840,12 +1842,22 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_march_kernel(const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 2) {
+        // clear all 512 columns: warp % 4 = lane quarter, the four warps of a quarter take 128 columns each
+        const int part = (warp - 2) >> 2;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st32_zero(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(part * 128 + c * 32));
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     if (warp == 0) {
         // ===================================================== TMA producer: the weight slices once, then one entry box per step
         if (elect_one()) {
             mbar_expect_tx(wfull, SM_W_BYTES);
-            for (int pr = 0; pr < 4; ++pr) tma_load_2d(w_tiles + pr * 8192, &mapB, wfull, pr * 64, 0);
+            for (int pr = 0; pr < 4; ++pr) tma_load_2d(w_tiles + (3 - pr) * 8192, &mapB, wfull, pr * 64, 0);      // stored in the order p = 3, 2, 1, 0
         }
         __syncwarp();
         int stage = 0;
@@ -1864,7 +1876,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_march_kernel(const __grid_
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);      // N is filled in per instruction
         const uint32_t w_addr = smem_u32(w_tiles);
         int stage = 0;
         uint32_t phase = 0;
@@ -1873,26 +1885,29 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_march_kernel(const __grid_
         for (int u = blockIdx.x; u < p.total_units; u += gridDim.x, t_base += p.seg_rows) {
             const int oy0 = (u % p.segs) * p.seg_rows;
             for (int j = oy0; j < oy0 + p.seg_rows + 3; ++j) {
-                if (j < oy0 + p.seg_rows) {              // the tile of output row j opens at this step: its TMEM slot must have been drained
-                    const int t = t_base + j - oy0;
-                    mbar_wait<32>(&tempty[t & (SM_SLOTS - 1)], ((uint32_t)(t >> 3) & 1) ^ 1);
-                }
+                const int T = t_base + j - oy0;          // tile index of output row j (virtual past the end of the segment)
+                if (j < oy0 + p.seg_rows)                // the tile of output row j opens at this step: its TMEM slot must have been drained (and cleared)
+                    mbar_wait<32>(&tempty[T & (SM_SLOTS - 1)], ((uint32_t)(T >> 3) & 1) ^ 1);
                 mbar_wait<0>(&a_full[stage], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t da = umma_desc<128>(smem_u32(a_tiles + stage * SM_A_BYTES));
+                // row pairs p_lo .. p_hi have their output row inside the segment: tiles T - p_hi .. T - p_lo, adjacent TMEM slots (mod 8)
+                const int p_lo = max(0, j - (oy0 + p.seg_rows - 1)), p_hi = min(3, j - oy0);
+                const int n = p_hi - p_lo + 1, slot_lo = (T - p_hi) & (SM_SLOTS - 1);
+                const int n1 = min(n, SM_SLOTS - slot_lo);                     // tiles before the ring wraps
                 if (elect_one()) {
+                    const uint64_t db1 = umma_desc<128>(w_addr + (uint32_t)(3 - p_hi) * 8192u);
+                    const uint32_t id1 = idesc0 | ((uint32_t)(n1 * 64 >> 3) << 17);
 #pragma unroll
-                    for (int pr = 0; pr < 4; ++pr) {
-                        const int oy = j - pr;
-                        if (oy >= oy0 && oy < oy0 + p.seg_rows) {
-                            const uint32_t d_tmem = tmem_base + (uint32_t)((t_base + oy - oy0) & (SM_SLOTS - 1)) * 64u;
-                            const uint64_t db = umma_desc<128>(w_addr + pr * 8192);
+                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + (uint32_t)slot_lo * 64u, da + 2 * k, db1 + 2 * k, id1, 1u);
+                    if (n1 < n) {
+                        const uint64_t db2 = umma_desc<128>(w_addr + (uint32_t)(3 - p_hi + n1) * 8192u);
+                        const uint32_t id2 = idesc0 | ((uint32_t)((n - n1) * 64 >> 3) << 17);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(pr == 0 && k == 0));
-                        }
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, da + 2 * k, db2 + 2 * k, id2, 1u);
                     }
                     umma_commit(&a_empty[stage]);
-                    if (j - 3 >= oy0) umma_commit(&tfull[(t_base + j - 3 - oy0) & (SM_SLOTS - 1)]);    // output row j - 3 is complete
+                    if (j - 3 >= oy0) umma_commit(&tfull[(T - 3) & (SM_SLOTS - 1)]);    // output row j - 3 is complete
                 }
                 __syncwarp();
                 if (++stage == SM_STAGES) { stage = 0; phase ^= 1; }
@@ -1923,6 +1938,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_march_kernel(const __grid_
                 uint32_t rr[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 64u + half * 32, rr);
                 TMEM_LD_WAIT();
+                tmem_st32_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 64u + half * 32);     // every MMA accumulates: leave the tile cleared
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[slot]);                  // the accumulator is in registers: the slot may be reopened
@@ -1975,24 +1992,21 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_march_kernel(const __grid_
 }
 }  // namespace
 
-size_t stem_tc_scratch_bytes(int N) { return (size_t)N * STEM_ROWS * STEM_PITCH_PX * 16; }
+size_t stem_tc_scratch_bytes(int N) { return (size_t)N * STEM_ENTRIES * STEM_PITCH_PX * 16; }
 
 // wstem: bf16 [64][4 row pairs][64], element (p, kx*8 + r*4 + c_bgr) = W[o][c][2p+r][kx]; scratch: stem_tc_scratch_bytes(N); out: bf16 [N,192,64,64]
 cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem, void *scratch, void *out,
                            double *stats, const float *img_w, cudaStream_t s) {
     if (N <= 0) return cudaSuccess;
-    const long long total_px = (long long)N * STEM_ROWS * STEM_PITCH_PX;
-    long long blocks = (total_px + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    cudaError_t e = launch_pdl(stem_prepass_kernel, dim3((int)blocks), dim3(256), 0, s, bank, slots, lut, (uint4 *)scratch, total_px);
+    static_assert(STEM_ENTRIES % STEM_EPB == 0, "pre-pass blocks");
+    cudaError_t e = launch_pdl(stem_prepass_kernel, dim3(STEM_ENTRIES / STEM_EPB, N), dim3(256), 0, s, bank, slots, lut, (uint4 *)scratch);
     if (e != cudaSuccess) return e;
-    static const bool march = !(getenv("BUSCA_STEM") && getenv("BUSCA_STEM")[0] == 't');      // BUSCA_STEM=tap: the tap-by-tap path below
-    if (march) {
+    {
         const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(scratch);
         const long long pitch = (long long)STEM_PITCH_PX * 8;
         CUtensorMap ma, mb, mo;
-        // dims {64 window elements, 64 ox (stride 16 el = 32 B), 196 even entries (stride 2 entries), N}; box = one entry of an image pair
-        bool ok = make_map4(&ma, in, 64, 64, 196, N, 16, 2 * pitch, (long long)STEM_ROWS * pitch, 64, 1, 2);
+        // dims {64 window elements, 64 ox (stride 16 el = 32 B), 196 entries, N}; box = one entry of an image pair
+        bool ok = make_map4(&ma, in, 64, 64, STEM_ENTRIES, N, 16, pitch, (long long)STEM_ENTRIES * pitch, 64, 1, 2);
         ok = ok && make_map2(&mb, wstem, 4 * 64, 64, 64);
         ok = ok && make_map4(&mo, out, 64, 64, 192, N, 64, 64 * 64, 192LL * 64 * 64, 64, 1, 2);
         if (!ok) return cudaErrorInvalidValue;
@@ -2015,25 +2029,4 @@ cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, con
         snprintf(g_last_kernel, sizeof(g_last_kernel), "stem_march_kernel");
         return e;
     }
-    TcParams p{};
-    p.BW = 64; p.BH = 2; p.BI = 1;
-    p.tiles_n = 1; p.h_tiles = 192 / 2; p.tiles_m = N * p.h_tiles;
-    p.cin_blocks = 1; p.ntaps = 4; p.k_iters = p.k1_iters = 4;
-    for (int pr = 0; pr < 4; ++pr) { p.tap_map[pr] = 0; p.tap_dh[pr] = pr; p.tap_dw[pr] = 0; }    // row pair p of output row oy starts at entry 2 (oy + p)
-    p.Ho = 192; p.Wo = 64; p.Nimg = N; p.Cout = 64; p.Hv = 192; p.Wv = 64;
-    p.mode = MODE_RAW;
-    p.out = out; p.stats = stats; p.alpha = 1.f;
-    p.img_w = img_w; p.img_shift = 7;                                 // BW*BH = 128 rows of one image
-    const __nv_bfloat16 *in = reinterpret_cast<const __nv_bfloat16 *>(scratch);
-    const long long pitch = (long long)STEM_PITCH_PX * 8;             // elements per padded row entry
-    TcMaps m;
-    // dims {64 window elements, 64 ox (stride 16 el = 32 B), 196 even entries (stride 2 entries), N}
-    bool ok = make_map4(&m.a[0], in, 64, 64, 196, N, 16, 2 * pitch, (long long)STEM_ROWS * pitch, 64, 2, 1);
-    m.a[1] = m.a[2] = m.a[3] = m.a[0];
-    ok = ok && make_map2(&m.b, wstem, 4 * 64, 64, 64);
-    ok = ok && make_map4(&m.out, out, 64, 64, 192, N, 64, 64 * 64, 192LL * 64 * 64, 64, 2, 1);
-    if (!ok) return cudaErrorInvalidValue;
-    m.b2 = m.b;
-    m.idt = m.out;
-    return launch_tc<64>(m, p, s);
 }

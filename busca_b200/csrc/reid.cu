@@ -671,31 +671,51 @@ __device__ __forceinline__ void gff_conv(const GffConv &cv, const GffParams &p, 
             sw[k][q] = __bfloat162float(cv.wq[(size_t)(c0 + q) * C + k]);
         }
         __syncthreads();
-        const int parts = 256 / C, i = t % C, part = t / C;     // C in {64, 128, 256}
+        // thread (ig, part): columns 4 ig .. 4 ig + 3 of G over the part-th slice of the j range (C in {64, 128, 256}: 4 / 8 / 16 slices of
+        // 64 / 16 / 4 rows); 128-bit loads, up to 16 in flight per thread - the loop is L2-latency bound (few blocks), not FMA bound
+        const int ngrp = C / 4, parts = 256 / ngrp, ig = t % ngrp, part = t / ngrp;
         const int jlen = C / parts, j0 = part * jlen;
-        float v[4][GFF_CH];
+        float v[GFF_CH][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int q = 0; q < GFF_CH; ++q)
 #pragma unroll
-            for (int q = 0; q < GFF_CH; ++q) v[u][q] = 0.f;
-        for (int jb = j0; jb < j0 + jlen; jb += 4) {
-            float g[4];
+            for (int e = 0; e < 4; ++e) v[q][e] = 0.f;
+        const float4 *G4 = reinterpret_cast<const float4 *>(cv.G) + ig;
+        auto step = [&](const float4 g, int j) {
+            const float4 wa = *reinterpret_cast<const float4 *>(&sw[j][0]), wb = *reinterpret_cast<const float4 *>(&sw[j][4]);
+            const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) g[u] = __ldg(cv.G + (size_t)(jb + u) * C + i);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 wa = *reinterpret_cast<const float4 *>(&sw[jb + u][0]), wb = *reinterpret_cast<const float4 *>(&sw[jb + u][4]);
-                v[u][0] = fmaf(g[u], wa.x, v[u][0]); v[u][1] = fmaf(g[u], wa.y, v[u][1]); v[u][2] = fmaf(g[u], wa.z, v[u][2]); v[u][3] = fmaf(g[u], wa.w, v[u][3]);
-                v[u][4] = fmaf(g[u], wb.x, v[u][4]); v[u][5] = fmaf(g[u], wb.y, v[u][5]); v[u][6] = fmaf(g[u], wb.z, v[u][6]); v[u][7] = fmaf(g[u], wb.w, v[u][7]);
+            for (int q = 0; q < GFF_CH; ++q) {
+                v[q][0] = fmaf(g.x, w8[q], v[q][0]); v[q][1] = fmaf(g.y, w8[q], v[q][1]);
+                v[q][2] = fmaf(g.z, w8[q], v[q][2]); v[q][3] = fmaf(g.w, w8[q], v[q][3]);
             }
+        };
+        if (jlen >= 16) {
+            for (int jb = j0; jb < j0 + jlen; jb += 16) {
+                float4 g[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) g[u] = __ldg(G4 + (size_t)(jb + u) * ngrp);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) step(g[u], jb + u);
+            }
+        } else {
+            float4 g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) g[u] = __ldg(G4 + (size_t)(j0 + u) * ngrp);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) step(g[u], j0 + u);
         }
-        const double mi = part == 0 ? (double)cv.m[i] : 0.0;
         double r[GFF_CH], s1[GFF_CH];
 #pragma unroll
         for (int q = 0; q < GFF_CH; ++q) {
-            const double wi = (double)sw[i][q];
-            r[q] = (((double)v[0][q] + (double)v[1][q]) + ((double)v[2][q] + (double)v[3][q])) * wi;
-            s1[q] = wi * mi;
+            r[q] = 0.0;
+            s1[q] = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const double wi = (double)sw[4 * ig + e][q];
+                r[q] = fma((double)v[q][e], wi, r[q]);
+                if (part == 0) s1[q] = fma(wi, (double)cv.m[4 * ig + e], s1[q]);
+            }
         }
 #pragma unroll
         for (int q = 0; q < GFF_CH; ++q)
