@@ -1036,12 +1036,34 @@ static int transformer_dev(busca_ctx *c, int T, int L, int C, const float *mem_e
     LAUNCH(c, "build_tokens", launch_build_tokens(me, ce, c->sep, c->non, c->bad, idx, pe, T, L, C, X, s));
     if (o.input_seq) CUDA_OK(cudaMemcpyAsync(o.input_seq, X, rows * d * 4, cudaMemcpyDeviceToDevice, s));
     const int act = c->cfg.activation == BUSCA_ACT_GELU ? 2 : 1;
+    if (tc) {
+        // tensor-core path: five launches per layer, every cast / residual / LayerNorm in a GEMM epilogue (linear_tc.cu).  X16 = bf16 copy of
+        // the token rows (A operand), ATT and the FFN hidden exist in bf16 only - the same rounding points as separate cast launches.
+        void *X16 = A16, *ATT16 = (void *)ATT, *H16 = (void *)Hd;
+        LAUNCH(c, "cast_bf16", launch_cast_bf16(X, X16, (long long)rows * d, s));
+        for (auto &ly : c->layers) {
+            LinearFusedArgs g{};
+            g.M = (int)rows;
+            g.epilogue = LE_F32; g.N = 3 * d; g.K = d; g.bias = ly.in_b; g.out_f32 = QKV;
+            LAUNCH(c, "linear_qkv", launch_linear_fused(X16, ly.in_w16, g, s));
+            LAUNCH(c, "attention", launch_attention(QKV, ATT16, 1, T, S, c->cfg.nhead, d / c->cfg.nhead, s));
+            g = LinearFusedArgs{};
+            g.M = (int)rows; g.epilogue = LE_LN; g.N = d; g.K = d; g.bias = ly.out_b; g.residual = X; g.gamma = ly.n1_g; g.beta = ly.n1_b; g.out_f32 = X; g.out_bf16 = X16;
+            LAUNCH(c, "linear_out_ln", launch_linear_fused(ATT16, ly.out_w16, g, s));
+            g = LinearFusedArgs{};
+            g.M = (int)rows; g.epilogue = LE_BF16; g.N = ff; g.K = d; g.bias = ly.l1_b; g.act = act; g.out_bf16 = H16;
+            LAUNCH(c, "linear_ffn1", launch_linear_fused(X16, ly.l1_w16, g, s));
+            g = LinearFusedArgs{};
+            g.M = (int)rows; g.epilogue = LE_LN; g.N = d; g.K = ff; g.bias = ly.l2_b; g.residual = X; g.gamma = ly.n2_g; g.beta = ly.n2_b; g.out_f32 = X; g.out_bf16 = X16;
+            LAUNCH(c, "linear_ffn2_ln", launch_linear_fused(H16, ly.l2_w16, g, s));
+        }
+    } else
     for (auto &ly : c->layers) {
         LinearArgs g{};
         g.alpha = 1.f; g.M = (int)rows;
         g.A = X; g.W = ly.in_w; g.bias = ly.in_b; g.residual = nullptr; g.out = QKV; g.N = 3 * d; g.K = d; g.act = 0;
         if ((rc = linear(g, ly.in_w16))) return rc;
-        LAUNCH(c, "attention", launch_attention(QKV, ATT, T, S, c->cfg.nhead, d / c->cfg.nhead, s));
+        LAUNCH(c, "attention", launch_attention(QKV, ATT, 0, T, S, c->cfg.nhead, d / c->cfg.nhead, s));
         g.A = ATT; g.W = ly.out_w; g.bias = ly.out_b; g.residual = X; g.out = Y; g.N = d; g.K = d;
         if ((rc = linear(g, ly.out_w16))) return rc;
         LAUNCH(c, "layernorm", launch_layernorm(Y, ly.n1_g, ly.n1_b, X, (int)rows, d, s));

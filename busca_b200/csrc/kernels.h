@@ -141,6 +141,20 @@ struct LinearArgs {
 cudaError_t launch_linear_f32(const LinearArgs &a, cudaStream_t s);
 cudaError_t launch_linear_tc(const void *A_bf16, const void *W_bf16, const LinearArgs &la, cudaStream_t s);
 cudaError_t launch_cast_bf16(const float *in, void *out_bf16, long long n, cudaStream_t s);
+// linear_tc.cu: Decision-Transformer linears on the tensor cores with fused epilogues (bf16 A and W, fp32 accumulate)
+enum { LE_F32 = 0,           // out_f32 = act((A W^T + bias) * alpha) + residual
+       LE_BF16 = 1,          // out_bf16 = the same, rounded to bf16
+       LE_LN = 2 };          // N == 512: y = A W^T + bias + residual; LayerNorm(y) * gamma + beta -> out_f32 and / or out_bf16 (may alias residual)
+struct LinearFusedArgs {
+    int epilogue = LE_F32;
+    int M = 0, N = 0, K = 0;
+    const float *bias = nullptr, *residual = nullptr, *gamma = nullptr, *beta = nullptr;
+    float alpha = 1.f;
+    int act = 0;
+    float *out_f32 = nullptr;
+    void *out_bf16 = nullptr;
+};
+cudaError_t launch_linear_fused(const void *A_bf16, const void *W_bf16, const LinearFusedArgs &a, cudaStream_t s);
 
 // ---------------------------------------------------------------- transformer.cu
 struct PeTables { const __half *xy, *size, *t; };
@@ -151,7 +165,8 @@ cudaError_t launch_pe_index(const double *mem_ltwh, const double *can_ltwh, int 
                             int32_t *idx /*[T,S,3]*/, cudaStream_t s);
 cudaError_t launch_build_tokens(const float *mem_enc, const float *can_enc, const float *sep, const float *non, const float *bad,
                                 const int32_t *idx, PeTables pe, int T, int L, int C, float *x, cudaStream_t s);
-cudaError_t launch_attention(const float *qkv, float *out, int T, int S, int nhead, int dh, cudaStream_t s);
+// out: fp32 [T*S, nhead*dh], or bf16 of the same shape when out_is_bf16 (the A operand of the tensor-core out_proj)
+cudaError_t launch_attention(const float *qkv, void *out, int out_is_bf16, int T, int S, int nhead, int dh, cudaStream_t s);
 cudaError_t launch_layernorm(const float *x, const float *gamma, const float *beta, float *out, int rows, int cols,
                              cudaStream_t s);
 cudaError_t launch_decoder(const float *x, int T, int S, int L, int C, const float *ln_g, const float *ln_b, const float *w,

@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(128) build_tokens_kernel(const float *__restri
 constexpr int ATT_WARPS = 4;
 constexpr int DH = 128;
 
-__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const float *__restrict__ qkv, float *__restrict__ out, int S,
+template <typename TOut>
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const float *__restrict__ qkv, TOut *__restrict__ out, int S,
                                                                   int nhead, float scale) {
     extern __shared__ float sm[];
     float *Ks = sm;                                // [S][DH+1]
@@ -209,9 +210,9 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const float *
 #pragma unroll
             for (int r = 0; r < 4; ++r) o[r] = fmaf(p, vr[lane + 32 * r], o[r]);
         }
-        float *dst = out + ((size_t)t * S + i) * Dm + h * DH;
+        TOut *dst = out + ((size_t)t * S + i) * Dm + h * DH;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) dst[lane + 32 * r] = o[r];
+        for (int r = 0; r < 4; ++r) ActIO<TOut>::st(dst + lane + 32 * r, o[r]);
         __syncwarp();
     }
 }
@@ -330,16 +331,18 @@ cudaError_t launch_build_tokens(const float *mem_enc, const float *can_enc, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_attention(const float *qkv, float *out, int T, int S, int nhead, int dh, cudaStream_t s) {
+cudaError_t launch_attention(const float *qkv, void *out, int out_is_bf16, int T, int S, int nhead, int dh, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
     if (dh != DH || S > 64) return cudaErrorInvalidValue;
     size_t smem = ((size_t)S * (DH + 1) + (size_t)S * DH + ATT_WARPS * DH) * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = out_is_bf16 ? cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                    : cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(nhead, T);
-    attention_kernel<<<grid, ATT_WARPS * 32, smem, s>>>(qkv, out, S, nhead, 1.f / sqrtf((float)dh));
+    if (out_is_bf16) attention_kernel<__nv_bfloat16><<<grid, ATT_WARPS * 32, smem, s>>>(qkv, (__nv_bfloat16 *)out, S, nhead, 1.f / sqrtf((float)dh));
+    else attention_kernel<float><<<grid, ATT_WARPS * 32, smem, s>>>(qkv, (float *)out, S, nhead, 1.f / sqrtf((float)dh));
     return cudaGetLastError();
 }
 
