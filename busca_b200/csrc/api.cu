@@ -103,6 +103,7 @@ struct busca_ctx {
     bool use_tc = false;                          // bf16 mode: tcgen05 convolutions (BUSCA_CONV=simt forces the SIMT bf16 path)
     // duplicate elimination inside a BatchNorm batch (tensor-core path; BUSCA_DEDUP=0 / busca_set_option("dedup", 0) disables)
     bool dedup = true;
+    bool tr_tc = true;                            // bf16 mode: Decision-Transformer GEMMs on the tensor cores (option "tr_tc" 0: the fp32 SIMT linears)
     int *dedup_table = nullptr;                   // [bank_slots + 1], all 0x7f7f7f7f between kernels
     DevBuf ws_dedup[2];                           // per planned batch: uniq | map | weight | count
     int *h_nuniq = nullptr;                       // pinned: distinct-image counts of the (up to two) planned batches
@@ -721,12 +722,15 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     const long long NT = rb.n_total;
     const float *img_w = rb.weight;
     const size_t big = (size_t)786432 * N * 2;
-    const size_t total = 3 * big + (size_t)393216 * N * 2 + (size_t)196608 * N * 2 + (size_t)N * 2048 * 4 + (size_t)N * 512 * 4 + 2048;
+    // two ping-pong block tensors (96x32x256 per patch) + the two bottleneck intermediates: 4.3 MB per patch, so the 30,000 distinct
+    // patches of BASELINE.json configs[4] (1000 tracks x 30 history frames) need 130 GB of the 180 GB part.  The stem's im2col entries
+    // live in X0 and its raw output in X1 (both dead before the first bottleneck writes them).
+    const size_t total = 2 * big + (size_t)393216 * N * 2 + (size_t)196608 * N * 2 + (size_t)N * 2048 * 4 + (size_t)N * 512 * 4 + 2048;
     cudaError_t e = c->ws_reid.ensure(total);
     if (e != cudaSuccess) return set_err(BUSCA_ERR_NOMEM, "ReID workspace for %d patches (%.1f GB): %s", N, total / 1e9, cudaGetErrorString(e));
     char *base = (char *)c->ws_reid.p;
-    void *X0 = base, *X1 = base + big, *RS = base + 2 * big;
-    void *R1 = base + 3 * big, *R2 = (char *)R1 + (size_t)393216 * N * 2;
+    void *X0 = base, *X1 = base + big;
+    void *R1 = base + 2 * big, *R2 = (char *)R1 + (size_t)393216 * N * 2;
     float *pooled = (float *)((char *)R2 + (size_t)196608 * N * 2);
     float *emb_u = rb.map ? pooled + (((size_t)N * 2048 + 63) & ~(size_t)63) : d_emb;      // embeddings of the distinct images
     cudaStream_t s = c->stream;
@@ -741,10 +745,10 @@ static int reid_forward_tc(busca_ctx *c, const ReidBatch &rb, float *d_emb) {
     ConvLayer &stem = c->convs[0];
     if (stem_tc_scratch_bytes(N) > big) return set_err(BUSCA_ERR_STATE, "stem scratch does not fit");
     if (c->profiling) { c->next_flops = 2.0 * N * 192 * 64 * 64.0 * 147; c->next_kernel = "conv_tc_kernel<64, 128, 0>"; }
-    LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, X1, RS, stem.stats, img_w, s));
+    LAUNCH(c, "stem_conv7x7", launch_stem_tc(c->bank, d_slots, N, c->lut, stem.w16, X0, X1, stem.stats, img_w, s));
     if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();
     LAUNCH(c, "bn_finalize", launch_bn_finalize(stem, NT * 192 * 64, s));
-    LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(RS, X0, N, 192, 64, 64, stem.scale, stem.shift, 1, s));
+    LAUNCH(c, "bn_relu_maxpool", launch_bn_relu_maxpool(X1, X0, N, 192, 64, 64, stem.scale, stem.shift, 1, s));
     void *x = X0, *other = X1;
     int H = 96, W = 32;
     size_t ci = 1;
@@ -1014,7 +1018,7 @@ static int transformer_dev(busca_ctx *c, int T, int L, int C, const float *mem_e
     cudaStream_t s = c->stream;
     const float alpha = (float)sqrt((double)d);                    // * np.sqrt(self.dim_model), network.py:203-204
     // bf16 mode: the GEMMs run on the tensor cores (A cast to bf16 per call, fp32 accumulate / bias / residual / output)
-    const bool tc = c->use_tc;
+    const bool tc = c->use_tc && c->tr_tc;
     void *A16 = b + o_a16;
     auto linear = [&](const LinearArgs &g, const void *w16) -> int {
         if (tc) {
@@ -1488,6 +1492,7 @@ extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return set_err(BUSCA_ERR_ARG, "null argument");
     if (strcmp(name, "dedup") == 0) { c->dedup = value != 0; return BUSCA_OK; }
     if (strcmp(name, "gram") == 0) { c->gram = value != 0; return BUSCA_OK; }
+    if (strcmp(name, "tr_tc") == 0) { c->tr_tc = value != 0; return BUSCA_OK; }
     if (strcmp(name, "pool_mono") == 0) { reid_set_pool_mono(value); return BUSCA_OK; } // process-wide (experimental max-pool kernel)
     if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
     if (strcmp(name, "pdl") == 0) { pdl_set(value != 0); return BUSCA_OK; }          // process-wide (programmatic dependent launch)
