@@ -6,9 +6,13 @@
 // 2x down-scale (oracle/crop.py is the CPU restatement).  No cut-out is materialised:
 // taps that fall outside the clipped window read the pad scalar.
 //
-// One CTA per crop.  Phase 1: window sum (for the pad value) with 128-bit loads where alignment allows.
-// Phase 2: coefficient tables in shared memory.  Phase 3: every thread produces 16 consecutive output bytes
-// per iteration and stores them with one 128-bit store (rows are 384 B = 24 x 16 B, patches are 16 B aligned).
+// CROP_PARTS CTAs per crop (96 output rows each; the window sum is recomputed by each - it hits L2).  Phase 1: window sum (for the pad value) with 128-bit loads where alignment allows.  Phase 2: coefficient tables
+// in shared memory and the partition of the 384 output rows into BANDS whose source rows fit a 16 KB staging buffer.  Phase 3, per
+// band: the source rows of the clipped window are STAGED in shared memory by the bulk-copy (TMA) engine - one cp.async.bulk per row
+// over the 16-byte-aligned span that covers it, completion on an mbarrier, two buffers so the copies of band b+1 run under the blend
+// of band b - and every thread blends 16 consecutive output bytes per iteration from shared memory (four byte taps each, no global
+// load in the loop) and stores them with one 128-bit store (rows are 384 B = 24 x 16 B, patches are 16 B aligned).  Windows wider than
+// the staging buffer allows (> 2700 pixels) take the direct path (taps read through the read-only cache).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,6 +20,14 @@ namespace {
 
 constexpr int CROP_THREADS = 256;
 constexpr float COEF_SCALE = 2048.f;
+constexpr int CROP_STAGE_BYTES = 16384;          // per staging buffer (two of them)
+constexpr int CROP_PARTS = 4;                    // CTAs per crop (blockIdx.y): 96 output rows each - a frame's few hundred crops fill the machine
+constexpr int CROP_ROWS = PATCH_H / CROP_PARTS;
+
+__device__ __forceinline__ uint32_t smem_u32_(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32_(bar)), "r"(count) : "memory");
+}
 
 struct CropWin {
     int X1, Y1, sw, sh;          // integer cut-out origin and size (may extend outside the frame)
@@ -38,9 +50,15 @@ __device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int
     __shared__ short xa0[PATCH_W], xa1[PATCH_W];
     __shared__ int yr0[PATCH_H], yr1[PATCH_H];
     __shared__ short yb0[PATCH_H], yb1[PATCH_H];
+    __shared__ __align__(128) uint8_t stage[2][CROP_STAGE_BYTES];
+    __shared__ uint64_t sbar[2];
+    __shared__ short bstart[PATCH_H + 1];
+    __shared__ int4 xt[PATCH_W];
+    __shared__ int nbands;
 
     if (slot < 0) return;
     const int tid = threadIdx.x;
+    const int dy_lo = blockIdx.y * CROP_ROWS, dy_hi = dy_lo + CROP_ROWS;      // this CTA's output rows
     uint8_t *out = bank + (size_t)slot * PATCH_BYTES;
 
     if (tid == 0) {
@@ -60,7 +78,7 @@ __device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int
 
     if (win.empty) {                                  // np.mean of an empty crop is NaN -> pad casts to 0
         uint4 z = make_uint4(0, 0, 0, 0);
-        for (int q = tid; q < PATCH_BYTES / 16; q += CROP_THREADS) reinterpret_cast<uint4 *>(out)[q] = z;
+        for (int q = dy_lo * (PATCH_W * 3 / 16) + tid; q < dy_hi * (PATCH_W * 3 / 16); q += CROP_THREADS) reinterpret_cast<uint4 *>(out)[q] = z;
         return;
     }
 
@@ -102,8 +120,12 @@ __device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int
         xs1[tid] = min(sx + 1, sw - 1);
         xa0[tid] = (short)__float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), COEF_SCALE));
         xa1[tid] = (short)__float2int_rn(__fmul_rn(fx, COEF_SCALE));
+        // the same, packed for the staged path: byte offsets of the two taps inside a window row (-1 = outside the clipped window)
+        const int f0 = xs0[tid] + win.X1, f1 = xs1[tid] + win.X1;
+        const int o0 = (f0 < win.X1c || f0 >= win.X2c) ? -1 : (f0 - win.X1c) * 3, o1 = (f1 < win.X1c || f1 >= win.X2c) ? -1 : (f1 - win.X1c) * 3;
+        xt[tid] = make_int4(o0, o1, (int)(((uint32_t)(uint16_t)xa0[tid]) | ((uint32_t)(uint16_t)xa1[tid] << 16)), 0);
     }
-    for (int dy = tid; dy < PATCH_H; dy += CROP_THREADS) {
+    for (int dy = dy_lo + tid; dy < dy_hi; dy += CROP_THREADS) {
         const int sh = win.sh;
         const double scale = 1.0 / ((double)PATCH_H / (double)sh);
         float fy = (float)__dsub_rn(__dmul_rn((double)dy + 0.5, scale), 0.5);
@@ -124,15 +146,143 @@ __device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int
     __syncthreads();
 
     const int X1 = win.X1, Y1 = win.Y1, X1c = win.X1c, X2c = win.X2c, Y1c = win.Y1c, Y2c = win.Y2c, pad = win.pad;
+    const bool area = win.area2x != 0;
+    const int wbytes = (X2c - X1c) * 3;
+    const int pitch = (wbytes + 15 + 15) & ~15;                 // staged row: the aligned span that covers [X1c*3, X2c*3) of a frame row
+    const int rows_max = CROP_STAGE_BYTES / pitch;
+    const bool staged = rows_max >= 4;
+    const uint8_t *win0 = frame + (size_t)X1c * 3;               // + frame row * row_stride = first byte of the window in that row
+
+    if (staged) {
+        // ---- band plan: output rows [bstart[b], bstart[b+1]) read cut-out rows lo_b .. hi_b with hi_b - lo_b + 1 <= rows_max
+        if (tid == 0) {
+            int nb = 0, lo = 0;
+            for (int dy = dy_lo; dy < dy_hi; ++dy) {
+                const int r0 = area ? 2 * dy : yr0[dy], r1 = area ? 2 * dy + 1 : yr1[dy];
+                if (dy == dy_lo || r1 - lo + 1 > rows_max) { bstart[nb++] = (short)dy; lo = r0; }
+            }
+            bstart[nb] = (short)dy_hi;
+            nbands = nb;
+            mbar_init_(&sbar[0], 1);
+            mbar_init_(&sbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        const int nb = nbands;
+        // source rows of band b, clipped to the window (cut-out row r is frame row r + Y1)
+        auto band_rows = [&](int b, int &lo, int &hi) {
+            const int dy0 = bstart[b], dy1 = bstart[b + 1] - 1;
+            lo = max(area ? 2 * dy0 : yr0[dy0], Y1c - Y1);
+            hi = min(area ? 2 * dy1 + 1 : yr1[dy1], Y2c - Y1 - 1);
+        };
+        auto issue = [&](int b) {                                 // warp 0: one bulk copy per source row of band b into buffer b & 1
+            int lo, hi;
+            band_rows(b, lo, hi);
+            const int lane = tid & 31;
+            uint32_t bytes = 0;
+            for (int r = lo + lane; r <= hi; r += 32) {
+                const uintptr_t a = (uintptr_t)(win0 + (size_t)(r + Y1) * row_stride);
+                bytes += (uint32_t)((((a & 15) + wbytes + 15) & ~(uintptr_t)15));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the buffer was read by ordinary loads two bands ago
+            if (lane == 0) {
+                if (bytes) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32_(&sbar[b & 1])), "r"(bytes) : "memory");
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32_(&sbar[b & 1])) : "memory");
+            }
+            __syncwarp();
+            for (int r = lo + lane; r <= hi; r += 32) {
+                const uintptr_t a = (uintptr_t)(win0 + (size_t)(r + Y1) * row_stride);
+                const uint32_t n = (uint32_t)((((a & 15) + wbytes + 15) & ~(uintptr_t)15));
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32_(&stage[b & 1][(r - lo) * pitch])),
+                             "l"((uint64_t)(a & ~(uintptr_t)15)), "r"(n), "r"(smem_u32_(&sbar[b & 1]))
+                             : "memory");
+            }
+        };
+        if (tid < 32) issue(0);
+        for (int b = 0; b < nb; ++b) {
+            if (tid < 32 && b + 1 < nb) issue(b + 1);
+            int lo, hi;
+            band_rows(b, lo, hi);
+            {
+                const uint32_t parity = (uint32_t)(b >> 1) & 1u;
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile(
+                        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                        : "=r"(ok)
+                        : "r"(smem_u32_(&sbar[b & 1])), "r"(parity)
+                        : "memory");
+            }
+            const uint8_t *sb = stage[b & 1];
+            const uint32_t mis0 = (uint32_t)((uintptr_t)win0 & 15), stride15 = (uint32_t)(row_stride & 15);
+            auto row_base = [&](int r) -> int {                 // staged offset of cut-out row r's first window byte, -1 outside the window
+                if (r < lo || r > hi) return -1;
+                return (r - lo) * pitch + (int)((mis0 + (uint32_t)(r + Y1) * stride15) & 15u);
+            };
+            // one unit = 16 output pixels of one row (48 bytes, three 128-bit stores): the per-pixel work (table entry, bounds, row bases) is
+            // shared by the three channels
+            const int u0 = bstart[b] * (PATCH_W / 16), u1 = bstart[b + 1] * (PATCH_W / 16);
+            for (int u = u0 + tid; u < u1; u += CROP_THREADS) {
+                const int dy = u / (PATCH_W / 16), px0 = (u - dy * (PATCH_W / 16)) * 16;
+                uint32_t wds[12];
+                if (!area) {
+                    const int base0 = row_base(yr0[dy]), base1 = row_base(yr1[dy]), wb0 = yb0[dy], wb1 = yb1[dy];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) wds[i] = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int4 t = xt[px0 + k];                 // byte offsets of the two taps inside a window row (-1: outside), coefficients
+                        const int a0 = (short)(t.z & 0xffff), a1 = t.z >> 16;
+                        const int i00 = (base0 < 0 || t.x < 0) ? -1 : base0 + t.x, i01 = (base0 < 0 || t.y < 0) ? -1 : base0 + t.y;
+                        const int i10 = (base1 < 0 || t.x < 0) ? -1 : base1 + t.x, i11 = (base1 < 0 || t.y < 0) ? -1 : base1 + t.y;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int p00 = i00 < 0 ? pad : (int)sb[i00 + c], p01 = i01 < 0 ? pad : (int)sb[i01 + c];
+                            const int p10 = i10 < 0 ? pad : (int)sb[i10 + c], p11 = i11 < 0 ? pad : (int)sb[i11 + c];
+                            const int h0 = p00 * a0 + p01 * a1, h1 = p10 * a0 + p11 * a1;
+                            const int v = ((((wb0 * (h0 >> 4)) >> 16) + ((wb1 * (h1 >> 4)) >> 16) + 2) >> 2);
+                            const int byte = k * 3 + c;
+                            wds[byte >> 2] |= (uint32_t)(v & 0xff) << (8 * (byte & 3));
+                        }
+                    }
+                } else {
+                    const int base0 = row_base(2 * dy), base1 = row_base(2 * dy + 1);
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) wds[i] = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const int x0 = 2 * (px0 + k) + X1, x1 = x0 + 1;                     // frame columns of the 2x2 block
+                        const int o0 = (x0 < X1c || x0 >= X2c) ? -1 : (x0 - X1c) * 3, o1 = (x1 < X1c || x1 >= X2c) ? -1 : (x1 - X1c) * 3;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int p00 = (base0 < 0 || o0 < 0) ? pad : (int)sb[base0 + o0 + c], p01 = (base0 < 0 || o1 < 0) ? pad : (int)sb[base0 + o1 + c];
+                            const int p10 = (base1 < 0 || o0 < 0) ? pad : (int)sb[base1 + o0 + c], p11 = (base1 < 0 || o1 < 0) ? pad : (int)sb[base1 + o1 + c];
+                            const int v = (p00 + p01 + p10 + p11 + 2) >> 2;
+                            const int byte = k * 3 + c;
+                            wds[byte >> 2] |= (uint32_t)(v & 0xff) << (8 * (byte & 3));
+                        }
+                    }
+                }
+                uint4 *o4 = reinterpret_cast<uint4 *>(out + ((size_t)dy * PATCH_W + px0) * 3);
+                o4[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                o4[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+                o4[2] = make_uint4(wds[8], wds[9], wds[10], wds[11]);
+            }
+            __syncthreads();                                      // buffer b & 1 may be refilled (band b + 2)
+        }
+        return;
+    }
+
+    // ---- direct path (window rows too wide to stage): taps through the read-only cache
     auto fetch = [&](int r, int x, int c) -> int {   // cut-out coordinates
         const int fy = r + Y1, fxp = x + X1;
         if (fy < Y1c || fy >= Y2c || fxp < X1c || fxp >= X2c) return pad;
         return (int)__ldg(frame + (size_t)fy * row_stride + (size_t)fxp * 3 + c);
     };
-
-    // ---- phase 3: 16 output bytes per thread per iteration
-    const bool area = win.area2x != 0;
-    for (int q = tid; q < PATCH_BYTES / 16; q += CROP_THREADS) {
+    for (int q = dy_lo * (PATCH_W * 3 / 16) + tid; q < dy_hi * (PATCH_W * 3 / 16); q += CROP_THREADS) {
         const int dy = q / (PATCH_W * 3 / 16);
         const int b0 = (q - dy * (PATCH_W * 3 / 16)) * 16;
         uint32_t wds[4];
@@ -194,13 +344,13 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_resize_small_kernel(const u
 
 cudaError_t launch_crop_resize_small(const uint8_t *frame, int H, int W, int64_t row_stride, const CropSmall &sm, uint8_t *bank, cudaStream_t s) {
     if (sm.n <= 0) return cudaSuccess;
-    crop_resize_small_kernel<<<sm.n, CROP_THREADS, 0, s>>>(frame, H, W, (long long)row_stride, sm, bank);
+    crop_resize_small_kernel<<<dim3(sm.n, CROP_PARTS), CROP_THREADS, 0, s>>>(frame, H, W, (long long)row_stride, sm, bank);
     return cudaGetLastError();
 }
 
 cudaError_t launch_crop_resize(const uint8_t *frame, int H, int W, int64_t row_stride, const double *boxes, int n,
                                const int32_t *slots, uint8_t *bank, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
-    crop_resize_kernel<<<n, CROP_THREADS, 0, s>>>(frame, H, W, (long long)row_stride, boxes, n, slots, bank);
+    crop_resize_kernel<<<dim3(n, CROP_PARTS), CROP_THREADS, 0, s>>>(frame, H, W, (long long)row_stride, boxes, n, slots, bank);
     return cudaGetLastError();
 }
