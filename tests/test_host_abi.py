@@ -97,3 +97,25 @@ def test_activation_trap_and_filler_box():
     crop = np.full((384, 128, 3), 255, np.uint8)
     n = tracking.normalize_crop(crop)
     assert n.dtype == np.float32 and np.allclose(n[0, 0], (1.0 - np.array([0.406, 0.456, 0.485])) / np.array([0.225, 0.224, 0.299]), rtol=1e-6)
+
+
+def test_install_as_busca_gives_the_adapters_their_imports():
+    """INTEGRATION.md route A: after install_as_busca() every `from busca.X import Y` the reference adapters execute
+    (adapters/*/…byte_tracker.py, strong_sort.py, tracker.py: network.BUSCA, tracking.center_distance, option.load_args_from_config /
+    merge_args, visualization.plot_box) resolves to this package - no device needed for the imports themselves."""
+    import importlib
+    import sys
+    import busca_b200
+    saved = {k: v for k, v in sys.modules.items() if k == "busca" or k.startswith("busca.")}
+    try:
+        busca_b200.install_as_busca()
+        for mod, names in (("busca.network", ["BUSCA"]), ("busca.tracking", ["center_distance", "get_bbox_crop", "missing_candidate_bbox"]),
+                           ("busca.option", ["load_args_from_config", "merge_args"]), ("busca.visualization", ["plot_box"])):
+            m = importlib.import_module(mod)
+            assert m.__name__.startswith("busca_b200"), (mod, m.__name__)
+            for n in names:
+                assert hasattr(m, n), (mod, n)
+    finally:
+        for k in [k for k in sys.modules if k == "busca" or k.startswith("busca.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
