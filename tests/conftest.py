@@ -14,9 +14,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_device_count():
+    """Devices the CUDA driver sees (0 without a driver): asked of libcuda itself, not of /dev names (those differ between boxes)."""
+    import ctypes
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+        if cu.cuInit(0) != 0:
+            return 0
+        n = ctypes.c_int(0)
+        return n.value if cu.cuDeviceGetCount(ctypes.byref(n)) == 0 else 0
+    except OSError:
+        return 0
+
+
 def pytest_collection_modifyitems(config, items):
     """`-m gpu` on a box without a CUDA device: skip instead of erroring inside busca_create."""
-    if os.path.exists("/dev/nvidia0") or os.environ.get("BUSCA_FORCE_GPU_TESTS"):
+    if not any("gpu" in it.keywords for it in items) or os.environ.get("BUSCA_FORCE_GPU_TESTS") or _cuda_device_count() > 0:
         return
     skip = pytest.mark.skip(reason="no CUDA device on this box")
     for it in items:
