@@ -1341,8 +1341,10 @@ extern "C" int busca_debug_conv_ex(busca_ctx *c, const busca_debug_conv_args *d)
         ff.L = &L; ff.in_scale = d->in_scale ? in_sc : nullptr; ff.count = (long long)N * Ho * Wo; ff.shift_out = L.shift;
         ff.gram_G = (const float *)gb; ff.gram_m = (const float *)(gb + o_sp);
         LAUNCH(c, "bn_fold_final", launch_bn_fold_final(ff, s));
-    } else if (d->use_tc) LAUNCH(c, "conv_tc", launch_conv_tc(L, a, o, s));
-    else LAUNCH(c, "conv_simt", launch_conv_simt(L, a, 1, s));
+    } else if (d->use_tc) {
+        LAUNCH(c, "conv_tc", launch_conv_tc(L, a, o, s));
+        if (c->profiling) c->prof.back().kernel = conv_tc_last_kernel();      // which instantiation ran (the tests check the variant they asked for)
+    } else LAUNCH(c, "conv_simt", launch_conv_simt(L, a, 1, s));
     if (d->out_bf16) CUDA_OK(cudaMemcpyAsync(d->out_bf16, b + o_out, out_b, cudaMemcpyDeviceToHost, s));
     if (d->stats_out) CUDA_OK(cudaMemcpyAsync(d->stats_out, L.stats, 2 * (size_t)L.cout * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
@@ -1495,6 +1497,7 @@ extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (strcmp(name, "tr_tc") == 0) { c->tr_tc = value != 0; return BUSCA_OK; }
     if (strcmp(name, "pool_mono") == 0) { reid_set_pool_mono(value); return BUSCA_OK; } // process-wide (experimental max-pool kernel)
     if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
+    if (strcmp(name, "mc_min_tiles") == 0) { conv_tc_set_mc_min_tiles((int)value); return BUSCA_OK; }   // process-wide
     if (strcmp(name, "pdl") == 0) { pdl_set(value != 0); return BUSCA_OK; }          // process-wide (programmatic dependent launch)
     return set_err(BUSCA_ERR_ARG, "unknown option '%s'", name);
 }

@@ -41,6 +41,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -83,6 +84,24 @@ struct TcParams {
 
 // Coordinates of the tiles a persistent CTA visits (tile = blockIdx.x + j * gridDim.x; tile = m_tile * tiles_n + n_tile;
 // m_tile = image-group * h_tiles + row-group), stepped without the three integer divisions per tile.
+// Tile sequence of a CTA PAIR (MC kernels): the two CTAs of a cluster take the pixel tiles 2 mp and 2 mp + 1 of the same channel tile in
+// lockstep (the weight tile is multicast to both).  Plain divisions: these kernels have >= 4 k-iterations per tile.
+struct PairWalk {
+    int tile, n_tile, hi, ni;        // tile = pair-tile index; hi / ni = row group / image group of THIS CTA's pixel tile
+    int step, cr;
+    __device__ __forceinline__ PairWalk(const TcParams &p, int rank) : step((int)gridDim.x >> 1), cr(rank) {
+        tile = (int)blockIdx.x >> 1;
+        set(p);
+    }
+    __device__ __forceinline__ void set(const TcParams &p) {
+        n_tile = tile % p.tiles_n;
+        const int m_tile = 2 * (tile / p.tiles_n) + cr;
+        hi = m_tile % p.h_tiles;
+        ni = m_tile / p.h_tiles;
+    }
+    __device__ __forceinline__ void next(const TcParams &p) { tile += step; set(p); }
+};
+
 struct TileWalk {
     int tile, n_tile, hi, ni;
     int rn, qh, qi;
@@ -108,6 +127,12 @@ struct TileWalk {
     }
 };
 
+template <bool MC>
+__device__ __forceinline__ typename std::conditional<MC, PairWalk, TileWalk>::type make_walk(const TcParams &p, int cr) {
+    if constexpr (MC) return PairWalk(p, cr);
+    else return TileWalk(p);
+}
+
 // RESB: the CTA's whole weight slab [BN x K] stays resident in shared memory (loaded once per launch; the host keeps a
 // CTA on one channel tile), so the ring only streams A boxes.  L2 -> SM delivery (~6300 B/clk chip-wide) is the bound of
 // every small-K convolution: with BN = 256 the weight tile is 2/3 of the bytes a k-iteration pulls.
@@ -126,13 +151,20 @@ struct TcCfg {
     static_assert(SMEM <= 232448, "shared memory budget (227 KB per CTA)");
 };
 
-template <int BN, int KB, bool DUAL, bool RESB>
+// MC: launched as clusters of two CTAs that walk pixel tiles 2 mp / 2 mp + 1 of the same channel tile in lockstep; each CTA loads HALF
+// of every weight tile and multicasts it to both (measured, profiles/r03i: the streamed-weight kernels move 48 KB per k-iteration and
+// SM against ~39 B/clk of L2 delivery - 1220 cycles where the MMAs need 770 - and two thirds of those bytes are the weight tile every
+// CTA fetches for itself).  A shared-memory stage is then free when BOTH CTAs' MMAs have retired (commit multicast to both).
+// S4 (statistics-only passes, BN = 256, streamed weights): the three staging tiles - unused in that mode - are a FOURTH ring stage.
+template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                                                                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                                                                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
                                                                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapIdt,
                                                                  const TcParams p) {
     using Cfg = TcCfg<BN, KB, DUAL, RESB>;
+    constexpr int STAGES = S4 ? Cfg::STAGES + 1 : Cfg::STAGES;
+    static_assert(!S4 || (!RESB && Cfg::STAGE_BYTES == TC_XBUFS * Cfg::XBUF_BYTES), "the extra stage aliases the staging tiles");
     constexpr int G = BN / 64;                                                            // 64-channel groups per tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
@@ -142,18 +174,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float *s_par = reinterpret_cast<float *>(xbuf + TC_XBUFS * Cfg::XBUF_BYTES);
     float *s_apar = s_par + Cfg::PAR_FLOATS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + Cfg::APAR_FLOATS);
-    uint64_t *full = bars, *empty = full + Cfg::STAGES, *ready = empty + Cfg::STAGES, *tfull = ready + Cfg::STAGES, *tempty = tfull + 2;
+    uint64_t *full = bars, *empty = full + STAGES, *ready = empty + STAGES, *tfull = ready + STAGES, *tempty = tfull + 2;
     uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS, *bfull = xfree + TC_XBUFS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
 
+    static_assert(!(MC && RESB), "the paired kernel streams its weights");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = p.tiles_m * p.tiles_n;
+    const int cr = MC ? (int)cluster_ctarank() : 0;                  // rank in the CTA pair
+    const int tile0 = MC ? (int)blockIdx.x >> 1 : (int)blockIdx.x, tile_step = MC ? (int)gridDim.x >> 1 : (int)gridDim.x;
+    const int total_tiles = MC ? ((p.tiles_m + 1) >> 1) * p.tiles_n : p.tiles_m * p.tiles_n;      // MC: pair tiles
     const bool xform = p.a_xf != nullptr;
     const bool want_stats = p.stats != nullptr && (p.mode == MODE_RAW || p.mode == MODE_STATS);
 
     pdl_trigger();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], (Cfg::STAGES % 2) == 0 ? 128 : 256); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? 2 : 1); mbar_init(&ready[s], (STAGES % 2) == 0 ? 128 : 256); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         for (int b = 0; b < TC_XBUFS; ++b) { mbar_init(&xfull[b], 1); mbar_init(&xfree[b], 1); }
         mbar_init(bfull, 1);
@@ -176,6 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_all();          // the peer's barriers are initialised before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -196,12 +232,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
                 __syncwarp();
             }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                const int n_tile = tile % p.tiles_n, m_tile = MC ? 2 * (tile / p.tiles_n) + cr : tile / p.tiles_n;
                 const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
                 int tap = 0, cb = 0;
                 for (int kt = 0; kt < p.k_iters; ++kt) {
-                    mbar_wait<32>(&empty[stage], phase ^ 1);
+                    mbar_wait<32>(&empty[stage], phase ^ 1);      // MC: both CTAs of the pair have retired the MMAs that read this stage
                     uint8_t *a_dst = tiles + stage * Cfg::STAGE_BYTES, *b_dst = a_dst + Cfg::A_BYTES;
                     const bool main_op = !DUAL || kt < p.k1_iters;
                     if (elect_one()) {
@@ -210,18 +246,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             const int m = p.tap_map[tap];
                             const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
                             tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                            if (!RESB) tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
+                            if (MC) tma_load_2d_mc(b_dst + cr * (Cfg::B_BYTES / 2), &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN + cr * (BN / 2), (uint16_t)3);
+                            else if (!RESB) tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
                         } else {                                     // downsample branch: 1x1 (strided view) on the block input
                             const int cb2 = kt - p.k1_iters;
                             tma_load_4d(a_dst, &mapA1, &full[stage], cb2 * Cfg::BKE, 0, h0, n0);
-                            if (!RESB) tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
+                            if (MC) tma_load_2d_mc(b_dst + cr * (Cfg::B_BYTES / 2), &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN + cr * (BN / 2), (uint16_t)3);
+                            else if (!RESB) tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
                         }
                     }
                     __syncwarp();
                     if (main_op) {
                         if (++cb == p.cin_blocks) { cb = 0; ++tap; }
                     }
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -234,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             uint32_t phase = 0;
             int it = 0;
             if (RESB) mbar_wait<32>(bfull, 0);                   // the resident weight slab has landed
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait<32>(&tempty[acc], acc_phase ^ 1);
@@ -263,11 +301,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
                                 umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
                         }
-                        umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs retire
+                        if (MC) umma_commit_mc(&empty[stage], (uint16_t)3);    // the stage holds halves written by both CTAs: it is free when both have read it
+                        else umma_commit(&empty[stage]);                        // frees the smem stage when these MMAs retire
                         if (kt == p.k_iters - 1) umma_commit(&tfull[acc]);
                     }
                     __syncwarp();
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -280,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // With an even number of stages a group owns the stages of its own parity: every phase of those barriers is its own,
             // so it never has to look at the other group's k-iterations.  With an odd number (3 stages of 48 KB, BN = 256) a
             // group meets a stage on every second phase only; it then OBSERVES the other group's k-iterations too (see below).
-            constexpr bool EVEN = (Cfg::STAGES % 2) == 0;
+            constexpr bool EVEN = (STAGES % 2) == 0;
             const int grp = (warp - TC_XF_WARP0) >> 2;        // this group handles k-iterations with (global index & 1) == grp
             const int tt = (threadIdx.x - TC_XF_WARP0 * 32) & 127;
             const int c = tt & 7, rb = tt >> 3;               // logical 16-byte chunk (8 channels), first row
@@ -301,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const uint32_t par0 = smem_u32(s_apar) + (uint32_t)c * 16;
             const uint32_t tiles0 = smem_u32(tiles) + col_off + (uint32_t)rb * 128;
             uint32_t ki = 0;                                  // global k-iteration counter (stage ring position) at the start of the tile
-            TileWalk tw(p);
+            typename std::conditional<MC, PairWalk, TileWalk>::type tw = make_walk<MC>(p, cr);
             for (; tw.tile < total_tiles; tw.next(p), ki += (uint32_t)p.k_iters) {
                 const int kt0 = EVEN ? (int)((ki ^ (uint32_t)grp) & 1u) : 0;    // first k-iteration of this tile the group owns
                 if (EVEN && kt0 >= p.k_iters) continue;                         // single-k-iteration tile of the other group
@@ -334,7 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int kt = kt0; kt < p.k_iters; kt += EVEN ? 2 : 1) {
                     const bool main_op = !DUAL || kt < p.k1_iters;
                     const uint32_t kig = ki + (uint32_t)kt;
-                    const uint32_t stage = kig % Cfg::STAGES, phase = (kig / Cfg::STAGES) & 1;
+                    const uint32_t stage = kig % STAGES, phase = (kig / STAGES) & 1;
                     // odd number of stages: BOTH groups observe every phase of every stage (a parity wait can only tell phases
                     // apart that are at most one apart) and BOTH arrive on ready[stage] (256 arrivals per phase): the observing
                     // group is then part of the MMA's dependency chain, so it can never fall two phases of a stage behind the ring
@@ -430,7 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const bool stats_t = BN == 256 && !DUAL && p.mode == MODE_STATS;
         const bool weighted = want_stats && p.img_w != nullptr;
         int it = 0, gcount = 0;
-        TileWalk tw(p);
+        typename std::conditional<MC, PairWalk, TileWalk>::type tw = make_walk<MC>(p, cr);
         for (; tw.tile < total_tiles; tw.next(p), ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -616,8 +655,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ===================================================== identity-tile loader (FINAL, single accumulator)
         if (p.mode == MODE_FINAL && !DUAL) {
             int gcount = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.tiles_n, m_tile = tile / p.tiles_n;
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                const int n_tile = tile % p.tiles_n, m_tile = MC ? 2 * (tile / p.tiles_n) + cr : tile / p.tiles_n;
                 const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
                 for (int g = 0; g < G; ++g, ++gcount) {
                     const int b = gcount % TC_XBUFS;
@@ -634,6 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
 
     __syncthreads();
+    if (MC) cluster_sync_all();          // neither CTA leaves while the other may still signal its barriers
     if (want_stats) {
         for (int i = threadIdx.x; i < 2 * p.Cout; i += TC_THREADS) {
             const float v = s_par[i];
@@ -1356,12 +1396,24 @@ bool resb_enabled() {
     return on != 0;
 }
 
-template <int BN, int KB, bool DUAL, bool RESB>
+// The paired (weight-multicast) variant is OFF unless BUSCA_MC=1: measured on a B200 (profiles/r03j) it changes nothing - 43.0 vs 42.9
+// ms/frame - i.e. the streamed-weight kernels are not bound by L2 delivery of the weight tiles but by the bytes the ring keeps in flight
+// per SM (see S4).  It stays because the tests hold it bit-identical and a cta_group::2 kernel would start from this lockstep pair.
+bool mc_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("BUSCA_MC");
+        on = (e && e[0] == '1');
+    }
+    return on != 0;
+}
+
+template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false>
 cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     using Cfg = TcCfg<BN, KB, DUAL, RESB>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL, RESB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -1370,15 +1422,36 @@ cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB, (int)MC, (int)S4);
+    if (MC) {
+        // clusters of two CTAs: pair tiles = ceil(tiles_m / 2) x tiles_n, one pair per two SMs, a pair stays on one channel tile when cheap
+        const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
+        int pairs = pair_tiles < g_num_sms / 2 ? pair_tiles : g_num_sms / 2;
+        if (p.tiles_n > 1 && pairs > p.tiles_n && pairs % p.tiles_n != 0 && (pairs % p.tiles_n) * 32 < pairs) pairs -= pairs % p.tiles_n;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = 2;
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4>, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+    }
     const int total = p.tiles_m * p.tiles_n;
     int grid = total < g_num_sms ? total : g_num_sms;
     // keep a CTA on one channel tile (its statistics accumulators stay in registers) when that costs < 3 % of the SMs;
     // with resident weights it is a requirement (total is a multiple of tiles_n, so grid >= tiles_n stays one)
     if (p.tiles_n > 1 && grid > p.tiles_n && grid % p.tiles_n != 0 && (RESB || (grid % p.tiles_n) * 32 < grid)) grid -= grid % p.tiles_n;
-    cudaError_t le = launch_pdl(conv_tc_kernel<BN, KB, DUAL, RESB>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
-    if (le != cudaSuccess) return le;
-    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB);
-    return cudaGetLastError();
+    return launch_pdl(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+}
+
+// whether a launch takes the paired variant: streamed weights, BN = 256, enough pixel tiles to keep every pair busy
+// (busca_set_option("mc_min_tiles", n): the tests lower the threshold to run small shapes through it)
+int g_mc_min_tiles = -1;
+bool tc_use_mc(int BN, const TcParams &p) {
+    const int min_tiles = g_mc_min_tiles >= 0 ? g_mc_min_tiles : 4 * (g_num_sms ? g_num_sms : 148);
+    return (mc_enabled() || g_mc_min_tiles >= 0) && BN == 256 && p.mode != MODE_F32 && p.k_iters > 2 && p.tiles_m >= min_tiles;
 }
 
 template <int BN, int KB = 128, bool DUAL = false>
@@ -1389,8 +1462,15 @@ cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     // longer k-loops keep the deeper ring, which hides the TMA + transform latency of a stage)
     if (resb_enabled() && p.k_iters <= 2 && (long long)p.k_iters * TcCfg<BN, KB, DUAL, true>::B_BYTES <= TcCfg<BN, KB, DUAL, true>::RES_BYTES &&
         total >= p.tiles_n)
-        return launch_tc_v<BN, KB, DUAL, true>(m, p, s);
-    return launch_tc_v<BN, KB, DUAL, false>(m, p, s);
+        return launch_tc_v<BN, KB, DUAL, true, false>(m, p, s);
+    if constexpr (BN == 256) {
+        if (tc_use_mc(BN, p)) return launch_tc_v<BN, KB, DUAL, false, true>(m, p, s);
+        if constexpr (!DUAL) {
+            static const bool s4 = !(getenv("BUSCA_S4") && getenv("BUSCA_S4")[0] == '0');
+            if (s4 && p.mode == MODE_STATS) return launch_tc_v<BN, KB, DUAL, false, false, true>(m, p, s);    // no staging tiles in that mode: a fourth ring stage
+        }
+    }
+    return launch_tc_v<BN, KB, DUAL, false, false>(m, p, s);
 }
 
 }  // namespace
@@ -1492,6 +1572,7 @@ cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStrea
 }  // namespace
 
 const char *conv_tc_last_kernel() { return g_last_kernel; }
+void conv_tc_set_mc_min_tiles(int n) { g_mc_min_tiles = n; }
 void conv_tc_set_halo(int on) { g_halo = on ? 1 : 0; }
 static bool tile_geometry(int Ho, int Wo, int &BW, int &BH, int &BI);
 namespace {
@@ -1637,7 +1718,10 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
             }
     }
     // w16s = bf16(W * |scale_in|); FINAL: w16f = bf16(W * |scale_in| * scale of this conv's BN)
-    ok = ok && make_map2(&m.b, p.mode == MODE_FINAL ? L.w16f : (a.in_xf ? L.w16s : L.w16), (long long)p.ntaps * L.cin, L.cout, BN);
+    // (paired variant: each CTA of a pair loads and multicasts half of a weight tile, so the box is BN / 2 rows)
+    const bool resb_fit = resb_enabled() && p.k_iters <= 2 && (long long)p.k_iters * BN * 128 <= 65536;
+    const int b_rows = (!resb_fit && tc_use_mc(BN, p)) ? BN / 2 : BN;
+    ok = ok && make_map2(&m.b, p.mode == MODE_FINAL ? L.w16f : (a.in_xf ? L.w16s : L.w16), (long long)p.ntaps * L.cin, L.cout, b_rows);
     m.b2 = m.b;
     if (dual) {
         // downsample branch: 1x1 conv (stride ds->stride) on the block input [N, ds_H, ds_W, ds->cin]; view (0,0) for stride 2
@@ -1645,7 +1729,7 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
         const int sd = o.ds->stride;
         if (Hd / sd != a.Ho || Wd / sd != a.Wo) return cudaErrorInvalidValue;
         ok = ok && make_map4(&m.a[1], o.ds_in, (int)Cd, (int)(Wd / sd), (int)(Hd / sd), a.N, sd * Cd, sd * Wd * Cd, Hd * Wd * Cd, p.BW, p.BH, p.BI);
-        ok = ok && make_map2(&m.b2, o.ds->w16f, Cd, L.cout, BN);
+        ok = ok && make_map2(&m.b2, o.ds->w16f, Cd, L.cout, b_rows);
     }
     // output [N][Ho][Wo][Cout] bf16, stored one 64-channel group of a tile at a time; images beyond N are clipped by TMA
     ok = ok && make_map4(&m.out, a.out, L.cout, a.Wo, a.Ho, a.N, L.cout, (long long)a.Wo * L.cout, (long long)a.Ho * a.Wo * L.cout, p.BW, p.BH, p.BI);

@@ -52,6 +52,23 @@ __device__ __forceinline__ void tma_load_2d(void *smem, const CUtensorMap *map, 
                  "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// ---- thread-block clusters (pairs of CTAs sharing the weight tiles through TMA multicast) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D tile load delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) in every CTA of cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void *smem, const CUtensorMap *map, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)map), "r"(smem_u32(smem)),
                  "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -108,6 +125,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same commit arriving on the mbarrier at this offset in every CTA of cta_mask (a shared-memory stage both CTAs of a pair filled)
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
