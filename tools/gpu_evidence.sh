@@ -12,6 +12,6 @@ timeout 500 ncu --set full --clock-control none --import-source on \
    --launch-skip 330 --launch-count 140 -f -o $O/full \
    python bench.py --sequences 1 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --adapter-frames 0 > $O/ncu_full.log 2>&1; echo "ncu full rc=$?"
 tail -3 $O/ncu_full.log | cut -c1-200
-ncu -i $O/full.ncu-rep --page raw --csv > $O/full_raw.csv 2>/dev/null
+ncu -i $O/full.ncu-rep --page raw --csv > $O/full_raw.csv 2>/dev/null; rm -f $O/full.ncu-rep
 python tools/ncu_full_summary.py $O/full_raw.csv > $O/full_summary.md 2>&1; head -60 $O/full_summary.md
 ls -la $O | head -20
