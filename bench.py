@@ -489,7 +489,7 @@ def run_reference(args):
     sample = (f"each step = {Ts} unmatched tracks x {wl['C']} proposals of the same workload ({Ts * (wl['L'] + wl['C'])} ReID patches); "
               f"oracle port of the reference algorithm, torch CPU fp32, {os.cpu_count()} threads")
     out = {"impl": "reference", "metric": "decisions/sec", "value": val, "unit": "decisions/s", "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": round(tot / len(times) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": round(tot / len(times) * 1e3, 3), "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": wl["desc"], "name": args.workload, "T": wl["T"], "D": wl["D"], "L": wl["L"], "C": wl["C"], "sequences": args.sequences},
            "cpu_baseline": {"value": val, "unit": "decisions/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
