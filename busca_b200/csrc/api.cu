@@ -635,6 +635,145 @@ extern "C" int busca_iou(busca_ctx *c, const double *a, int32_t na, const double
     return pair_matrix(c, a, na, b, nb, out, 1);
 }
 
+extern "C" int busca_detection_coverage(busca_ctx *c, const double *tlbr, int32_t n, int32_t H, int32_t W, int64_t *nonzero_out, double *bbox_areas_out) {
+    if (!c || n < 0 || H <= 0 || W <= 0 || !nonzero_out || (n > 0 && !tlbr)) return set_err(BUSCA_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t bb = (size_t)(n > 0 ? n : 1) * 32, ab = (size_t)(n > 0 ? n : 1) * 8;
+    CUDA_OK(c->ws_small.ensure(bb + ab + 64));
+    double *dbox = (double *)c->ws_small.p, *dar = dbox + (size_t)(n > 0 ? n : 1) * 4;
+    unsigned long long *dcnt = (unsigned long long *)((char *)c->ws_small.p + bb + ab);
+    if (n > 0) CUDA_OK(cudaMemcpyAsync(dbox, tlbr, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(dcnt, 0, 8, c->stream));
+    prof_reset(c);
+    LAUNCH(c, "detection_coverage", launch_coverage(dbox, n, H, W, dcnt, dar, c->stream));
+    unsigned long long cnt = 0;
+    CUDA_OK(cudaMemcpyAsync(&cnt, dcnt, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (bbox_areas_out && n > 0) CUDA_OK(cudaMemcpyAsync(bbox_areas_out, dar, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    *nonzero_out = (int64_t)cnt;
+    return BUSCA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-tracker rounds: rounds.cu
+// ------------------------------------------------------------------------------------------------
+extern "C" int busca_kalman_predict(busca_ctx *c, const double *mean, const double *cov, const uint8_t *tracked, int32_t n,
+                                    double *mean_out, double *cov_out) {
+    if (!c || n < 0) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (n == 0) return BUSCA_OK;
+    if (!mean || !cov || !mean_out || !cov_out) return set_err(BUSCA_ERR_ARG, "null pointer");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t mb = (size_t)n * 64, cb = (size_t)n * 512, tb = ((size_t)n + 63) / 64 * 64;
+    CUDA_OK(c->ws_small.ensure(2 * mb + 2 * cb + tb + 64));
+    double *dm = (double *)c->ws_small.p, *dc = dm + (size_t)n * 8, *dmo = dc + (size_t)n * 64, *dco = dmo + (size_t)n * 8;
+    uint8_t *dt = (uint8_t *)(dco + (size_t)n * 64);
+    CUDA_OK(cudaMemcpyAsync(dm, mean, mb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dc, cov, cb, cudaMemcpyHostToDevice, c->stream));
+    if (tracked) CUDA_OK(cudaMemcpyAsync(dt, tracked, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    prof_reset(c);
+    LAUNCH(c, "kalman_predict", launch_kalman_predict(dm, dc, tracked ? dt : nullptr, n, dmo, dco, c->stream));
+    CUDA_OK(cudaMemcpyAsync(mean_out, dmo, mb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(cov_out, dco, cb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+extern "C" int busca_kalman_update(busca_ctx *c, const double *mean, const double *cov, const double *xyah, int32_t n, double *mean_out,
+                                   double *cov_out) {
+    if (!c || n < 0) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (n == 0) return BUSCA_OK;
+    if (!mean || !cov || !xyah || !mean_out || !cov_out) return set_err(BUSCA_ERR_ARG, "null pointer");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t mb = (size_t)n * 64, cb = (size_t)n * 512, zb = (size_t)n * 32;
+    CUDA_OK(c->ws_small.ensure(2 * mb + 2 * cb + zb + 64));
+    double *dm = (double *)c->ws_small.p, *dc = dm + (size_t)n * 8, *dmo = dc + (size_t)n * 64, *dco = dmo + (size_t)n * 8,
+           *dz = dco + (size_t)n * 64;
+    CUDA_OK(cudaMemcpyAsync(dm, mean, mb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dc, cov, cb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dz, xyah, zb, cudaMemcpyHostToDevice, c->stream));
+    prof_reset(c);
+    LAUNCH(c, "kalman_update", launch_kalman_update(dm, dc, dz, n, dmo, dco, c->stream));
+    CUDA_OK(cudaMemcpyAsync(mean_out, dmo, mb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(cov_out, dco, cb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
+// One association round without a host visit between its stages: cost matrix (IoU distance, optionally fused with the detection
+// scores) -> assignment with a cost limit.  cost_in != NULL solves a caller-supplied matrix instead (busca_linear_assignment).
+static int match_round(busca_ctx *c, const double *a, int32_t na, const double *b, int32_t nb, const double *score, const double *cost_in,
+                       double limit, int32_t *x, int32_t *y, double *cost_out) {
+    if (!c || na < 0 || nb < 0) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if ((na > 0 && !x) || (nb > 0 && !y)) return set_err(BUSCA_ERR_ARG, "null pointer");
+    if (na == 0 || nb == 0) {                                    // matching.linear_assignment: empty matrix -> everything unmatched
+        for (int i = 0; i < na; ++i) x[i] = -1;
+        for (int j = 0; j < nb; ++j) y[j] = -1;
+        return BUSCA_OK;
+    }
+    if (!cost_in && (!a || !b)) return set_err(BUSCA_ERR_ARG, "null pointer");
+    if (assignment_smem_bytes(na, nb) > 200 * 1024) return set_err(BUSCA_ERR_ARG, "assignment: rows + columns exceed the shared-memory solver (about 5000)");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t ab = (size_t)na * 32, bb = (size_t)nb * 32, sb = (size_t)nb * 8, cb = (size_t)na * nb * 8;
+    CUDA_OK(c->ws_small.ensure(ab + bb + sb + cb + (size_t)(na + nb) * 4 + 64));
+    double *da = (double *)c->ws_small.p, *db = da + (size_t)na * 4, *ds = db + (size_t)nb * 4, *dcost = ds + nb;
+    int *dx = (int *)(dcost + (size_t)na * nb), *dy = dx + na;
+    prof_reset(c);
+    if (cost_in) {
+        CUDA_OK(cudaMemcpyAsync(dcost, cost_in, cb, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CUDA_OK(cudaMemcpyAsync(da, a, ab, cudaMemcpyHostToDevice, c->stream));
+        CUDA_OK(cudaMemcpyAsync(db, b, bb, cudaMemcpyHostToDevice, c->stream));
+        if (score) CUDA_OK(cudaMemcpyAsync(ds, score, sb, cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, "match_cost", launch_match_cost(da, na, db, nb, score ? ds : nullptr, dcost, c->stream));
+    }
+    LAUNCH(c, "assignment", launch_assignment(dcost, na, nb, limit, dx, dy, c->stream));
+    CUDA_OK(cudaMemcpyAsync(x, dx, (size_t)na * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(y, dy, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (cost_out) CUDA_OK(cudaMemcpyAsync(cost_out, dcost, cb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+extern "C" int busca_match_round(busca_ctx *c, const double *a_tlbr, int32_t na, const double *b_tlbr, int32_t nb, const double *b_score,
+                                 double cost_limit, int32_t *x, int32_t *y, double *cost_out) {
+    return match_round(c, a_tlbr, na, b_tlbr, nb, b_score, nullptr, cost_limit, x, y, cost_out);
+}
+extern "C" int busca_linear_assignment(busca_ctx *c, const double *cost, int32_t n, int32_t m, double cost_limit, int32_t *x, int32_t *y) {
+    if (n > 0 && m > 0 && !cost) return set_err(BUSCA_ERR_ARG, "null pointer");
+    return match_round(c, nullptr, n, nullptr, m, nullptr, cost, cost_limit, x, y, nullptr);
+}
+
+extern "C" int busca_duplicate_tracks(busca_ctx *c, const double *a_tlbr, const int32_t *a_age, int32_t na, const double *b_tlbr,
+                                      const int32_t *b_age, int32_t nb, double thresh, uint8_t *drop_a, uint8_t *drop_b) {
+    if (!c || na < 0 || nb < 0) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if ((na > 0 && !drop_a) || (nb > 0 && !drop_b)) return set_err(BUSCA_ERR_ARG, "null pointer");
+    for (int i = 0; i < na; ++i) drop_a[i] = 0;
+    for (int j = 0; j < nb; ++j) drop_b[j] = 0;
+    if (na == 0 || nb == 0) return BUSCA_OK;
+    if (!a_tlbr || !b_tlbr || !a_age || !b_age) return set_err(BUSCA_ERR_ARG, "null pointer");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t ab = (size_t)na * 32, bb = (size_t)nb * 32, fa = ((size_t)na + 7) / 8 * 8, fb = ((size_t)nb + 7) / 8 * 8;
+    CUDA_OK(c->ws_small.ensure(ab + bb + (size_t)(na + nb) * 4 + fa + fb + 64));
+    double *da = (double *)c->ws_small.p, *db = da + (size_t)na * 4;
+    int *dga = (int *)(db + (size_t)nb * 4), *dgb = dga + na;
+    uint8_t *dfa = (uint8_t *)(dgb + nb), *dfb = dfa + fa;
+    CUDA_OK(cudaMemcpyAsync(da, a_tlbr, ab, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(db, b_tlbr, bb, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dga, a_age, (size_t)na * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(dgb, b_age, (size_t)nb * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(dfa, 0, fa + fb, c->stream));
+    prof_reset(c);
+    LAUNCH(c, "duplicate_tracks", launch_duplicates(da, dga, na, db, dgb, nb, thresh, dfa, dfb, c->stream));
+    CUDA_OK(cudaMemcpyAsync(drop_a, dfa, (size_t)na, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(drop_b, dfb, (size_t)nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
 extern "C" int busca_frame_geometry(busca_ctx *c, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
                                     int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
                                     int32_t *cand) {

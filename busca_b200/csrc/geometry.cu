@@ -6,31 +6,9 @@
 // (center_distance); matching.py:53-70 -> cython_bbox.bbox_overlaps; busca/network.py:324-380 (selection).
 #include "common.cuh"
 #include "kernels.h"
+#include "box_math.cuh"
 
 namespace {
-
-struct Box { double x1, y1, x2, y2; };
-
-__device__ __forceinline__ double center_dist(const Box &a, const Box &b) {
-    // (tlbr[:2] + tlbr[2:]) / 2.0 ; cdist 'euclidean': s = dx*dx; s += dy*dy; sqrt(s)
-    double acx = __ddiv_rn(__dadd_rn(a.x1, a.x2), 2.0), acy = __ddiv_rn(__dadd_rn(a.y1, a.y2), 2.0);
-    double bcx = __ddiv_rn(__dadd_rn(b.x1, b.x2), 2.0), bcy = __ddiv_rn(__dadd_rn(b.y1, b.y2), 2.0);
-    double dx = __dsub_rn(acx, bcx), dy = __dsub_rn(acy, bcy);
-    return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-}
-
-__device__ __forceinline__ double box_iou(const Box &a, const Box &q) {
-    // cython_bbox: +1 pixel convention; 0 unless iw > 0 and ih > 0
-    double iw = __dadd_rn(__dsub_rn(fmin(a.x2, q.x2), fmax(a.x1, q.x1)), 1.0);
-    if (!(iw > 0.0)) return 0.0;
-    double ih = __dadd_rn(__dsub_rn(fmin(a.y2, q.y2), fmax(a.y1, q.y1)), 1.0);
-    if (!(ih > 0.0)) return 0.0;
-    double qa = __dmul_rn(__dadd_rn(__dsub_rn(q.x2, q.x1), 1.0), __dadd_rn(__dsub_rn(q.y2, q.y1), 1.0));
-    double aa = __dmul_rn(__dadd_rn(__dsub_rn(a.x2, a.x1), 1.0), __dadd_rn(__dsub_rn(a.y2, a.y1), 1.0));
-    double inter = __dmul_rn(iw, ih);
-    double ua = __dsub_rn(__dadd_rn(aa, qa), inter);
-    return __ddiv_rn(inter, ua);
-}
 
 __device__ __forceinline__ bool lex_less(double v1, int i1, double v2, int i2) {
     return (v1 < v2) || (v1 == v2 && i1 < i2);
@@ -133,6 +111,52 @@ __global__ void pair_matrix_kernel(const double *__restrict__ a, int na, const d
     out[i] = want_iou ? box_iou(A, B) : center_dist(A, B);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Detection-coverage gate of Step 3b: BYTETracker.get_detection_coverage / is_reliable
+// (adapters/ByteTrack/yolox/tracker/byte_tracker.py:574-623, 459-465).  The reference draws every active
+// track's box as a filled cv2.rectangle (int()-truncated corners, both inclusive, either order, clipped) on a frame-sized canvas and
+// counts the non-black pixels: here one warp owns a canvas row as a bit mask (32 columns per lane and pass), ORs in the column span
+// of every rectangle that covers the row and pop-counts - the union area, exactly, without a canvas in memory.  The per-box relative
+// areas (fp64, one rounding per operation, the reference's width/height swap included) are written alongside.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int COV_WARPS = 8;
+__global__ void __launch_bounds__(COV_WARPS * 32) coverage_kernel(const double *__restrict__ tlbr, int n, int H, int W, unsigned long long *__restrict__ nonzero,
+                                                                  double *__restrict__ areas) {
+    extern __shared__ int4 rects[];                           // clipped inclusive integer corners (xa, ya, xb, yb); xa > xb = empty
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double x1d = tlbr[4 * i], y1d = tlbr[4 * i + 1], x2d = tlbr[4 * i + 2], y2d = tlbr[4 * i + 3];
+        const int x1 = (int)x1d, y1 = (int)y1d, x2 = (int)x2d, y2 = (int)y2d;            // truncation toward zero = Python's int()
+        int4 r;
+        r.x = max(min(x1, x2), 0); r.y = max(min(y1, y2), 0); r.z = min(max(x1, x2), W - 1); r.w = min(max(y1, y2), H - 1);
+        rects[i] = r;
+        if (areas && blockIdx.x == 0) {
+            double v = __dmul_rn(__ddiv_rn(__dsub_rn(x2d, x1d), (double)H), __ddiv_rn(__dsub_rn(y2d, y1d), (double)W));
+            v = (1.0 < v) ? 1.0 : v;                           // Python: max(min(v, 1.0), 0.0)
+            v = (v < 0.0) ? 0.0 : v;
+            areas[i] = v;
+        }
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned int cnt = 0;
+    for (int y = blockIdx.x * COV_WARPS + warp; y < H; y += gridDim.x * COV_WARPS) {
+        for (int w0 = 0; w0 < W; w0 += 1024) {                 // 32 lanes x 32 columns per pass
+            const int c0 = w0 + lane * 32;                      // this lane's columns c0 .. c0 + 31
+            unsigned int m = 0;
+            for (int i = 0; i < n; ++i) {
+                const int4 r = rects[i];
+                if (y < r.y || y > r.w) continue;
+                const int a = max(r.x, c0), b = min(r.z, c0 + 31);
+                if (a <= b) m |= (0xffffffffu >> (31 - (b - a))) << (a - c0);
+            }
+            cnt += __popc(m);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(nonzero, (unsigned long long)cnt);
+}
+
 }  // namespace
 
 cudaError_t launch_frame_geometry(const GeomParams &p, cudaStream_t s) {
@@ -152,5 +176,19 @@ cudaError_t launch_pair_matrix(const double *a, int na, const double *b, int nb,
     long long n = (long long)na * nb;
     if (n == 0) return cudaSuccess;
     pair_matrix_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, na, b, nb, out, want_iou);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_coverage(const double *tlbr, int n, int H, int W, unsigned long long *nonzero, double *areas, cudaStream_t s) {
+    if (H <= 0 || W <= 0 || n < 0) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)(n > 0 ? n : 1) * sizeof(int4);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(coverage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int grid = (H + COV_WARPS - 1) / COV_WARPS;
+    if (grid > 148 * 4) grid = 148 * 4;
+    coverage_kernel<<<grid, COV_WARPS * 32, smem, s>>>(tlbr, n, H, W, nonzero, areas);
     return cudaGetLastError();
 }

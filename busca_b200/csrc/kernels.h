@@ -20,7 +20,23 @@ struct GeomParams {
     int *cand_out;             // [B,T,C] | null
 };
 cudaError_t launch_frame_geometry(const GeomParams &p, cudaStream_t s);
+// union area (pixels) of the filled, int()-truncated, inclusive rectangles of `tlbr` [n,4] on an H x W canvas, ADDED to *nonzero (zero it
+// first), and the per-box relative areas [n] (may be null): BYTETracker.get_detection_coverage
+cudaError_t launch_coverage(const double *tlbr, int n, int H, int W, unsigned long long *nonzero, double *areas, cudaStream_t s);
 cudaError_t launch_pair_matrix(const double *a, int na, const double *b, int nb, double *out, int want_iou, cudaStream_t s);
+
+// ---------------------------------------------------------------- rounds.cu (host-tracker rounds)
+cudaError_t launch_kalman_predict(const double *mean, const double *cov, const uint8_t *tracked, int n, double *mean_out, double *cov_out,
+                                  cudaStream_t s);
+cudaError_t launch_kalman_update(const double *mean, const double *cov, const double *meas_xyah, int n, double *mean_out, double *cov_out,
+                                 cudaStream_t s);
+// cost [na,nb] = 1 - IoU (+1 convention); score [nb] (may be null): fused with the detection scores as matching.fuse_score does
+cudaError_t launch_match_cost(const double *a, int na, const double *b, int nb, const double *score, double *cost, cudaStream_t s);
+// optimum of lap.lapjv(cost, extend_cost=True, cost_limit=limit): x [N] column of each row or -1, y [M] row of each column or -1
+cudaError_t launch_assignment(const double *cost, int N, int M, double limit, int *x, int *y, cudaStream_t s);
+size_t assignment_smem_bytes(int N, int M);
+cudaError_t launch_duplicates(const double *a, const int *age_a, int na, const double *b, const int *age_b, int nb, double thresh,
+                              uint8_t *drop_a, uint8_t *drop_b, cudaStream_t s);
 
 // ---------------------------------------------------------------- crop.cu
 // boxes [n,4] (x1,y1,x2,y2) fp64 device; slots [n] device; bank = patch bank base.

@@ -259,6 +259,59 @@ class Engine:
         check(self.L.busca_center_distance(self.h, _ptr(a), len(a), _ptr(b), len(b), _ptr(out)))
         return out
 
+    def detection_coverage(self, boxes: np.ndarray, H: int, W: int) -> Tuple[int, np.ndarray]:
+        """Union area in pixels of the filled int()-truncated rectangles on an H x W canvas, and the per-box relative areas."""
+        boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+        areas = np.zeros(len(boxes), np.float64)
+        cnt = C.c_int64(0)
+        check(self.L.busca_detection_coverage(self.h, _ptr(boxes), len(boxes), int(H), int(W), C.byref(cnt), _ptr(areas)))
+        return int(cnt.value), areas
+
+    # ---- host-tracker rounds on the device (SURVEY.md 8f row 1) ---------------------------------------------------------
+    def kalman_predict(self, mean: np.ndarray, cov: np.ndarray, tracked: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """KalmanFilter.multi_predict (mean and covariance) for [n,8] / [n,8,8] float64; bit-identical to numpy."""
+        mean = np.ascontiguousarray(mean, np.float64).reshape(-1, 8)
+        cov = np.ascontiguousarray(cov, np.float64).reshape(-1, 8, 8)
+        mo, co = np.empty_like(mean), np.empty_like(cov)
+        tr = None if tracked is None else np.ascontiguousarray(tracked, np.uint8)
+        check(self.L.busca_kalman_predict(self.h, _ptr(mean), _ptr(cov), None if tr is None else _ptr(tr), len(mean), _ptr(mo), _ptr(co)))
+        return mo, co
+
+    def kalman_update(self, mean: np.ndarray, cov: np.ndarray, xyah: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """KalmanFilter.update for n independent (track, measurement) pairs."""
+        mean = np.ascontiguousarray(mean, np.float64).reshape(-1, 8)
+        cov = np.ascontiguousarray(cov, np.float64).reshape(-1, 8, 8)
+        z = np.ascontiguousarray(xyah, np.float64).reshape(-1, 4)
+        mo, co = np.empty_like(mean), np.empty_like(cov)
+        check(self.L.busca_kalman_update(self.h, _ptr(mean), _ptr(cov), _ptr(z), len(mean), _ptr(mo), _ptr(co)))
+        return mo, co
+
+    def match_round(self, a_tlbr: np.ndarray, b_tlbr: np.ndarray, b_score: Optional[np.ndarray], cost_limit: float, want_cost: bool = False):
+        """iou_distance (+ fuse_score) + linear_assignment in one call: (x [na], y [nb], cost or None)."""
+        a = np.ascontiguousarray(a_tlbr, np.float64).reshape(-1, 4)
+        b = np.ascontiguousarray(b_tlbr, np.float64).reshape(-1, 4)
+        sc = None if b_score is None else np.ascontiguousarray(b_score, np.float64).reshape(-1)
+        x, y = np.empty(len(a), np.int32), np.empty(len(b), np.int32)
+        cost = np.empty((len(a), len(b)), np.float64) if want_cost else None
+        check(self.L.busca_match_round(self.h, _ptr(a), len(a), _ptr(b), len(b), None if sc is None else _ptr(sc), float(cost_limit),
+                                       _ptr(x), _ptr(y), None if cost is None else _ptr(cost)))
+        return x, y, cost
+
+    def linear_assignment(self, cost: np.ndarray, cost_limit: float) -> Tuple[np.ndarray, np.ndarray]:
+        cost = np.ascontiguousarray(cost, np.float64)
+        n, m = cost.shape
+        x, y = np.empty(n, np.int32), np.empty(m, np.int32)
+        check(self.L.busca_linear_assignment(self.h, _ptr(cost), n, m, float(cost_limit), _ptr(x), _ptr(y)))
+        return x, y
+
+    def duplicate_tracks(self, a_tlbr, a_age, b_tlbr, b_age, thresh: float = 0.15) -> Tuple[np.ndarray, np.ndarray]:
+        a = np.ascontiguousarray(a_tlbr, np.float64).reshape(-1, 4)
+        b = np.ascontiguousarray(b_tlbr, np.float64).reshape(-1, 4)
+        ga, gb = np.ascontiguousarray(a_age, np.int32), np.ascontiguousarray(b_age, np.int32)
+        da, db = np.zeros(len(a), np.uint8), np.zeros(len(b), np.uint8)
+        check(self.L.busca_duplicate_tracks(self.h, _ptr(a), _ptr(ga), len(a), _ptr(b), _ptr(gb), len(b), float(thresh), _ptr(da), _ptr(db)))
+        return da.astype(bool), db.astype(bool)
+
     def iou(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(a, np.float64).reshape(-1, 4)
         b = np.ascontiguousarray(b, np.float64).reshape(-1, 4)

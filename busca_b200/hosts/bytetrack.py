@@ -10,9 +10,11 @@ whole sequences - with the adapter's exact call pattern into BUSCA - on a box wh
                         winners that are still Tracked are updated at their Kalman box with update_mems=False (:385-391)
               unconfirmed tracks, new tracks, lost / removed bookkeeping, duplicate removal  (:399-444, 685-698)
 
-Everything numeric that is not BUSCA's is injected (``iou_fn``, ``center_distance_fn``) so the same driver runs on the
-GPU library or, in the CPU tests, on the oracle.  Camera-motion compensation and the detection-coverage gate
- are not implemented: configs that enable them raise.
+Everything numeric that is not BUSCA's is injected (``iou_fn``, ``center_distance_fn``, ``reliable_fn``, ``rounds``) so the same
+driver runs on the GPU library or, in the CPU tests, on the oracle.  With ``rounds=DeviceRounds(engine)`` the association rounds
+themselves run on the device: batched Kalman predict / update, IoU cost + score fusion + assignment in one
+call per round, duplicate removal.  The detection-coverage gate (8f row 2, ``reliable_thresh``) needs ``reliable_fn``;
+camera-motion compensation (8f row 3) needs ``camera_motion_fn``: configs that enable them without it raise.
 
 Pinned: tests/test_host_bytetrack.py replays tests/golden/adapter_seq.npz, produced by the UNMODIFIED reference adapter,
 and requires identical track ids frame by frame.
@@ -111,6 +113,19 @@ class Track:
             self.images_mem.extend(other.images_mem)
 
 
+def apply_camera_motion(t: "Track", warp: np.ndarray):
+    """STrack.apply_camera_motion + BYTETracker.warp_pos (byte_tracker.py:123-138, 660-664): the track centre (frame coordinates) goes
+    through the 2x3 warp in FLOAT32 (the reference builds torch.Tensor([x, y, 1]) and multiplies with the float32 warp matrix) and is
+    written back into the float64 state."""
+    pos = (t._tlwh[:2] if t.mean is None else t.mean[:2]) * t.scale
+    p = np.array([pos[0], pos[1], 1.0], np.float32)
+    new = (np.asarray(warp, np.float32) @ p).astype(np.float32) / np.float32(t.scale)
+    if t.mean is None:
+        t._tlwh[:2] = new
+    else:
+        t.mean[:2] = new
+
+
 def assign(cost, thresh):
     """lap.lapjv(cost, extend_cost=True, cost_limit=thresh) as matching.linear_assignment uses it (matching.py:39-50):
     the optimum of the cost matrix extended by thresh/2 'unassigned' blocks.  Returns (matches[k,2], unmatched rows, unmatched cols)."""
@@ -130,6 +145,26 @@ def assign(cost, thresh):
     return matches, [i for i in range(n) if x[i] < 0], [j for j in range(m) if j not in taken]
 
 
+class DeviceRounds:
+    """The association rounds on libbusca_b200 (csrc/rounds.cu) behind the four operations the driver needs."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    def predict(self, mean, cov, tracked):
+        return self.e.kalman_predict(mean, cov, tracked)
+
+    def update(self, mean, cov, xyah):
+        return self.e.kalman_update(mean, cov, xyah)
+
+    def match(self, a_tlbr, b_tlbr, scores, thresh):
+        x, _y, _ = self.e.match_round(a_tlbr, b_tlbr, scores, thresh)
+        return x
+
+    def duplicates(self, a_tlbr, a_age, b_tlbr, b_age):
+        return self.e.duplicate_tracks(a_tlbr, a_age, b_tlbr, b_age, 0.15)
+
+
 def _merge(a: List[Track], b: List[Track]) -> List[Track]:
     seen = {t.track_id for t in a}
     out = list(a)
@@ -146,14 +181,20 @@ def _minus(a: List[Track], b: List[Track]) -> List[Track]:
 
 
 class ByteTrackHost:
-    def __init__(self, busca, args, iou_fn: Callable, center_distance_fn: Callable, frame_rate: int = 30):
+    def __init__(self, busca, args, iou_fn: Callable, center_distance_fn: Callable, frame_rate: int = 30,
+                 reliable_fn: Optional[Callable] = None, camera_motion_fn: Optional[Callable] = None, rounds=None):
         """``busca``: object with get_image_crops / associate_embeddings (busca_b200.network.BUSCA).  ``args``: the
         tracker namespace of option.load_args_from_config plus track_thresh, track_buffer, match_thresh, mot20.
-        ``iou_fn(a_tlbr[N,4], b_tlbr[M,4]) -> [N,M]`` (+1 convention), ``center_distance_fn(tracks, dets) -> [T,D]``."""
-        if getattr(args, "use_camera_motion_compensation", False) or hasattr(args, "reliable_thresh"):
-            raise NotImplementedError("camera-motion compensation / detection-coverage gate (SURVEY.md 8f) are not implemented")
+        ``iou_fn(a_tlbr[N,4], b_tlbr[M,4]) -> [N,M]`` (+1 convention), ``center_distance_fn(tracks, dets) -> [T,D]``,
+        ``reliable_fn(frame_shape, tracks, p) -> bool`` (BYTETracker.is_reliable), ``camera_motion_fn(previous_frame, frame) ->
+        2x3 float32 warp`` (cv2.findTransformECC, byte_tracker.py:626-657), ``rounds``: None (numpy / scipy on the host) or a DeviceRounds."""
+        if hasattr(args, "reliable_thresh") and reliable_fn is None:
+            raise NotImplementedError("the detection-coverage gate (reliable_thresh) needs reliable_fn")
+        if getattr(args, "use_camera_motion_compensation", False) and camera_motion_fn is None:
+            raise NotImplementedError("camera-motion compensation needs camera_motion_fn")
         self.busca, self.args = busca, args
-        self.iou_fn, self.cdist_fn = iou_fn, center_distance_fn
+        self.iou_fn, self.cdist_fn, self.reliable_fn, self.camera_motion_fn, self.rounds = iou_fn, center_distance_fn, reliable_fn, camera_motion_fn, rounds
+        self.last_image = None
         self.det_thresh = args.track_thresh + 0.1
         self.max_time_lost = int(frame_rate / 30.0 * args.track_buffer)
         self.kf = KalmanXYAH()
@@ -175,6 +216,33 @@ class ByteTrackHost:
             return cost
         scores = np.array([d.score for d in dets])
         return 1.0 - (1.0 - cost) * scores[None, :].repeat(cost.shape[0], axis=0)
+
+    def _match(self, a: Sequence[Track], b: Sequence[Track], fuse: bool, thresh: float):
+        """One round: IoU cost (+ score fusion) and the assignment with a cost limit -> (matches, unmatched a, unmatched b)."""
+        if self.rounds is None or len(a) == 0 or len(b) == 0:
+            cost = self._iou_cost(a, b)
+            return assign(self._fuse(cost, b) if fuse else cost, thresh)
+        scores = np.array([d.score for d in b], dtype=np.float64) if (fuse and not self.args.mot20) else None
+        x = self.rounds.match(np.ascontiguousarray([t.tlbr for t in a], dtype=np.float64), np.ascontiguousarray([t.tlbr for t in b], dtype=np.float64),
+                              scores, thresh)
+        matches = np.asarray([[i, j] for i, j in enumerate(x) if j >= 0], dtype=int).reshape(-1, 2)
+        taken = set(matches[:, 1].tolist())
+        return matches, [i for i in range(len(a)) if x[i] < 0], [j for j in range(len(b)) if j not in taken]
+
+    def _update_many(self, jobs):
+        """jobs: (track, detection, update_mems, reactivate) of ONE round - every track at most once, so the Kalman updates are
+        independent and run as one batch on the device."""
+        if self.rounds is None or not jobs:
+            for t, d, um, re in jobs:
+                self._update(t, d, update_mems=um, reactivate=re)
+            return
+        mean, cov = self.rounds.update(np.asarray([t.mean for t, *_ in jobs]), np.asarray([t.cov for t, *_ in jobs]),
+                                       np.asarray([tlwh_to_xyah(d.tlwh) for _, d, *_ in jobs]))
+        for k, (t, d, um, re) in enumerate(jobs):
+            t.mean, t.cov = mean[k], cov[k]
+            t.tracklet_len = 0 if re else t.tracklet_len + 1
+            t.state, t.is_activated, t.frame_id = TRACKED, True, self.frame_id
+            t._absorb(d, um)
 
     def _activate(self, t: Track):
         self._next_id += 1
@@ -199,7 +267,11 @@ class ByteTrackHost:
         for i, t in enumerate(pool):
             if t.state != TRACKED:
                 mean[i][7] = 0
-        mean, cov = self.kf.predict_many(mean, cov)
+        if self.rounds is not None:
+            mean = np.asarray([t.mean for t in pool])            # the device zeroes the height velocity of non-Tracked tracks itself
+            mean, cov = self.rounds.predict(mean, cov, np.array([t.state == TRACKED for t in pool], np.uint8))
+        else:
+            mean, cov = self.kf.predict_many(mean, cov)
         for t, m, c in zip(pool, mean, cov):
             t.mean, t.cov = m, c
 
@@ -261,36 +333,36 @@ class ByteTrackHost:
         # round 1: confirmed + lost tracks vs high-score detections
         pool = _merge(confirmed, self.lost)
         self._predict(pool)
-        matches, u_trk, u_det = assign(self._fuse(self._iou_cost(pool, dets1), dets1), a.match_thresh)
+        matches, u_trk, u_det = self._match(pool, dets1, True, a.match_thresh)
+        jobs = []
         for it, idet in matches:
             t, d = pool[it], dets1[idet]
-            if t.state == TRACKED:
-                self._update(t, d, update_mems=d.score >= self.det_thresh)
-                activated.append(t)
-            else:
-                self._update(t, d, update_mems=d.score >= self.det_thresh, reactivate=True)
-                refind.append(t)
+            jobs.append((t, d, d.score >= self.det_thresh, t.state != TRACKED))
+            (activated if t.state == TRACKED else refind).append(t)
+        self._update_many(jobs)
 
         # round 2: still-tracked leftovers vs low-score detections
         dets2 = make(second, im2)
         r_tracked = [pool[i] for i in u_trk if pool[i].state == TRACKED]
         r_lost = [pool[i] for i in u_trk if pool[i].state != TRACKED]
-        matches, u_trk2, _ = assign(self._iou_cost(r_tracked, dets2), 0.5)
+        matches, u_trk2, _ = self._match(r_tracked, dets2, False, 0.5)
         mems2 = not getattr(a, "transformer_update_mems_only_first_round", False)
-        for it, idet in matches:
-            self._update(r_tracked[it], dets2[idet], update_mems=mems2)
-            activated.append(r_tracked[it])
+        self._update_many([(r_tracked[it], dets2[idet], mems2, False) for it, idet in matches])
+        activated.extend(r_tracked[it] for it, _ in matches)
         unassigned = _merge([r_tracked[i] for i in u_trk2], r_lost)
         u_final = list(range(len(unassigned)))
 
         # Step 3b: BUSCA
-        if use_busca:
+        if use_busca and not (hasattr(a, "reliable_thresh") and not self.reliable_fn(current_frame.shape, self.tracked, a.reliable_thresh)):
+            if getattr(a, "use_camera_motion_compensation", False) and self.frame_id > 1:
+                warp = np.asarray(self.camera_motion_fn(self.last_image, current_frame), np.float32)
+                for t in unassigned:
+                    apply_camera_motion(t, warp)
             kalman = self._kalman_candidates(unassigned, current_frame)
             m3, u_final = self._third_round(unassigned, dets_all, kalman)
-            for it, _p in m3:
-                if unassigned[it].state == TRACKED:          # Lost winners are dropped (byte_tracker.py:389)
-                    self._update(unassigned[it], kalman[it], update_mems=False)
-                    activated.append(unassigned[it])
+            winners = [it for it, _p in m3 if unassigned[it].state == TRACKED]   # Lost winners are dropped (byte_tracker.py:389)
+            self._update_many([(unassigned[it], kalman[it], False, False) for it in winners])
+            activated.extend(unassigned[it] for it in winners)
         for it in u_final:
             t = unassigned[it]
             if t.state != LOST:
@@ -299,10 +371,9 @@ class ByteTrackHost:
 
         # unconfirmed tracks vs what round 1 left over
         rest = [dets1[i] for i in u_det]
-        matches, u_unc, u_rest = assign(self._fuse(self._iou_cost(unconfirmed, rest), rest), 0.7)
-        for it, idet in matches:
-            self._update(unconfirmed[it], rest[idet], update_mems=True)
-            activated.append(unconfirmed[it])
+        matches, u_unc, u_rest = self._match(unconfirmed, rest, True, 0.7)
+        self._update_many([(unconfirmed[it], rest[idet], True, False) for it, idet in matches])
+        activated.extend(unconfirmed[it] for it, _ in matches)
         for it in u_unc:
             unconfirmed[it].state = REMOVED
             removed.append(unconfirmed[it])
@@ -322,9 +393,19 @@ class ByteTrackHost:
         self.removed.extend(removed)
         self.removed = [t for t in self.removed if self.frame_id - t.frame_id < 10 * self.max_time_lost]
         self._dedupe()
+        if getattr(a, "use_camera_motion_compensation", False):
+            self.last_image = None if current_frame is None else np.copy(current_frame)
         return [t for t in self.tracked if t.is_activated]
 
     def _dedupe(self):
+        if self.rounds is not None and self.tracked and self.lost:
+            da, db = self.rounds.duplicates(np.ascontiguousarray([t.tlbr for t in self.tracked], dtype=np.float64),
+                                            [t.frame_id - t.start_frame for t in self.tracked],
+                                            np.ascontiguousarray([t.tlbr for t in self.lost], dtype=np.float64),
+                                            [t.frame_id - t.start_frame for t in self.lost])
+            self.tracked = [t for t, d in zip(self.tracked, da) if not d]
+            self.lost = [t for t, d in zip(self.lost, db) if not d]
+            return
         cost = self._iou_cost(self.tracked, self.lost)
         drop_a, drop_b = set(), set()
         for p, q in zip(*np.where(cost < 0.15)):

@@ -83,6 +83,35 @@ def iou_distance(atlbrs, btlbrs, engine=None):
     return 1 - (engine or default_engine()).iou(a, b)
 
 
+def get_detection_coverage(frame_shape, active_stracks, inactive_stracks=(), engine=None):
+    """BYTETracker.get_detection_coverage (adapters/ByteTrack/yolox/tracker/byte_tracker.py:574-623): the fraction of the frame covered by
+    the union of the tracks' boxes (filled cv2.rectangle at the int()-truncated corners of ``tlbr * scale``), the same per object, and the
+    per-box relative areas.  ``frame_shape`` = ``frame.shape`` (only H and W are used); tracks are objects with ``tlbr`` / ``scale`` or
+    rows (x1, y1, x2, y2) already multiplied by the scale.  The raster count runs on the device; the scalar bookkeeping is the reference's
+    numpy arithmetic on the same values."""
+    H, W = int(frame_shape[0]), int(frame_shape[1])
+    rows = []
+    for t in list(active_stracks) + list(inactive_stracks):
+        rows.append(np.asarray(t.tlbr, np.float64) * t.scale if hasattr(t, "tlbr") else np.asarray(t, np.float64).reshape(4))
+    boxes = np.stack(rows) if rows else np.zeros((0, 4))
+    count, areas = (engine or default_engine()).detection_coverage(boxes, H, W)
+    bbox_areas = [float(a) for a in areas]
+    percentage_covered = count / (H * W)
+    if len(rows) > 0:
+        avg_area_covered = percentage_covered / len(rows)
+        average_bbox_area = np.sqrt(np.array(bbox_areas)).mean() ** 2
+    else:
+        avg_area_covered, average_bbox_area = 0.0, 0.0
+    return {"area_covered": percentage_covered, "area_covered_per_obj": avg_area_covered, "max_bbox_area": max([0.0] + bbox_areas),
+            "average_bbox_area": average_bbox_area, "bbox_areas": bbox_areas}
+
+
+def is_reliable(frame_shape, active_stracks, p, engine=None):
+    """BYTETracker.is_reliable (byte_tracker.py:459-465): the gate of the whole Step 3b in the MOT17 configurations (``reliable_thresh``)."""
+    c = get_detection_coverage(frame_shape, active_stracks, (), engine=engine)
+    return bool(c["area_covered"] > c["area_covered_per_obj"] * p[0] + p[1])
+
+
 def get_bbox_crop(im, bbox_real_scale, output_size=(128, 384), normalize=True, ghost_normalize=True, engine=None):
     """One crop (x1,y1,x2,y2 in ``im`` pixels) -> [384,128,3]; uint8 BGR, or float32 normalised when
     ``normalize`` (host LUT, bit-equal to the reference's float arithmetic)."""

@@ -91,6 +91,32 @@ int busca_iou(busca_ctx *ctx, const double *a, int32_t na, const double *b, int3
  * Outputs (any may be NULL): mean_out [n,8], tlwh [n,4], tlbr [n,4]. */
 int busca_motion_proposals(busca_ctx *ctx, const double *mean, const uint8_t *tracked, int32_t n, double *mean_out,
                            double *tlwh, double *tlbr);
+/* BYTETracker.get_detection_coverage (the is_reliable gate of Step 3b)    byte_tracker.py:574-623, 459-465
+ * tlbr [n,4] float64 = track.tlbr * track.scale of the active tracks; frame size H x W.
+ * nonzero_out: pixels of the union of the filled rectangles (int()-truncated corners, both inclusive, clipped) = np.count_nonzero of the
+ * reference's canvas; bbox_areas_out [n] (may be NULL): max(min(((x2-x1)/H) * ((y2-y1)/W), 1), 0) per box (the reference's H/W swap kept). */
+int busca_detection_coverage(busca_ctx *ctx, const double *tlbr, int32_t n, int32_t H, int32_t W, int64_t *nonzero_out,
+                             double *bbox_areas_out);
+/* ---- host-tracker rounds on the device ---------------------------------------------------------------
+ * KalmanFilter.multi_predict with the covariance                      mot_online/kalman_filter.py:154-191; byte_tracker.py:50-61
+ * mean [n,8], cov [n,8,8] float64; tracked [n] uint8 or NULL (0 = the height velocity is zeroed first). Bit-identical to numpy. */
+int busca_kalman_predict(busca_ctx *ctx, const double *mean, const double *cov, const uint8_t *tracked, int32_t n, double *mean_out,
+                         double *cov_out);
+/* KalmanFilter.update (project, 4x4 Cholesky solve, gain) for n independent tracks   kalman_filter.py:126-152, 193-225
+ * xyah [n,4] = the matched detections as (cx, cy, w/h, h). Agrees with scipy/LAPACK to ~1e-13 relative (not bit-wise). */
+int busca_kalman_update(busca_ctx *ctx, const double *mean, const double *cov, const double *xyah, int32_t n, double *mean_out,
+                        double *cov_out);
+/* One association round: matching.iou_distance (+ matching.fuse_score when b_score != NULL) -> matching.linear_assignment
+ * (lap.lapjv(cost, extend_cost=True, cost_limit))                      matching.py:39-50, 73-91, 165-180; byte_tracker.py:312-362
+ * x [na]: matched column or -1; y [nb]: matched row or -1; cost_out [na,nb] may be NULL. na == 0 or nb == 0: all -1. */
+int busca_match_round(busca_ctx *ctx, const double *a_tlbr, int32_t na, const double *b_tlbr, int32_t nb, const double *b_score,
+                      double cost_limit, int32_t *x, int32_t *y, double *cost_out);
+/* matching.linear_assignment on a caller-supplied cost matrix [n,m] float64       matching.py:39-50 */
+int busca_linear_assignment(busca_ctx *ctx, const double *cost, int32_t n, int32_t m, double cost_limit, int32_t *x, int32_t *y);
+/* remove_duplicate_stracks: pairs with IoU distance < thresh (0.15); age = frame_id - start_frame; the younger one is flagged, the
+ * first list's on equal age.  drop_a [na], drop_b [nb] uint8.                       byte_tracker.py:685-698 */
+int busca_duplicate_tracks(busca_ctx *ctx, const double *a_tlbr, const int32_t *a_age, int32_t na, const double *b_tlbr,
+                           const int32_t *b_age, int32_t nb, double thresh, uint8_t *drop_a, uint8_t *drop_b);
 /* All of the above plus candidate selection in ONE launch (north_star: "one vectorised kernel per frame"):
  * proposals from Kalman means, T x D centre-distance and IoU matrices, per-track top-C detections.
  * Outputs may be NULL. cand [T,C] int32: detection index, D+t for the motion proposal, -1 = missing. */

@@ -421,8 +421,132 @@ def golden_adapter(weights_path):
     print("adapter: kept-alive decisions", int(np.sum(b3_keep)), "of", len(b3_keep))
 
 
+def golden_coverage():
+    """8f row 2: BYTETracker.get_detection_coverage / is_reliable of the UNMODIFIED adapter (called unbound on a stub self - the two
+    methods read nothing from the tracker), on seeded boxes that include negative / out-of-frame / reversed / degenerate corners."""
+    import importlib
+    sys.path.insert(0, os.path.join(REF, "adapters/CenterTrack/src/lib"))
+    bt = importlib.import_module("utils.byte_tracker")
+
+    class Stub:
+        get_detection_coverage = bt.BYTETracker.get_detection_coverage
+        is_reliable = bt.BYTETracker.is_reliable
+
+    class Trk:
+        def __init__(self, tlbr, scale):
+            self.tlbr, self.scale = tlbr, scale
+
+    rng = np.random.default_rng(23)
+    store, cases = {}, []
+    for k, (H, W, n, scale) in enumerate([(1080, 1920, 0, 1.0), (1080, 1920, 1, 1.0), (1080, 1920, 60, 1.0), (1080, 1920, 300, 0.75),
+                                          (480, 640, 25, 1.6), (97, 1031, 40, 1.0), (720, 2500, 500, 1.0)]):
+        b = synth.random_boxes(rng, n) if n else np.zeros((0, 4))
+        b = b * np.array([W / 1920.0, H / 1080.0, W / 1920.0, H / 1080.0]) / scale
+        b[:, 2:] += b[:, :2]
+        if n >= 25:
+            b[0] = [-40.7, -12.2, 31.9, 55.5] / np.float64(scale)          # negative corners: int() truncates toward zero
+            b[1] = [W - 20.5, H - 30.5, W + 80.0, H + 15.0] / np.float64(scale)
+            b[2] = [300.9, 200.9, 250.1, 120.1] / np.float64(scale)       # reversed corners
+            b[3] = [-300.0, -300.0, -10.0, -10.0] / np.float64(scale)     # wholly outside
+            b[4] = [77.3, 88.8, 77.9, 88.9] / np.float64(scale)           # a single pixel
+            b[5] = [-0.9, 10.0, 0.9, 12.0] / np.float64(scale)            # -0.9 -> 0
+        frame = np.zeros((H, W, 3), np.uint8)
+        trks = [Trk(r.copy(), scale) for r in b]
+        out = Stub().get_detection_coverage(frame, trks, [])
+        store[f"c{k}_boxes"] = b
+        store[f"c{k}_meta"] = np.array([H, W, scale], np.float64)
+        store[f"c{k}_scalars"] = np.array([out["area_covered"], out["area_covered_per_obj"], out["max_bbox_area"], out["average_bbox_area"]], np.float64)
+        store[f"c{k}_areas"] = np.array(out["bbox_areas"], np.float64)
+        ps = [(0.0, 0.0), (5.0, 0.1), (1.0, 0.05), (n * 0.5, 0.0), (float(n), -1e-9)]
+        store[f"c{k}_p"] = np.array(ps)
+        store[f"c{k}_reliable"] = np.array([Stub().is_reliable(frame, trks, p) for p in ps], bool)
+        cases.append(k)
+        print("coverage case", k, H, W, n, "covered %.4f" % out["area_covered"], store[f"c{k}_reliable"])
+    store["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "coverage.npz"), **store)
+
+
+def golden_rounds():
+    """8f row 1: the UNMODIFIED reference KalmanFilter (initiate / multi_predict / update), matching.iou_distance / fuse_score and
+    remove_duplicate_stracks on seeded inputs.  cython_bbox is the shim that executes the reference's in-tree restatement; lap is not
+    involved (the assignment has no reference-side golden: third-party, absent)."""
+    import importlib
+    sys.path.insert(0, os.path.join(REF, "adapters/CenterTrack/src/lib"))
+    bt = importlib.import_module("utils.byte_tracker")
+    from utils.mot_online import kalman_filter as KF
+    from utils.mot_online import matching
+    kf = KF.KalmanFilter()
+    rng = np.random.default_rng(41)
+    n, steps = 48, 6
+    boxes = synth.random_boxes(rng, n)
+    xyah = np.stack([boxes[:, 0] + boxes[:, 2] / 2, boxes[:, 1] + boxes[:, 3] / 2, boxes[:, 2] / boxes[:, 3], boxes[:, 3]], axis=1)
+    mean = np.zeros((n, 8))
+    cov = np.zeros((n, 8, 8))
+    for i in range(n):
+        mean[i], cov[i] = kf.initiate(xyah[i])
+    store = {"kf_mean0": mean.copy(), "kf_cov0": cov.copy()}
+    for s in range(steps):
+        tracked = rng.uniform(size=n) < 0.8
+        m_in = mean.copy()
+        m_in[~tracked, 7] = 0                                   # STrack.multi_predict (byte_tracker.py:55-56)
+        mean_p, cov_p = kf.multi_predict(m_in, cov)
+        z = mean_p[:, :4] + rng.normal(0, 1, (n, 4)) * np.array([4.0, 4.0, 0.01, 5.0])
+        upd = rng.uniform(size=n) < 0.7
+        mean_u, cov_u = mean_p.copy(), cov_p.copy()
+        for i in np.where(upd)[0]:
+            mean_u[i], cov_u[i] = kf.update(mean_p[i], cov_p[i], z[i])
+        store.update({f"kf{s}_tracked": tracked, f"kf{s}_mean_pred": mean_p, f"kf{s}_cov_pred": cov_p, f"kf{s}_z": z, f"kf{s}_upd": upd,
+                      f"kf{s}_mean_upd": mean_u, f"kf{s}_cov_upd": cov_u})
+        mean, cov = mean_u, cov_u
+    store["kf_steps"] = np.array(steps)
+    # cost matrices
+    for k, (na, nb) in enumerate([(37, 53), (200, 300), (1, 7), (60, 3)]):
+        a = synth.random_boxes(rng, na)
+        b = synth.random_boxes(rng, nb)
+        m = min(na, nb) // 2 + 1
+        b[:m] = a[:m] + rng.normal(0, 6, (m, 4))
+        a[:, 2:] += a[:, :2]
+        b[:, 2:] += b[:, :2]
+        sc = rng.uniform(0.1, 0.99, nb).astype(np.float32)        # detector scores reach the tracker as float32
+        cost = matching.iou_distance(list(a), list(b))
+        fused = matching.fuse_score(cost.copy(), [types.SimpleNamespace(score=v) for v in sc])
+        store.update({f"m{k}_a": a, f"m{k}_b": b, f"m{k}_score": sc, f"m{k}_cost": cost, f"m{k}_fused": fused})
+    store["m_cases"] = np.array(4)
+
+    class Trk:
+        def __init__(self, tlbr, frame_id, start):
+            self.tlbr, self.frame_id, self.start_frame = tlbr, frame_id, start
+
+    for k, (na, nb) in enumerate([(40, 25), (5, 1)]):
+        a = synth.random_boxes(rng, na)
+        b = synth.random_boxes(rng, nb)
+        m = min(na, nb)
+        b[:m] = a[:m] + rng.normal(0, 3, (m, 4))
+        a[:, 2:] += a[:, :2]
+        b[:, 2:] += b[:, :2]
+        fa, sa = rng.integers(20, 60, na), rng.integers(0, 20, na)
+        fb, sb = rng.integers(20, 60, nb), rng.integers(0, 20, nb)
+        e = min(3, m)
+        fb[:e], sb[:e] = fa[:e], sa[:e]                            # equal ages: the first list's track goes
+        ta = [Trk(a[i], int(fa[i]), int(sa[i])) for i in range(na)]
+        tb = [Trk(b[i], int(fb[i]), int(sb[i])) for i in range(nb)]
+        ra, rb = bt.remove_duplicate_stracks(ta, tb)
+        store.update({f"d{k}_a": a, f"d{k}_b": b, f"d{k}_age_a": fa - sa, f"d{k}_age_b": fb - sb,
+                      f"d{k}_keep_a": np.array([t in ra for t in ta]), f"d{k}_keep_b": np.array([t in rb for t in tb])})
+        print("duplicates case", k, "dropped", na - len(ra), nb - len(rb))
+    store["d_cases"] = np.array(2)
+    np.savez_compressed(os.path.join(HERE, "rounds.npz"), **store)
+    print("rounds golden written")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["crops", "geometry", "pe", "assoc"]
+    if "coverage" in which or "rounds" in which:
+        if "coverage" in which:
+            golden_coverage()
+        if "rounds" in which:
+            golden_rounds()
+        sys.exit(0)
     if any(w in ("cond", "scene", "scene_mot20", "adapter") for w in which):
         model, targs = build_reference(profile="conditioned")
         if "cond" in which:

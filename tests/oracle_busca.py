@@ -33,3 +33,26 @@ def center_distance(tracks, dets):
 
 def iou(a, b):
     return ogeo.bbox_overlaps(a, b)
+
+
+class OracleRounds:
+    """The DeviceRounds protocol of busca_b200/hosts/bytetrack.py on the oracle (numpy / scipy): exercises the driver's batched
+    round path on a box without a GPU."""
+
+    def predict(self, mean, cov, tracked):
+        from oracle import rounds as ornd
+        return ornd.kf_multi_predict(mean, cov, tracked)
+
+    def update(self, mean, cov, xyah):
+        from oracle import rounds as ornd
+        out = [ornd.kf_update(m, c, z) for m, c, z in zip(mean, cov, xyah)]
+        return np.asarray([o[0] for o in out]), np.asarray([o[1] for o in out])
+
+    def match(self, a_tlbr, b_tlbr, scores, thresh):
+        from oracle import rounds as ornd
+        cost = ornd.iou_distance(a_tlbr, b_tlbr)
+        return ornd.linear_assignment(cost if scores is None else ornd.fuse_score(cost, scores), thresh)[0]
+
+    def duplicates(self, a_tlbr, a_age, b_tlbr, b_age):
+        from oracle import rounds as ornd
+        return ornd.remove_duplicates(a_tlbr, a_age, b_tlbr, b_age)

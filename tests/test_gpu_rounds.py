@@ -1,0 +1,153 @@
+"""GPU parity tests (-m gpu) of the SURVEY.md 8(f) rows: the host tracker's association rounds (rounds.cu) and the detection-coverage
+gate (geometry.cu), through the C ABI, against fixtures of the unmodified reference (tests/golden/rounds.npz, coverage.npz) and the
+oracle.  Bit-exact wherever the reference's arithmetic is order-independent; the Kalman update (LAPACK in the reference) within 1e-10."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from busca_b200 import synth
+
+KF_UPDATE_TOL = 1e-10          # relative to the largest entry of the track's state / covariance; measured ~1e-13
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from busca_b200.engine import Engine
+    return Engine(device=0, bank_slots=8)
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "rounds.npz"))
+
+
+# ------------------------------------------------------------------------------------------------ 8f row 2
+def test_detection_coverage_equals_reference(engine, golden_dir):
+    from busca_b200 import tracking
+    c = np.load(os.path.join(golden_dir, "coverage.npz"))
+    for k in c["cases"]:
+        H, W, scale = c[f"c{k}_meta"]
+        H, W = int(H), int(W)
+        boxes = c[f"c{k}_boxes"] * scale
+        out = tracking.get_detection_coverage((H, W, 3), boxes, engine=engine)
+        got = np.array([out["area_covered"], out["area_covered_per_obj"], out["max_bbox_area"], out["average_bbox_area"]])
+        assert np.array_equal(got, c[f"c{k}_scalars"]), (k, got, c[f"c{k}_scalars"])
+        assert np.array_equal(np.array(out["bbox_areas"], np.float64), c[f"c{k}_areas"])
+        rel = [tracking.is_reliable((H, W, 3), boxes, p, engine=engine) for p in c[f"c{k}_p"]]
+        assert np.array_equal(np.array(rel, bool), c[f"c{k}_reliable"])
+
+
+def test_detection_coverage_random_vs_oracle(engine):
+    from oracle import coverage as ocov
+    rng = np.random.default_rng(77)
+    for H, W, n in [(1080, 1920, 700), (33, 47, 20), (2160, 3840, 150), (5, 1025, 3)]:
+        b = np.concatenate([rng.uniform(-50, W + 50, (n, 1)), rng.uniform(-50, H + 50, (n, 1)),
+                            rng.uniform(-50, W + 50, (n, 1)), rng.uniform(-50, H + 50, (n, 1))], axis=1)
+        if n >= 100:
+            b[:, 2:] = b[:, :2] + rng.uniform(0, 120, (n, 2))
+        cnt, areas = engine.detection_coverage(b, H, W)
+        want = ocov.detection_coverage((H, W), b)
+        assert cnt == want["nonzero"], (H, W, n)
+        assert np.array_equal(areas, np.array(want["bbox_areas"]))
+
+
+# ------------------------------------------------------------------------------------------------ 8f row 1
+def test_kalman_predict_bit_exact(engine, g):
+    mean, cov = g["kf_mean0"], g["kf_cov0"]
+    for s in range(int(g["kf_steps"])):
+        mp, cp = engine.kalman_predict(mean, cov, g[f"kf{s}_tracked"])
+        assert np.array_equal(mp, g[f"kf{s}_mean_pred"]), s
+        assert np.array_equal(cp, g[f"kf{s}_cov_pred"]), s
+        mean, cov = g[f"kf{s}_mean_upd"], g[f"kf{s}_cov_upd"]
+    m2, c2 = engine.kalman_predict(g["kf_mean0"], g["kf_cov0"], None)                 # no flags: nothing is zeroed
+    from oracle import rounds as ornd
+    mo, co = ornd.kf_multi_predict(g["kf_mean0"], g["kf_cov0"], None)
+    assert np.array_equal(m2, mo) and np.array_equal(c2, co)
+
+
+def test_kalman_update_vs_reference(engine, g):
+    worst = 0.0
+    for s in range(int(g["kf_steps"])):
+        mp, cp, z, upd = g[f"kf{s}_mean_pred"], g[f"kf{s}_cov_pred"], g[f"kf{s}_z"], g[f"kf{s}_upd"]
+        mu, cu = engine.kalman_update(mp[upd], cp[upd], z[upd])
+        wm, wc = g[f"kf{s}_mean_upd"][upd], g[f"kf{s}_cov_upd"][upd]
+        em = np.abs(mu - wm).max(axis=1) / np.abs(wm).max(axis=1)
+        ec = np.abs(cu - wc).reshape(len(wc), -1).max(axis=1) / np.abs(wc).reshape(len(wc), -1).max(axis=1)
+        worst = max(worst, em.max(), ec.max())
+    print(f"kalman update: worst relative deviation from scipy/LAPACK {worst:.2e}")
+    assert worst < KF_UPDATE_TOL
+
+
+def test_match_cost_bit_exact(engine, g):
+    for k in range(int(g["m_cases"])):
+        a, b, sc = g[f"m{k}_a"], g[f"m{k}_b"], g[f"m{k}_score"]
+        _, _, cost = engine.match_round(a, b, None, 0.9, want_cost=True)
+        assert np.array_equal(cost, g[f"m{k}_cost"]), k
+        _, _, fused = engine.match_round(a, b, sc.astype(np.float64), 0.9, want_cost=True)
+        assert np.array_equal(fused, g[f"m{k}_fused"]), k
+
+
+def _check_assignment(cost, thresh, x, y):
+    from oracle import rounds as ornd
+    xo, yo = ornd.linear_assignment(cost, thresh)
+    n, m = cost.shape
+    # a valid partial matching
+    assert all(0 <= j < m and y[j] == i for i, j in enumerate(x) if j >= 0)
+    assert all(0 <= i < n and x[i] == j for j, i in enumerate(y) if i >= 0)
+    if not np.array_equal(x, xo):                                   # only legitimate when the optimum is not unique
+        assert abs(ornd.assignment_objective(cost, x, thresh) - ornd.assignment_objective(cost, xo, thresh)) < 1e-9
+        return False
+    return True
+
+
+def test_assignment_equals_oracle(engine, g):
+    rng = np.random.default_rng(123)
+    same = total = 0
+    for n, m in [(1, 1), (1, 9), (9, 1), (7, 7), (37, 53), (64, 20), (200, 300), (500, 300), (300, 520)]:
+        for thresh in (0.5, 0.7, 0.9):
+            cost = rng.uniform(0, 1.3, (n, m))
+            x, y = engine.linear_assignment(cost, thresh)
+            same += _check_assignment(cost, thresh, x, y)
+            total += 1
+    assert same == total                                            # continuous random costs: the optimum is unique
+    # IoU-distance matrices (many exact 1.0 entries), as the rounds see them, straight from boxes
+    for k in range(int(g["m_cases"])):
+        for sc, thresh in ((None, 0.5), (g[f"m{k}_score"].astype(np.float64), 0.9)):
+            x, y, cost = engine.match_round(g[f"m{k}_a"], g[f"m{k}_b"], sc, thresh, want_cost=True)
+            assert _check_assignment(cost, thresh, x, y)
+    x, y = engine.linear_assignment(np.zeros((0, 5)), 0.9)
+    assert len(x) == 0 and (y == -1).all()
+    x, y, _ = engine.match_round(np.zeros((3, 4)), np.zeros((0, 4)), None, 0.9)
+    assert (x == -1).all() and len(y) == 0
+
+
+def test_assignment_mot20_scale_latency(engine):
+    """A crowded frame: 500 pooled tracks against 400 detections placed on them (IoU costs), one call = cost matrix + assignment."""
+    rng = np.random.default_rng(5)
+    a = synth.random_boxes(rng, 500)
+    b = np.concatenate([a[:350] + rng.normal(0, 4, (350, 4)), synth.random_boxes(rng, 50)])
+    a[:, 2:] += a[:, :2]
+    b[:, 2:] += b[:, :2]
+    x, y, cost = engine.match_round(a, b, None, 0.9, want_cost=True)
+    assert _check_assignment(cost, 0.9, x, y)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        engine.match_round(a, b, None, 0.9)
+    ms = (time.perf_counter() - t0) / 5 * 1e3
+    from oracle import rounds as ornd
+    t0 = time.perf_counter()
+    ornd.linear_assignment(ornd.iou_distance(a, b), 0.9)
+    print(f"match_round 500 x 400: {ms:.2f} ms on the device (host buffers in and out); scipy on the extended matrix: {(time.perf_counter() - t0) * 1e3:.2f} ms")
+    assert (x >= 0).sum() >= 300
+
+
+def test_duplicates_equal_reference(engine, g):
+    for k in range(int(g["d_cases"])):
+        da, db = engine.duplicate_tracks(g[f"d{k}_a"], g[f"d{k}_age_a"], g[f"d{k}_b"], g[f"d{k}_age_b"], 0.15)
+        assert np.array_equal(~da, g[f"d{k}_keep_a"]) and np.array_equal(~db, g[f"d{k}_keep_b"])
+    da, db = engine.duplicate_tracks(np.zeros((0, 4)), np.zeros(0), g["d0_b"], g["d0_age_b"], 0.15)
+    assert len(da) == 0 and not db.any()

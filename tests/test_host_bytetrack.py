@@ -25,7 +25,7 @@ def tracker_args():
     return args
 
 
-def replay(busca, iou_fn, cdist_fn, golden, n_frames=None, near_tie=0.0):
+def replay(busca, iou_fn, cdist_fn, golden, n_frames=None, near_tie=0.0, **host_kw):
     """Run the driver over the golden's sequence; returns the list of frames whose Step-3b pool contained a documented
     near-tie (|p - busca_thresh| < near_tie in the reference) - from the first such frame on, ids may legitimately differ."""
     g = golden
@@ -33,7 +33,7 @@ def replay(busca, iou_fn, cdist_fn, golden, n_frames=None, near_tie=0.0):
     n_frames = n_frames or total
     seq = synth.make_sequence(seed, total, n_obj, miss=float(g["miss"]))
     args = tracker_args()
-    host = ByteTrackHost(busca, args, iou_fn=iou_fn, center_distance_fn=cdist_fn)
+    host = ByteTrackHost(busca, args, iou_fn=iou_fn, center_distance_fn=cdist_fn, **host_kw)
     for f in range(n_frames):
         out = host.update(seq.dets[f].copy(), [seq.H, seq.W], [seq.H, seq.W], current_frame=seq.frames[f])
         a, b = int(g["off"][f]), int(g["off"][f + 1])
@@ -73,6 +73,13 @@ def test_driver_reproduces_the_reference_adapter_on_cpu(golden):
     assert busca.calls >= 5
 
 
+def test_driver_with_batched_rounds_on_cpu(golden):
+    """The driver's batched-round path (what DeviceRounds plugs into) on the oracle: same ids as the reference adapter."""
+    from oracle_busca import OracleBUSCA, OracleRounds, center_distance, iou
+    busca = OracleBUSCA(synth.make_weights(0, profile="conditioned"))
+    assert replay(busca, iou, center_distance, golden, n_frames=16, rounds=OracleRounds()) is None
+
+
 def test_assignment_matches_lapjv_semantics():
     from busca_b200.hosts.bytetrack import assign
     cost = np.array([[0.1, 0.9, 0.8], [0.95, 0.2, 0.97]])
@@ -101,4 +108,22 @@ def test_track_ids_equal_reference_adapter_gpu(golden, precision):
     stop = replay(m, lambda x, y: m.engine.iou(x, y), lambda t, d: tracking.center_distance(t, d), golden,
                   near_tie=2e-3 if precision == "fp32" else 3e-2)
     assert m.engine.launches - launches0 > 1000
+    assert stop is None or stop > 20, f"a near-tie flipped already at frame {stop}"
+
+
+@pytest.mark.gpu
+def test_track_ids_with_the_rounds_on_the_device(golden):
+    """the same 36 frames with the association rounds themselves on the device (batched Kalman predict / update,
+    IoU cost + assignment per round, duplicate removal: csrc/rounds.cu) - ids, boxes (1e-6) and Step-3b decisions as the reference's."""
+    from busca_b200 import tracking
+    from busca_b200.hosts.bytetrack import DeviceRounds
+    from busca_b200.network import BUSCA
+    args = tracker_args()
+    a = args.transformer
+    a.device, a.precision = "cuda:0", "fp32"
+    m = BUSCA(a).eval()
+    m.load_state_dict(synth.make_weights(0, profile="conditioned"))
+    stop = replay(m, lambda x, y: m.engine.iou(x, y), lambda t, d: tracking.center_distance(t, d), golden, near_tie=2e-3,
+                  rounds=DeviceRounds(m.engine))
+    prof = m.engine.counter("launches") if hasattr(m.engine, "counter") else None
     assert stop is None or stop > 20, f"a near-tie flipped already at frame {stop}"
