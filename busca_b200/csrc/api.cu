@@ -509,6 +509,43 @@ extern "C" int busca_sync_frame(busca_ctx *c, const uint8_t *bgr, int32_t H, int
     return BUSCA_OK;
 }
 
+// Frame ingest on the device (mot_evaluator.py:198-204).  The result becomes the current frame of the context (what
+// busca_crop reads) AND the page-locked mirror, so that a later busca_sync_frame with the returned host copy finds it in place.
+extern "C" int busca_ingest_frame(busca_ctx *c, const float *chw, int32_t chw_on_device, int32_t H, int32_t W, const float *rgb_mean,
+                                  const float *rgb_std, uint8_t *frame_out) {
+    if (!c || !chw || H <= 0 || W <= 0 || !rgb_mean || !rgb_std) return set_err(BUSCA_ERR_ARG, "bad argument");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t npix = (size_t)H * W, bytes = npix * 3;
+    const float *src = chw;
+    if (!chw_on_device) {
+        CUDA_OK(c->ws_io.ensure(npix * 12 + 64));
+        CUDA_OK(cudaMemcpyAsync(c->ws_io.p, chw, npix * 12, cudaMemcpyHostToDevice, c->stream));
+        src = (const float *)c->ws_io.p;
+    }
+    CUDA_OK(c->frame.ensure(bytes + 64));
+    prof_reset(c);
+    LAUNCH(c, "frame_ingest", launch_frame_ingest(src, H, W, rgb_mean, rgb_std, (uint8_t *)c->frame.p, c->stream));
+    c->fH = H; c->fW = W; c->fstride = (int64_t)W * 3;
+    c->mirror_valid = false;
+    if (frame_out) {
+        if (bytes > c->mirror_cap) {
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+            if (c->mirror) cudaFreeHost(c->mirror);
+            c->mirror = nullptr; c->mirror_cap = 0;
+            CUDA_OK(cudaHostAlloc((void **)&c->mirror, bytes, cudaHostAllocPortable));
+            c->mirror_cap = bytes;
+        }
+        CUDA_OK(cudaMemcpyAsync(c->mirror, c->frame.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        memcpy(frame_out, c->mirror, bytes);
+        c->mirror_valid = true;
+    } else {
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    prof_collect(c);
+    return BUSCA_OK;
+}
+
 extern "C" int busca_bank_reserve(busca_ctx *c, int64_t n_slots) {
     if (!c) return set_err(BUSCA_ERR_ARG, "null ctx");
     if (n_slots <= c->bank_slots) return BUSCA_OK;

@@ -39,6 +39,8 @@ cudaError_t launch_duplicates(const double *a, const int *age_a, int na, const d
                               uint8_t *drop_a, uint8_t *drop_b, cudaStream_t s);
 
 // ---------------------------------------------------------------- crop.cu
+// detector tensor [3,H,W] fp32 (RGB, normalised) -> uint8 BGR HWC (mot_evaluator.py:198-204), both in device memory
+cudaError_t launch_frame_ingest(const float *chw, int H, int W, const float mean[3], const float sd[3], uint8_t *bgr, cudaStream_t s);
 // boxes [n,4] (x1,y1,x2,y2) fp64 device; slots [n] device; bank = patch bank base.
 cudaError_t launch_crop_resize(const uint8_t *frame, int H, int W, int64_t row_stride, const double *boxes, int n,
                                const int32_t *slots, uint8_t *bank, cudaStream_t s);

@@ -196,6 +196,24 @@ class Engine:
             image = np.ascontiguousarray(image)
         check(self.L.busca_upload_frame(self.h, _ptr(image), image.shape[0], image.shape[1], image.strides[0]))
 
+    def ingest_frame(self, chw, mean, std, H: Optional[int] = None, W: Optional[int] = None, to_host: bool = True) -> Optional[np.ndarray]:
+        """mot_evaluator.py:198-204 on the device: ``chw`` is the detector's input, either a float32 numpy array [3,H,W] or an integer
+        DEVICE address of one (``tensor.data_ptr()``; give H and W) - RGB, normalised with ``mean`` / ``std``.  The de-normalised uint8 BGR
+        frame becomes the engine's current frame; returned on the host as well unless ``to_host`` is False."""
+        mean = np.ascontiguousarray(mean, np.float32).reshape(3)
+        std = np.ascontiguousarray(std, np.float32).reshape(3)
+        if isinstance(chw, (int, np.integer)):
+            ptr, on_dev = C.c_void_p(int(chw)), 1
+        else:
+            chw = np.ascontiguousarray(chw, np.float32)
+            if chw.ndim != 3 or chw.shape[0] != 3:
+                raise ValueError("detector tensor must be float32 [3,H,W]")
+            H, W = chw.shape[1], chw.shape[2]
+            ptr, on_dev = _ptr(chw), 0
+        out = np.empty((H, W, 3), np.uint8) if to_host else None
+        check(self.L.busca_ingest_frame(self.h, ptr, on_dev, int(H), int(W), _ptr(mean), _ptr(std), _ptr(out)))
+        return out
+
     def sync_frame(self, image: np.ndarray, boxes: Optional[np.ndarray] = None) -> bool:
         """Upload ``image`` unless the pixels ``boxes`` read (all pixels without boxes) already are in HBM (busca_sync_frame)."""
         if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:

@@ -160,6 +160,14 @@ class BUSCA:
         identity); different -> upload."""
         self.engine.sync_frame(image, boxes if boxes is not None and 0 < len(boxes) <= 8 else None)
 
+    def ingest_frame(self, detector_tensor, means, std, height=None, width=None, to_host=True):
+        """What the evaluators do before tracker.update (adapters/ByteTrack/yolox/evaluators/mot_evaluator.py:198-204), on the device:
+        the detector's normalised RGB CHW float32 input becomes the uint8 BGR frame the crops read - already in HBM, so the following
+        get_image_crops calls upload nothing.  ``detector_tensor``: numpy [3,H,W] float32, or the integer device address of such a tensor
+        on this engine's GPU (``imgs[0].data_ptr()``, with height / width).  Returns the host copy the adapter hands on as
+        ``current_frame`` (``to_host=False``: None; pass the frame's shape with ``device_frame_shape`` instead)."""
+        return self.engine.ingest_frame(detector_tensor, means, std, height, width, to_host=to_host)
+
     def set_frame(self, image: np.ndarray):
         """Explicitly (re)upload the current frame."""
         self.engine.upload_frame(image)

@@ -323,3 +323,16 @@ def make_sequence(seed: int, n_frames: int, n_objects: int, H: int = 1080, W: in
                 rows.append([b[0], b[1], b[0] + b[2], b[1] + b[3], rng.uniform(0.15, 0.9)])
         dets.append(np.asarray(rows, dtype=np.float32).reshape(-1, 5))
     return Sequence(frames=[frames[f % n_img] for f in range(n_frames)], dets=dets, H=H, W=W)
+
+
+YOLOX_MEANS, YOLOX_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def make_detector_tensor(seed: int, H: int, W: int, means=YOLOX_MEANS, std=YOLOX_STD) -> np.ndarray:
+    """A detector input as the evaluators hold it (mot_evaluator.py:198-204): float32 [3,H,W], RGB, normalised; a few percent of the
+    values de-normalise outside [0, 1] (the clip matters) and the first pixels sit on rounding edges."""
+    rng = np.random.default_rng(seed)
+    img = rng.uniform(-0.15, 1.15, (H, W, 3)).astype(np.float32)
+    img[0, :8] = np.array([0.0, 1.0, 0.5, 1.0 / 255, 254.999 / 255, 0.999999, 1e-8, 0.25], np.float32)[:, None]
+    chw = ((img - np.array(means, np.float32)) / np.array(std, np.float32)).astype(np.float32)
+    return np.ascontiguousarray(chw.transpose(2, 0, 1))

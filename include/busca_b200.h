@@ -70,6 +70,12 @@ int busca_upload_frame(busca_ctx *ctx, const uint8_t *bgr, int32_t H, int32_t W,
  * crop calls per frame without saying so (get_image_crops, network.py:492-507; byte_tracker.py:278-282, 468-479). */
 int busca_sync_frame(busca_ctx *ctx, const uint8_t *bgr, int32_t H, int32_t W, int64_t row_stride, const double *boxes, int32_t n_boxes,
                      int32_t *uploaded);
+/* Frame ingest on the device: the detector's input tensor [3,H,W] float32 (RGB, normalised) becomes the context's current uint8 BGR
+ * frame: v = x*std + mean (fp32), RGB->BGR, clip [0,1], *255, truncate - bit-identical to the evaluator's torch/numpy code.
+ * chw_on_device != 0: `chw` is a device pointer (the detector's own tensor: the frame never crosses PCIe).  frame_out: host [H,W,3]
+ * uint8 copy for the caller (the adapters pass it on as current_frame), or NULL.       yolox/evaluators/mot_evaluator.py:198-204 */
+int busca_ingest_frame(busca_ctx *ctx, const float *chw, int32_t chw_on_device, int32_t H, int32_t W, const float *rgb_mean,
+                       const float *rgb_std, uint8_t *frame_out);
 int busca_bank_reserve(busca_ctx *ctx, int64_t n_slots);
 int64_t busca_bank_capacity(busca_ctx *ctx);
 /* get_image_crops -> get_bbox_crop -> _cutout_with_pad + cv2.resize     network.py:492-507; tracking.py:62-113

@@ -539,8 +539,55 @@ def golden_rounds():
     print("rounds golden written")
 
 
+def golden_ingest():
+    """8f row 4: the evaluator's de-normalisation statements (adapters/ByteTrack/yolox/evaluators/mot_evaluator.py:198-204) executed
+    as they stand - the source lines are read from the reference file and exec'd with `.cuda()` stripped (no GPU in this container;
+    the fp32 multiply and add are IEEE operations on either device) - and write_results (:30-40) through a temp file."""
+    path = os.path.join(REF, "adapters/ByteTrack/yolox/evaluators/mot_evaluator.py")
+    lines = open(path).read().split("\n")
+    first = next(i for i, l in enumerate(lines) if "rgb_means = torch.tensor" in l)
+    block = [l.strip().replace(".cuda()", "") for l in lines[first:first + 7]]
+    assert block[-1].startswith("vot_img = (vot_img * 255.0).astype(np.uint8)"), block
+    rng = np.random.default_rng(61)
+    store = {}
+    for k, (H, W) in enumerate([(800, 1440), (37, 53), (608, 1088)]):
+        means, std = synth.YOLOX_MEANS, synth.YOLOX_STD
+        chw = synth.make_detector_tensor(61 + k, H, W)
+        pre = types.SimpleNamespace(means=means, std=std)
+        ns = {"torch": torch, "np": np, "imgs": [torch.from_numpy(chw)],
+              "self": types.SimpleNamespace(dataloader=types.SimpleNamespace(dataset=types.SimpleNamespace(preproc=pre)))}
+        exec("\n".join(block), ns)
+        store[f"i{k}_seed"] = np.array(61 + k)
+        store[f"i{k}_shape"] = np.array([H, W])
+        store[f"i{k}_sha"] = sha(ns["vot_img"])
+        if H * W < 4000:
+            store[f"i{k}_bgr"] = ns["vot_img"]
+        print("ingest case", k, H, W, store[f"i{k}_sha"][:16])
+    store["i_cases"] = np.array(3)
+    # write_results
+    import importlib.util, tempfile
+    src = open(path).read()
+    a = src.index("def write_results(")
+    b = src.index("def write_results_no_score(")
+    ns = {"logger": types.SimpleNamespace(info=lambda *a, **k: None)}
+    exec(src[a:b], ns)
+    res = []
+    for f in range(1, 6):
+        n = int(rng.integers(0, 6))
+        res.append((f, [tuple(rng.uniform(-5, 1900, 4)) for _ in range(n)], [int(v) for v in rng.integers(-1, 40, n)],
+                    [float(np.float32(v)) for v in rng.uniform(0.1, 1, n)]))
+    with tempfile.NamedTemporaryFile("r", suffix=".txt") as tf:
+        ns["write_results"](tf.name, res)
+        store["mot_txt"] = np.array(open(tf.name).read())
+    store["mot_rows"] = np.array([[f, tid, *tlwh, s] for f, tl, ids, sc in res for tlwh, tid, s in zip(tl, ids, sc)], np.float64)
+    np.savez_compressed(os.path.join(HERE, "ingest.npz"), **store)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["crops", "geometry", "pe", "assoc"]
+    if "ingest" in which:
+        golden_ingest()
+        sys.exit(0)
     if "coverage" in which or "rounds" in which:
         if "coverage" in which:
             golden_coverage()

@@ -151,3 +151,45 @@ def test_duplicates_equal_reference(engine, g):
         assert np.array_equal(~da, g[f"d{k}_keep_a"]) and np.array_equal(~db, g[f"d{k}_keep_b"])
     da, db = engine.duplicate_tracks(np.zeros((0, 4)), np.zeros(0), g["d0_b"], g["d0_age_b"], 0.15)
     assert len(da) == 0 and not db.any()
+
+
+# ------------------------------------------------------------------------------------------------ 8f row 4
+def test_frame_ingest_bit_exact(engine, golden_dir):
+    """mot_evaluator.py:198-204 on the device: sha256 of the uint8 BGR frame equal to the reference's, from a host tensor and from a
+    tensor that already lives in HBM; the ingested frame is the one the crops read."""
+    import hashlib
+    from oracle import crop as ocrop
+    gi = np.load(os.path.join(golden_dir, "ingest.npz"))
+    for k in range(int(gi["i_cases"])):
+        H, W = (int(v) for v in gi[f"i{k}_shape"])
+        chw = synth.make_detector_tensor(int(gi[f"i{k}_seed"]), H, W)
+        out = engine.ingest_frame(chw, synth.YOLOX_MEANS, synth.YOLOX_STD)
+        assert hashlib.sha256(out.tobytes()).hexdigest() == str(gi[f"i{k}_sha"]), k
+        p = engine.dev_alloc(chw.nbytes)
+        engine.h2d(p, chw)
+        out2 = engine.ingest_frame(p, synth.YOLOX_MEANS, synth.YOLOX_STD, H, W)
+        engine.dev_free(p)
+        assert np.array_equal(out, out2)
+        # crops come from the ingested frame without an upload
+        boxes = np.array([[3.2, 4.1, 30.7, 33.9], [-5.0, -3.0, 20.0, 25.0]])
+        slots = engine.alloc_slots(2)
+        got = engine.crop(boxes, slots)
+        engine.free_slots(slots)
+        assert np.array_equal(got, ocrop.get_image_crops(out, boxes))
+        assert engine.sync_frame(out) is False                      # the returned host copy is recognised as the resident frame
+
+
+def test_frame_ingest_bandwidth(engine):
+    H, W = 1080, 1920
+    chw = synth.make_detector_tensor(1, H, W)
+    p = engine.dev_alloc(chw.nbytes)
+    engine.h2d(p, chw)
+    engine.ingest_frame(p, synth.YOLOX_MEANS, synth.YOLOX_STD, H, W, to_host=False)
+    engine.set_profiling(True)
+    engine.ingest_frame(p, synth.YOLOX_MEANS, synth.YOLOX_STD, H, W, to_host=False)
+    prof = engine.last_profile()
+    engine.set_profiling(False)
+    engine.dev_free(p)
+    assert "frame_ingest" in prof, prof
+    ms = prof["frame_ingest"]["ms"]
+    print(f"frame_ingest 1080p: {ms * 1e3:.1f} us, {H * W * 15 / ms / 1e6:.0f} GB/s of algorithmic bytes (12 B read + 3 B written per pixel)")

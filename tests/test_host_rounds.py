@@ -144,3 +144,34 @@ def test_device_assignment_algorithm_equals_the_extended_problem():
             x = private_column_assignment(cost, thresh)
             xo, _ = ornd.linear_assignment(cost, thresh)
             assert np.array_equal(x, xo), (n, m, thresh)
+
+
+# ------------------------------------------------------------------------------------------------ 8f row 4: ingest + result format
+def test_ingest_oracle_equals_reference(golden_dir):
+    import hashlib
+    from busca_b200 import synth
+    from oracle import ingest as oing
+    g = np.load(os.path.join(golden_dir, "ingest.npz"))
+    for k in range(int(g["i_cases"])):
+        H, W = (int(v) for v in g[f"i{k}_shape"])
+        out = oing.denormalize_frame(synth.make_detector_tensor(int(g[f"i{k}_seed"]), H, W), synth.YOLOX_MEANS, synth.YOLOX_STD)
+        assert out.shape == (H, W, 3) and out.dtype == np.uint8
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == str(g[f"i{k}_sha"])
+        if f"i{k}_bgr" in g:
+            assert np.array_equal(out, g[f"i{k}_bgr"])
+
+
+def test_mot_txt_equals_reference(golden_dir):
+    from busca_b200.sharding import write_mot_txt
+    from oracle import ingest as oing
+    g = np.load(os.path.join(golden_dir, "ingest.npz"))
+    rows = g["mot_rows"]
+    res = {}
+    for r in rows:
+        res.setdefault(int(r[0]), ([], [], []))
+        res[int(r[0])][0].append(tuple(r[2:6]))
+        res[int(r[0])][1].append(int(r[1]))
+        res[int(r[0])][2].append(float(r[6]))
+    assert oing.mot_lines([(f, *v) for f, v in sorted(res.items())]) == str(g["mot_txt"])
+    table = np.concatenate([np.zeros((len(rows), 1)), rows], axis=1)          # sharding's result rows: seq, frame, id, x, y, w, h, score
+    assert write_mot_txt(table, 0) == str(g["mot_txt"])
