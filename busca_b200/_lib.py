@@ -53,7 +53,7 @@ class DebugConvArgs(C.Structure):
 
 EXPORTS = [
     "busca_version", "busca_last_error", "busca_create", "busca_destroy", "busca_load_tensor", "busca_finalize",
-    "busca_upload_frame", "busca_sync_frame", "busca_ingest_frame", "busca_bank_reserve", "busca_bank_capacity", "busca_crop", "busca_bank_upload",
+    "busca_upload_frame", "busca_sync_frame", "busca_ingest_frame", "busca_camera_motion", "busca_bank_reserve", "busca_bank_capacity", "busca_crop", "busca_bank_upload",
     "busca_bank_download", "busca_center_distance", "busca_iou", "busca_detection_coverage", "busca_kalman_predict", "busca_kalman_update", "busca_match_round", "busca_linear_assignment", "busca_duplicate_tracks", "busca_motion_proposals", "busca_frame_geometry",
     "busca_reid_embed", "busca_associate", "busca_transformer", "busca_frame_step_dev", "busca_dev_alloc",
     "busca_dev_free", "busca_host_alloc", "busca_host_free", "busca_memcpy_h2d", "busca_memcpy_d2h", "busca_sync", "busca_stream", "busca_kernel_launches",
@@ -97,6 +97,7 @@ def load(build_if_missing: bool = True):
     L.busca_iou.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.busca_detection_coverage.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), vp]
     L.busca_ingest_frame.argtypes = [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
+    L.busca_camera_motion.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_double, vp, vp, vp]
     L.busca_kalman_predict.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp]
     L.busca_kalman_update.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp]
     L.busca_match_round.argtypes = [vp, vp, C.c_int32, vp, C.c_int32, vp, C.c_double, vp, vp, vp]

@@ -96,6 +96,9 @@ struct busca_ctx {
     int64_t bank_slots = 0;
     // scratch
     DevBuf ws_reid, ws_tr, ws_io, ws_small, ws_gram;
+    DevBuf ws_ecc;                                // camera-motion compensation: 5 fp32 planes + partial sums + state
+    int ecc_H = 0, ecc_W = 0, ecc_cur = 0;        // size of the cached planes; which of the two smoothed planes holds the LAST current frame
+    bool ecc_have_prev = false;
     bool gram = true;                             // Gram-matrix statistics for the 1x1 convolutions with Cin <= 256 (BUSCA_GRAM=0 / option "gram")
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -263,6 +266,7 @@ extern "C" void busca_destroy(busca_ctx *c) {
     c->ws_io.release();
     c->ws_small.release();
     c->ws_gram.release();
+    c->ws_ecc.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -543,6 +547,74 @@ extern "C" int busca_ingest_frame(busca_ctx *c, const float *chw, int32_t chw_on
         CUDA_OK(cudaStreamSynchronize(c->stream));
     }
     prof_collect(c);
+    return BUSCA_OK;
+}
+
+// Camera-motion compensation (byte_tracker.py:626-657): ecc.cu
+extern "C" int busca_camera_motion(busca_ctx *c, const uint8_t *prev_bgr, const uint8_t *cur_bgr, int32_t H, int32_t W, int64_t row_stride,
+                                   int32_t iterations, double eps, float *warp_out, double *rho_out, int32_t *iterations_out) {
+    if (!c || H < 5 || W < 5 || !warp_out) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if ((prev_bgr || cur_bgr) && row_stride < (int64_t)W * 3) return set_err(BUSCA_ERR_ARG, "bad row stride");
+    if (!prev_bgr && !(c->ecc_have_prev && c->ecc_H == H && c->ecc_W == W))
+        return set_err(BUSCA_ERR_STATE, "camera motion: no previous frame of this size is cached (pass prev_bgr)");
+    if (!cur_bgr && !(c->frame.p && c->fH == H && c->fW == W)) return set_err(BUSCA_ERR_STATE, "camera motion: no current frame of this size in HBM");
+    CUDA_OK(cudaSetDevice(c->cfg.device));
+    const size_t plane = ((size_t)H * W * 4 + 255) / 256 * 256;
+    int bx, by, rpb;
+    ecc_grid(H, W, &bx, &by, &rpb);
+    const size_t part = ((size_t)bx * by * 21 * 8 + 255) / 256 * 256;
+    if (c->ecc_H != H || c->ecc_W != W) { c->ecc_have_prev = false; c->ecc_H = H; c->ecc_W = W; c->ecc_cur = 0; }
+    const size_t need = 5 * plane + part + 512;
+    if (need > c->ws_ecc.cap) {
+        if (!prev_bgr) return set_err(BUSCA_ERR_STATE, "camera motion: cache lost");     // cannot happen: the size check above
+        CUDA_OK(c->ws_ecc.ensure(need));
+    }
+    char *base = (char *)c->ws_ecc.p;
+    float *smooth[2] = {(float *)base, (float *)(base + plane)};
+    float *gx = (float *)(base + 2 * plane), *gy = (float *)(base + 3 * plane), *rows = (float *)(base + 4 * plane);
+    double *partials = (double *)(base + 5 * plane);
+    EccState *dst = (EccState *)(base + 5 * plane + part);
+    unsigned int *ticket = (unsigned int *)(base + 5 * plane + part + 256);
+    prof_reset(c);
+    const size_t fbytes = (size_t)H * row_stride;
+    // the previous call's current frame sits in smooth[ecc_cur]; it becomes the template, the new frame goes into the other plane
+    int t_idx = c->ecc_cur, i_idx = c->ecc_cur ^ 1;
+    if (prev_bgr) {
+        CUDA_OK(c->ws_io.ensure(fbytes + 64));
+        CUDA_OK(cudaMemcpyAsync(c->ws_io.p, prev_bgr, fbytes, cudaMemcpyHostToDevice, c->stream));
+        LAUNCH(c, "ecc_prepare", launch_ecc_prepare((const uint8_t *)c->ws_io.p, row_stride, H, W, rows, smooth[t_idx], nullptr, nullptr, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));           // ws_io is reused for the current frame below
+    }
+    const uint8_t *cur_dev = (const uint8_t *)c->frame.p;
+    long long cur_stride = c->fstride;
+    if (cur_bgr) {
+        CUDA_OK(c->ws_io.ensure(fbytes + 64));
+        CUDA_OK(cudaMemcpyAsync(c->ws_io.p, cur_bgr, fbytes, cudaMemcpyHostToDevice, c->stream));
+        cur_dev = (const uint8_t *)c->ws_io.p;
+        cur_stride = row_stride;
+    }
+    LAUNCH(c, "ecc_prepare", launch_ecc_prepare(cur_dev, cur_stride, H, W, rows, smooth[i_idx], gx, gy, c->stream));
+    EccState st = {};
+    st.map[0] = st.map[4] = 1.0f;
+    st.rho = -1.0; st.last_rho = -eps;
+    st.max_iterations = iterations;
+    st.done = iterations <= 0 ? 1 : 0;
+    CUDA_OK(cudaMemcpyAsync(dst, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(ticket, 0, 4, c->stream));
+    while (!st.done) {
+        for (int k = 0; k < 4; ++k)
+            LAUNCH(c, "ecc_iteration", launch_ecc_iteration(smooth[t_idx], smooth[i_idx], gx, gy, H, W, dst, partials, ticket, eps, c->stream));
+        CUDA_OK(cudaMemcpyAsync(&st, dst, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    prof_collect(c);
+    c->ecc_cur = i_idx;
+    c->ecc_have_prev = true;
+    for (int k = 0; k < 6; ++k) warp_out[k] = st.map[k];
+    if (rho_out) *rho_out = st.rho;
+    if (iterations_out) *iterations_out = st.iterations;
+    if (st.status == 1) return set_err(BUSCA_ERR_STATE, "ECC: the correlation is going to be minimized - images may be uncorrelated or non-overlapped (cv2 raises StsNoConv)");
+    if (st.status == 2) return set_err(BUSCA_ERR_STATE, "ECC: NaN encountered (cv2 raises StsNoConv)");
     return BUSCA_OK;
 }
 

@@ -38,6 +38,21 @@ size_t assignment_smem_bytes(int N, int M);
 cudaError_t launch_duplicates(const double *a, const int *age_a, int na, const double *b, const int *age_b, int nb, double thresh,
                               uint8_t *drop_a, uint8_t *drop_b, cudaStream_t s);
 
+// ---------------------------------------------------------------- ecc.cu (camera-motion compensation)
+struct EccState {
+    float map[6];              // the 2x3 warp, row major (cv2's warpMatrix)
+    double rho, last_rho;      // enhanced correlation coefficient of the last two iterations
+    int iterations, max_iterations;
+    int done;                  // the loop condition of cv2.findTransformECC failed (converged or out of iterations) or status != 0
+    int status;                // 0 ok; 1 "the correlation is going to be minimized" (cv2 raises); 2 NaN
+};
+// gray (BGR2GRAY, integer-exact) + 5x5 Gaussian into `smooth`; central-difference gradients into gx / gy unless null
+cudaError_t launch_ecc_prepare(const uint8_t *bgr, long long stride, int H, int W, float *scratch_rows, float *smooth, float *gx, float *gy,
+                               cudaStream_t s);
+void ecc_grid(int H, int W, int *gx, int *gy, int *rows_per_block);
+cudaError_t launch_ecc_iteration(const float *tmpl, const float *img, const float *gx, const float *gy, int H, int W, EccState *st,
+                                 double *partials, unsigned int *ticket, double eps, cudaStream_t s);
+
 // ---------------------------------------------------------------- crop.cu
 // detector tensor [3,H,W] fp32 (RGB, normalised) -> uint8 BGR HWC (mot_evaluator.py:198-204), both in device memory
 cudaError_t launch_frame_ingest(const float *chw, int H, int W, const float mean[3], const float sd[3], uint8_t *bgr, cudaStream_t s);

@@ -214,6 +214,29 @@ class Engine:
         check(self.L.busca_ingest_frame(self.h, ptr, on_dev, int(H), int(W), _ptr(mean), _ptr(std), _ptr(out)))
         return out
 
+    def camera_motion(self, previous: Optional[np.ndarray], current: Optional[np.ndarray], shape=None, iterations: int = 100,
+                      eps: float = 1e-5) -> Tuple[np.ndarray, float, int]:
+        """cv2.findTransformECC(gray(previous), gray(current), eye(2,3), MOTION_EUCLIDEAN, (EPS | COUNT, iterations, eps)) on the device
+        -> (warp 2x3 float32, rho, iterations run).  previous None: the current frame of the last call; current None: the frame in HBM
+        (give ``shape``).  Raises where cv2 raises (uncorrelated images)."""
+        def prep(a):
+            if a is None:
+                return None
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError("frame must be uint8 [H,W,3] BGR")
+            return a if (a.strides[2] == 1 and a.strides[1] == 3) else np.ascontiguousarray(a)
+        previous, current = prep(previous), prep(current)
+        ref = current if current is not None else previous
+        H, W = (ref.shape[0], ref.shape[1]) if ref is not None else (int(shape[0]), int(shape[1]))
+        if previous is not None and current is not None and previous.strides[0] != current.strides[0]:
+            previous, current = np.ascontiguousarray(previous), np.ascontiguousarray(current)
+        stride = ref.strides[0] if ref is not None else W * 3
+        warp = np.zeros((2, 3), np.float32)
+        rho, it = C.c_double(0.0), C.c_int32(0)
+        check(self.L.busca_camera_motion(self.h, _ptr(previous), _ptr(current), H, W, stride, int(iterations), float(eps), _ptr(warp),
+                                         C.byref(rho), C.byref(it)))
+        return warp, float(rho.value), int(it.value)
+
     def sync_frame(self, image: np.ndarray, boxes: Optional[np.ndarray] = None) -> bool:
         """Upload ``image`` unless the pixels ``boxes`` read (all pixels without boxes) already are in HBM (busca_sync_frame)."""
         if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:

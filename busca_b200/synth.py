@@ -336,3 +336,18 @@ def make_detector_tensor(seed: int, H: int, W: int, means=YOLOX_MEANS, std=YOLOX
     img[0, :8] = np.array([0.0, 1.0, 0.5, 1.0 / 255, 254.999 / 255, 0.999999, 1e-8, 0.25], np.float32)[:, None]
     chw = ((img - np.array(means, np.float32)) / np.array(std, np.float32)).astype(np.float32)
     return np.ascontiguousarray(chw.transpose(2, 0, 1))
+
+
+def make_moved_frame(frame: np.ndarray, theta: float, tx: float, ty: float, seed: int) -> np.ndarray:
+    """``frame`` seen from a camera that moved: every pixel (x, y) shows the source at the Euclidean map
+    (cos x - sin y + tx, sin x + cos y + ty), bilinear, border replicated, plus +-3 levels of fresh noise (numpy only)."""
+    H, W = frame.shape[:2]
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    sx = np.clip(np.cos(theta) * xs - np.sin(theta) * ys + tx, 0, W - 1.001)
+    sy = np.clip(np.sin(theta) * xs + np.cos(theta) * ys + ty, 0, H - 1.001)
+    x0, y0 = sx.astype(np.int64), sy.astype(np.int64)
+    fx, fy = (sx - x0)[..., None], (sy - y0)[..., None]
+    f = frame.astype(np.float64)
+    out = (f[y0, x0] * (1 - fx) + f[y0, x0 + 1] * fx) * (1 - fy) + (f[y0 + 1, x0] * (1 - fx) + f[y0 + 1, x0 + 1] * fx) * fy
+    rng = np.random.default_rng(seed)
+    return np.clip(np.rint(out) + rng.integers(-3, 4, out.shape), 0, 255).astype(np.uint8)

@@ -103,6 +103,14 @@ int busca_motion_proposals(busca_ctx *ctx, const double *mean, const uint8_t *tr
  * reference's canvas; bbox_areas_out [n] (may be NULL): max(min(((x2-x1)/H) * ((y2-y1)/W), 1), 0) per box (the reference's H/W swap kept). */
 int busca_detection_coverage(busca_ctx *ctx, const double *tlbr, int32_t n, int32_t H, int32_t W, int64_t *nonzero_out,
                              double *bbox_areas_out);
+/* BYTETracker.camera_motion_compensation up to the warp matrix: BGR2GRAY of both frames + cv2.findTransformECC(template = previous,
+ * input = current, eye(2,3), MOTION_EUCLIDEAN, (EPS | COUNT, iterations, eps), gaussFiltSize 5).      byte_tracker.py:626-651
+ * prev_bgr / cur_bgr: host uint8 [H,W,3] with row_stride bytes per row.  prev_bgr == NULL: the current frame of the previous call (its
+ * smoothed plane is kept in HBM); cur_bgr == NULL: the context's current frame (busca_upload_frame / busca_sync_frame / busca_ingest_frame).
+ * warp_out [6] float32 row-major 2x3; rho_out: the correlation coefficient cv2 returns; BUSCA_ERR_STATE where cv2 raises StsNoConv.
+ * Agrees with cv2 to ~1e-5 px (not bit-wise: cv2's summation order is unspecified). */
+int busca_camera_motion(busca_ctx *ctx, const uint8_t *prev_bgr, const uint8_t *cur_bgr, int32_t H, int32_t W, int64_t row_stride,
+                        int32_t iterations, double eps, float *warp_out, double *rho_out, int32_t *iterations_out);
 /* ---- host-tracker rounds on the device ---------------------------------------------------------------
  * KalmanFilter.multi_predict with the covariance                      mot_online/kalman_filter.py:154-191; byte_tracker.py:50-61
  * mean [n,8], cov [n,8,8] float64; tracked [n] uint8 or NULL (0 = the height velocity is zeroed first). Bit-identical to numpy. */

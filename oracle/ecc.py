@@ -16,9 +16,10 @@ AB_SCALE, TAB = 1 << AB_BITS, 1 << INTER_BITS
 
 
 def bgr2gray(img):
-    """cv2.cvtColor(COLOR_BGR2GRAY) on uint8: (B*1868 + G*9617 + R*4899 + 8192) >> 14 - integer-exact."""
+    """cv2.cvtColor(COLOR_BGR2GRAY) on uint8: (B*3735 + G*19235 + R*9798 + 16384) >> 15 (OpenCV 4's 15-bit coefficients; checked
+    against cv2 4.13 on 16.7 M random colours) - integer-exact."""
     i = img.astype(np.int32)
-    return ((i[..., 0] * 1868 + i[..., 1] * 9617 + i[..., 2] * 4899 + 8192) >> 14).astype(np.uint8)
+    return ((i[..., 0] * 3735 + i[..., 1] * 19235 + i[..., 2] * 9798 + 16384) >> 15).astype(np.uint8)
 
 
 def _reflect101(n, idx):

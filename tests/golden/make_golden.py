@@ -583,8 +583,35 @@ def golden_ingest():
     np.savez_compressed(os.path.join(HERE, "ingest.npz"), **store)
 
 
+ECC_CASES = [(3, 1080, 1920, 0.004, 3.3, -2.1), (4, 1080, 1920, 0.0, 1.0, 0.0), (5, 1080, 1920, -0.01, -6.5, 4.25), (6, 480, 640, 0.002, 0.4, 0.7),
+             (7, 97, 131, 0.0, -1.5, 2.0)]
+
+
+def golden_ecc():
+    """8f row 3: cv2.cvtColor + cv2.findTransformECC exactly as BYTETracker.camera_motion_compensation calls them
+    (byte_tracker.py:640-645) on seeded frame pairs."""
+    import cv2
+    store = {"cases": np.array(ECC_CASES, np.float64), "cv2_version": np.array(cv2.__version__)}
+    for k, (seed, H, W, th, tx, ty) in enumerate(ECC_CASES):
+        f1 = synth.make_frame(seed, H, W)
+        f2 = synth.make_moved_frame(f1, th, tx, ty, seed)
+        im1_gray = cv2.cvtColor(f1, cv2.COLOR_BGR2GRAY)
+        im2_gray = cv2.cvtColor(f2, cv2.COLOR_BGR2GRAY)
+        warp_matrix = np.eye(2, 3, dtype=np.float32)
+        criteria = (cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 100, 0.00001)
+        cc, warp_matrix = cv2.findTransformECC(templateImage=im1_gray, inputImage=im2_gray, warpMatrix=warp_matrix, motionType=cv2.MOTION_EUCLIDEAN,
+                                               criteria=criteria)
+        store[f"e{k}_warp"], store[f"e{k}_cc"] = warp_matrix, np.array(cc)
+        store[f"e{k}_gray_sha"] = np.array(sha(im2_gray))
+        print("ecc case", k, cc, warp_matrix.ravel())
+    np.savez_compressed(os.path.join(HERE, "ecc.npz"), **store)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["crops", "geometry", "pe", "assoc"]
+    if "ecc" in which:
+        golden_ecc()
+        sys.exit(0)
     if "ingest" in which:
         golden_ingest()
         sys.exit(0)

@@ -193,3 +193,43 @@ def test_frame_ingest_bandwidth(engine):
     assert "frame_ingest" in prof, prof
     ms = prof["frame_ingest"]["ms"]
     print(f"frame_ingest 1080p: {ms * 1e3:.1f} us, {H * W * 15 / ms / 1e6:.0f} GB/s of algorithmic bytes (12 B read + 3 B written per pixel)")
+
+
+# ------------------------------------------------------------------------------------------------ 8f row 3
+def test_camera_motion_equals_cv2(engine, golden_dir):
+    """BYTETracker.camera_motion_compensation's warp matrix (cv2.cvtColor + cv2.findTransformECC, Euclidean, 100 iterations, eps 1e-5)
+    against tests/golden/ecc.npz (cv2 4.13 outputs): translation within 2e-3 px, rotation entries within 2e-6, rho within 1e-5."""
+    from test_host_rounds import check_warp, ecc_cases
+    worst_t = worst_r = 0.0
+    for k, f1, f2, want, want_rho, _sha in ecc_cases(golden_dir):
+        warp, rho, it = engine.camera_motion(f1, f2)
+        check_warp(k, warp, rho, want, want_rho)
+        worst_t, worst_r = max(worst_t, np.abs(warp[:, 2] - want[:, 2]).max()), max(worst_r, np.abs(warp[:, :2] - want[:, :2]).max())
+        # the cached path: the same pair again, the current frame first as a 'previous' call, then from the frame in HBM
+        engine.camera_motion(f2, f1)                                   # now f1 is the cached previous frame
+        engine.upload_frame(f2)
+        warp2, rho2, _ = engine.camera_motion(None, None, shape=f2.shape)
+        assert np.array_equal(warp, warp2) and rho == rho2, k           # deterministic (fixed-order reduction)
+    print(f"camera motion vs cv2: worst translation deviation {worst_t:.2e} px, worst rotation-entry deviation {worst_r:.2e}")
+
+
+def test_camera_motion_latency_and_errors(engine):
+    from busca_b200._lib import BuscaError
+    f1 = synth.make_frame(21)
+    f2 = synth.make_moved_frame(f1, 0.003, 2.2, -1.3, 21)
+    engine.camera_motion(f1, f2)
+    engine.set_profiling(True)
+    t0 = time.perf_counter()
+    warp, rho, it = engine.camera_motion(f1, f2)
+    ms = (time.perf_counter() - t0) * 1e3
+    prof = engine.last_profile()
+    engine.set_profiling(False)
+    print(f"camera motion 1080p: {ms:.2f} ms host to host ({it} iterations; kernels: "
+          f"{prof['ecc_iteration']['ms']:.3f} ms in {prof['ecc_iteration']['launches']} launches, prepare {prof['ecc_prepare']['ms']:.3f} ms)")
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    b = 255 - a                                                         # anti-correlated: cv2 raises StsNoConv
+    with pytest.raises(BuscaError):
+        engine.camera_motion(a, b)
+    with pytest.raises(BuscaError):
+        engine.camera_motion(None, f2[:100, :100])                      # no cached frame of that size

@@ -175,3 +175,51 @@ def test_mot_txt_equals_reference(golden_dir):
     assert oing.mot_lines([(f, *v) for f, v in sorted(res.items())]) == str(g["mot_txt"])
     table = np.concatenate([np.zeros((len(rows), 1)), rows], axis=1)          # sharding's result rows: seq, frame, id, x, y, w, h, score
     assert write_mot_txt(table, 0) == str(g["mot_txt"])
+
+
+# ------------------------------------------------------------------------------------------------ 8f row 3: camera motion (ECC)
+ECC_TOL_T, ECC_TOL_R = 2e-3, 2e-6          # pixels of translation / rotation-matrix entries, against cv2.findTransformECC
+
+
+def ecc_cases(golden_dir):
+    from busca_b200 import synth
+    g = np.load(os.path.join(golden_dir, "ecc.npz"))
+    for k, (seed, H, W, th, tx, ty) in enumerate(g["cases"]):
+        f1 = synth.make_frame(int(seed), int(H), int(W))
+        yield k, f1, synth.make_moved_frame(f1, th, tx, ty, int(seed)), g[f"e{k}_warp"], float(g[f"e{k}_cc"]), str(g[f"e{k}_gray_sha"])
+
+
+def check_warp(k, warp, rho, want, want_rho):
+    assert np.abs(warp[:, 2] - want[:, 2]).max() < ECC_TOL_T, (k, warp, want)
+    assert np.abs(warp[:, :2] - want[:, :2]).max() < ECC_TOL_R, (k, warp, want)
+    assert abs(rho - want_rho) < 1e-5, (k, rho, want_rho)
+
+
+def test_ecc_oracle_equals_cv2_golden(golden_dir):
+    import hashlib
+    from oracle import ecc as oecc
+    for k, f1, f2, want, want_rho, gray_sha in ecc_cases(golden_dir):
+        assert hashlib.sha256(oecc.bgr2gray(f2).tobytes()).hexdigest() == gray_sha          # BGR2GRAY is integer-exact
+        if f1.shape[0] * f1.shape[1] > 640 * 480 and k != 0:
+            continue                                                                        # one full-HD case keeps the CPU suite short
+        rho, warp = oecc.camera_motion(f1, f2)
+        check_warp(k, warp, rho, want, want_rho)
+
+
+def test_ecc_building_blocks_equal_cv2_live():
+    cv2 = pytest.importorskip("cv2")
+    from busca_b200 import synth
+    from oracle import ecc as oecc
+    f = synth.make_frame(12, 240, 320)
+    g = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY)
+    assert np.array_equal(g, oecc.bgr2gray(f))
+    b = cv2.GaussianBlur(g.astype(np.float32), (5, 5), 0)
+    assert np.array_equal(b, oecc.gaussian5(g.astype(np.float32)))
+    gx, gy = oecc.gradients(b)
+    assert np.array_equal(gx, cv2.filter2D(b, -1, np.array([[-0.5, 0, 0.5]], np.float32)))
+    assert np.array_equal(gy, cv2.filter2D(b, -1, np.array([[-0.5], [0], [0.5]], np.float32)))
+    M = np.array([[0.9999, -0.0141, 2.79], [0.0141, 0.9999, -1.44]], np.float32)
+    w = cv2.warpAffine(b, M, (320, 240), flags=cv2.INTER_LINEAR + cv2.WARP_INVERSE_MAP)
+    assert np.abs(w - oecc.warp_linear([b], M)[0]).max() < 1e-4
+    mk = cv2.warpAffine(np.ones((240, 320), np.uint8), M, (320, 240), flags=cv2.INTER_NEAREST + cv2.WARP_INVERSE_MAP)
+    assert np.array_equal(mk.astype(bool), oecc.warp_mask(M, 240, 320))
