@@ -375,23 +375,24 @@ __global__ void __launch_bounds__(256) frame_ingest_kernel(const float *__restri
     if (p0 >= npix) return;
     const float *R = chw, *G = chw + npix, *B = chw + 2 * npix;
     if (p0 + 16 <= npix && (npix & 3) == 0) {
-        unsigned char out[48];
+        unsigned int w[12];                                  // 16 pixels = 48 bytes = 12 words, packed in registers
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float4 r = *reinterpret_cast<const float4 *>(R + p0 + 4 * q);
-            const float4 gg = *reinterpret_cast<const float4 *>(G + p0 + 4 * q);
-            const float4 b = *reinterpret_cast<const float4 *>(B + p0 + 4 * q);
-            const float rr[4] = {r.x, r.y, r.z, r.w}, gv[4] = {gg.x, gg.y, gg.z, gg.w}, bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                out[(4 * q + k) * 3 + 0] = (unsigned char)ingest_px(bb[k], sd.z, mean.z);
-                out[(4 * q + k) * 3 + 1] = (unsigned char)ingest_px(gv[k], sd.y, mean.y);
-                out[(4 * q + k) * 3 + 2] = (unsigned char)ingest_px(rr[k], sd.x, mean.x);
-            }
+            const float4 r = __ldg(reinterpret_cast<const float4 *>(R + p0 + 4 * q));
+            const float4 gg = __ldg(reinterpret_cast<const float4 *>(G + p0 + 4 * q));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(B + p0 + 4 * q));
+            const unsigned int B0 = ingest_px(b.x, sd.z, mean.z), G0 = ingest_px(gg.x, sd.y, mean.y), R0 = ingest_px(r.x, sd.x, mean.x);
+            const unsigned int B1 = ingest_px(b.y, sd.z, mean.z), G1 = ingest_px(gg.y, sd.y, mean.y), R1 = ingest_px(r.y, sd.x, mean.x);
+            const unsigned int B2 = ingest_px(b.z, sd.z, mean.z), G2 = ingest_px(gg.z, sd.y, mean.y), R2 = ingest_px(r.z, sd.x, mean.x);
+            const unsigned int B3 = ingest_px(b.w, sd.z, mean.z), G3 = ingest_px(gg.w, sd.y, mean.y), R3 = ingest_px(r.w, sd.x, mean.x);
+            w[3 * q + 0] = B0 | (G0 << 8) | (R0 << 16) | (B1 << 24);
+            w[3 * q + 1] = G1 | (R1 << 8) | (B2 << 16) | (G2 << 24);
+            w[3 * q + 2] = R2 | (B3 << 8) | (G3 << 16) | (R3 << 24);
         }
         uint4 *dst = reinterpret_cast<uint4 *>(bgr + p0 * 3);                      // p0 * 3 = 48 g: 16-byte aligned
-        const uint4 *src = reinterpret_cast<const uint4 *>(out);
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
     } else {
         for (long long p = p0; p < npix && p < p0 + 16; ++p) {
             bgr[p * 3 + 0] = (unsigned char)ingest_px(B[p], sd.z, mean.z);

@@ -362,7 +362,7 @@ class SimpleCase:
         self.tracks, self.dets, self.kalman = tracks, dets, kalman
 
 
-def golden_adapter(weights_path):
+def golden_adapter(weights_path, config="MOT20", out_name="adapter_seq", n_frames=36, n_obj=10, seed=5):
     """Drive the UNMODIFIED adapter (adapters/CenterTrack/src/lib/utils/byte_tracker.py, md5-identical to the ByteTrack copy)
     over a synthetic sequence and record, per frame, the ids / boxes it outputs and what Step 3b decided.  Shims: lap, cython_bbox
     (tests/golden/shims), np.float."""
@@ -370,11 +370,10 @@ def golden_adapter(weights_path):
     sys.path.insert(0, os.path.join(REF, "adapters/CenterTrack/src/lib"))
     bt = importlib.import_module("utils.byte_tracker")
     from utils.mot_online.basetrack import BaseTrack
-    n_frames, n_obj, seed = 36, 10, 5
     seq = synth.make_sequence(seed, n_frames, n_obj, miss=0.25)
-    args, _ = load_args_from_config(os.path.join(REF, "config/ByteTrack/MOT20/config_bytetrack_mot20.yml"))
+    args, _ = load_args_from_config(os.path.join(REF, f"config/ByteTrack/{config}/config_bytetrack_{config.lower()}.yml"))
     args.use_busca, args.device, args.busca_ckpt = True, "cpu", weights_path
-    args.track_thresh, args.track_buffer, args.match_thresh, args.mot20 = 0.6, 30, 0.9, True
+    args.track_thresh, args.track_buffer, args.match_thresh, args.mot20 = 0.6, 30, 0.9, config == "MOT20"
     args.transformer.reid_weights_file = "no"
     BaseTrack._count = 0
     tracker = bt.BYTETracker(args)
@@ -396,6 +395,24 @@ def golden_adapter(weights_path):
         return m, u
 
     tracker.third_round_association = third
+    gate, warps = [], []
+    if hasattr(args, "reliable_thresh"):
+        orig_rel = tracker.is_reliable
+
+        def rel(current_frame, active_stracks, p):
+            r = orig_rel(current_frame=current_frame, active_stracks=active_stracks, p=p)
+            rec3["gate"] = bool(r)
+            return r
+        tracker.is_reliable = rel
+    if args.use_camera_motion_compensation:
+        import cv2
+        orig_ecc = cv2.findTransformECC
+
+        def ecc(**kw):
+            cc, w = orig_ecc(**kw)
+            rec3["warp"] = np.array(w)
+            return cc, w
+        bt.cv2.findTransformECC = ecc
     ids, boxes, off, b3_ids, b3_keep, b3_prob, b3_off = [], [], [0], [], [], [], [0]
     import time
     t0 = time.time()
@@ -411,11 +428,15 @@ def golden_adapter(weights_path):
             b3_keep += [i in kept for i in range(rec3["n"])]
             b3_prob += [kept.get(i, -1.0) for i in range(rec3["n"])]
         b3_off.append(len(b3_ids))
+        gate.append(int(rec3.get("gate", -1)))
+        warps.append(rec3.get("warp", np.full((2, 3), np.nan, np.float32)))
         print("frame", f + 1, "ids", [t.track_id for t in out], "3b pool", rec3.get("pool_ids"), "kept", [rec3["pool_ids"][i] for i, _ in rec3.get("matches", [])],
               "%.0f s" % (time.time() - t0), flush=True)
     ref_enc.missing_candidate_bbox = ref_trk.missing_candidate_bbox
     ref_net.missing_candidate_bbox = ref_trk.missing_candidate_bbox
-    np.savez_compressed(os.path.join(HERE, "adapter_seq.npz"), meta=np.array([seed, n_frames, n_obj]), miss=0.25,
+    if args.use_camera_motion_compensation:
+        bt.cv2.findTransformECC = orig_ecc
+    np.savez_compressed(os.path.join(HERE, f"{out_name}.npz"), meta=np.array([seed, n_frames, n_obj]), miss=0.25, gate=np.array(gate), warps=np.array(warps),
                         ids=np.array(ids), boxes=np.array(boxes).reshape(-1, 4), off=np.array(off),
                         b3_ids=np.array(b3_ids), b3_keep=np.array(b3_keep, bool), b3_prob=np.array(b3_prob), b3_off=np.array(b3_off))
     print("adapter: kept-alive decisions", int(np.sum(b3_keep)), "of", len(b3_keep))
@@ -621,7 +642,7 @@ if __name__ == "__main__":
         if "rounds" in which:
             golden_rounds()
         sys.exit(0)
-    if any(w in ("cond", "scene", "scene_mot20", "adapter") for w in which):
+    if any(w in ("cond", "scene", "scene_mot20", "adapter", "adapter_mot17") for w in which):
         model, targs = build_reference(profile="conditioned")
         if "cond" in which:
             golden_assoc_cond(model)
@@ -631,6 +652,8 @@ if __name__ == "__main__":
             golden_scene(model, "scene_mot20_cond", 200, 300, seed=0, emb_stride=8)
         if "adapter" in which:
             golden_adapter("/tmp/busca_golden_weights_conditioned.pth")
+        if "adapter_mot17" in which:
+            golden_adapter("/tmp/busca_golden_weights_conditioned.pth", config="MOT17", out_name="adapter_seq_mot17", n_frames=24, n_obj=30, seed=8)
         sys.exit(0)
     model, targs = build_reference()
     if "crops" in which:
