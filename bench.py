@@ -131,14 +131,14 @@ def build_model(precision: str, device: int, bank_slots: int = 8192):
     return m, targs
 
 
-def adapter_leg(model, targs, args):
+def adapter_leg(model, targs, args, device_rounds=False):
     """The adapter's real call pattern (busca_b200/hosts/bytetrack.py after byte_tracker.py:226-456) on a MOT20-scale synthetic
     sequence: per frame 3 detection-crop calls, one single-box crop call per unmatched track, center_distance without a handle,
     associate_embeddings; tracker state evolves (histories appended, patch-bank slots recycled).  Times only what runs inside
     BUSCA's API (the host tracker's own Python is the caller's cost, reported beside it)."""
     import copy
     from busca_b200 import tracking
-    from busca_b200.hosts.bytetrack import ByteTrackHost
+    from busca_b200.hosts.bytetrack import ByteTrackHost, DeviceRounds
     warm = 13
     seq = synth.make_sequence(4242, warm + args.adapter_frames, args.adapter_objects, miss=0.33, low_score=0.05, clutter=2.0, frame_ring=6)
     a = copy.copy(targs)
@@ -158,7 +158,8 @@ def adapter_leg(model, targs, args):
         get_image_crops = staticmethod(timed(model.get_image_crops))
         associate_embeddings = staticmethod(timed(model.associate_embeddings))
 
-    host = ByteTrackHost(Timed, a, iou_fn=lambda x, y: model.engine.iou(x, y), center_distance_fn=timed(lambda t, d: tracking.center_distance(t, d)))
+    host = ByteTrackHost(Timed, a, iou_fn=lambda x, y: model.engine.iou(x, y), center_distance_fn=timed(lambda t, d: tracking.center_distance(t, d)),
+                         rounds=DeviceRounds(model.engine) if device_rounds else None)   # the rounds themselves on the device
     busca_ms, total_ms, n_unmatched, kept = [], [], [], 0
     pr = None
     if args.profile_e2e:
@@ -334,6 +335,11 @@ def run_ours(args):
             gc.collect()
         barrier()
     adapter = adapter_leg(model, targs, args) if (rank == 0 and args.adapter_frames > 0) else None
+    if adapter is not None:
+        dev = adapter_leg(model, targs, args, device_rounds=True)
+        if dev is not None:
+            adapter["with_device_rounds"] = {k: dev[k] for k in ("value", "busca_ms_per_frame_p50", "host_tracker_ms_per_frame_p50", "kept_alive", "decisions")}
+            adapter["with_device_rounds"]["what"] = "same sequence with the host tracker's rounds on libbusca_b200 (batched Kalman predict / update, IoU cost + assignment per round, duplicate removal: csrc/rounds.cu)"
 
     # NCCL only here: max over ranks of the device-timed regions, and the gather of the per-rank result tables
     ms_max, e2e_ms_max = sharding.reduce_max([ms, e2e_s * 1e3], dist, device=f"cuda:{local}")

@@ -9,8 +9,9 @@ struct Box { double x1, y1, x2, y2; };
 
 static __device__ __forceinline__ double center_dist(const Box &a, const Box &b) {
     // (tlbr[:2] + tlbr[2:]) / 2.0 ; cdist 'euclidean': s = dx*dx; s += dy*dy; sqrt(s)
-    double acx = __ddiv_rn(__dadd_rn(a.x1, a.x2), 2.0), acy = __ddiv_rn(__dadd_rn(a.y1, a.y2), 2.0);
-    double bcx = __ddiv_rn(__dadd_rn(b.x1, b.x2), 2.0), bcy = __ddiv_rn(__dadd_rn(b.y1, b.y2), 2.0);
+    // x / 2.0 == x * 0.5 bit for bit (scaling by a power of two is the same single rounding either way): no software division
+    double acx = __dmul_rn(__dadd_rn(a.x1, a.x2), 0.5), acy = __dmul_rn(__dadd_rn(a.y1, a.y2), 0.5);
+    double bcx = __dmul_rn(__dadd_rn(b.x1, b.x2), 0.5), bcy = __dmul_rn(__dadd_rn(b.y1, b.y2), 0.5);
     double dx = __dsub_rn(acx, bcx), dy = __dsub_rn(acy, bcy);
     return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }

@@ -101,14 +101,19 @@ __global__ void __launch_bounds__(GEOM_THREADS) frame_geometry_kernel(GeomParams
     }
 }
 
-__global__ void pair_matrix_kernel(const double *__restrict__ a, int na, const double *__restrict__ b, int nb,
-                                   double *__restrict__ out, int want_iou) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)na * nb) return;
-    int r = (int)(i / nb), c = (int)(i % nb);
-    Box A{a[4 * r], a[4 * r + 1], a[4 * r + 2], a[4 * r + 3]};
-    Box B{b[4 * c], b[4 * c + 1], b[4 * c + 2], b[4 * c + 3]};
-    out[i] = want_iou ? box_iou(A, B) : center_dist(A, B);
+// grid (column blocks, row groups): a thread keeps ONE column box in registers and walks PAIR_ROWS rows (row boxes are warp-uniform
+// loads); no 64-bit index division, consecutive threads write consecutive doubles
+constexpr int PAIR_ROWS = 8;
+__global__ void __launch_bounds__(256) pair_matrix_kernel(const double *__restrict__ a, int na, const double *__restrict__ b, int nb,
+                                                          double *__restrict__ out, int want_iou) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nb) return;
+    const Box B{b[4 * c], b[4 * c + 1], b[4 * c + 2], b[4 * c + 3]};
+    const int r0 = blockIdx.y * PAIR_ROWS, r1 = min(na, r0 + PAIR_ROWS);
+    for (int r = r0; r < r1; ++r) {
+        const Box A{__ldg(a + 4 * r), __ldg(a + 4 * r + 1), __ldg(a + 4 * r + 2), __ldg(a + 4 * r + 3)};
+        out[(size_t)r * nb + c] = want_iou ? box_iou(A, B) : center_dist(A, B);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -175,7 +180,7 @@ cudaError_t launch_frame_geometry(const GeomParams &p, cudaStream_t s) {
 cudaError_t launch_pair_matrix(const double *a, int na, const double *b, int nb, double *out, int want_iou, cudaStream_t s) {
     long long n = (long long)na * nb;
     if (n == 0) return cudaSuccess;
-    pair_matrix_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, na, b, nb, out, want_iou);
+    pair_matrix_kernel<<<dim3(ceil_div(nb, 256), ceil_div(na, PAIR_ROWS)), 256, 0, s>>>(a, na, b, nb, out, want_iou);
     return cudaGetLastError();
 }
 

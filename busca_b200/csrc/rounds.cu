@@ -142,15 +142,20 @@ __global__ void kalman_update_kernel(const double *__restrict__ mean, const doub
 // ------------------------------------------------------------------------------------------------------------------
 // cost[i][j] = 1 - IoU(a_i, b_j); with scores: 1 - (1 - cost) * score_j  (fuse_score recomputes the similarity from the cost)
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int RND_ROWS = 8;       // rows per thread of the pair kernels: grid (column blocks, row groups), no index division
 __global__ void match_cost_kernel(const double *__restrict__ a, int na, const double *__restrict__ b, int nb, const double *__restrict__ score,
                                   double *__restrict__ cost) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)na * nb) return;
-    const int r = (int)(i / nb), c = (int)(i % nb);
-    const Box A{a[r * 4], a[r * 4 + 1], a[r * 4 + 2], a[r * 4 + 3]}, B{b[c * 4], b[c * 4 + 1], b[c * 4 + 2], b[c * 4 + 3]};
-    double v = __dsub_rn(1.0, box_iou(A, B));
-    if (score) v = __dsub_rn(1.0, __dmul_rn(__dsub_rn(1.0, v), score[c]));
-    cost[i] = v;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nb) return;
+    const Box B{b[c * 4], b[c * 4 + 1], b[c * 4 + 2], b[c * 4 + 3]};
+    const double sc = score ? score[c] : 0.0;
+    const int r0 = blockIdx.y * RND_ROWS, r1 = min(na, r0 + RND_ROWS);
+    for (int r = r0; r < r1; ++r) {
+        const Box A{__ldg(a + r * 4), __ldg(a + r * 4 + 1), __ldg(a + r * 4 + 2), __ldg(a + r * 4 + 3)};
+        double v = __dsub_rn(1.0, box_iou(A, B));
+        if (score) v = __dsub_rn(1.0, __dmul_rn(__dsub_rn(1.0, v), sc));
+        cost[(size_t)r * nb + c] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -258,13 +263,17 @@ __global__ void __launch_bounds__(ASG_THREADS) assignment_kernel(const double *_
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void duplicate_kernel(const double *__restrict__ a, const int *__restrict__ age_a, int na, const double *__restrict__ b,
                                  const int *__restrict__ age_b, int nb, double thresh, uint8_t *__restrict__ drop_a, uint8_t *__restrict__ drop_b) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)na * nb) return;
-    const int r = (int)(i / nb), c = (int)(i % nb);
-    const Box A{a[r * 4], a[r * 4 + 1], a[r * 4 + 2], a[r * 4 + 3]}, B{b[c * 4], b[c * 4 + 1], b[c * 4 + 2], b[c * 4 + 3]};
-    if (__dsub_rn(1.0, box_iou(A, B)) < thresh) {
-        if (age_a[r] > age_b[c]) drop_b[c] = 1;
-        else drop_a[r] = 1;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nb) return;
+    const Box B{b[c * 4], b[c * 4 + 1], b[c * 4 + 2], b[c * 4 + 3]};
+    const int gb = age_b[c];
+    const int r0 = blockIdx.y * RND_ROWS, r1 = min(na, r0 + RND_ROWS);
+    for (int r = r0; r < r1; ++r) {
+        const Box A{__ldg(a + r * 4), __ldg(a + r * 4 + 1), __ldg(a + r * 4 + 2), __ldg(a + r * 4 + 3)};
+        if (__dsub_rn(1.0, box_iou(A, B)) < thresh) {
+            if (__ldg(age_a + r) > gb) drop_b[c] = 1;
+            else drop_a[r] = 1;
+        }
     }
 }
 
@@ -287,7 +296,7 @@ cudaError_t launch_kalman_update(const double *mean, const double *cov, const do
 cudaError_t launch_match_cost(const double *a, int na, const double *b, int nb, const double *score, double *cost, cudaStream_t s) {
     const long long n = (long long)na * nb;
     if (n <= 0) return cudaSuccess;
-    match_cost_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, na, b, nb, score, cost);
+    match_cost_kernel<<<dim3(ceil_div(nb, 128), ceil_div(na, RND_ROWS)), 128, 0, s>>>(a, na, b, nb, score, cost);
     return cudaGetLastError();
 }
 
@@ -317,6 +326,6 @@ cudaError_t launch_duplicates(const double *a, const int *age_a, int na, const d
                               uint8_t *drop_a, uint8_t *drop_b, cudaStream_t s) {
     const long long n = (long long)na * nb;
     if (n <= 0) return cudaSuccess;
-    duplicate_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a, age_a, na, b, age_b, nb, thresh, drop_a, drop_b);
+    duplicate_kernel<<<dim3(ceil_div(nb, 128), ceil_div(na, RND_ROWS)), 128, 0, s>>>(a, age_a, na, b, age_b, nb, thresh, drop_a, drop_b);
     return cudaGetLastError();
 }
