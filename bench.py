@@ -131,7 +131,7 @@ def build_model(precision: str, device: int, bank_slots: int = 8192):
     return m, targs
 
 
-def adapter_leg(model, targs, args, device_rounds=False):
+def adapter_leg(model, targs, args, device_rounds=False, config="mot20"):
     """The adapter's real call pattern (busca_b200/hosts/bytetrack.py after byte_tracker.py:226-456) on a MOT20-scale synthetic
     sequence: per frame 3 detection-crop calls, one single-box crop call per unmatched track, center_distance without a handle,
     associate_embeddings; tracker state evolves (histories appended, patch-bank slots recycled).  Times only what runs inside
@@ -142,7 +142,10 @@ def adapter_leg(model, targs, args, device_rounds=False):
     warm = 13
     seq = synth.make_sequence(4242, warm + args.adapter_frames, args.adapter_objects, miss=0.33, low_score=0.05, clutter=2.0, frame_ring=6)
     a = copy.copy(targs)
-    a.use_busca, a.track_thresh, a.track_buffer, a.match_thresh, a.mot20 = True, 0.6, 30, 0.9, True
+    if config == "mot17":                                   # BASELINE.json configs[1]: the MOT17 YAML (coverage gate, camera-motion compensation, score fusion)
+        from busca_b200.option import load_args_from_config
+        a, _ = load_args_from_config(os.path.join(REPO, "busca_b200", "configs", "bytetrack_mot17.yml"))
+    a.use_busca, a.track_thresh, a.track_buffer, a.match_thresh, a.mot20 = True, 0.6, 30, 0.9, config != "mot17"
     clock = {"t": 0.0}
 
     def timed(fn):
@@ -159,7 +162,9 @@ def adapter_leg(model, targs, args, device_rounds=False):
         associate_embeddings = staticmethod(timed(model.associate_embeddings))
 
     host = ByteTrackHost(Timed, a, iou_fn=lambda x, y: model.engine.iou(x, y), center_distance_fn=timed(lambda t, d: tracking.center_distance(t, d)),
-                         rounds=DeviceRounds(model.engine) if device_rounds else None)   # the rounds themselves on the device
+                         rounds=DeviceRounds(model.engine) if device_rounds else None,   # the rounds themselves on the device
+                         reliable_fn=timed(lambda shape, tracks, p: tracking.is_reliable(shape, tracks, p, engine=model.engine)),
+                         camera_motion_fn=timed(lambda prev, cur: model.engine.camera_motion(prev, cur)[0]))
     busca_ms, total_ms, n_unmatched, kept = [], [], [], 0
     pr = None
     if args.profile_e2e:
@@ -184,7 +189,9 @@ def adapter_leg(model, targs, args, device_rounds=False):
     if not busca_ms:
         return None
     dec = float(np.sum(n_unmatched))
-    return {"frames": len(busca_ms), "objects": args.adapter_objects, "unmatched_tracks_per_frame": round(float(np.mean(n_unmatched)), 1),
+    return {"frames": len(busca_ms), "objects": args.adapter_objects, "config": config, "bank_slots_in_use": int(model.engine.slots_in_use()) if hasattr(model.engine, "slots_in_use") else None,
+            "total_ms_per_frame_p50": round(float(np.percentile(total_ms, 50)), 2), "total_ms_per_frame_p99": round(float(np.percentile(total_ms, 99)), 2),
+            "unmatched_tracks_per_frame": round(float(np.mean(n_unmatched)), 1),
             "value": round(dec / (np.sum(busca_ms) * 1e-3), 1), "unit": "decisions/s (time inside BUSCA's API only)",
             "busca_ms_per_frame_p50": round(float(np.percentile(busca_ms, 50)), 2), "busca_ms_per_frame_p99": round(float(np.percentile(busca_ms, 99)), 2),
             "host_tracker_ms_per_frame_p50": round(float(np.percentile(np.array(total_ms) - np.array(busca_ms), 50)), 2),
@@ -212,6 +219,13 @@ def run_ours(args):
     mine = sharding.partition_sequences([args.steps + args.warmup] * S, world, policy="round_robin")[rank]
     model, targs = build_model(args.precision, local, bank_slots=max(8192, len(mine) * (T * L + D + T) + 4096))
     eng = model.engine
+    if args.adapter_only:
+        if rank == 0:
+            if os.environ.get("BUSCA_DEFER_CROP_COPIES") == "1":
+                model.engine.set_option("defer_crop_copies", 1)
+            out = adapter_leg(model, targs, args, device_rounds=True, config=args.adapter_config)
+            print(json.dumps({"metric": "decisions/sec (adapter pattern, whole sequence)", "impl": "ours", "dtype": args.precision, "e2e_adapter": out}), flush=True)
+        return
     frame_sets = {}
 
     def frames_for(sid):                                     # 4 distinct frame sets (synthesis costs ~1 s each); set 0 = the golden scene's
@@ -340,6 +354,14 @@ def run_ours(args):
         if dev is not None:
             adapter["with_device_rounds"] = {k: dev[k] for k in ("value", "busca_ms_per_frame_p50", "host_tracker_ms_per_frame_p50", "kept_alive", "decisions")}
             adapter["with_device_rounds"]["what"] = "same sequence with the host tracker's rounds on libbusca_b200 (batched Kalman predict / update, IoU cost + assignment per round, duplicate removal: csrc/rounds.cu)"
+        model.engine.set_option("defer_crop_copies", 1)
+        try:
+            dev = adapter_leg(model, targs, args, device_rounds=True)
+        finally:
+            model.engine.set_option("defer_crop_copies", 0)
+        if dev is not None:
+            adapter["with_device_rounds_and_deferred_crop_copies"] = {k: dev[k] for k in ("value", "busca_ms_per_frame_p50", "host_tracker_ms_per_frame_p50", "total_ms_per_frame_p50", "kept_alive", "decisions")}
+            adapter["with_device_rounds_and_deferred_crop_copies"]["what"] = "plus the opt-in defer_crop_copies: get_image_crops returns before its device->host copy has landed (valid after the next waiting call)"
 
     # NCCL only here: max over ranks of the device-timed regions, and the gather of the per-rank result tables
     ms_max, e2e_ms_max = sharding.reduce_max([ms, e2e_s * 1e3], dist, device=f"cuda:{local}")
@@ -394,6 +416,23 @@ def run_ours(args):
         except Exception:
             pass
         ms_step = ms / n_frames_timed                            # per FRAME (one sequence): what the per-frame FLOP / byte counts refer to
+        # The chain is layer-serialised (a grid-wide BatchNorm dependency after every convolution), so the bound of a frame is the SUM over
+        # its launches of max(tensor time, HBM time), not one roofline: per kernel instantiation, algorithmic FLOPs / tensor peak against ncu
+        # DRAM bytes / copy peak (an instantiation mixes tensor- and HBM-bound layers, which only lowers this bound: conservative).
+        composite = None
+        try:
+            cb = 0.0
+            for k, v in by_kernel.items():
+                t_tensor = v["flops"] / n_frames_prof / (peak_tf * 1e12)
+                t_hbm = tr["kernels"][k]["dram_bytes_per_launch"] * (v["launches"] / n_frames_prof) / (peak_hbm * 1e9) if k in tr["kernels"] else 0.0
+                cb += max(t_tensor, t_hbm)
+            hbm_only = sum(v["dram_bytes_per_launch"] * v["launches"] for kk, v in tr["kernels"].items()
+                           if kk not in by_kernel and v.get("dram_bytes_per_launch")) / (peak_hbm * 1e9)   # pooling, BN folds, gather ...
+            composite = {"bound_ms_per_frame": round((cb + hbm_only) * 1e3, 3), "frac": round((cb + hbm_only) / (ms_step * 1e-3), 5),
+                         "what": "sum over kernel instantiations of max(algorithmic FLOPs / sustained bf16 peak, ncu DRAM bytes / copy peak), "
+                                 "plus DRAM time of the non-GEMM kernels, over ms_per_frame"}
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": dom, "achieved": round(achieved, 3), "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": round(achieved / peak_tf, 5), "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": round(avg_ms, 4), "launches": d["launches"],
@@ -403,7 +442,7 @@ def run_ours(args):
                     "step_frac": round(step_flops / (ms_step * 1e-3) / 1e12 / peak_tf, 5),
                     "step_tflops": round(step_flops / (ms_step * 1e-3) / 1e12, 1),
                     "step_hbm_frac": round(step_dram / (ms_step * 1e-3) / 1e9 / peak_hbm, 5) if step_dram else None,
-                    "step_dram_bytes_ncu": step_dram,
+                    "step_dram_bytes_ncu": step_dram, "composite": composite,
                     "all_conv_kernels": {k: {"tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1), "executed_tflops": round(v["xflops"] / (v["ms"] * 1e-3) / 1e12, 1),
                                              "ms_per_frame": round(v["ms"] / n_frames_prof, 3), "launches_per_frame": v["launches"] / n_frames_prof}
                                          for k, v in by_kernel.items()},
@@ -516,6 +555,8 @@ if __name__ == "__main__":
     ap.add_argument("--sequences", type=int, default=64, help="independent sequences of the fixed job (BASELINE.json configs[3]: 64)")
     ap.add_argument("--adapter-frames", type=int, default=30, help="frames of the adapter-pattern leg after 13 warm-up frames (0 = skip)")
     ap.add_argument("--adapter-objects", type=int, default=560, help="objects of the adapter-pattern sequence (~200 unmatched tracks per frame at 560)")
+    ap.add_argument("--adapter-config", default="mot20", choices=["mot20", "mot17"], help="YAML of the adapter-pattern leg (mot17: coverage gate + camera-motion compensation + score fusion)")
+    ap.add_argument("--adapter-only", action="store_true", help="run only the adapter-pattern leg (whole sequences: BASELINE.json configs[1] / [2]) with the rounds on the device and print its JSON")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the plug-in API leg (profiler runs)")
     ap.add_argument("--profile-e2e", action="store_true", help="after the timed plug-in leg, cProfile the same loop to stderr")

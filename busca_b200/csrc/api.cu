@@ -5,6 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -96,6 +100,8 @@ struct busca_ctx {
     int64_t bank_slots = 0;
     // scratch
     DevBuf ws_reid, ws_tr, ws_io, ws_small, ws_gram;
+    uint8_t *d2h_ring = nullptr;                  // page-locked staging ring of d2h_pageable
+    cudaEvent_t d2h_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf ws_ecc;                                // camera-motion compensation: 5 fp32 planes + partial sums + state
     int ecc_H = 0, ecc_W = 0, ecc_cur = 0;        // size of the cached planes; which of the two smoothed planes holds the LAST current frame
     bool ecc_have_prev = false;
@@ -106,6 +112,7 @@ struct busca_ctx {
     bool use_tc = false;                          // bf16 mode: tcgen05 convolutions (BUSCA_CONV=simt forces the SIMT bf16 path)
     // duplicate elimination inside a BatchNorm batch (tensor-core path; BUSCA_DEDUP=0 / busca_set_option("dedup", 0) disables)
     bool dedup = true;
+    bool defer_crop_copies = false;               // option "defer_crop_copies": busca_crop returns before its device->host copy has landed
     bool tr_tc = true;                            // bf16 mode: Decision-Transformer GEMMs on the tensor cores (option "tr_tc" 0: the fp32 SIMT linears)
     int *dedup_table = nullptr;                   // [bank_slots + 1], all 0x7f7f7f7f between kernels
     DevBuf ws_dedup[2];                           // per planned batch: uniq | map | weight | count
@@ -168,6 +175,27 @@ static void prof_collect(busca_ctx *c) {
     }
     js += "}";
     c->prof_json = js;
+}
+
+// Wait for the stream after a SHORT operation (a single-box crop, a T x D matrix, one association round): the adapters make hundreds
+// of such calls per frame (byte_tracker.py:468-479) and a blocking cudaStreamSynchronize costs a futex sleep / wake-up (tens of
+// microseconds) each time.  Poll the stream for up to ~300 us first (BUSCA_SPIN=0 disables), then fall back to the blocking wait.
+static int g_spin = -1;
+static cudaError_t stream_wait_short(busca_ctx *c) {
+    if (g_spin < 0) {
+        const char *e = getenv("BUSCA_SPIN");
+        g_spin = !(e && e[0] == '0');
+    }
+    if (g_spin) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int it = 0;; ++it) {
+            cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) return cudaSuccess;
+            if (q != cudaErrorNotReady) return q;
+            if ((it & 15) == 15 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
+        }
+    }
+    return cudaStreamSynchronize(c->stream);
 }
 
 // programmatic dependent launch of the ReID kernel chain (common.cuh); BUSCA_PDL=1 enables
@@ -267,6 +295,8 @@ extern "C" void busca_destroy(busca_ctx *c) {
     c->ws_small.release();
     c->ws_gram.release();
     c->ws_ecc.release();
+    if (c->d2h_ring) cudaFreeHost(c->d2h_ring);
+    for (auto e : c->d2h_ev) if (e) cudaEventDestroy(e);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -647,9 +677,65 @@ static int check_slots(busca_ctx *c, const int32_t *slots, int n, bool allow_neg
     return BUSCA_OK;
 }
 
+// Device -> PAGEABLE host for the big crop arrays the adapters keep (byte_tracker.py:278-282 returns ~45 MB per call at MOT20 scale and
+// every track keeps a row of it alive, so those arrays cannot come from the page-locked pool).  A plain cudaMemcpyAsync into pageable
+// memory is staged by the driver on one thread (~6.5 GB/s measured, page faults of the fresh array included); here the DMA lands in a
+// ring of page-locked chunks at PCIe speed and worker threads copy finished chunks into the destination (first-touch faults in
+// parallel).  The stream is idle when this returns.
+constexpr size_t D2H_CHUNK = 4u << 20;
+constexpr int D2H_RING = 4, D2H_WORKERS = 3;
+static int d2h_pageable(busca_ctx *c, uint8_t *dst, const uint8_t *src, size_t bytes) {
+    if (!c->d2h_ring) {
+        CUDA_OK(cudaHostAlloc((void **)&c->d2h_ring, D2H_CHUNK * D2H_RING, cudaHostAllocPortable));
+        for (int i = 0; i < D2H_RING; ++i) CUDA_OK(cudaEventCreateWithFlags(&c->d2h_ev[i], cudaEventDisableTiming));
+    }
+    const int K = (int)((bytes + D2H_CHUNK - 1) / D2H_CHUNK);
+    std::vector<std::atomic<int>> state(K);                 // 0 = not enqueued, 1 = DMA enqueued (event recorded), 2 = copied out
+    for (auto &x : state) x.store(0);
+    std::atomic<int> next{0};
+    std::atomic<int> failed{0};
+    auto worker = [&]() {
+        cudaSetDevice(c->cfg.device);
+        for (;;) {
+            const int k = next.fetch_add(1);
+            if (k >= K) return;
+            while (state[k].load(std::memory_order_acquire) == 0 && !failed.load()) std::this_thread::yield();
+            if (failed.load()) return;
+            if (cudaEventSynchronize(c->d2h_ev[k % D2H_RING]) != cudaSuccess) { failed.store(1); return; }
+            const size_t off = (size_t)k * D2H_CHUNK, nb = std::min(D2H_CHUNK, bytes - off);
+            memcpy(dst + off, c->d2h_ring + (size_t)(k % D2H_RING) * D2H_CHUNK, nb);
+            state[k].store(2, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < std::min(D2H_WORKERS, K); ++w) pool.emplace_back(worker);
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < K && err == cudaSuccess && !failed.load(); ++k) {
+        if (k >= D2H_RING)
+            while (state[k - D2H_RING].load(std::memory_order_acquire) != 2 && !failed.load()) std::this_thread::yield();   // ring slot free again
+        const size_t off = (size_t)k * D2H_CHUNK, nb = std::min(D2H_CHUNK, bytes - off);
+        err = cudaMemcpyAsync(c->d2h_ring + (size_t)(k % D2H_RING) * D2H_CHUNK, src + off, nb, cudaMemcpyDeviceToHost, c->stream);
+        if (err == cudaSuccess) err = cudaEventRecord(c->d2h_ev[k % D2H_RING], c->stream);
+        if (err != cudaSuccess) { failed.store(1); break; }
+        state[k].store(1, std::memory_order_release);
+    }
+    for (auto &t : pool) t.join();
+    if (err != cudaSuccess) return set_err(BUSCA_ERR_CUDA, "device->host copy: %s", cudaGetErrorString(err));
+    if (failed.load()) return set_err(BUSCA_ERR_CUDA, "device->host copy failed");
+    return BUSCA_OK;
+}
+static bool host_is_pageable(const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 // bank <-> host, one copy per run of consecutive slots (alloc_slots hands out ascending runs, so a frame's crops are
 // usually a single DMA; with page-locked host memory it runs at PCIe speed)
 static int bank_copy_runs(busca_ctx *c, const int32_t *slots, int n, uint8_t *host, bool to_bank) {
+    static int pipelined = -1;
+    if (pipelined < 0) { const char *e = getenv("BUSCA_D2H_PIPELINE"); pipelined = !(e && e[0] == '0'); }
+    const bool big_pageable = !to_bank && pipelined && (size_t)n * PATCH_BYTES >= 2 * D2H_CHUNK && host_is_pageable(host);
     int i = 0;
     while (i < n) {
         int j = i + 1;
@@ -657,6 +743,7 @@ static int bank_copy_runs(busca_ctx *c, const int32_t *slots, int n, uint8_t *ho
         uint8_t *dev = c->bank + (size_t)slots[i] * PATCH_BYTES, *h = host + (size_t)i * PATCH_BYTES;
         const size_t bytes = (size_t)(j - i) * PATCH_BYTES;
         if (to_bank) CUDA_OK(cudaMemcpyAsync(dev, h, bytes, cudaMemcpyHostToDevice, c->stream));
+        else if (big_pageable && bytes >= D2H_CHUNK) { int rc = d2h_pageable(c, h, dev, bytes); if (rc) return rc; }
         else CUDA_OK(cudaMemcpyAsync(h, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
         i = j;
     }
@@ -690,7 +777,11 @@ extern "C" int busca_crop(busca_ctx *c, const double *boxes, int32_t n, const in
         int rc2 = bank_copy_runs(c, slots, n, host_out, false);
         if (rc2) return rc2;
     }
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    // Opt-in (busca_set_option "defer_crop_copies"): return once the gather and its device->host copy are ENQUEUED.  The bank slot is
+    // valid for every later call on this context (same stream); the HOST bytes are valid after the next call that waits for the stream
+    // (busca_associate, busca_sync, any matrix call ...).  The adapters only store the crops between the two (byte_tracker.py:468-479).
+    if (c->defer_crop_copies && !c->profiling) return BUSCA_OK;
+    CUDA_OK((n <= 8) ? stream_wait_short(c) : cudaStreamSynchronize(c->stream));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -733,7 +824,7 @@ static int pair_matrix(busca_ctx *c, const double *a, int na, const double *b, i
     prof_reset(c);
     LAUNCH(c, want_iou ? "iou_matrix" : "center_distance", launch_pair_matrix(da, na, db, nb, dout, want_iou, c->stream));
     CUDA_OK(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -758,7 +849,7 @@ extern "C" int busca_detection_coverage(busca_ctx *c, const double *tlbr, int32_
     unsigned long long cnt = 0;
     CUDA_OK(cudaMemcpyAsync(&cnt, dcnt, 8, cudaMemcpyDeviceToHost, c->stream));
     if (bbox_areas_out && n > 0) CUDA_OK(cudaMemcpyAsync(bbox_areas_out, dar, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     *nonzero_out = (int64_t)cnt;
     return BUSCA_OK;
@@ -784,7 +875,7 @@ extern "C" int busca_kalman_predict(busca_ctx *c, const double *mean, const doub
     LAUNCH(c, "kalman_predict", launch_kalman_predict(dm, dc, tracked ? dt : nullptr, n, dmo, dco, c->stream));
     CUDA_OK(cudaMemcpyAsync(mean_out, dmo, mb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(cov_out, dco, cb, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -806,7 +897,7 @@ extern "C" int busca_kalman_update(busca_ctx *c, const double *mean, const doubl
     LAUNCH(c, "kalman_update", launch_kalman_update(dm, dc, dz, n, dmo, dco, c->stream));
     CUDA_OK(cudaMemcpyAsync(mean_out, dmo, mb, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(cov_out, dco, cb, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -842,7 +933,7 @@ static int match_round(busca_ctx *c, const double *a, int32_t na, const double *
     CUDA_OK(cudaMemcpyAsync(x, dx, (size_t)na * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(y, dy, (size_t)nb * 4, cudaMemcpyDeviceToHost, c->stream));
     if (cost_out) CUDA_OK(cudaMemcpyAsync(cost_out, dcost, cb, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -878,7 +969,7 @@ extern "C" int busca_duplicate_tracks(busca_ctx *c, const double *a_tlbr, const 
     LAUNCH(c, "duplicate_tracks", launch_duplicates(da, dga, na, db, dgb, nb, thresh, dfa, dfb, c->stream));
     CUDA_OK(cudaMemcpyAsync(drop_a, dfa, (size_t)na, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaMemcpyAsync(drop_b, dfb, (size_t)nb, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -916,7 +1007,7 @@ extern "C" int busca_frame_geometry(busca_ctx *c, const double *mean, const uint
     if (dist && D) CUDA_OK(cudaMemcpyAsync(dist, base + o_dist, (size_t)T * D * 8, cudaMemcpyDeviceToHost, c->stream));
     if (iou && D) CUDA_OK(cudaMemcpyAsync(iou, base + o_iou, (size_t)T * D * 8, cudaMemcpyDeviceToHost, c->stream));
     if (cand) CUDA_OK(cudaMemcpyAsync(cand, base + o_cand, (size_t)T * C * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -942,7 +1033,7 @@ extern "C" int busca_motion_proposals(busca_ctx *c, const double *mean, const ui
     if (mean_out) CUDA_OK(cudaMemcpyAsync(mean_out, dmo, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream));
     if (tlwh) CUDA_OK(cudaMemcpyAsync(tlwh, dtlwh, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
     if (tlbr) CUDA_OK(cudaMemcpyAsync(tlbr, dtlbr, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
 }
@@ -1743,6 +1834,7 @@ extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (strcmp(name, "dedup") == 0) { c->dedup = value != 0; return BUSCA_OK; }
     if (strcmp(name, "gram") == 0) { c->gram = value != 0; return BUSCA_OK; }
     if (strcmp(name, "tr_tc") == 0) { c->tr_tc = value != 0; return BUSCA_OK; }
+    if (strcmp(name, "defer_crop_copies") == 0) { c->defer_crop_copies = value != 0; return BUSCA_OK; }
     if (strcmp(name, "pool_mono") == 0) { reid_set_pool_mono(value); return BUSCA_OK; } // process-wide (experimental max-pool kernel)
     if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
     if (strcmp(name, "mc_min_tiles") == 0) { conv_tc_set_mc_min_tiles((int)value); return BUSCA_OK; }   // process-wide

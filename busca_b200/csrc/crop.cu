@@ -23,6 +23,7 @@ constexpr float COEF_SCALE = 2048.f;
 constexpr int CROP_STAGE_BYTES = 16384;          // per staging buffer (two of them)
 constexpr int CROP_PARTS = 4;                    // CTAs per crop (blockIdx.y): 96 output rows each - a frame's few hundred crops fill the machine
 constexpr int CROP_ROWS = PATCH_H / CROP_PARTS;
+constexpr int CROP_PARTS_SMALL = 16;             // single-box calls (the adapters' Kalman proposals): 24 rows per CTA - the launch is pure latency
 
 __device__ __forceinline__ uint32_t smem_u32_(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init_(uint64_t *bar, uint32_t count) {
@@ -43,7 +44,7 @@ __device__ __forceinline__ int clamp_coord(double v) {
 }
 
 __device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int H, int W, long long row_stride, const double *b,
-                                          int slot, uint8_t *__restrict__ bank) {
+                                          int slot, uint8_t *__restrict__ bank, int rows_per_cta) {
     __shared__ CropWin win;
     __shared__ unsigned long long ssum[CROP_THREADS / 32];
     __shared__ int xs0[PATCH_W], xs1[PATCH_W];
@@ -58,7 +59,7 @@ __device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int
 
     if (slot < 0) return;
     const int tid = threadIdx.x;
-    const int dy_lo = blockIdx.y * CROP_ROWS, dy_hi = dy_lo + CROP_ROWS;      // this CTA's output rows
+    const int dy_lo = blockIdx.y * rows_per_cta, dy_hi = dy_lo + rows_per_cta;      // this CTA's output rows
     uint8_t *out = bank + (size_t)slot * PATCH_BYTES;
 
     if (tid == 0) {
@@ -82,8 +83,12 @@ __device__ __forceinline__ void crop_body(const uint8_t *__restrict__ frame, int
         return;
     }
 
-    // ---- phase 1: sum of the clipped window over all three channels
-    {
+    // ---- phase 1: sum of the clipped window over all three channels - only when the cut-out leaves the frame (no tap reads the pad
+    // value otherwise; most boxes are inside, and for the adapters' single-box calls this dependent-load chain was a third of the launch)
+    const bool clipped = win.X1c != win.X1 || win.Y1c != win.Y1 || win.X2c != win.X1 + win.sw || win.Y2c != win.Y1 + win.sh;
+    if (!clipped) {
+        if ((tid & 31) == 0) ssum[tid >> 5] = 0;
+    } else {
         const int wbytes = (win.X2c - win.X1c) * 3, rows = win.Y2c - win.Y1c;
         unsigned long long acc = 0;
         for (int r = tid >> 5; r < rows; r += CROP_THREADS / 32) {         // one warp per row
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_resize_kernel(const uint8_t
                                                                    uint8_t *__restrict__ bank) {
     const int i = blockIdx.x;
     if (i >= n) return;
-    crop_body(frame, H, W, row_stride, boxes + 4 * (size_t)i, slots[i], bank);
+    crop_body(frame, H, W, row_stride, boxes + 4 * (size_t)i, slots[i], bank, CROP_ROWS);
 }
 
 // up to 4 boxes passed BY VALUE in the kernel parameters: the adapters crop the Kalman proposal of every unmatched track with
@@ -337,14 +342,14 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_resize_small_kernel(const u
                                                                          const __grid_constant__ CropSmall s, uint8_t *__restrict__ bank) {
     const int i = blockIdx.x;
     if (i >= s.n) return;
-    crop_body(frame, H, W, row_stride, &s.boxes[4 * i], s.slots[i], bank);
+    crop_body(frame, H, W, row_stride, &s.boxes[4 * i], s.slots[i], bank, PATCH_H / CROP_PARTS_SMALL);
 }
 
 }  // namespace
 
 cudaError_t launch_crop_resize_small(const uint8_t *frame, int H, int W, int64_t row_stride, const CropSmall &sm, uint8_t *bank, cudaStream_t s) {
     if (sm.n <= 0) return cudaSuccess;
-    crop_resize_small_kernel<<<dim3(sm.n, CROP_PARTS), CROP_THREADS, 0, s>>>(frame, H, W, (long long)row_stride, sm, bank);
+    crop_resize_small_kernel<<<dim3(sm.n, CROP_PARTS_SMALL), CROP_THREADS, 0, s>>>(frame, H, W, (long long)row_stride, sm, bank);
     return cudaGetLastError();
 }
 

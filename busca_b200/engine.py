@@ -21,7 +21,9 @@ STD_BGR = np.array([0.225, 0.224, 0.299])    # sic: the reference's "ghost_norma
 
 
 def _ptr(a: Optional[np.ndarray]):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    # the address as a plain int (argtypes are c_void_p): a third of the cost of a.ctypes.data_as(...) - the adapters make hundreds of
+    # small calls per frame
+    return None if a is None else a.__array_interface__["data"][0]
 
 
 def normalize_lut() -> np.ndarray:
@@ -107,6 +109,10 @@ class Engine:
         # for the life of a track, so those blocks rarely come back)
         self._pin_max = int(float(os.environ.get("BUSCA_PINNED_MAX_GB", "1")) * (1 << 30))
         self._arena: Optional[_PinnedBlock] = None
+        self._frame_key = None                              # sync_frame: the last validated frame object
+        self._frame_args = None
+        self._frame_keep = None
+        self._frame_up = C.c_int32(0)
         self._arena_used = 0
         self.device = device
         global _last_engine
@@ -186,6 +192,10 @@ class Engine:
         out = np.array([self._free.pop() for _ in range(n)], dtype=np.int32)
         return out
 
+    def slots_in_use(self) -> int:
+        """Patch-bank slots currently handed out (crops some track still references)."""
+        return self._cap - len(self._free)
+
     def free_slots(self, slots: Iterable[int]):
         self._free.extend(int(s) for s in slots)
 
@@ -239,14 +249,21 @@ class Engine:
 
     def sync_frame(self, image: np.ndarray, boxes: Optional[np.ndarray] = None) -> bool:
         """Upload ``image`` unless the pixels ``boxes`` read (all pixels without boxes) already are in HBM (busca_sync_frame)."""
-        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
-            raise ValueError("frame must be uint8 [H,W,3] BGR")
-        if image.strides[2] != 1 or image.strides[1] != 3:
-            image = np.ascontiguousarray(image)
-        up = C.c_int32(0)
+        ai = image.__array_interface__
+        key = (id(image), ai["data"][0], ai["shape"], ai["strides"])
+        if key != self._frame_key:                          # validate once per frame object; the PIXELS are compared by the library every call
+            if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+                raise ValueError("frame must be uint8 [H,W,3] BGR")
+            if image.strides[2] != 1 or image.strides[1] != 3:
+                image = np.ascontiguousarray(image)
+                self._frame_key = None
+            else:
+                self._frame_key = key
+            self._frame_args = (image.__array_interface__["data"][0], image.shape[0], image.shape[1], image.strides[0])
+            self._frame_keep = image
+        up = self._frame_up
         nb = 0 if boxes is None else len(boxes)
-        check(self.L.busca_sync_frame(self.h, _ptr(image), image.shape[0], image.shape[1], image.strides[0],
-                                      _ptr(boxes) if nb else None, nb, C.byref(up)))
+        check(self.L.busca_sync_frame(self.h, *self._frame_args, _ptr(boxes) if nb else None, nb, C.byref(up)))
         return bool(up.value)
 
     def crop(self, boxes: np.ndarray, slots: np.ndarray, to_host: bool = True) -> Optional[np.ndarray]:
@@ -260,9 +277,11 @@ class Engine:
         """Crops to bank slots AND to the host, into page-locked memory from the pool.  Returns ``(array, owner)``:
         ``owner`` is the object that dies when the array and all of its views are gone (the pinned block, or the
         array itself on the pageable fallback) - hang slot-recycling finalizers on it."""
-        boxes = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 4)
-        slots = np.ascontiguousarray(slots, dtype=np.int32)
-        n = len(boxes)
+        if boxes.dtype != np.float64 or not boxes.flags["C_CONTIGUOUS"]:
+            boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        if slots.dtype != np.int32 or not slots.flags["C_CONTIGUOUS"]:
+            slots = np.ascontiguousarray(slots, dtype=np.int32)
+        n = boxes.size // 4
         blk = None
         if n * 8 <= ARENA_PATCHES:                          # small call: a slice of the current arena
             if self._arena is None or self._arena_used + n > ARENA_PATCHES:

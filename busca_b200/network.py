@@ -16,6 +16,8 @@ afterwards would not reach the GPU.  Copy the row (a copy is an unknown array an
 """
 from __future__ import annotations
 
+import os
+
 import weakref
 from typing import Dict, List, Optional
 
@@ -105,6 +107,12 @@ class BUSCA:
                              ff_size=args.ff_size, num_layers=args.num_layer, activation=self.activation,
                              precision=self.precision, sentinel_fp64=self.legacy_float64_sentinel,
                              bank_slots=int(getattr(args, "bank_slots", 2048)))
+        # opt-in (args.defer_crop_copies / BUSCA_DEFER_CROP_COPIES=1): get_image_crops returns before the device->host copy of the crops
+        # has landed; the returned arrays hold valid bytes after the next BUSCA call that waits for the device (associate_embeddings,
+        # center_distance, sync()).  For adapters that only STORE the crops in between - every shipped one does (byte_tracker.py:278-282,
+        # 468-479) - it takes the per-call wait out of the T single-box crop calls.  Off by default: strict reference semantics.
+        if bool(getattr(args, "defer_crop_copies", False)) or os.environ.get("BUSCA_DEFER_CROP_COPIES") == "1":
+            self.engine.set_option("defer_crop_copies", 1)
         self.expected_image_size = (384, 128)           # ReID_Encoder.PRETRAINED_SIZE (network.py:512)
         self._registry = _PatchRegistry(self.engine)
         self.attentions = None
@@ -168,6 +176,10 @@ class BUSCA:
         ``current_frame`` (``to_host=False``: None; pass the frame's shape with ``device_frame_shape`` instead)."""
         return self.engine.ingest_frame(detector_tensor, means, std, height, width, to_host=to_host)
 
+    def sync(self):
+        """Wait for everything enqueued on this tracker's stream (with ``defer_crop_copies``: the crops' host bytes are valid afterwards)."""
+        self.engine.sync()
+
     def set_frame(self, image: np.ndarray):
         """Explicitly (re)upload the current frame."""
         self.engine.upload_frame(image)
@@ -179,6 +191,8 @@ class BUSCA:
             raise NotImplementedError("crops are fixed at 128x384")
         if isinstance(bboxes, np.ndarray) and bboxes.ndim == 2 and bboxes.shape[1] == 4:
             boxes = np.ascontiguousarray(bboxes, dtype=np.float64)
+        elif len(bboxes) == 1:                                # the adapters' per-track call (byte_tracker.py:468-479): one box in a list
+            boxes = np.array(bboxes[0], dtype=np.float64).reshape(1, 4)
         else:
             rows = [np.asarray(b, dtype=np.float64).reshape(4) for b in bboxes]
             boxes = np.stack(rows) if rows else np.zeros((0, 4))

@@ -255,7 +255,10 @@ const char *busca_last_profile(busca_ctx *ctx);
  * the batch statistics by the multiplicities - the batches the reference stacks (network.py:313-316, 383-386) repeat
  * every detection crop for each track that lists it as a candidate, and every incomplete history is the same zero image;
  * "halo" (default 1, process-wide): halo-box kernel for the stride-1 3x3 convolutions (csrc/conv_tc.cu), 0 = tap-by-tap kernel;
- * "pool_mono" (default 1, process-wide): max-pool kernel that pools before BN + ReLU (csrc/reid.cu) */
+ * "pool_mono" (default 1, process-wide): max-pool kernel that pools before BN + ReLU (csrc/reid.cu);
+ * "defer_crop_copies" (default 0): busca_crop returns once the gather and its device->host copy are enqueued; the host bytes of the
+ * crops are valid after the next call on the context that waits for the stream (busca_associate, busca_sync, ...) - for callers
+ * that, like the adapters between get_extra_kalman_candidates and associate_embeddings, only store the crops in between */
 int busca_set_option(busca_ctx *ctx, const char *name, int64_t value);
 /* counters: "reid_images_run" / "reid_images_total" (encoder images executed / images of the stacked batches), "kernel_launches" */
 int64_t busca_counter(busca_ctx *ctx, const char *name);

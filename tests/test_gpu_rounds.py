@@ -233,3 +233,33 @@ def test_camera_motion_latency_and_errors(engine):
         engine.camera_motion(a, b)
     with pytest.raises(BuscaError):
         engine.camera_motion(None, f2[:100, :100])                      # no cached frame of that size
+
+
+def test_deferred_crop_copies_are_the_same_bytes(golden_dir):
+    """Option defer_crop_copies: get_image_crops returns before the device->host copy has landed; after the next waiting call the host
+    bytes (and the bank slots the association reads) are identical to the strict path."""
+    from types import SimpleNamespace
+    from busca_b200.network import BUSCA
+    from busca_b200.option import load_args_from_config
+    here = os.path.dirname(os.path.abspath(__file__))
+    targs, _ = load_args_from_config(os.path.join(os.path.dirname(here), "busca_b200", "configs", "bytetrack_mot20.yml"))
+    a = targs.transformer
+    a.device = "cuda:0"
+    strict = BUSCA(a)
+    a.defer_crop_copies = True
+    lazy = BUSCA(a)
+    frame = synth.make_frame(2)
+    rng = np.random.default_rng(4)
+    b = synth.random_boxes(rng, 40)
+    b[:, 2:] += b[:, :2]
+    want_big = strict.get_image_crops(frame, b, normalize=False)
+    got_big = lazy.get_image_crops(frame, b, normalize=False)
+    singles_w = [strict.get_image_crops(frame, [r], normalize=False)[0] for r in b[:12]]
+    singles_g = [lazy.get_image_crops(frame, [r], normalize=False)[0] for r in b[:12]]
+    lazy.sync()
+    assert np.array_equal(want_big, got_big)
+    for w, g2 in zip(singles_w, singles_g):
+        assert np.array_equal(w, g2)
+    slots = [lazy._registry.lookup(g2) for g2 in singles_g]
+    assert all(s is not None for s in slots)
+    assert np.array_equal(lazy.engine.bank_download(np.array(slots, np.int32)), np.stack(singles_w))
