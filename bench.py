@@ -454,6 +454,7 @@ def run_ours(args):
     kernels = {k: {"ms_per_frame": round(v["ms"] / n_frames_prof, 4), "launches_per_frame": v["launches"] / n_frames_prof,
                    "share": round(v["ms"] / max(total_prof, 1e-9), 4)} for k, v in sorted(prof_acc.items(), key=lambda kv: -kv[1]["ms"])}
     cpu = cpu_baseline(args) if not args.no_cpu_baseline else None
+    host_rows = host_rows_leg(eng) if (rank == 0 and not args.no_cpu_baseline) else None
     out = {
         "metric": "decisions/sec", "value": round(S * T * args.steps / (ms_max * 1e-3), 3), "unit": "decisions/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
@@ -472,7 +473,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(h2d) * S, "d2h_bytes_per_step": int(d2h) * S, "h2d_bytes_per_frame": int(h2d), "d2h_bytes_per_frame": int(d2h),
                 "ms_per_frame": round(e2e_ms_max / frames_max, 4) if e2e_ms_max == e2e_ms_max else None,
                 "api": "BUSCA.get_image_crops + center_distance + associate_embeddings (host numpy in/out), every sequence for K frames"},
-        "e2e_adapter": adapter,
+        "e2e_adapter": adapter, "host_rows": host_rows,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -511,6 +512,65 @@ def time_oracle(T, D, L, C, reps, warm):
         if i >= warm:
             times.append(dt)
     return times
+
+
+def host_rows_leg(eng):
+    """SURVEY.md 8(f) rows at MOT20 scale, device call (host buffers in and out, wall clock) beside the CPU path of the same row (part of
+    the cpu_baseline leg: oracle/ restatements, and cv2 itself for the ECC row when the box has it).  Milliseconds, best of 3."""
+    from oracle import coverage as ocov
+    from oracle import rounds as ornd
+    rng = np.random.default_rng(0)
+
+    def best(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return round(min(ts) * 1e3, 3)
+
+    def boxes(n):
+        b = synth.random_boxes(rng, n)
+        b[:, 2:] += b[:, :2]
+        return b
+
+    a = boxes(500)
+    b = np.concatenate([a[:350] + rng.normal(0, 4, (350, 4)), boxes(50)])
+    sc = rng.uniform(0.1, 1.0, len(b))
+    out = {"match_round_500x400": {"device_ms": best(lambda: eng.match_round(a, b, sc, 0.9)),
+                                   "cpu_ms": best(lambda: ornd.linear_assignment(ornd.fuse_score(ornd.iou_distance(a, b), sc), 0.9), 1),
+                                   "cpu": "numpy IoU + scipy linear_sum_assignment on lapjv's extended matrix"}}
+    n = 500
+    mean = np.concatenate([rng.uniform(0, 1900, (n, 2)), rng.uniform(0.2, 0.8, (n, 1)), rng.uniform(60, 300, (n, 1)), rng.normal(0, 3, (n, 4))], axis=1)
+    cov = np.stack([np.diag(rng.uniform(0.5, 4.0, 8)) for _ in range(n)])
+    z = mean[:, :4] + 1.0
+    out["kalman_predict_update_500"] = {"device_ms": best(lambda: eng.kalman_update(*eng.kalman_predict(mean, cov, None), z)),
+                                        "cpu_ms": best(lambda: [ornd.kf_update(m, c, zz) for m, c, zz in zip(*ornd.kf_multi_predict(mean, cov, None), z)], 1),
+                                        "cpu": "numpy multi_predict + one scipy cho_factor / cho_solve update per track, as the reference"}
+    cb = boxes(300)
+    out["detection_coverage_1080p_300"] = {"device_ms": best(lambda: eng.detection_coverage(cb, 1080, 1920)),
+                                           "cpu_ms": best(lambda: ocov.detection_coverage((1080, 1920), cb), 1), "cpu": "numpy canvas fill + count_nonzero"}
+    f1 = synth.make_frame(21)
+    f2 = synth.make_moved_frame(f1, 0.003, 2.2, -1.3, 21)
+    row = {"device_ms": best(lambda: eng.camera_motion(f1, f2))}
+    try:
+        import cv2
+        g1, g2 = cv2.cvtColor(f1, cv2.COLOR_BGR2GRAY), cv2.cvtColor(f2, cv2.COLOR_BGR2GRAY)
+        crit = (cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 100, 1e-5)
+        row["cpu_ms"] = best(lambda: cv2.findTransformECC(g1, g2, np.eye(2, 3, dtype=np.float32), cv2.MOTION_EUCLIDEAN, crit), 1)
+        row["cpu"] = f"cv2 {cv2.__version__} cvtColor + findTransformECC (the reference's own call), {cv2.getNumThreads()} threads"
+    except Exception:
+        from oracle import ecc as oecc
+        row["cpu_ms"] = best(lambda: oecc.camera_motion(f1, f2), 1)
+        row["cpu"] = "numpy restatement of cv2.findTransformECC (cv2 not importable on this box)"
+    out["camera_motion_1080p"] = row
+    chw = synth.make_detector_tensor(1, 1080, 1920)
+    from oracle import ingest as oing
+    out["frame_ingest_1080p"] = {"device_ms": best(lambda: eng.ingest_frame(chw, synth.YOLOX_MEANS, synth.YOLOX_STD)),
+                                 "cpu_ms": best(lambda: oing.denormalize_frame(chw, synth.YOLOX_MEANS, synth.YOLOX_STD), 1),
+                                 "cpu": "numpy de-normalisation (the evaluator's statements)", "note": "device_ms includes the 25 MB host->device and 6 MB device->host copies"}
+    return out
 
 
 def cpu_baseline(args):

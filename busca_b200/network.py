@@ -111,6 +111,7 @@ class BUSCA:
         # has landed; the returned arrays hold valid bytes after the next BUSCA call that waits for the device (associate_embeddings,
         # center_distance, sync()).  For adapters that only STORE the crops in between - every shipped one does (byte_tracker.py:278-282,
         # 468-479) - it takes the per-call wait out of the T single-box crop calls.  Off by default: strict reference semantics.
+        self.verify_patches = bool(getattr(args, "verify_patches", False)) or os.environ.get("BUSCA_VERIFY_PATCHES") == "1"
         if bool(getattr(args, "defer_crop_copies", False)) or os.environ.get("BUSCA_DEFER_CROP_COPIES") == "1":
             self.engine.set_option("defer_crop_copies", 1)
         self.expected_image_size = (384, 128)           # ReID_Encoder.PRETRAINED_SIZE (network.py:512)
@@ -175,6 +176,28 @@ class BUSCA:
         on this engine's GPU (``imgs[0].data_ptr()``, with height / width).  Returns the host copy the adapter hands on as
         ``current_frame`` (``to_host=False``: None; pass the frame's shape with ``device_frame_shape`` instead)."""
         return self.engine.ingest_frame(detector_tensor, means, std, height, width, to_host=to_host)
+
+    def _verify_patches(self, tracks, dets, kalman, mem_slots, det_slots, kal_slots, L, broader):
+        """Debug aid (args.verify_patches / BUSCA_VERIFY_PATCHES=1): the patch bank is addressed through the HOST arrays the adapter keeps in
+        ``images_mem`` (a crop is uploaded / gathered once, then found again by its address), which assumes the adapter never rewrites a
+        stored crop in place - none of the shipped ones does.  This check downloads every slot the call is about to read and compares it
+        with the bytes of the host array it stands for; a mismatch raises instead of silently associating on stale pixels."""
+        pairs = []
+        for t, track in enumerate(tracks):
+            sel = self._memory_indices(len(track.images_mem), L, broader)
+            if len(sel) == L:
+                pairs += [(int(mem_slots[t, k]), track.images_mem[j]) for k, j in enumerate(sel)]
+        pairs += [(int(s), d.images_mem[-1]) for s, d in zip(det_slots, dets)]
+        if kal_slots is not None:
+            pairs += [(int(s), k.images_mem[-1]) for s, k in zip(kal_slots, kalman)]
+        if not pairs:
+            return
+        self.engine.sync()
+        got = self.engine.bank_download(np.array([s for s, _ in pairs], np.int32))
+        for (slot, host), dev in zip(pairs, got):
+            if not np.array_equal(np.asarray(host), dev):
+                raise RuntimeError(f"patch-bank slot {slot} no longer matches the host crop it was registered for: a stored crop was modified in place "
+                                   "(busca_b200 addresses device patches through the arrays in images_mem; replace the array instead of writing into it)")
 
     def sync(self):
         """Wait for everything enqueued on this tracker's stream (with ``defer_crop_copies``: the crops' host bytes are valid afterwards)."""
@@ -296,6 +319,8 @@ class BUSCA:
                     * np.array([kd.scale for kd in extra_kalman_candidates], np.float64).reshape(T, 1)
             if pending:
                 self.engine.bank_upload(np.stack([p for p, _ in pending]), np.array([s for _, s in pending], np.int32))
+            if self.verify_patches:
+                self._verify_patches(tracks_embeddings, dets_embeddings, extra_kalman_candidates, mem_slots, det_slots, kal_slots, L, use_broader_memory)
             dists = np.asarray(dists_matrix, np.float64).reshape(T, D) if D else None
             want = ("probs", "cand") + (("cand_rows", "mem_logits") if self.store_logits else ())
             out = self.engine.associate(mem_slots, mem_ltwh, det_slots if D else None, det_ltwh if D else None, dists,

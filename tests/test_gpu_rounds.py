@@ -263,3 +263,43 @@ def test_deferred_crop_copies_are_the_same_bytes(golden_dir):
     slots = [lazy._registry.lookup(g2) for g2 in singles_g]
     assert all(s is not None for s in slots)
     assert np.array_equal(lazy.engine.bank_download(np.array(slots, np.int32)), np.stack(singles_w))
+
+
+def test_patch_bank_eviction_and_verification():
+    """8f row 4 (avoid_memory_leak, GHOST tracker.py:249-258): bank slots return to the pool when the adapter drops a crop; and the debug
+    option verify_patches catches an adapter that rewrites a stored crop in place (the bank would serve the old pixels)."""
+    import gc
+    from busca_b200.network import BUSCA
+    from busca_b200.option import load_args_from_config
+    from oracle import crop as ocrop
+    here = os.path.dirname(os.path.abspath(__file__))
+    targs, _ = load_args_from_config(os.path.join(os.path.dirname(here), "busca_b200", "configs", "bytetrack_mot20.yml"))
+    a = targs.transformer
+    a.device, a.verify_patches = "cuda:0", True
+    m = BUSCA(a).eval()
+    m.load_state_dict(synth.make_weights(0, profile="conditioned"))
+    base = m.engine.slots_in_use()
+    case = synth.make_assoc_case(7, 3, 6, targs.seq_len, crop_fn=lambda f, b: m.get_image_crops(f, b, normalize=False))
+    used = m.engine.slots_in_use()
+    assert used > base
+    from busca_b200 import tracking
+    dists = tracking.center_distance(case.tracks, case.dets, engine=m.engine)
+    kw = dict(seq_len=targs.seq_len, num_candidates=targs.num_candidates, use_broader_memory=targs.use_broader_memory,
+              select_highest_candidate=False, normalize_ims=True)
+    pm, rel = m.associate_embeddings(case.tracks, case.dets, dists, extra_kalman_candidates=case.kalman, **kw)   # verification passes on untouched crops
+    assert pm is not None and m.engine.slots_in_use() == used                        # temporary slots of the call are returned
+    del case, pm, rel, dists
+    gc.collect()
+    assert m.engine.slots_in_use() == base, (m.engine.slots_in_use(), base)           # the adapter dropped its crops: every slot is back
+
+    def tampered():
+        c2 = synth.make_assoc_case(8, 3, 6, targs.seq_len, crop_fn=lambda f, b: m.get_image_crops(f, b, normalize=False))
+        d2 = tracking.center_distance(c2.tracks, c2.dets, engine=m.engine)
+        kw2 = dict(kw, extra_kalman_candidates=c2.kalman)
+        c2.tracks[0].images_mem[-1][10:20, 10:20] ^= 0xFF                            # an adapter writing into a stored crop
+        try:
+            m.associate_embeddings(c2.tracks, c2.dets, d2, **kw2)
+        except RuntimeError as ex:
+            return "modified in place" in str(ex)
+        return False
+    assert tampered()
