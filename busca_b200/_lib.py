@@ -54,7 +54,7 @@ class DebugConvArgs(C.Structure):
 EXPORTS = [
     "busca_version", "busca_last_error", "busca_create", "busca_destroy", "busca_load_tensor", "busca_finalize",
     "busca_upload_frame", "busca_sync_frame", "busca_ingest_frame", "busca_camera_motion", "busca_bank_reserve", "busca_bank_capacity", "busca_crop", "busca_bank_upload",
-    "busca_bank_download", "busca_center_distance", "busca_iou", "busca_detection_coverage", "busca_kalman_predict", "busca_kalman_update", "busca_match_round", "busca_linear_assignment", "busca_duplicate_tracks", "busca_motion_proposals", "busca_frame_geometry",
+    "busca_bank_download", "busca_center_distance", "busca_iou", "busca_detection_coverage", "busca_kalman_predict", "busca_kalman_update", "busca_match_round", "busca_linear_assignment", "busca_duplicate_tracks", "busca_motion_proposals", "busca_frame_geometry", "busca_frame_geometry_batch",
     "busca_reid_embed", "busca_associate", "busca_transformer", "busca_frame_step_dev", "busca_dev_alloc",
     "busca_dev_free", "busca_host_alloc", "busca_host_free", "busca_memcpy_h2d", "busca_memcpy_d2h", "busca_sync", "busca_stream", "busca_kernel_launches",
     "busca_set_profiling", "busca_last_profile", "busca_set_option", "busca_counter", "busca_debug_conv", "busca_debug_conv_ex", "busca_conv_info", "busca_debug_stem", "busca_debug_umma_rowshift", "busca_debug_maxpool", "busca_debug_gram",
@@ -105,6 +105,7 @@ def load(build_if_missing: bool = True):
     L.busca_duplicate_tracks.argtypes = [vp, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_double, vp, vp]
     L.busca_motion_proposals.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp]
     L.busca_frame_geometry.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+    L.busca_frame_geometry_batch.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
     L.busca_reid_embed.argtypes = [vp, vp, C.c_int32, vp]
     L.busca_associate.argtypes = [vp, C.POINTER(AssocArgs)]
     L.busca_transformer.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -974,24 +974,27 @@ extern "C" int busca_duplicate_tracks(busca_ctx *c, const double *a_tlbr, const 
     return BUSCA_OK;
 }
 
-extern "C" int busca_frame_geometry(busca_ctx *c, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
-                                    int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
-                                    int32_t *cand) {
-    if (!c || T < 0 || D < 0 || C < 1 || !mean) return set_err(BUSCA_ERR_ARG, "bad argument");
-    if (T == 0) return BUSCA_OK;
+// B frames (of B independent sequences: one tracker process usually owns several) in ONE launch: grid (T, B)
+static int frame_geometry_batch(busca_ctx *c, int32_t B, const double *mean, const uint8_t *tracked, int32_t T0, const double *det_tlbr,
+                                int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
+                                int32_t *cand) {
+    if (!c || B < 1 || T0 < 0 || D < 0 || C < 1 || !mean) return set_err(BUSCA_ERR_ARG, "bad argument");
+    if (T0 == 0) return BUSCA_OK;
+    if ((long long)B * T0 > 0x7fffffffLL / 64 || B > 65535) return set_err(BUSCA_ERR_ARG, "batch too large");
+    const int32_t T = B * T0;                                   // rows of every per-track array below
     CUDA_OK(cudaSetDevice(c->cfg.device));
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 63) & ~(size_t)63; return o; };
-    size_t o_mean = take((size_t)T * 64), o_trk = take(T), o_det = take((size_t)(D ? D : 1) * 32), o_tlwh = take((size_t)T * 32),
+    size_t o_mean = take((size_t)T * 64), o_trk = take(T), o_det = take((size_t)B * (D ? D : 1) * 32), o_tlwh = take((size_t)T * 32),
            o_tlbr = take((size_t)T * 32), o_dist = take((size_t)T * (D ? D : 1) * 8), o_iou = take((size_t)T * (D ? D : 1) * 8),
            o_cand = take((size_t)T * C * 4);
     CUDA_OK(c->ws_small.ensure(off));
     char *base = (char *)c->ws_small.p;
     CUDA_OK(cudaMemcpyAsync(base + o_mean, mean, (size_t)T * 64, cudaMemcpyHostToDevice, c->stream));
     if (tracked) CUDA_OK(cudaMemcpyAsync(base + o_trk, tracked, T, cudaMemcpyHostToDevice, c->stream));
-    if (D) CUDA_OK(cudaMemcpyAsync(base + o_det, det_tlbr, (size_t)D * 32, cudaMemcpyHostToDevice, c->stream));
+    if (D) CUDA_OK(cudaMemcpyAsync(base + o_det, det_tlbr, (size_t)B * D * 32, cudaMemcpyHostToDevice, c->stream));
     GeomParams p{};
-    p.T = T; p.D = D; p.C = C; p.use_kalman = use_kalman; p.nbatch = 1;
+    p.T = T0; p.D = D; p.C = C; p.use_kalman = use_kalman; p.nbatch = B;
     p.mean = (const double *)(base + o_mean);
     p.tracked = tracked ? (const uint8_t *)(base + o_trk) : nullptr;
     p.det_tlbr = (const double *)(base + o_det);
@@ -1010,6 +1013,16 @@ extern "C" int busca_frame_geometry(busca_ctx *c, const double *mean, const uint
     CUDA_OK(stream_wait_short(c));
     prof_collect(c);
     return BUSCA_OK;
+}
+extern "C" int busca_frame_geometry(busca_ctx *c, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
+                                    int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
+                                    int32_t *cand) {
+    return frame_geometry_batch(c, 1, mean, tracked, T, det_tlbr, D, C, use_kalman, tlwh, tlbr, dist, iou, cand);
+}
+extern "C" int busca_frame_geometry_batch(busca_ctx *c, int32_t B, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
+                                          int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
+                                          int32_t *cand) {
+    return frame_geometry_batch(c, B, mean, tracked, T, det_tlbr, D, C, use_kalman, tlwh, tlbr, dist, iou, cand);
 }
 
 extern "C" int busca_motion_proposals(busca_ctx *c, const double *mean, const uint8_t *tracked, int32_t n, double *mean_out,

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(GEOM_THREADS) frame_geometry_kernel(GeomParams
             }
             // tlwh: ret[2] *= ret[3]; ret[:2] -= ret[2:] / 2
             double w = __dmul_rn(a, h);
-            double x = __dsub_rn(cx, __ddiv_rn(w, 2.0)), y = __dsub_rn(cy, __ddiv_rn(h, 2.0));
+            double x = __dsub_rn(cx, __dmul_rn(w, 0.5)), y = __dsub_rn(cy, __dmul_rn(h, 0.5));   // v / 2 == v * 0.5 bit for bit
             b.x1 = x; b.y1 = y; b.x2 = __dadd_rn(w, x); b.y2 = __dadd_rn(h, y);      // tlbr: ret[2:] += ret[:2]
             if (p.tlwh_out) { double *o = p.tlwh_out + row * 4; o[0] = x; o[1] = y; o[2] = w; o[3] = h; }
         } else {

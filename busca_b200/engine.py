@@ -399,6 +399,19 @@ class Engine:
                                           _ptr(tlwh), _ptr(tlbr), _ptr(dist), _ptr(iou), _ptr(cand)))
         return dict(tlwh=tlwh, tlbr=tlbr, dist=dist, iou=iou, cand=cand)
 
+    def frame_geometry_batch(self, mean, tracked, det_tlbr, C_: int, use_kalman: bool = True):
+        """frame_geometry for B frames in one launch: mean [B,T,8], tracked [B,T] or None, det_tlbr [B,D,4]."""
+        mean = np.ascontiguousarray(mean, np.float64)
+        det = np.ascontiguousarray(det_tlbr, np.float64)
+        B, T, D = mean.shape[0], mean.shape[1], det.shape[1]
+        trk = None if tracked is None else np.ascontiguousarray(tracked, np.uint8)
+        tlwh, tlbr = np.empty((B, T, 4)), np.empty((B, T, 4))
+        dist, iou = np.zeros((B, T, D)), np.zeros((B, T, D))
+        cand = np.empty((B, T, C_), np.int32)
+        check(self.L.busca_frame_geometry_batch(self.h, B, _ptr(mean), _ptr(trk), T, _ptr(det), D, C_, int(use_kalman),
+                                                _ptr(tlwh), _ptr(tlbr), _ptr(dist), _ptr(iou), _ptr(cand)))
+        return dict(tlwh=tlwh, tlbr=tlbr, dist=dist, iou=iou, cand=cand)
+
     # ---- network --------------------------------------------------------------------------
     def reid_embed(self, slots: np.ndarray) -> np.ndarray:
         slots = np.ascontiguousarray(slots, dtype=np.int32).reshape(-1)

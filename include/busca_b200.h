@@ -137,6 +137,11 @@ int busca_duplicate_tracks(busca_ctx *ctx, const double *a_tlbr, const int32_t *
 int busca_frame_geometry(busca_ctx *ctx, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
                          int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
                          int32_t *cand);
+/* The same for B frames of B independent sequences in one launch (one tracker process usually owns several sequences):
+ * mean [B,T,8], tracked [B,T], det_tlbr [B,D,4]; outputs [B,T,...]; cand holds per-frame indices (detection id, D + t, -1). */
+int busca_frame_geometry_batch(busca_ctx *ctx, int32_t B, const double *mean, const uint8_t *tracked, int32_t T, const double *det_tlbr,
+                               int32_t D, int32_t C, int32_t use_kalman, double *tlwh, double *tlbr, double *dist, double *iou,
+                               int32_t *cand);
 
 /* ---- appearance embedding -------------------------------------------------------------------- */
 /* ReID_Encoder.get_features on ONE BatchNorm batch                      network.py:542-570; resnet.py:266-322

@@ -303,3 +303,18 @@ def test_patch_bank_eviction_and_verification():
             return "modified in place" in str(ex)
         return False
     assert tampered()
+
+
+def test_frame_geometry_batch_equals_per_frame_calls(engine):
+    """busca_frame_geometry_batch (B frames of B sequences in one launch) = B calls of busca_frame_geometry, bit for bit."""
+    rng = np.random.default_rng(31)
+    B, T, D, Cn = 7, 23, 41, 5
+    mean = np.concatenate([rng.uniform(0, 1900, (B, T, 2)), rng.uniform(0.2, 0.8, (B, T, 1)), rng.uniform(60, 300, (B, T, 1)), rng.normal(0, 3, (B, T, 4))], axis=2)
+    tracked = rng.uniform(size=(B, T)) < 0.7
+    det = np.stack([synth.random_boxes(rng, D) for _ in range(B)])
+    det[:, :, 2:] += det[:, :, :2]
+    got = engine.frame_geometry_batch(mean, tracked, det, Cn)
+    for b in range(B):
+        want = engine.frame_geometry(mean[b], tracked[b], det[b], Cn)
+        for k in ("tlwh", "tlbr", "dist", "iou", "cand"):
+            assert np.array_equal(got[k][b], want[k]), (b, k)

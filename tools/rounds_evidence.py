@@ -39,6 +39,12 @@ def boxes(n):
 a, b = boxes(4096), boxes(4096)
 timed("iou_matrix", lambda: e.iou(a, b), 4096 * 4096 * 8 + 2 * 4096 * 32)
 timed("center_distance", lambda: e.center_distance(a, b), 4096 * 4096 * 8 + 2 * 4096 * 32)
+# the per-frame kernel over a batch of frames (64 sequences x one MOT20-scale frame): 2 x 30.7 MB of fp64 matrices + the candidate tables
+Bn, Tn, Dn = 64, 200, 300
+gm = np.concatenate([rng.uniform(0, 1900, (Bn, Tn, 2)), rng.uniform(0.2, 0.8, (Bn, Tn, 1)), rng.uniform(60, 300, (Bn, Tn, 1)), rng.normal(0, 3, (Bn, Tn, 4))], axis=2)
+gd = np.stack([boxes(Dn) for _ in range(Bn)])
+timed("frame_geometry", lambda: e.frame_geometry_batch(gm, None, gd, 5), Bn * Tn * Dn * 16 + Bn * (Tn * 64 + Dn * 32 + Tn * (64 + 20)))
+out["frame_geometry_batch64"] = out.pop("frame_geometry")
 # 8f row 1
 ta, tb = boxes(500), np.concatenate([boxes(500)[:350] + rng.normal(0, 4, (350, 4)), boxes(50)])
 sc = rng.uniform(0.1, 1, len(tb))
