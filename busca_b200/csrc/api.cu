@@ -908,6 +908,8 @@ static int match_round(busca_ctx *c, const double *a, int32_t na, const double *
                        double limit, int32_t *x, int32_t *y, double *cost_out) {
     if (!c || na < 0 || nb < 0) return set_err(BUSCA_ERR_ARG, "bad argument");
     if ((na > 0 && !x) || (nb > 0 && !y)) return set_err(BUSCA_ERR_ARG, "null pointer");
+    if (!(limit == limit) || limit >= 1e290 || limit <= -1e290)           // every row needs its finite 'unassigned' option: the solver terminates on it
+        return set_err(BUSCA_ERR_ARG, "assignment: cost_limit must be finite (lap.lapjv without a limit needs a square matrix; the trackers always pass one)");
     if (na == 0 || nb == 0) {                                    // matching.linear_assignment: empty matrix -> everything unmatched
         for (int i = 0; i < na; ++i) x[i] = -1;
         for (int j = 0; j < nb; ++j) y[j] = -1;

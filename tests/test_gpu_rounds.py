@@ -318,3 +318,15 @@ def test_frame_geometry_batch_equals_per_frame_calls(engine):
         want = engine.frame_geometry(mean[b], tracked[b], det[b], Cn)
         for k in ("tlwh", "tlbr", "dist", "iou", "cand"):
             assert np.array_equal(got[k][b], want[k]), (b, k)
+
+
+def test_round_argument_errors(engine):
+    from busca_b200._lib import BuscaError
+    with pytest.raises(BuscaError):
+        engine.linear_assignment(np.zeros((3, 3)), float("inf"))            # no finite 'unassigned' option: rejected, not a hang
+    with pytest.raises(BuscaError):
+        engine.linear_assignment(np.zeros((1, 9000)), 0.5)                  # rows + columns beyond the shared-memory solver
+    x, y = engine.linear_assignment(np.full((4, 3), np.nan), 0.5)           # NaN costs: nothing is assignable
+    assert (x == -1).all() and (y == -1).all()
+    x, y = engine.linear_assignment(np.full((2, 2), 0.5), 0.5)              # cost == limit: a tie between matching and not; either is optimal
+    assert set(x.tolist()) <= {-1, 0, 1}
