@@ -1853,6 +1853,7 @@ extern "C" int busca_set_option(busca_ctx *c, const char *name, int64_t value) {
     if (strcmp(name, "pool_mono") == 0) { reid_set_pool_mono(value); return BUSCA_OK; } // process-wide (experimental max-pool kernel)
     if (strcmp(name, "halo") == 0) { conv_tc_set_halo(value); return BUSCA_OK; }     // process-wide (experimental 3x3 kernel)
     if (strcmp(name, "mc_min_tiles") == 0) { conv_tc_set_mc_min_tiles((int)value); return BUSCA_OK; }   // process-wide
+    if (strcmp(name, "cg2_min_tiles") == 0) { conv_tc_set_cg2_min_tiles((int)value); return BUSCA_OK; } // process-wide (cta_group::2 convolutions)
     if (strcmp(name, "pdl") == 0) { pdl_set(value != 0); return BUSCA_OK; }          // process-wide (programmatic dependent launch)
     return set_err(BUSCA_ERR_ARG, "unknown option '%s'", name);
 }

@@ -156,14 +156,20 @@ struct TcCfg {
 // SM against ~39 B/clk of L2 delivery - 1220 cycles where the MMAs need 770 - and two thirds of those bytes are the weight tile every
 // CTA fetches for itself).  A shared-memory stage is then free when BOTH CTAs' MMAs have retired (commit multicast to both).
 // S4 (statistics-only passes, BN = 256, streamed weights): the three staging tiles - unused in that mode - are a FOURTH ring stage.
-template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false>
+template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool CG2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                                                                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                                                                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
                                                                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapIdt,
                                                                  const TcParams p) {
     using Cfg = TcCfg<BN, KB, DUAL, RESB>;
-    constexpr int STAGES = S4 ? Cfg::STAGES + 1 : Cfg::STAGES;
+    // CG2 (always together with MC's lockstep pair walk): ONE tcgen05.mma.cta_group::2 per K step covers both pixel tiles of the pair
+    // (M = 256); each CTA keeps its own A tile and only ITS HALF of the weight tile (32 KB per stage instead of 48 KB: four stages, a
+    // third fewer bytes into every SM per k-iteration, and the tensor core fetches half of B from each SM's shared memory).  The leader
+    // CTA issues; the peer's MMA warp relays "my stage is full / transformed" and "my accumulator is drained" to the leader's barriers.
+    static_assert(!CG2 || (MC && !RESB && !S4 && BN == 256), "cta_group::2 variant: paired, streamed weights, BN = 256");
+    constexpr int STAGES = CG2 ? 4 : (S4 ? Cfg::STAGES + 1 : Cfg::STAGES);
+    constexpr int STAGE_BYTES = CG2 ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
     static_assert(!S4 || (!RESB && Cfg::STAGE_BYTES == TC_XBUFS * Cfg::XBUF_BYTES), "the extra stage aliases the staging tiles");
     constexpr int G = BN / 64;                                                            // 64-channel groups per tile
     extern __shared__ uint8_t smem_raw[];
@@ -176,7 +182,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + Cfg::APAR_FLOATS);
     uint64_t *full = bars, *empty = full + STAGES, *ready = empty + STAGES, *tfull = ready + STAGES, *tempty = tfull + 2;
     uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS, *bfull = xfree + TC_XBUFS;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bfull + 1);
+    uint64_t *pfull = bfull + 1, *ptempty = pfull + STAGES;          // CG2, leader CTA: the peer's stage is ready / the peer's accumulator is drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptempty + 2);
+    uint32_t *xcnt = tmem_slot + 1;                                  // CG2, peer CTA: transform threads done with a stage (the 128th reports to the leader)
 
     static_assert(!(MC && RESB), "the paired kernel streams its weights");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,18 +196,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
     pdl_trigger();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? 2 : 1); mbar_init(&ready[s], (STAGES % 2) == 0 ? 128 : 256); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (MC && !CG2) ? 2 : 1); mbar_init(&ready[s], CG2 ? 129 : ((STAGES % 2) == 0 ? 128 : 256)); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
         for (int b = 0; b < TC_XBUFS; ++b) { mbar_init(&xfull[b], 1); mbar_init(&xfree[b], 1); }
         mbar_init(bfull, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&pfull[s], 1); xcnt[s] = 0; }
+        for (int a = 0; a < 2; ++a) mbar_init(&ptempty[a], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
     }
     if (want_stats)
         for (int i = threadIdx.x; i < 2 * p.Cout; i += TC_THREADS) s_par[i] = 0.f;
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     pdl_wait();              // everything above is private to this CTA; from here on the predecessor's results are read
     if (p.mode == MODE_FINAL)
@@ -238,20 +253,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 int tap = 0, cb = 0;
                 for (int kt = 0; kt < p.k_iters; ++kt) {
                     mbar_wait<32>(&empty[stage], phase ^ 1);      // MC: both CTAs of the pair have retired the MMAs that read this stage
-                    uint8_t *a_dst = tiles + stage * Cfg::STAGE_BYTES, *b_dst = a_dst + Cfg::A_BYTES;
+                    uint8_t *a_dst = tiles + stage * STAGE_BYTES, *b_dst = a_dst + Cfg::A_BYTES;
                     const bool main_op = !DUAL || kt < p.k1_iters;
-                    if (elect_one()) {
-                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    if (CG2 && !xform) {
+                        // no transform role in the way: both CTAs' loads complete on the LEADER's barrier (twice the bytes), no relay hop
+                        if (elect_one()) {
+                            if (cr == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                            const uint32_t lf = cluster_addr_of(&full[stage], 0);
+                            if (main_op) {
+                                const int m = p.tap_map[tap];
+                                const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
+                                tma_load_4d_cg2(a_dst, mp, lf, cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+                                tma_load_2d_cg2(b_dst, &mapB, lf, kt * Cfg::BKE, n_tile * BN + cr * (BN / 2));
+                            } else {
+                                const int cb2 = kt - p.k1_iters;
+                                tma_load_4d_cg2(a_dst, &mapA1, lf, cb2 * Cfg::BKE, 0, h0, n0);
+                                tma_load_2d_cg2(b_dst, &mapB2, lf, cb2 * Cfg::BKE, n_tile * BN + cr * (BN / 2));
+                            }
+                        }
+                    } else if (elect_one()) {
+                        mbar_expect_tx(&full[stage], STAGE_BYTES);
                         if (main_op) {
                             const int m = p.tap_map[tap];
                             const CUtensorMap *mp = m == 0 ? &mapA0 : (m == 1 ? &mapA1 : (m == 2 ? &mapA2 : &mapA3));
                             tma_load_4d(a_dst, mp, &full[stage], cb * Cfg::BKE, p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-                            if (MC) tma_load_2d_mc(b_dst + cr * (Cfg::B_BYTES / 2), &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN + cr * (BN / 2), (uint16_t)3);
+                            if (CG2) tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN + cr * (BN / 2));     // this CTA's half only
+                            else if (MC) tma_load_2d_mc(b_dst + cr * (Cfg::B_BYTES / 2), &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN + cr * (BN / 2), (uint16_t)3);
                             else if (!RESB) tma_load_2d(b_dst, &mapB, &full[stage], kt * Cfg::BKE, n_tile * BN);
                         } else {                                     // downsample branch: 1x1 (strided view) on the block input
                             const int cb2 = kt - p.k1_iters;
                             tma_load_4d(a_dst, &mapA1, &full[stage], cb2 * Cfg::BKE, 0, h0, n0);
-                            if (MC) tma_load_2d_mc(b_dst + cr * (Cfg::B_BYTES / 2), &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN + cr * (BN / 2), (uint16_t)3);
+                            if (CG2) tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN + cr * (BN / 2));
+                            else if (MC) tma_load_2d_mc(b_dst + cr * (Cfg::B_BYTES / 2), &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN + cr * (BN / 2), (uint16_t)3);
                             else if (!RESB) tma_load_2d(b_dst, &mapB2, &full[stage], cb2 * Cfg::BKE, n_tile * BN);
                         }
                     }
@@ -262,6 +295,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+        }
+    } else if (warp == 1 && CG2 && cr == 1) {
+        // ===================================================== CG2, peer CTA: no MMA issue - relay this CTA's pipeline state to the leader
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait<32>(&tempty[acc], acc_phase ^ 1);                 // this CTA's epilogue has drained its half of the accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive_remote(&ptempty[acc], 0);
+            __syncwarp();
+            // (the stages report to the leader directly: the loads complete on its full barrier when there is no transform, else this
+            // CTA's transform threads arrive on its ready barrier)
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer (the warp walks the loops, one elected lane issues: r02d)
@@ -276,14 +325,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait<32>(&tempty[acc], acc_phase ^ 1);
+                if (CG2) mbar_wait_cluster(&ptempty[acc], acc_phase);       // ... and the peer's half (its relay arrives once per tile)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kt = 0; kt < p.k_iters; ++kt) {
                     mbar_wait<0>(&full[stage], phase);
-                    if (xform) mbar_wait<0>(&ready[stage], phase);      // the transform warps have rewritten the A tile
+                    if (xform) {                                        // the transform warps have rewritten the A tile (CG2: of both CTAs)
+                        if (CG2) mbar_wait_cluster(&ready[stage], phase);
+                        else mbar_wait<0>(&ready[stage], phase);
+                    }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem_base + acc * 256;        // DUAL: the downsample conv accumulates into the same tile
                     const bool first = kt == 0;
-                    const uint32_t a_addr = smem_u32(tiles + stage * Cfg::STAGE_BYTES);
+                    const uint32_t a_addr = smem_u32(tiles + stage * STAGE_BYTES);
                     const uint64_t da = umma_desc<KB>(a_addr);
                     const uint64_t db = umma_desc<KB>(RESB ? smem_u32(resb) + (uint32_t)kt * Cfg::B_BYTES : a_addr + Cfg::A_BYTES);
                     if (elect_one()) {
@@ -296,14 +349,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                                 for (int k = 0; k < Cfg::BKE / 16; ++k)
                                     umma_bf16(tmem_base + acc * 256 + h * 128, db + (uint64_t)(h * (128 * KB / 16)) + 2 * k, da + 2 * k, idesc_t, !(first && k == 0));
+                        } else if (CG2) {
+                            // M = 256 over the pair, N = 256: A descriptor = this stage's pixel tile in EACH CTA, B descriptor = each CTA's weight half
+                            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+#pragma unroll
+                            for (int k = 0; k < Cfg::BKE / 16; ++k)
+                                umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc2, !(first && k == 0));
                         } else {
 #pragma unroll
                             for (int k = 0; k < Cfg::BKE / 16; ++k)     // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
                                 umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, !(first && k == 0));
                         }
-                        if (MC) umma_commit_mc(&empty[stage], (uint16_t)3);    // the stage holds halves written by both CTAs: it is free when both have read it
+                        if (CG2) umma_commit_cg2(&empty[stage], (uint16_t)3);  // both CTAs' stages are free when the pair's MMAs retire
+                        else if (MC) umma_commit_mc(&empty[stage], (uint16_t)3);    // the stage holds halves written by both CTAs: it is free when both have read it
                         else umma_commit(&empty[stage]);                        // frees the smem stage when these MMAs retire
-                        if (kt == p.k_iters - 1) umma_commit(&tfull[acc]);
+                        if (kt == p.k_iters - 1) {
+                            if (CG2) umma_commit_cg2(&tfull[acc], (uint16_t)3);     // each CTA's epilogue reads its own 128 accumulator rows
+                            else umma_commit(&tfull[acc]);
+                        }
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -386,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             const int bit = p.tap_bit[tap];
                             const uint4 th = lds128(par0 + (uint32_t)cb * 128), sg = lds128(par0 + (uint32_t)cb * 128 + 1024);
                             mbar_wait<0>(&full[stage], phase);
-                            const uint32_t base = tiles0 + stage * Cfg::STAGE_BYTES;
+                            const uint32_t base = tiles0 + stage * STAGE_BYTES;
                             if ((all9 >> bit) & 1) {
                                 uint4 v[8];
 #pragma unroll
@@ -415,7 +478,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         } else {
                             mbar_wait<0>(&full[stage], phase);
                         }
-                        mbar_arrive(&ready[stage]);     // every k-iteration, so the barrier phase tracks the stage ring
+                        if (CG2 && cr == 1) {
+                            // the peer's transform reports to the LEADER (the only MMA issuer) with ONE remote arrival per stage: its 128 threads
+                            // count themselves in shared memory (acq_rel: the last one has observed everybody's writes and proxy fences)
+                            uint32_t old;
+                            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&xcnt[stage])) : "memory");
+                            if (old == 127u) {
+                                xcnt[stage] = 0;                 // next use of this stage's counter is ordered behind the stage's empty -> full cycle
+                                mbar_arrive_remote(&ready[stage], 0);
+                            }
+                        } else {
+                            mbar_arrive(&ready[stage]);     // every k-iteration, so the barrier phase tracks the stage ring (CG2 leader: 128 + 1 arrivals)
+                        }
                     }
                     if (main_op) {
                         cb += EVEN ? 2 : 1;
@@ -682,7 +756,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -1408,12 +1483,12 @@ bool mc_enabled() {
     return on != 0;
 }
 
-template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false>
+template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool CG2 = false>
 cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     using Cfg = TcCfg<BN, KB, DUAL, RESB>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -1422,7 +1497,7 @@ cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB, (int)MC, (int)S4);
+    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB, (int)MC, (int)S4, (int)CG2);
     if (MC) {
         // clusters of two CTAs: pair tiles = ceil(tiles_m / 2) x tiles_n, one pair per two SMs, a pair stays on one channel tile when cheap
         const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
@@ -1436,14 +1511,14 @@ cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
         cfg.attrs = at; cfg.numAttrs = 2;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4>, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2>, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
     }
     const int total = p.tiles_m * p.tiles_n;
     int grid = total < g_num_sms ? total : g_num_sms;
     // keep a CTA on one channel tile (its statistics accumulators stay in registers) when that costs < 3 % of the SMs;
     // with resident weights it is a requirement (total is a multiple of tiles_n, so grid >= tiles_n stays one)
     if (p.tiles_n > 1 && grid > p.tiles_n && grid % p.tiles_n != 0 && (RESB || (grid % p.tiles_n) * 32 < grid)) grid -= grid % p.tiles_n;
-    return launch_pdl(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+    return launch_pdl(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
 }
 
 // whether a launch takes the paired variant: streamed weights, BN = 256, enough pixel tiles to keep every pair busy
@@ -1452,6 +1527,29 @@ int g_mc_min_tiles = -1;
 bool tc_use_mc(int BN, const TcParams &p) {
     const int min_tiles = g_mc_min_tiles >= 0 ? g_mc_min_tiles : 4 * (g_num_sms ? g_num_sms : 148);
     return (mc_enabled() || g_mc_min_tiles >= 0) && BN == 256 && p.mode != MODE_F32 && p.k_iters > 2 && p.tiles_m >= min_tiles;
+}
+
+// cta_group::2 variant: BN = 256, streamed weights, RAW or FINAL epilogues.  Measured per launch on a B200 (profiles/r04x_cg2_per_launch.txt,
+// bit-identical outputs): convolutions WITHOUT an A-tile transform (the 1x1 conv1 of layers 3-4, whose input is a finished block output)
+// run 10-13 % faster - a third fewer bytes into every SM per k-iteration, four ring stages instead of three, half of B fetched per SM;
+// launches WITH the transform run 7-26 % slower - their critical path is the transform role, which the pair only adds a cross-CTA
+// dependency to (the MMA waits for the slower of two CTAs every stage).  Default: on for the first kind only.
+// BUSCA_CG2=0: never; BUSCA_CG2=2 or busca_set_option("cg2_min_tiles", n): every eligible launch (tests, A/B runs).
+int g_cg2_min_tiles = -1;
+int cg2_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("BUSCA_CG2");
+        mode = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
+    }
+    return mode;
+}
+bool tc_use_cg2(int BN, const TcParams &p) {
+    if (BN != 256 || !(p.mode == MODE_RAW || p.mode == MODE_FINAL) || p.k_iters <= 2) return false;
+    if (g_cg2_min_tiles >= 0) return p.tiles_m >= g_cg2_min_tiles;
+    const int min_tiles = 2 * (g_num_sms ? g_num_sms : 148);
+    if (cg2_mode() == 0 || p.tiles_m < min_tiles) return false;
+    return cg2_mode() == 2 || p.a_xf == nullptr;
 }
 
 template <int BN, int KB = 128, bool DUAL = false>
@@ -1464,6 +1562,7 @@ cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
         total >= p.tiles_n)
         return launch_tc_v<BN, KB, DUAL, true, false>(m, p, s);
     if constexpr (BN == 256) {
+        if (tc_use_cg2(BN, p)) return launch_tc_v<BN, KB, DUAL, false, true, false, true>(m, p, s);
         if (tc_use_mc(BN, p)) return launch_tc_v<BN, KB, DUAL, false, true>(m, p, s);
         if constexpr (!DUAL) {
             static const bool s4 = !(getenv("BUSCA_S4") && getenv("BUSCA_S4")[0] == '0');
@@ -1573,6 +1672,7 @@ cudaError_t launch_conv3x3_halo(const ConvLayer &L, const ConvArgs &a, cudaStrea
 
 const char *conv_tc_last_kernel() { return g_last_kernel; }
 void conv_tc_set_mc_min_tiles(int n) { g_mc_min_tiles = n; }
+void conv_tc_set_cg2_min_tiles(int n) { g_cg2_min_tiles = n; }
 void conv_tc_set_halo(int on) { g_halo = on ? 1 : 0; }
 static bool tile_geometry(int Ho, int Wo, int &BW, int &BH, int &BI);
 namespace {
@@ -1720,7 +1820,7 @@ cudaError_t launch_conv_tc(const ConvLayer &L, const ConvArgs &a, const ConvTcOp
     // w16s = bf16(W * |scale_in|); FINAL: w16f = bf16(W * |scale_in| * scale of this conv's BN)
     // (paired variant: each CTA of a pair loads and multicasts half of a weight tile, so the box is BN / 2 rows)
     const bool resb_fit = resb_enabled() && p.k_iters <= 2 && (long long)p.k_iters * BN * 128 <= 65536;
-    const int b_rows = (!resb_fit && tc_use_mc(BN, p)) ? BN / 2 : BN;
+    const int b_rows = (!resb_fit && (tc_use_mc(BN, p) || tc_use_cg2(BN, p))) ? BN / 2 : BN;
     ok = ok && make_map2(&m.b, p.mode == MODE_FINAL ? L.w16f : (a.in_xf ? L.w16s : L.w16), (long long)p.ntaps * L.cin, L.cout, b_rows);
     m.b2 = m.b;
     if (dual) {

@@ -141,6 +141,7 @@ cudaError_t launch_umma_gram_probe(const uint16_t *a_dev /* [128][64*nb] bf16 */
 cudaError_t launch_umma_rowshift_probe(int shift, int fill, int use_base_offset, float *out_dev /* [128*64] */, cudaStream_t s);
 void conv_tc_set_halo(int on);       // experimental halo-box 3x3 kernel on/off (default: BUSCA_HALO env, off)
 void conv_tc_set_mc_min_tiles(int n); // paired (weight-multicast) variant from this many pixel tiles on (-1 = default, a huge value = never)
+void conv_tc_set_cg2_min_tiles(int n); // cta_group::2 variant from this many pixel tiles on (-1 = only with BUSCA_CG2=1)
 const char *conv_tc_last_kernel();   // "conv_tc_kernel<BN, KB, DUAL, RESB>" of the last tensor-core launch (profiling labels)
 cudaError_t launch_stem_tc(const uint8_t *bank, const int32_t *slots, int N, const float *lut, const void *wstem_bf16, void *scratch, void *out,
                            double *stats, const float *img_w, cudaStream_t s);

@@ -131,6 +131,59 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t cta_mask)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
                  : "memory");
 }
+// ---- cta_group::2: one MMA over a CTA pair (M = 256: each CTA holds 128 accumulator rows in its own TMEM, its own A tile and HALF of the
+// B tile in its own shared memory at the same offsets); issued by the leader CTA only, completion multicast to both CTAs' barriers
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask)
+                 : "memory");
+}
+// TMA loads of a CTA pair whose completion is signalled on an mbarrier that may live in the PEER CTA (`bar_cluster_addr` = mapa address):
+// both CTAs of a cta_group::2 pipeline report "my part of this stage has landed" straight to the leader's barrier
+__device__ __forceinline__ uint32_t cluster_addr_of(const void *p, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(p)), "r"(cta));
+    return remote;
+}
+__device__ __forceinline__ void tma_load_4d_cg2(void *smem, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem)),
+                 "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void *smem, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+                 "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait for a phase completed by a peer CTA's arrival (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

@@ -407,3 +407,52 @@ def test_paired_multicast_variant_is_bit_identical(engine, name, mode, N):
     assert targs(k0)[4] == 0 and targs(k1)[4] == 1, (k0, k1)           # ... and the second run really took the paired kernel (template argument MC)
     assert np.array_equal(o0, o1)
     assert np.allclose(s0, s1, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(s0).max()))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# cta_group::2 variant: one MMA over a CTA pair (M = 256), each CTA holding its own pixel tile and HALF of the weight tile
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,mode", [("layer3.1.conv1", 0), ("layer3.0.conv2", 0), ("layer4.1.conv2", 0),
+                                       ("layer3.1.conv3", 2), ("layer3.0.conv3", 2), ("layer4.0.conv3", 2)])
+@pytest.mark.parametrize("N", [5, 16])
+def test_cta_pair_mma_variant_is_bit_identical(engine, name, mode, N):
+    """conv_tc_kernel<.., MC=1, S4=0, CG2=1> (tcgen05.mma.cta_group::2 issued by the leader CTA of a pair, completion multicast to both)
+    against the one-CTA kernel: the same products accumulated in the same order, so the same bits - RAW (1x1, stride-2 and stride-1 3x3
+    through the tap loop), FINAL with an identity tensor and FINAL with the downsample conv, odd and even numbers of pixel tiles."""
+    _n, idx, H, W = _role(name)
+    rng = np.random.default_rng(idx * 5 + N + mode)
+    info = (C.c_int32 * 4)()
+    engine.L.busca_conv_info(engine.h, idx, info)
+    cin, cout, k, stride = list(info)
+    xb, _ = bf16_round(rng.standard_normal((N, H, W, cin)).astype(np.float32))
+    kw = {}
+    if name.endswith("conv2") or name.endswith("conv3"):
+        sc, sh = bn_params(rng, cin)
+        kw.update(in_scale=sc, in_shift=sh)
+    if mode == 2:
+        es, et = bn_params(rng, cout)
+        kw.update(e_scale=es, e_shift=et)
+        if name.split(".")[1] == "0":
+            engine.L.busca_conv_info(engine.h, idx + 1, info)
+            dcin, dstride = info[0], info[3]
+            db, _ = bf16_round(np.maximum(rng.standard_normal((N, H * dstride, W * dstride, dcin)), 0).astype(np.float32))
+            dsc, dsh = bn_params(rng, cout)
+            kw.update(ds_index=idx + 1, ds_in=db, ds_H=H * dstride, ds_W=W * dstride, ds_scale=dsc, ds_shift=dsh)
+        else:
+            ib, _ = bf16_round(np.maximum(rng.standard_normal((N, H // stride, W // stride, cout)), 0).astype(np.float32))
+            kw.update(idt=ib)
+    outs = []
+    try:
+        engine.set_profiling(True)
+        for min_tiles in (-1, 1):
+            engine.set_option("cg2_min_tiles", min_tiles)
+            o, st, _ = run_conv(engine, idx, xb, N, H, W, use_tc=1, mode=mode, **kw)
+            outs.append((o.copy(), st.copy(), engine.last_profile()["conv_tc"]["kernel"]))
+    finally:
+        engine.set_option("cg2_min_tiles", -1)
+        engine.set_profiling(False)
+    (o0, s0, k0), (o1, s1, k1) = outs
+    targs = lambda k: [int(v) for v in k[k.index("<") + 1:k.index(">")].split(",")]
+    assert targs(k0)[6] == 0 and targs(k1)[6] == 1, (k0, k1)     # the second run took the cta_group::2 kernel (template argument CG2)
+    assert np.array_equal(o0, o1)
+    assert np.allclose(s0, s1, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(s0).max()))
