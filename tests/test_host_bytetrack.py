@@ -28,7 +28,7 @@ def tracker_args(config="MOT20"):
     return args
 
 
-def replay(busca, iou_fn, cdist_fn, golden, n_frames=None, near_tie=0.0, config="MOT20", box_atol=1e-6, **host_kw):
+def replay(busca, iou_fn, cdist_fn, golden, n_frames=None, near_tie=0.0, config="MOT20", box_atol=1e-6, on_frame=None, **host_kw):
     """Run the driver over the golden's sequence; returns the list of frames whose Step-3b pool contained a documented
     near-tie (|p - busca_thresh| < near_tie in the reference) - from the first such frame on, ids may legitimately differ."""
     g = golden
@@ -38,7 +38,8 @@ def replay(busca, iou_fn, cdist_fn, golden, n_frames=None, near_tie=0.0, config=
     args = tracker_args(config)
     host = ByteTrackHost(busca, args, iou_fn=iou_fn, center_distance_fn=cdist_fn, **host_kw)
     for f in range(n_frames):
-        host.replay_frame = f
+        if on_frame is not None:
+            on_frame(f)
         out = host.update(seq.dets[f].copy(), [seq.H, seq.W], [seq.H, seq.W], current_frame=seq.frames[f])
         a, b = int(g["off"][f]), int(g["off"][f + 1])
         want_ids = g["ids"][a:b].tolist()
@@ -150,27 +151,13 @@ def test_driver_mot17_config_on_cpu(golden17):
     from oracle_busca import OracleBUSCA, OracleRounds, center_distance, iou
     busca = OracleBUSCA(synth.make_weights(0, profile="conditioned"))
     g = golden17
-    holder = {}
+    frame = [0]
 
     def reliable(shape, tracks, p):
         return ocov.is_reliable(shape, [np.asarray(t.tlbr) * t.scale for t in tracks], p)
 
-    def camera(prev, cur):
-        return g["warps"][holder["host"].replay_frame]
-
-    class Host(ByteTrackHost):
-        def __init__(self, *a, **k):
-            super().__init__(*a, **k)
-            holder["host"] = self
-
-    import busca_b200.hosts.bytetrack as hb
-    orig = hb.ByteTrackHost
-    try:
-        globals()["ByteTrackHost"] = Host
-        assert replay(busca, iou, center_distance, g, n_frames=16, config="MOT17", reliable_fn=reliable, camera_motion_fn=camera,
-                      rounds=OracleRounds()) is None
-    finally:
-        globals()["ByteTrackHost"] = orig
+    assert replay(busca, iou, center_distance, g, n_frames=16, config="MOT17", reliable_fn=reliable, camera_motion_fn=lambda prev, cur: g["warps"][frame[0]],
+                  rounds=OracleRounds(), on_frame=lambda f: frame.__setitem__(0, f)) is None
     assert (g["gate"][:16] == 1).any() and busca.calls >= 2
 
 
