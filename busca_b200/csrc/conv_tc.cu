@@ -156,7 +156,7 @@ struct TcCfg {
 // SM against ~39 B/clk of L2 delivery - 1220 cycles where the MMAs need 770 - and two thirds of those bytes are the weight tile every
 // CTA fetches for itself).  A shared-memory stage is then free when BOTH CTAs' MMAs have retired (commit multicast to both).
 // S4 (statistics-only passes, BN = 256, streamed weights): the three staging tiles - unused in that mode - are a FOURTH ring stage.
-template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool CG2 = false>
+template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool CG2 = false, bool RAW4 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                                                                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                                                                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
@@ -168,7 +168,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // third fewer bytes into every SM per k-iteration, and the tensor core fetches half of B from each SM's shared memory).  The leader
     // CTA issues; the peer's MMA warp relays "my stage is full / transformed" and "my accumulator is drained" to the leader's barriers.
     static_assert(!CG2 || (MC && !RESB && !S4 && BN == 256), "cta_group::2 variant: paired, streamed weights, BN = 256");
-    constexpr int STAGES = CG2 ? 4 : (S4 ? Cfg::STAGES + 1 : Cfg::STAGES);
+    // RAW4 (RAW epilogue, BN = 256, streamed weights, long k-loops: the 3x3 convolutions of the tap loop): these launches are bound by the
+    // round trip of a ring stage (load -> transform -> MMA -> commit: ~2 us over three 48 KB stages), not by the MMAs (0.4 us per
+    // k-iteration).  A FOURTH stage in place of two of the three staging tiles: the epilogue then packs, stores and waits on ONE tile (a
+    // fraction of a microsecond per 36-k-iteration tile), the statistics block shrinks to the 2 x 512 channels RAW launches can have.
+    // CG2 + RAW4: the same trade for the pair kernel - SIX 32 KB stages.
+    // BN = 128 (32 KB stages): two more stages, six in all.
+    static_assert(!RAW4 || (!RESB && MC == CG2 && !S4 && !DUAL && (BN == 256 || (BN == 128 && !CG2))), "deeper-ring RAW variant");
+    constexpr int STAGES = CG2 ? (RAW4 ? 6 : 4) : (RAW4 ? Cfg::STAGES + (BN == 128 ? 2 : 1) : (S4 ? Cfg::STAGES + 1 : Cfg::STAGES));
+    constexpr int XB = RAW4 ? 1 : TC_XBUFS;                           // staging tiles of the epilogue
+    constexpr int PAR_F = RAW4 ? 1024 : Cfg::PAR_FLOATS;
     constexpr int STAGE_BYTES = CG2 ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
     static_assert(!S4 || (!RESB && Cfg::STAGE_BYTES == TC_XBUFS * Cfg::XBUF_BYTES), "the extra stage aliases the staging tiles");
     constexpr int G = BN / 64;                                                            // 64-channel groups per tile
@@ -176,9 +185,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t *tiles = smem;
     uint8_t *resb = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                                // RESB: k_iters x [BN rows][KB bytes], swizzled
-    uint8_t *xbuf = resb + Cfg::RES_BYTES;                                                // TC_XBUFS x [128 rows][128 B], swizzled
-    float *s_par = reinterpret_cast<float *>(xbuf + TC_XBUFS * Cfg::XBUF_BYTES);
-    float *s_apar = s_par + Cfg::PAR_FLOATS;
+    uint8_t *xbuf = RAW4 ? smem + STAGES * STAGE_BYTES : resb + Cfg::RES_BYTES;     // XB x [128 rows][128 B], swizzled
+    float *s_par = reinterpret_cast<float *>(xbuf + XB * Cfg::XBUF_BYTES);
+    float *s_apar = s_par + PAR_F;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + Cfg::APAR_FLOATS);
     uint64_t *full = bars, *empty = full + STAGES, *ready = empty + STAGES, *tfull = ready + STAGES, *tempty = tfull + 2;
     uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS, *bfull = xfree + TC_XBUFS;
@@ -596,11 +605,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 for (int g = 0; g < G; ++g, ++gcount) {
                     // three staging tiles in rotation: the store of group g-1 may still be reading its tile while group g is packed and
                     // handed to the TMA engine (wait_group.read 1 only retires the stores up to g-2, whose tile group g+1 overwrites)
-                    const int xb = gcount % TC_XBUFS;
+                    const int xb = gcount % XB;
                     const uint32_t st = xb0 + xb * Cfg::XBUF_BYTES;
                     uint32_t r[32];
                     tmem_ld32(t_acc + g * 64 + half * 32, r);
                     TMEM_LD_WAIT();
+                    if (RAW4) {                                     // one staging tile: the previous store must have read it before it is packed again
+                        if (p.mode == MODE_RAW && e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        EPI_BAR();
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {       // 4 x 16 B = this thread's 32 channels of its row, swizzled like the TMA box
                         uint4 w;
@@ -612,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                     if (p.mode == MODE_RAW) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store(g-2) has released the tile group g+1 will overwrite
+                        if (!RAW4 && e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store(g-2) has released the tile group g+1 will overwrite
                     }
                     EPI_BAR();
                     if (p.mode == MODE_RAW && e == 0) tma_store_4d(xbuf + xb * Cfg::XBUF_BYTES, &mapOut, n_tile * BN + g * 64, 0, h0, n0);
@@ -1483,12 +1496,15 @@ bool mc_enabled() {
     return on != 0;
 }
 
-template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool CG2 = false>
+template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool CG2 = false, bool RAW4 = false>
 cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     using Cfg = TcCfg<BN, KB, DUAL, RESB>;
+    // RAW4: four 48 KB stages + one staging tile + 2 x 512 statistics floats + transform parameters + barriers
+    constexpr int SMEM_BYTES = RAW4 ? 1024 + 196608 + Cfg::XBUF_BYTES + (1024 + Cfg::APAR_FLOATS) * 4 + 512 : Cfg::SMEM;   // 4 x 48 KB or 6 x 32 KB of ring
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA)");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2, RAW4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -1497,28 +1513,28 @@ cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB, (int)MC, (int)S4, (int)CG2);
+    snprintf(g_last_kernel, sizeof(g_last_kernel), "conv_tc_kernel<%d, %d, %d, %d, %d, %d, %d, %d>", BN, KB, (int)DUAL, (int)RESB, (int)MC, (int)S4, (int)CG2, (int)RAW4);
     if (MC) {
         // clusters of two CTAs: pair tiles = ceil(tiles_m / 2) x tiles_n, one pair per two SMs, a pair stays on one channel tile when cheap
         const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
         int pairs = pair_tiles < g_num_sms / 2 ? pair_tiles : g_num_sms / 2;
         if (p.tiles_n > 1 && pairs > p.tiles_n && pairs % p.tiles_n != 0 && (pairs % p.tiles_n) * 32 < pairs) pairs -= pairs % p.tiles_n;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
         cfg.attrs = at; cfg.numAttrs = 2;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2>, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2, RAW4>, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
     }
     const int total = p.tiles_m * p.tiles_n;
     int grid = total < g_num_sms ? total : g_num_sms;
     // keep a CTA on one channel tile (its statistics accumulators stay in registers) when that costs < 3 % of the SMs;
     // with resident weights it is a requirement (total is a multiple of tiles_n, so grid >= tiles_n stays one)
     if (p.tiles_n > 1 && grid > p.tiles_n && grid % p.tiles_n != 0 && (RESB || (grid % p.tiles_n) * 32 < grid)) grid -= grid % p.tiles_n;
-    return launch_pdl(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM, s, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
+    return launch_pdl(conv_tc_kernel<BN, KB, DUAL, RESB, MC, S4, CG2, RAW4>, dim3(grid), dim3(TC_THREADS), SMEM_BYTES, s, m.a[0], m.a[1], m.a[2], m.a[3], m.b, m.b2, m.out, m.idt, p);
 }
 
 // whether a launch takes the paired variant: streamed weights, BN = 256, enough pixel tiles to keep every pair busy
@@ -1561,10 +1577,24 @@ cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     if (resb_enabled() && p.k_iters <= 2 && (long long)p.k_iters * TcCfg<BN, KB, DUAL, true>::B_BYTES <= TcCfg<BN, KB, DUAL, true>::RES_BYTES &&
         total >= p.tiles_n)
         return launch_tc_v<BN, KB, DUAL, true, false>(m, p, s);
+    if constexpr (BN == 128 && !DUAL) {
+        static const bool raw4 = !(getenv("BUSCA_RAW4") && getenv("BUSCA_RAW4")[0] == '0');
+        if (raw4 && p.mode == MODE_RAW && p.k_iters >= 8 && p.Cout <= 512 && p.a_xf != nullptr)
+            return launch_tc_v<BN, KB, DUAL, false, false, false, false, true>(m, p, s);         // six ring stages, one staging tile
+    }
     if constexpr (BN == 256) {
-        if (tc_use_cg2(BN, p)) return launch_tc_v<BN, KB, DUAL, false, true, false, true>(m, p, s);
+        if (tc_use_cg2(BN, p)) {
+            if constexpr (!DUAL) {
+                static const bool raw4 = !(getenv("BUSCA_RAW4") && getenv("BUSCA_RAW4")[0] == '0');
+                if (raw4 && p.mode == MODE_RAW && p.Cout <= 512) return launch_tc_v<BN, KB, DUAL, false, true, false, true, true>(m, p, s);   // six ring stages
+            }
+            return launch_tc_v<BN, KB, DUAL, false, true, false, true>(m, p, s);
+        }
         if (tc_use_mc(BN, p)) return launch_tc_v<BN, KB, DUAL, false, true>(m, p, s);
         if constexpr (!DUAL) {
+            static const bool raw4 = !(getenv("BUSCA_RAW4") && getenv("BUSCA_RAW4")[0] == '0');
+            if (raw4 && p.mode == MODE_RAW && p.k_iters >= 8 && p.Cout <= 512 && p.a_xf != nullptr)
+                return launch_tc_v<BN, KB, DUAL, false, false, false, false, true>(m, p, s);     // four ring stages, one staging tile
             static const bool s4 = !(getenv("BUSCA_S4") && getenv("BUSCA_S4")[0] == '0');
             if (s4 && p.mode == MODE_STATS) return launch_tc_v<BN, KB, DUAL, false, false, true>(m, p, s);    // no staging tiles in that mode: a fourth ring stage
         }
