@@ -174,10 +174,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // fraction of a microsecond per 36-k-iteration tile), the statistics block shrinks to the 2 x 512 channels RAW launches can have.
     // CG2 + RAW4: the same trade for the pair kernel - SIX 32 KB stages.
     // BN = 128 (32 KB stages): two more stages, six in all.
-    static_assert(!RAW4 || (!RESB && MC == CG2 && !S4 && !DUAL && (BN == 256 || (BN == 128 && !CG2))), "deeper-ring RAW variant");
+    // DUAL (FINAL epilogue with the downsample conv in the same accumulator: no identity loader, the staging tiles only rotate between the
+    // stores): the same trade, with the 2048-float shift block FINAL needs.
+    static_assert(!RAW4 || (!RESB && MC == CG2 && !S4 && (!DUAL || (BN == 256 && !CG2)) && (BN == 256 || (BN == 128 && !CG2))), "deeper-ring variant");
     constexpr int STAGES = CG2 ? (RAW4 ? 6 : 4) : (RAW4 ? Cfg::STAGES + (BN == 128 ? 2 : 1) : (S4 ? Cfg::STAGES + 1 : Cfg::STAGES));
     constexpr int XB = RAW4 ? 1 : TC_XBUFS;                           // staging tiles of the epilogue
-    constexpr int PAR_F = RAW4 ? 1024 : Cfg::PAR_FLOATS;
+    constexpr int PAR_F = RAW4 ? (DUAL ? 2048 : 1024) : Cfg::PAR_FLOATS;
     constexpr int STAGE_BYTES = CG2 ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
     static_assert(!S4 || (!RESB && Cfg::STAGE_BYTES == TC_XBUFS * Cfg::XBUF_BYTES), "the extra stage aliases the staging tiles");
     constexpr int G = BN / 64;                                                            // 64-channel groups per tile
@@ -647,8 +649,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
                 for (int g = 0; g < G; ++g, ++gcount) {
-                    const int b = gcount % TC_XBUFS;
-                    const uint32_t xph = (uint32_t)(gcount / TC_XBUFS) & 1;
+                    const int b = gcount % XB;
+                    const uint32_t xph = (uint32_t)(gcount / XB) & 1;
                     const uint32_t st = xb0 + b * Cfg::XBUF_BYTES;
                     const int col0 = n_tile * BN + g * 64 + half * 32;
                     // shift of this thread's 32 channels first (shared-memory latency overlaps the TMEM load), then the accumulator
@@ -667,6 +669,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + t4[j].w);
                     }
                     if (!DUAL) mbar_wait<0>(&xfull[b], xph);    // identity tile of this group has landed in the staging buffer
+                    if (DUAL && RAW4) {                         // one staging tile: the previous group's store must have read it
+                        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        EPI_BAR();
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint32_t addr = st + row_off + (uint32_t)(((half * 4 + j) ^ (row & 7)) << 4);
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (e == 0) {
                         if (DUAL) {
                             // no identity loader: the three staging tiles only rotate between the stores (as in the RAW epilogue)
-                            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            if (!RAW4) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         } else {
                             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // every earlier store has finished reading its buffer
                             if (gcount > 0) mbar_arrive(&xfree[(gcount - 1) % TC_XBUFS]);
@@ -1500,7 +1506,7 @@ template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool C
 cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     using Cfg = TcCfg<BN, KB, DUAL, RESB>;
     // RAW4: four 48 KB stages + one staging tile + 2 x 512 statistics floats + transform parameters + barriers
-    constexpr int SMEM_BYTES = RAW4 ? 1024 + 196608 + Cfg::XBUF_BYTES + (1024 + Cfg::APAR_FLOATS) * 4 + 512 : Cfg::SMEM;   // 4 x 48 KB or 6 x 32 KB of ring
+    constexpr int SMEM_BYTES = RAW4 ? 1024 + 196608 + Cfg::XBUF_BYTES + ((DUAL ? 2048 : 1024) + Cfg::APAR_FLOATS) * 4 + 512 : Cfg::SMEM;   // 4 x 48 KB or 6 x 32 KB of ring
     static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA)");
     static bool attr_set = false;
     if (!attr_set) {
@@ -1591,6 +1597,11 @@ cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
             return launch_tc_v<BN, KB, DUAL, false, true, false, true>(m, p, s);
         }
         if (tc_use_mc(BN, p)) return launch_tc_v<BN, KB, DUAL, false, true>(m, p, s);
+        if constexpr (DUAL) {
+            static const bool raw4d = !(getenv("BUSCA_RAW4") && getenv("BUSCA_RAW4")[0] == '0');
+            if (raw4d && p.mode == MODE_FINAL && p.k_iters >= 8 && p.Cout <= 2048)
+                return launch_tc_v<BN, KB, DUAL, false, false, false, false, true>(m, p, s);     // four ring stages, one staging tile
+        }
         if constexpr (!DUAL) {
             static const bool raw4 = !(getenv("BUSCA_RAW4") && getenv("BUSCA_RAW4")[0] == '0');
             if (raw4 && p.mode == MODE_RAW && p.k_iters >= 8 && p.Cout <= 512 && p.a_xf != nullptr)
