@@ -58,6 +58,7 @@ constexpr int TC_EPI_WARP0 = 10;     // epilogue warps 10..17
 constexpr int TC_IDT_WARP = 18;
 constexpr int TC_MAX_TAPS = 9;
 constexpr int TC_XBUFS = 3;          // staging tiles (128 rows x 128 B)
+constexpr int TC_XBUFS_MAX = 5;      // ... of the resident-weight FINAL launches (identity tiles in flight: see XB in conv_tc_kernel)
 
 enum { MODE_RAW = 0, MODE_STATS = 1, MODE_FINAL = 2, MODE_F32 = 3 };
 
@@ -178,8 +179,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // stores): the same trade, with the 2048-float shift block FINAL needs.
     static_assert(!RAW4 || (!RESB && MC == CG2 && !S4 && (!DUAL || (BN == 256 && !CG2)) && (BN == 256 || (BN == 128 && !CG2))), "deeper-ring variant");
     constexpr int STAGES = CG2 ? (RAW4 ? 6 : 4) : (RAW4 ? Cfg::STAGES + (BN == 128 ? 2 : 1) : (S4 ? Cfg::STAGES + 1 : Cfg::STAGES));
-    constexpr int XB = RAW4 ? 1 : TC_XBUFS;                           // staging tiles of the epilogue
-    constexpr int PAR_F = RAW4 ? (DUAL ? 2048 : 1024) : Cfg::PAR_FLOATS;
+    // Resident weights, FINAL with an identity tensor (layers 1-2: at the HBM roofline, 64 KB of identity and 64 KB of output per 16-32 KB
+    // of A): FIVE staging tiles, i.e. five identity tiles in flight per SM instead of three (the 32 KB were unused).
+    constexpr int XB = RAW4 ? 1 : ((RESB && !DUAL && BN == 256) ? TC_XBUFS_MAX : TC_XBUFS);   // staging tiles of the epilogue
+    constexpr int PAR_F = RAW4 ? (DUAL ? 2048 : 1024) : ((RESB && !DUAL && BN == 256) ? 2048 : Cfg::PAR_FLOATS);   // five staging tiles: a smaller statistics / shift block
     constexpr int STAGE_BYTES = CG2 ? Cfg::A_BYTES + Cfg::B_BYTES / 2 : Cfg::STAGE_BYTES;
     static_assert(!S4 || (!RESB && Cfg::STAGE_BYTES == TC_XBUFS * Cfg::XBUF_BYTES), "the extra stage aliases the staging tiles");
     constexpr int G = BN / 64;                                                            // 64-channel groups per tile
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     float *s_apar = s_par + PAR_F;
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_apar + Cfg::APAR_FLOATS);
     uint64_t *full = bars, *empty = full + STAGES, *ready = empty + STAGES, *tfull = ready + STAGES, *tempty = tfull + 2;
-    uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS, *bfull = xfree + TC_XBUFS;
+    uint64_t *xfull = tempty + 2, *xfree = xfull + TC_XBUFS_MAX, *bfull = xfree + TC_XBUFS_MAX;
     uint64_t *pfull = bfull + 1, *ptempty = pfull + STAGES;          // CG2, leader CTA: the peer's stage is ready / the peer's accumulator is drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ptempty + 2);
     uint32_t *xcnt = tmem_slot + 1;                                  // CG2, peer CTA: transform threads done with a stage (the 128th reports to the leader)
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (MC && !CG2) ? 2 : 1); mbar_init(&ready[s], CG2 ? 129 : ((STAGES % 2) == 0 ? 128 : 256)); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
-        for (int b = 0; b < TC_XBUFS; ++b) { mbar_init(&xfull[b], 1); mbar_init(&xfree[b], 1); }
+        for (int b = 0; b < TC_XBUFS_MAX; ++b) { mbar_init(&xfull[b], 1); mbar_init(&xfree[b], 1); }
         mbar_init(bfull, 1);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&pfull[s], 1); xcnt[s] = 0; }
         for (int a = 0; a < 2; ++a) mbar_init(&ptempty[a], 1);
@@ -700,7 +703,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             if (!RAW4) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         } else {
                             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // every earlier store has finished reading its buffer
-                            if (gcount > 0) mbar_arrive(&xfree[(gcount - 1) % TC_XBUFS]);
+                            if (gcount > 0) mbar_arrive(&xfree[(gcount - 1) % XB]);
                         }
                     }
                     EPI_BAR();
@@ -752,8 +755,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int n_tile = tile % p.tiles_n, m_tile = MC ? 2 * (tile / p.tiles_n) + cr : tile / p.tiles_n;
                 const int h0 = (m_tile % p.h_tiles) * p.BH, n0 = (m_tile / p.h_tiles) * p.BI;
                 for (int g = 0; g < G; ++g, ++gcount) {
-                    const int b = gcount % TC_XBUFS;
-                    const uint32_t xph = (uint32_t)(gcount / TC_XBUFS) & 1;
+                    const int b = gcount % XB;
+                    const uint32_t xph = (uint32_t)(gcount / XB) & 1;
                     mbar_wait<64>(&xfree[b], xph ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&xfull[b], Cfg::XBUF_BYTES);
@@ -1506,7 +1509,8 @@ template <int BN, int KB, bool DUAL, bool RESB, bool MC, bool S4 = false, bool C
 cudaError_t launch_tc_v(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     using Cfg = TcCfg<BN, KB, DUAL, RESB>;
     // RAW4: four 48 KB stages + one staging tile + 2 x 512 statistics floats + transform parameters + barriers
-    constexpr int SMEM_BYTES = RAW4 ? 1024 + 196608 + Cfg::XBUF_BYTES + ((DUAL ? 2048 : 1024) + Cfg::APAR_FLOATS) * 4 + 512 : Cfg::SMEM;   // 4 x 48 KB or 6 x 32 KB of ring
+    constexpr int SMEM_BYTES = RAW4 ? 1024 + 196608 + Cfg::XBUF_BYTES + ((DUAL ? 2048 : 1024) + Cfg::APAR_FLOATS) * 4 + 512     // 4 x 48 KB or 6 x 32 KB of ring
+                               : Cfg::SMEM + ((RESB && !DUAL && BN == 256) ? (TC_XBUFS_MAX - TC_XBUFS) * Cfg::XBUF_BYTES - (Cfg::PAR_FLOATS - 2048) * 4 : 0);
     static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB per CTA)");
     static bool attr_set = false;
     if (!attr_set) {
@@ -1581,7 +1585,7 @@ cudaError_t launch_tc(const TcMaps &m, const TcParams &p, cudaStream_t s) {
     // (only for tiles of one or two k-iterations: there the weight tile would otherwise be re-fetched for every 16 KB of A;
     // longer k-loops keep the deeper ring, which hides the TMA + transform latency of a stage)
     if (resb_enabled() && p.k_iters <= 2 && (long long)p.k_iters * TcCfg<BN, KB, DUAL, true>::B_BYTES <= TcCfg<BN, KB, DUAL, true>::RES_BYTES &&
-        total >= p.tiles_n)
+        total >= p.tiles_n && (BN != 256 || DUAL || (p.mode == MODE_FINAL ? p.Cout <= 2048 : 2 * p.Cout <= 2048)))
         return launch_tc_v<BN, KB, DUAL, true, false>(m, p, s);
     if constexpr (BN == 128 && !DUAL) {
         static const bool raw4 = !(getenv("BUSCA_RAW4") && getenv("BUSCA_RAW4")[0] == '0');
