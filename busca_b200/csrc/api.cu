@@ -101,7 +101,7 @@ struct busca_ctx {
     // scratch
     DevBuf ws_reid, ws_tr, ws_io, ws_small, ws_gram;
     uint8_t *d2h_ring = nullptr;                  // page-locked staging ring of d2h_pageable
-    cudaEvent_t d2h_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t d2h_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf ws_ecc;                                // camera-motion compensation: 5 fp32 planes + partial sums + state
     int ecc_H = 0, ecc_W = 0, ecc_cur = 0;        // size of the cached planes; which of the two smoothed planes holds the LAST current frame
     bool ecc_have_prev = false;
@@ -682,8 +682,8 @@ static int check_slots(busca_ctx *c, const int32_t *slots, int n, bool allow_neg
 // memory is staged by the driver on one thread (~6.5 GB/s measured, page faults of the fresh array included); here the DMA lands in a
 // ring of page-locked chunks at PCIe speed and worker threads copy finished chunks into the destination (first-touch faults in
 // parallel).  The stream is idle when this returns.
-constexpr size_t D2H_CHUNK = 4u << 20;
-constexpr int D2H_RING = 4, D2H_WORKERS = 3;
+constexpr size_t D2H_CHUNK = 2u << 20;
+constexpr int D2H_RING = 8, D2H_WORKERS_DEFAULT = 6;       // BUSCA_D2H_WORKERS overrides (1..16)
 static int d2h_pageable(busca_ctx *c, uint8_t *dst, const uint8_t *src, size_t bytes) {
     if (!c->d2h_ring) {
         CUDA_OK(cudaHostAlloc((void **)&c->d2h_ring, D2H_CHUNK * D2H_RING, cudaHostAllocPortable));
@@ -708,7 +708,12 @@ static int d2h_pageable(busca_ctx *c, uint8_t *dst, const uint8_t *src, size_t b
         }
     };
     std::vector<std::thread> pool;
-    for (int w = 0; w < std::min(D2H_WORKERS, K); ++w) pool.emplace_back(worker);
+    static int n_workers = 0;
+    if (!n_workers) {
+        const char *e = getenv("BUSCA_D2H_WORKERS");
+        n_workers = e ? std::max(1, std::min(16, atoi(e))) : D2H_WORKERS_DEFAULT;
+    }
+    for (int w = 0; w < std::min(n_workers, K); ++w) pool.emplace_back(worker);
     cudaError_t err = cudaSuccess;
     for (int k = 0; k < K && err == cudaSuccess && !failed.load(); ++k) {
         if (k >= D2H_RING)
