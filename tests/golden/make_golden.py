@@ -2,7 +2,11 @@
 """Generate the golden fixtures under tests/golden/ by running the UNMODIFIED reference
 (/root/reference, imported read-only with the shims next to this file) on CPU.
 
-Run in the build container only:   python tests/golden/make_golden.py
+Run in the build container only:   python tests/golden/make_golden.py [crops geometry pe assoc]      (default set)
+                                   python tests/golden/make_golden.py cond scene scene_mot20 adapter adapter_mot17   (conditioned weights)
+                                   python tests/golden/make_golden.py coverage rounds                  
+                                   python tests/golden/make_golden.py ingest                           (8f row 4)
+                                   python tests/golden/make_golden.py ecc                              (8f row 3: cv2 itself)
 The GPU box never runs this (it has no /root/reference); it only reads the .npz files.
 
 Inputs are not stored: they are regenerated from seeds by busca_b200.synth (numpy PCG64), so
